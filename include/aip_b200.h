@@ -1,0 +1,140 @@
+/* aip_b200.h -- C ABI of the B200-native spectrogram front-end / back-end.
+ *
+ * One shared object (libaip_b200.so, sm_100a SASS only) that replaces, for batches of clips that
+ * are already resident in GPU memory, the numeric core of the reference's Python functions
+ * (savage-hacker14/ml-audio-inpainting; file:line relative to the reference root):
+ *
+ *   aip_stft_fwd_f32        librosa.stft as called by utils.extract_spectrogram   utils.py:192-234
+ *                           + the callers' epilogues: |S|, log10(|S|+eps)          models/CNNBLSTM/dataset.py:103-119
+ *                             log1p(|S|**p), angle(S), frame masks                 models/GAN/dataset.py:121-152
+ *                             spectrum-domain gap                                  models/model_eval.py:146-154
+ *                           + time-domain gap zeroing before the transform         utils.py:141-142, :180-183, add_gaps.py:28-32
+ *   aip_istft_f32           librosa.istft as called by utils.spectrogram_to_audio  utils.py:316-327
+ *                           (complex input, or magnitude * exp(j*phase), dB / 10** / expm1 prologue)
+ *   aip_griffinlim_f32      librosa.griffinlim (momentum 0.99)                     utils.py:328-332
+ *   aip_db_heuristic_f32    "max < 0 and mean < 0 => dB" test                      utils.py:313-314
+ *   aip_gap_zero_f32        zero a sample range per clip                           utils.py:180-183, add_gaps.py:28-32, pre_process_dataset.py:38
+ *   aip_gap_mask_f32        dense sample-domain 1/0 mask                           utils.py:141-142
+ *   aip_frame_mask_f32      dense [F,T] frame mask                                 models/CNNBLSTM/dataset.py:115-118, models/GAN/dataset.py:150-152
+ *   aip_peak_normalize_f32  librosa.util.normalize (norm=inf)                      utils.py:84
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless stated otherwise;
+ *   - the caller allocates every output and every workspace; nothing is allocated, freed or
+ *     synchronised inside; work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - spectrogram layout is the reference's: [B, F = n_fft/2 + 1, T] with T contiguous
+ *     (complex as interleaved float pairs); waveforms are [B, L] rows with an explicit pitch;
+ *   - return value: 0 = ok, < 0 = argument / support error (AIP_ERR_*), > 0 = cudaError_t;
+ *   - re-entrant and thread-safe: there is no mutable global state (twiddle tables are constants
+ *     in the image; windows are caller-supplied);
+ *   - there is NO CPU fallback: on a device that is not compute capability 10.x every entry point
+ *     returns AIP_ERR_DEVICE.
+ */
+#ifndef AIP_B200_H_
+#define AIP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AIP_OK 0
+#define AIP_ERR_ARG (-1)          /* null pointer / negative size / inconsistent sizes */
+#define AIP_ERR_UNSUPPORTED (-2)  /* parameter combination not implemented (e.g. n_fft not a power of two) */
+#define AIP_ERR_DEVICE (-3)       /* current device is not sm_100 */
+#define AIP_ERR_WORKSPACE (-4)    /* workspace too small */
+
+/* forward magnitude epilogue */
+#define AIP_MAG_NONE 0
+#define AIP_MAG_ABS 1
+#define AIP_MAG_LOG10_EPS 2       /* log10(|S| + eps) */
+#define AIP_MAG_LOG1P_POW 3       /* log1p(|S| ** power) */
+#define AIP_MAG_POW 4             /* |S| ** power */
+
+/* inverse magnitude prologue */
+#define AIP_DOM_LINEAR 0
+#define AIP_DOM_POW10 1           /* 10 ** x */
+#define AIP_DOM_DB 2              /* 10 ** (x / 20) */
+#define AIP_DOM_EXPM1 3           /* expm1(x) */
+
+typedef struct aip_stft_desc {
+  int32_t n_fft;        /* power of two, 32 .. 4096; 512 runs the register-FFT kernels */
+  int32_t hop;          /* > 0 */
+  int32_t center;       /* 1: zero-pad n_fft/2 on both sides (librosa >= 0.10 pad_mode="constant") */
+  int32_t reserved;
+  const float* window;  /* device [n_fft]: the centre-padded fft window (librosa.filters.get_window + pad_center) */
+} aip_stft_desc;
+
+/* Number of frames librosa.stft yields for L samples; < 0 on error. */
+int64_t aip_num_frames(int64_t L, int32_t n_fft, int32_t hop, int32_t center);
+/* Output length of librosa.istft for T frames (length == 0: natural length). */
+int64_t aip_istft_length(int64_t T, int32_t n_fft, int32_t hop, int32_t center, int64_t length);
+
+/* Forward transform + fused epilogues.  Any of the four outputs may be null (mag_out must be
+ * non-null iff mag_kind != AIP_MAG_NONE).  T_out <= aip_num_frames(...) frames are written.
+ *   gap_samples  [B,2] int32 or null: samples [g0,g1) of clip b are treated as zero;
+ *   zero_frames  [B,2] int32 or null: the spectrum of frames [f0,f1) is zeroed before the epilogue;
+ *   mask_frames  [B,2] int32 or null: frame range for mask_out; mask_in_gap_is_one selects the
+ *                CNNBLSTM (1 inside, 0 outside) or GAN (0 inside, 1 outside) convention.          */
+int aip_stft_fwd_f32(const aip_stft_desc* desc,
+                     const float* wave, int64_t B, int64_t L, int64_t wave_pitch,
+                     const int32_t* gap_samples, const int32_t* zero_frames,
+                     const int32_t* mask_frames, int32_t mask_in_gap_is_one,
+                     int32_t mag_kind, float eps, float power, int64_t T_out,
+                     float* spec_out /* [B,F,T_out,2] */, float* mag_out, float* phase_out, float* mask_out,
+                     void* stream);
+
+/* Inverse transform.  Input: spec (complex) or mag (+ optional phase).  `T` is the frame count
+ * (row length) of the inputs; `length` = 0 for librosa's natural length hop*(T-1) (center) else the
+ * requested length.  inv_wss: device [out_len] from aip_inv_window_sumsquare_f32.
+ * db_flags: [B] int32 or null; non-zero entries force the dB prologue for that clip.
+ * workspace: only needed when n_fft != 512 (aip_istft_workspace_bytes).                            */
+int aip_istft_f32(const aip_stft_desc* desc,
+                  const float* spec, const float* mag, const float* phase, int32_t mag_domain,
+                  const int32_t* db_flags,
+                  int64_t B, int64_t T, int64_t length, const float* inv_wss,
+                  float* wave_out, int64_t out_pitch,
+                  void* workspace, size_t workspace_bytes, void* stream);
+size_t aip_istft_workspace_bytes(int64_t B, int64_t T, int32_t n_fft);
+
+/* 1 / window_sumsquare (where > FLT_MIN, else 1), accumulated in float32 frame by frame exactly as
+ * librosa.filters.window_sumsquare does; written to inv_wss[out_len].                              */
+int aip_inv_window_sumsquare_f32(const aip_stft_desc* desc, int64_t T, int64_t length,
+                                 float* inv_wss, int64_t out_len, void* stream);
+
+/* Griffin-Lim: n_iter x (istft, stft + fused phase update) and a final istft.
+ *   mag     [B,F,T] linear magnitudes;
+ *   angles  [B,F,T,2] in: initial unit phasors (caller-drawn); used as the iteration state;
+ *   tprev   [B,F,T,2] scratch;  wave_tmp / wave_out [B, out_len] (wave_out doubles as the iteration buffer). */
+int aip_griffinlim_f32(const aip_stft_desc* desc, const float* mag, float* angles, float* tprev,
+                       int64_t B, int64_t T, int32_t n_iter, float momentum, const float* inv_wss,
+                       float* wave_out, int64_t out_pitch,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* flags[b] = (max(x_b) < 0 && mean(x_b) < 0), x_b = x[b*n .. (b+1)*n). */
+int aip_db_heuristic_f32(const float* x, int64_t B, int64_t n, int32_t* flags, void* stream);
+
+/* out[b, s] = (g0_b <= s < g1_b) ? 0 : in[b, s]   (in == out allowed). */
+int aip_gap_zero_f32(const float* in, int64_t in_pitch, float* out, int64_t out_pitch,
+                     int64_t B, int64_t L, const int32_t* gap_samples, void* stream);
+/* mask[b, s] = (g0_b <= s < g1_b) ? 0 : 1 */
+int aip_gap_mask_f32(float* mask, int64_t pitch, int64_t B, int64_t L, const int32_t* gap_samples, void* stream);
+/* mask[b, f, t] = 1/0 by frame range (see aip_stft_fwd_f32). */
+int aip_frame_mask_f32(float* mask, int64_t B, int64_t F, int64_t T, const int32_t* mask_frames,
+                       int32_t mask_in_gap_is_one, void* stream);
+/* y_b / max|y_b| unless max|y_b| < FLT_MIN; peaks: [B] float scratch/out (the per-clip max|y|). */
+int aip_peak_normalize_f32(const float* in, int64_t in_pitch, float* out, int64_t out_pitch,
+                           int64_t B, int64_t L, float* peaks, void* stream);
+
+const char* aip_status_string(int status);
+/* "aip_b200 <version> sm_100a" */
+const char* aip_version(void);
+/* 1 when the current device can run the kernels (compute capability 10.x), else 0. */
+int aip_device_supported(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AIP_B200_H_ */

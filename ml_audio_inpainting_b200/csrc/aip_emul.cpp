@@ -1,0 +1,89 @@
+// Host replay of the n_fft = 512 kernels (TEST SUPPORT, not a product path and not a fallback:
+// nothing in the package loads this library; tests/ builds and calls it).
+//
+// It compiles csrc/aip_tiles.cuh with g++ and runs the kernels' phase functions thread by thread
+// -- for tile: for phase: for tid in 0..255 -- i.e. the same indexing and arithmetic the GPU runs,
+// so that the lane/warp -> (frame, job) maps, the exchange-buffer layout, the split pass and the
+// overlap-add can be checked against the oracle in the CPU-only test tier.
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "aip_tiles.cuh"
+
+using namespace aip;
+
+extern "C" {
+
+int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, int center,
+                     const float* window, const int* gap_samples, const int* zero_frames,
+                     const int* mask_frames, int mask_in_gap_is_one, int mag_kind, float eps, float power,
+                     int T_out, float* spec, float* mag, float* phase, float* mask, int vec_ok) {
+  FwdParams P;
+  memset(&P, 0, sizeof(P));
+  P.wave = wave; P.wave_pitch = pitch; P.B = B; P.L = L;
+  P.hop = hop; P.pad = center ? 256 : 0;
+  P.T = 1 + (L + 2 * P.pad - 512) / hop;
+  if (T_out > P.T || (hop & 1)) return -1;
+  P.T_out = T_out;
+  P.window = window;
+  P.gap_samples = gap_samples; P.zero_frames = zero_frames; P.mask_frames = mask_frames;
+  P.mask_in_gap_is_one = mask_in_gap_is_one;
+  P.mag_kind = mag_kind; P.eps = eps; P.power = power;
+  P.spec = reinterpret_cast<float2*>(spec); P.mag = mag; P.phase = phase; P.mask = mask;
+  P.tiles_per_clip = (T_out + kFR - 1) / kFR;
+  P.n_tiles = (long long)B * P.tiles_per_clip;
+  P.tile_floats = (fwd_tile_len(hop) + 3) & ~3;
+  P.vec_ok = vec_ok && ((hop & 3) == 0) && ((pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(wave) & 15) == 0);
+  std::vector<float> tile(P.tile_floats);
+  std::vector<float2> exch(kExch);
+  std::vector<LaneConst> lc(kThreads);
+  for (int tid = 0; tid < kThreads; ++tid) lane_const_init(lc[tid], window, tid & 15, 0.5f);
+  const bool extra = spec || phase || mask || zero_frames || !(mag_kind == MAG_ABS || mag_kind == MAG_LOG10_EPS);
+  for (long long tix = 0; tix < P.n_tiles; ++tix) {
+    for (int tid = 0; tid < kThreads; ++tid) fwd_phase0(P, tid, tix, tile.data());
+    for (int tid = 0; tid < kThreads; ++tid) fwd_phase1(P, tid, tile.data(), exch.data(), lc[tid]);
+    for (int tid = 0; tid < kThreads; ++tid) {
+      if (extra) fwd_phase2<MAG_NONE, true>(P, tid, tix, exch.data());
+      else if (mag_kind == MAG_ABS) fwd_phase2<MAG_ABS, false>(P, tid, tix, exch.data());
+      else fwd_phase2<MAG_LOG10_EPS, false>(P, tid, tix, exch.data());
+    }
+  }
+  return 0;
+}
+
+int emul_istft512(const float* spec, const float* mag, const float* phase, int mag_domain,
+                  const int* db_flags, int B, int T, int length, int hop, int center,
+                  const float* window, const float* inv_wss, float* out, long long out_pitch) {
+  InvParams P;
+  memset(&P, 0, sizeof(P));
+  P.spec = reinterpret_cast<const float2*>(spec); P.mag = mag; P.phase = phase; P.mag_domain = mag_domain;
+  P.db_flags = db_flags; P.B = B; P.T = T;
+  P.hop = hop; P.pad = center ? 256 : 0;
+  if (hop & 1) return -1;
+  P.g = inv_geom(hop, P.pad);
+  if (P.g.FO < 4) return -2;
+  int out_len = length > 0 ? length : 512 + hop * (T - 1) - 2 * P.pad;
+  P.n_frames = T;
+  if (length > 0) {
+    const int nf = (length + 2 * P.pad + hop - 1) / hop;
+    P.n_frames = nf < T ? nf : T;
+  }
+  P.out_len = out_len;
+  P.window = window; P.inv_wss = inv_wss; P.out = out; P.out_pitch = out_pitch;
+  P.vec_ok = ((out_pitch & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
+  const long long span = (long long)P.g.FO * hop;
+  P.tiles_per_clip = (int)((out_len + span - 1) / span);
+  P.n_tiles = (long long)B * P.tiles_per_clip;
+  std::vector<float2> exch(kExch);
+  std::vector<LaneConst> lc(kThreads);
+  for (int tid = 0; tid < kThreads; ++tid) lane_const_init(lc[tid], window, tid & 15, 1.0f / 512.0f);
+  for (long long tix = 0; tix < P.n_tiles; ++tix) {
+    for (int tid = 0; tid < kThreads; ++tid) inv_phase0(P, tid, tix, exch.data());
+    for (int tid = 0; tid < kThreads; ++tid) inv_phase1(P, tid, exch.data(), lc[tid]);
+    for (int tid = 0; tid < kThreads; ++tid) inv_phase2(P, tid, tix, exch.data());
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,648 @@
+// sm_100a kernels + C ABI (include/aip_b200.h) of the spectrogram front-end / back-end.
+//
+// Kernels
+//   stft512_fwd_kernel   persistent; tile = 32 frames of one clip; waveform staged once in shared
+//                        memory, register 16x16 FFT, split pass, fused |S| / log / phase / mask /
+//                        Griffin-Lim epilogue, coalesced [F,T] stores (see aip_core.cuh).
+//   istft512_kernel      persistent; tile = 32 frames -> FO hops of output; split-pass prologue,
+//                        register inverse FFT, synthesis window, overlap-add and window-sum-square
+//                        normalisation out of shared memory (no global atomics, halo frames recomputed).
+//   stft_generic_* / istft_generic_*   any power-of-two n_fft in [32, 4096] (or odd hop): one frame
+//                        per CTA, shared-memory radix-2.  Correct, not tuned: the reference's
+//                        models only ever use n_fft = 512 (config.py:28, GAN/config.yaml:12).
+//   small elementwise / reduction kernels for the gap, mask, dB-heuristic and peak-normalise rows.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/aip_b200.h"
+#include "aip_tiles.cuh"
+
+namespace aip {
+
+// ---------------------------------------------------------------------------------------------------
+// n_fft = 512 kernels
+// ---------------------------------------------------------------------------------------------------
+template <int kMag, bool kExtra>
+__global__ void __launch_bounds__(kThreads, 2) stft512_fwd_kernel(const FwdParams P) {
+  extern __shared__ __align__(16) float smem[];
+  float* tile = smem;
+  float2* exch = reinterpret_cast<float2*>(smem + P.tile_floats);
+  const int tid = threadIdx.x;
+  LaneConst lc;
+  lane_const_init(lc, P.window, tid & 15, 0.5f);
+  for (long long tix = blockIdx.x; tix < P.n_tiles; tix += gridDim.x) {
+    fwd_phase0(P, tid, tix, tile);
+    __syncthreads();
+    fwd_phase1(P, tid, tile, exch, lc);
+    __syncthreads();
+    fwd_phase2<kMag, kExtra>(P, tid, tix, exch);
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 2) istft512_kernel(const InvParams P) {
+  extern __shared__ __align__(16) float smem[];
+  float2* exch = reinterpret_cast<float2*>(smem);
+  const int tid = threadIdx.x;
+  LaneConst lc;
+  lane_const_init(lc, P.window, tid & 15, 1.0f / 512.0f);
+  for (long long tix = blockIdx.x; tix < P.n_tiles; tix += gridDim.x) {
+    inv_phase0(P, tid, tix, exch);
+    __syncthreads();
+    inv_phase1(P, tid, exch, lc);
+    __syncthreads();
+    inv_phase2(P, tid, tix, exch);
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// generic power-of-two path: one frame per CTA, radix-2 DIT in shared memory
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void smem_fft(float2* buf, int N, int logN, bool inverse) {
+  // input already in bit-reversed order
+  for (int s = 1; s <= logN; ++s) {
+    const int half = 1 << (s - 1);
+    for (int j = threadIdx.x; j < (N >> 1); j += blockDim.x) {
+      const int pos = j & (half - 1);
+      const int i0 = ((j >> (s - 1)) << s) + pos;
+      const int i1 = i0 + half;
+      float sn, cs;
+      sincospif((float)pos / (float)half, &sn, &cs);   // exp(-j pi pos/half) = cs - j sn
+      if (inverse) sn = -sn;
+      const float2 a = buf[i0], b = buf[i1];
+      const float tr = b.x * cs + b.y * sn;
+      const float ti = b.y * cs - b.x * sn;
+      buf[i0] = make_float2(a.x + tr, a.y + ti);
+      buf[i1] = make_float2(a.x - tr, a.y - ti);
+    }
+    __syncthreads();
+  }
+}
+
+struct GenericFwdParams {
+  FwdParams P;
+  int N, logN, F;
+};
+
+__global__ void __launch_bounds__(256) stft_generic_fwd_kernel(const GenericFwdParams G) {
+  extern __shared__ __align__(16) float smem[];
+  float2* buf = reinterpret_cast<float2*>(smem);
+  const FwdParams& P = G.P;
+  const int N = G.N;
+  for (long long fix = blockIdx.x; fix < P.n_tiles; fix += gridDim.x) {
+    const int b = (int)(fix / P.T_out);
+    const int t = (int)(fix % P.T_out);
+    const float* src = P.wave + (long long)b * P.wave_pitch;
+    int gs = 0, ge = 0;
+    if (P.gap_samples) { gs = P.gap_samples[2 * b]; ge = P.gap_samples[2 * b + 1]; }
+    const long long g0 = (long long)t * P.hop - P.pad;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      const long long g = g0 + n;
+      float v = (g >= 0 && g < P.L && !(g >= gs && g < ge)) ? src[g] : 0.0f;
+      v *= P.window[n];
+      buf[__brev((unsigned)n) >> (32 - G.logN)] = make_float2(v, 0.0f);
+    }
+    __syncthreads();
+    smem_fft(buf, N, G.logN, false);
+    FwdEmit<MAG_NONE, true> emit{P, (long long)b * G.F * P.T_out + t, true, false, 0.0f};
+    if (P.zero_frames) emit.zero = (t >= P.zero_frames[2 * b] && t < P.zero_frames[2 * b + 1]);
+    if (P.mask) {
+      bool in = false;
+      if (P.mask_frames) in = (t >= P.mask_frames[2 * b] && t < P.mask_frames[2 * b + 1]);
+      emit.maskv = (in == (P.mask_in_gap_is_one != 0)) ? 1.0f : 0.0f;
+    }
+    for (int k = threadIdx.x; k < G.F; k += blockDim.x) {
+      const float2 x = buf[k];
+      emit(k, x.x, (k == 0 || k == N / 2) ? 0.0f : x.y);
+    }
+    __syncthreads();
+  }
+}
+
+struct GenericInvParams {
+  InvParams P;
+  int N, logN, F;
+  float* frames;   // workspace [B, T, N]
+};
+
+__global__ void __launch_bounds__(256) istft_generic_frames_kernel(const GenericInvParams G) {
+  extern __shared__ __align__(16) float smem[];
+  float2* buf = reinterpret_cast<float2*>(smem);
+  const InvParams& P = G.P;
+  const int N = G.N;
+  for (long long fix = blockIdx.x; fix < P.n_tiles; fix += gridDim.x) {
+    const int b = (int)(fix / P.n_frames);
+    const int t = (int)(fix % P.n_frames);
+    InvLoad load{P, (long long)b * G.F * P.T + t, P.db_flags ? (P.db_flags[b] != 0) : false};
+    for (int k = threadIdx.x; k < G.F; k += blockDim.x) {
+      float xr, xi;
+      load(k, xr, xi);
+      if (k == 0 || k == N / 2) xi = 0.0f;
+      buf[__brev((unsigned)k) >> (32 - G.logN)] = make_float2(xr, xi);
+      if (k != 0 && k != N / 2) buf[__brev((unsigned)(N - k)) >> (32 - G.logN)] = make_float2(xr, -xi);
+    }
+    __syncthreads();
+    smem_fft(buf, N, G.logN, true);
+    float* dst = G.frames + ((long long)b * P.T + t) * N;
+    const float scale = 1.0f / (float)N;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) dst[n] = buf[n].x * scale * P.window[n];
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) istft_generic_ola_kernel(const GenericInvParams G) {
+  const InvParams& P = G.P;
+  const int N = G.N;
+  const long long total = (long long)P.B * P.out_len;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / P.out_len);
+    const int s = (int)(i % P.out_len);
+    const long long p = (long long)s + P.pad;
+    long long f_lo = p - (N - 1) + P.hop - 1;
+    f_lo = f_lo > 0 ? f_lo / P.hop : 0;
+    long long f_hi = p / P.hop;
+    if (f_hi > P.n_frames - 1) f_hi = P.n_frames - 1;
+    float acc = 0.0f;
+    for (long long f = f_lo; f <= f_hi; ++f)
+      acc += G.frames[((long long)b * P.T + f) * N + (p - f * P.hop)];
+    P.out[(long long)b * P.out_pitch + s] = acc * P.inv_wss[s];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------------
+// librosa.filters.window_sumsquare accumulates float32 x += float64 w^2 frame by frame; replayed here
+// per sample in the same (increasing frame) order.
+__global__ void inv_wss_kernel(const float* window, int N, int hop, int pad, int n_frames,
+                               float* inv_wss, int out_len) {
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < out_len; s += gridDim.x * blockDim.x) {
+    const long long p = (long long)s + pad;
+    long long f_lo = p - (N - 1) + hop - 1;
+    f_lo = f_lo > 0 ? f_lo / hop : 0;
+    long long f_hi = p / hop;
+    if (f_hi > n_frames - 1) f_hi = n_frames - 1;
+    float acc = 0.0f;
+    for (long long f = f_lo; f <= f_hi; ++f) {
+      const double w = (double)window[p - f * hop];
+      acc = (float)((double)acc + w * w);
+    }
+    inv_wss[s] = acc > kFltMin ? 1.0f / acc : 1.0f;
+  }
+}
+
+__global__ void __launch_bounds__(1024) db_heuristic_kernel(const float* x, long long n, int* flags) {
+  __shared__ float smax[32];
+  __shared__ double ssum[32];
+  const float* xb = x + (long long)blockIdx.x * n;
+  float mx = -INFINITY;
+  double sm = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = xb[i];
+    mx = fmaxf(mx, v);
+    sm += (double)v;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    sm += __shfl_xor_sync(0xffffffffu, sm, o);
+  }
+  if ((threadIdx.x & 31) == 0) { smax[threadIdx.x >> 5] = mx; ssum[threadIdx.x >> 5] = sm; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = blockDim.x >> 5;
+    mx = threadIdx.x < nw ? smax[threadIdx.x] : -INFINITY;
+    sm = threadIdx.x < nw ? ssum[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      sm += __shfl_xor_sync(0xffffffffu, sm, o);
+    }
+    if (threadIdx.x == 0) flags[blockIdx.x] = (mx < 0.0f && sm < 0.0) ? 1 : 0;
+  }
+}
+
+__global__ void gap_zero_kernel(const float* in, long long in_pitch, float* out, long long out_pitch,
+                                long long B, long long L, const int* gaps) {
+  const long long total = B * L;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / L, s = i % L;
+    const bool in_gap = gaps && s >= gaps[2 * b] && s < gaps[2 * b + 1];
+    out[b * out_pitch + s] = in_gap ? 0.0f : in[b * in_pitch + s];
+  }
+}
+
+__global__ void gap_mask_kernel(float* mask, long long pitch, long long B, long long L, const int* gaps) {
+  const long long total = B * L;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / L, s = i % L;
+    const bool in_gap = gaps && s >= gaps[2 * b] && s < gaps[2 * b + 1];
+    mask[b * pitch + s] = in_gap ? 0.0f : 1.0f;
+  }
+}
+
+__global__ void frame_mask_kernel(float* mask, long long B, long long F, long long T, const int* fr, int one_in_gap) {
+  const long long total = B * F * T;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / (F * T), t = i % T;
+    const bool in = fr && t >= fr[2 * b] && t < fr[2 * b + 1];
+    mask[i] = (in == (one_in_gap != 0)) ? 1.0f : 0.0f;
+  }
+}
+
+__global__ void __launch_bounds__(256) peak_kernel(const float* in, long long pitch, long long L, float* peaks) {
+  __shared__ float sm[8];
+  const long long b = blockIdx.y;
+  const float* x = in + b * pitch;
+  float mx = 0.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < L;
+       i += (long long)gridDim.x * blockDim.x)
+    mx = fmaxf(mx, fabsf(x[i]));
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, sm[w]);
+    // non-negative floats order like their bit patterns
+    atomicMax(reinterpret_cast<int*>(peaks + b), __float_as_int(mx));
+  }
+}
+
+__global__ void peak_scale_kernel(const float* in, long long in_pitch, float* out, long long out_pitch,
+                                  long long B, long long L, const float* peaks) {
+  const long long total = B * L;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / L, s = i % L;
+    const float pk = peaks[b];
+    const float v = in[b * in_pitch + s];
+    out[b * out_pitch + s] = pk < kFltMin ? v : __fdiv_rn(v, pk);
+  }
+}
+
+__global__ void scale_angles_kernel(float2* angles, const float* mag, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float m = mag[i];
+    float2 a = angles[i];
+    a.x *= m; a.y *= m;
+    angles[i] = a;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+struct DevInfo { int ok; int sms; int max_smem; };
+
+static DevInfo dev_info() {
+  DevInfo d{0, 0, 0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return d;
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&d.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  d.ok = (major == 10);
+  return d;
+}
+
+static inline int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+static inline bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+static inline int ew_grid(long long total, int sms) {
+  long long g = (total + 255) / 256;
+  const long long cap = (long long)sms * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+static long long num_frames(long long L, int n_fft, int hop, int center) {
+  if (L < 0 || n_fft <= 0 || hop <= 0) return -1;
+  const long long padded = L + (center ? 2LL * (n_fft / 2) : 0);
+  if (padded < n_fft) return -1;
+  return 1 + (padded - n_fft) / hop;
+}
+
+static long long istft_length(long long T, int n_fft, int hop, int center, long long length) {
+  if (length > 0) return length;
+  long long n = (long long)n_fft + (long long)hop * (T - 1);
+  if (center) n -= 2LL * (n_fft / 2);
+  return n;
+}
+
+static long long istft_used_frames(long long T, int n_fft, int hop, int center, long long length) {
+  if (length <= 0) return T;
+  const long long padded = length + (center ? 2LL * (n_fft / 2) : 0);
+  const long long nf = (padded + hop - 1) / hop;
+  return nf < T ? nf : T;
+}
+
+static bool fwd_fast_ok(const aip_stft_desc* d, const DevInfo& di) {
+  if (d->n_fft != 512 || (d->hop & 1)) return false;
+  const size_t smem = ((size_t)((fwd_tile_len(d->hop) + 3) & ~3) + 2 * (size_t)kExch) * sizeof(float);
+  return smem <= (size_t)di.max_smem;
+}
+
+static bool inv_fast_ok(const aip_stft_desc* d) {
+  if (d->n_fft != 512 || (d->hop & 1)) return false;
+  return inv_geom(d->hop, d->center ? 256 : 0).FO >= 4;
+}
+
+template <int kMag, bool kExtra>
+static cudaError_t launch_fwd512_t(const FwdParams& P, const DevInfo& di, cudaStream_t st) {
+  auto kern = stft512_fwd_kernel<kMag, kExtra>;
+  const size_t smem = ((size_t)P.tile_floats + 2 * (size_t)kExch) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int occ = 1;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) occ = 1;
+  long long grid = (long long)di.sms * occ;
+  if (grid > P.n_tiles) grid = P.n_tiles;
+  kern<<<(unsigned)grid, kThreads, smem, st>>>(P);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_fwd512(const FwdParams& P, const DevInfo& di, cudaStream_t st) {
+  const bool extra = P.spec || P.phase || P.mask || P.zero_frames || P.gl_mag ||
+                     !(P.mag_kind == MAG_ABS || P.mag_kind == MAG_LOG10_EPS);
+  if (!extra && P.mag_kind == MAG_ABS) return launch_fwd512_t<MAG_ABS, false>(P, di, st);
+  if (!extra && P.mag_kind == MAG_LOG10_EPS) return launch_fwd512_t<MAG_LOG10_EPS, false>(P, di, st);
+  return launch_fwd512_t<MAG_NONE, true>(P, di, st);
+}
+
+static cudaError_t launch_fwd_generic(FwdParams P, int n_fft, const DevInfo& di, cudaStream_t st) {
+  GenericFwdParams G;
+  G.N = n_fft; G.logN = ilog2(n_fft); G.F = n_fft / 2 + 1;
+  P.n_tiles = (long long)P.B * P.T_out;
+  G.P = P;
+  const size_t smem = (size_t)n_fft * sizeof(float2);
+  cudaError_t e = cudaFuncSetAttribute(stft_generic_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  long long grid = (long long)di.sms * 8;
+  if (grid > P.n_tiles) grid = P.n_tiles;
+  stft_generic_fwd_kernel<<<(unsigned)grid, 256, smem, st>>>(G);
+  return cudaGetLastError();
+}
+
+// fills the geometry-dependent fields and launches; P carries pointers / epilogue settings already
+static int run_fwd(const aip_stft_desc* desc, FwdParams P, long long T_out, cudaStream_t st) {
+  const DevInfo di = dev_info();
+  if (!di.ok) return AIP_ERR_DEVICE;
+  if (!desc || !desc->window || !P.wave) return AIP_ERR_ARG;
+  if (!is_pow2(desc->n_fft) || desc->n_fft < 32 || desc->n_fft > 4096 || desc->hop <= 0) return AIP_ERR_UNSUPPORTED;
+  if (P.B < 0 || P.L < 0 || P.wave_pitch < P.L) return AIP_ERR_ARG;
+  const long long T = num_frames(P.L, desc->n_fft, desc->hop, desc->center);
+  if (T < 1 || T_out < 0 || T_out > T) return AIP_ERR_ARG;
+  if ((P.mag_kind != MAG_NONE) != (P.mag != nullptr)) return AIP_ERR_ARG;
+  if (P.mag_kind < MAG_NONE || P.mag_kind > MAG_POW) return AIP_ERR_ARG;
+  if (P.B == 0 || T_out == 0) return AIP_OK;
+  P.hop = desc->hop;
+  P.pad = desc->center ? desc->n_fft / 2 : 0;
+  P.T = (int)T;
+  P.T_out = (int)T_out;
+  P.window = desc->window;
+  cudaError_t e;
+  if (fwd_fast_ok(desc, di)) {
+    P.tiles_per_clip = (int)((T_out + kFR - 1) / kFR);
+    P.n_tiles = (long long)P.B * P.tiles_per_clip;
+    P.tile_floats = (fwd_tile_len(P.hop) + 3) & ~3;
+    P.vec_ok = ((P.hop & 3) == 0) && ((P.pad & 3) == 0) && ((P.wave_pitch & 3) == 0) &&
+               ((reinterpret_cast<uintptr_t>(P.wave) & 15) == 0);
+    e = launch_fwd512(P, di, st);
+  } else {
+    e = launch_fwd_generic(P, desc->n_fft, di, st);
+  }
+  return (int)e;
+}
+
+static int run_inv(const aip_stft_desc* desc, InvParams P, long long length, void* workspace,
+                   size_t workspace_bytes, cudaStream_t st) {
+  const DevInfo di = dev_info();
+  if (!di.ok) return AIP_ERR_DEVICE;
+  if (!desc || !desc->window || !P.out || !P.inv_wss || (!P.spec && !P.mag)) return AIP_ERR_ARG;
+  if (!is_pow2(desc->n_fft) || desc->n_fft < 32 || desc->n_fft > 4096 || desc->hop <= 0) return AIP_ERR_UNSUPPORTED;
+  if (P.B < 0 || P.T < 1 || length < 0) return AIP_ERR_ARG;
+  if (P.mag_domain < DOM_LINEAR || P.mag_domain > DOM_EXPM1) return AIP_ERR_ARG;
+  const long long out_len = istft_length(P.T, desc->n_fft, desc->hop, desc->center, length);
+  if (out_len < 0 || P.out_pitch < out_len) return AIP_ERR_ARG;
+  if (P.B == 0 || out_len == 0) return AIP_OK;
+  P.hop = desc->hop;
+  P.pad = desc->center ? desc->n_fft / 2 : 0;
+  P.n_frames = (int)istft_used_frames(P.T, desc->n_fft, desc->hop, desc->center, length);
+  P.out_len = (int)out_len;
+  P.window = desc->window;
+  cudaError_t e;
+  if (inv_fast_ok(desc)) {
+    P.g = inv_geom(P.hop, P.pad);
+    const long long span = (long long)P.g.FO * P.hop;
+    P.tiles_per_clip = (int)((out_len + span - 1) / span);
+    P.n_tiles = (long long)P.B * P.tiles_per_clip;
+    P.vec_ok = ((P.out_pitch & 1) == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 7) == 0);
+    const size_t smem = (size_t)kExch * sizeof(float2);
+    e = cudaFuncSetAttribute(istft512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int occ = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, istft512_kernel, kThreads, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (occ < 1) occ = 1;
+    long long grid = (long long)di.sms * occ;
+    if (grid > P.n_tiles) grid = P.n_tiles;
+    istft512_kernel<<<(unsigned)grid, kThreads, smem, st>>>(P);
+    e = cudaGetLastError();
+  } else {
+    const size_t need = aip_istft_workspace_bytes(P.B, P.T, desc->n_fft);
+    if (!workspace || workspace_bytes < need) return AIP_ERR_WORKSPACE;
+    GenericInvParams G;
+    G.N = desc->n_fft; G.logN = ilog2(desc->n_fft); G.F = desc->n_fft / 2 + 1;
+    G.frames = static_cast<float*>(workspace);
+    P.n_tiles = (long long)P.B * P.n_frames;
+    G.P = P;
+    const size_t smem = (size_t)desc->n_fft * sizeof(float2);
+    e = cudaFuncSetAttribute(istft_generic_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    long long grid = (long long)di.sms * 8;
+    if (grid > P.n_tiles) grid = P.n_tiles;
+    istft_generic_frames_kernel<<<(unsigned)grid, 256, smem, st>>>(G);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    istft_generic_ola_kernel<<<ew_grid((long long)P.B * P.out_len, di.sms), 256, 0, st>>>(G);
+    e = cudaGetLastError();
+  }
+  return (int)e;
+}
+
+}  // namespace aip
+
+// ===================================================================================================
+// C ABI
+// ===================================================================================================
+using namespace aip;
+
+extern "C" {
+
+int64_t aip_num_frames(int64_t L, int32_t n_fft, int32_t hop, int32_t center) {
+  return num_frames(L, n_fft, hop, center);
+}
+
+int64_t aip_istft_length(int64_t T, int32_t n_fft, int32_t hop, int32_t center, int64_t length) {
+  if (T < 1 || n_fft <= 0 || hop <= 0 || length < 0) return -1;
+  return istft_length(T, n_fft, hop, center, length);
+}
+
+int aip_stft_fwd_f32(const aip_stft_desc* desc, const float* wave, int64_t B, int64_t L, int64_t wave_pitch,
+                     const int32_t* gap_samples, const int32_t* zero_frames, const int32_t* mask_frames,
+                     int32_t mask_in_gap_is_one, int32_t mag_kind, float eps, float power, int64_t T_out,
+                     float* spec_out, float* mag_out, float* phase_out, float* mask_out, void* stream) {
+  if (B > 0x7fffffffLL || L > 0x7fffffffLL) return AIP_ERR_ARG;
+  FwdParams P{};
+  P.wave = wave; P.wave_pitch = wave_pitch; P.B = (int)B; P.L = (int)L;
+  P.gap_samples = gap_samples; P.zero_frames = zero_frames; P.mask_frames = mask_frames;
+  P.mask_in_gap_is_one = mask_in_gap_is_one;
+  P.mag_kind = mag_kind; P.eps = eps; P.power = power;
+  P.spec = reinterpret_cast<float2*>(spec_out); P.mag = mag_out; P.phase = phase_out; P.mask = mask_out;
+  return run_fwd(desc, P, T_out, static_cast<cudaStream_t>(stream));
+}
+
+size_t aip_istft_workspace_bytes(int64_t B, int64_t T, int32_t n_fft) {
+  if (n_fft == 512 || B <= 0 || T <= 0) return n_fft == 512 ? 0 : 0;
+  return (size_t)B * (size_t)T * (size_t)n_fft * sizeof(float);
+}
+
+int aip_istft_f32(const aip_stft_desc* desc, const float* spec, const float* mag, const float* phase,
+                  int32_t mag_domain, const int32_t* db_flags, int64_t B, int64_t T, int64_t length,
+                  const float* inv_wss, float* wave_out, int64_t out_pitch, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  if (B > 0x7fffffffLL || T > 0x7fffffffLL) return AIP_ERR_ARG;
+  InvParams P{};
+  P.spec = reinterpret_cast<const float2*>(spec); P.mag = mag; P.phase = phase; P.mag_domain = mag_domain;
+  P.db_flags = db_flags; P.B = (int)B; P.T = (int)T; P.inv_wss = inv_wss; P.out = wave_out; P.out_pitch = out_pitch;
+  return run_inv(desc, P, length, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int aip_inv_window_sumsquare_f32(const aip_stft_desc* desc, int64_t T, int64_t length, float* inv_wss,
+                                 int64_t out_len, void* stream) {
+  const DevInfo di = dev_info();
+  if (!di.ok) return AIP_ERR_DEVICE;
+  if (!desc || !desc->window || !inv_wss || T < 1 || desc->hop <= 0 || desc->n_fft <= 0) return AIP_ERR_ARG;
+  if (out_len != istft_length(T, desc->n_fft, desc->hop, desc->center, length)) return AIP_ERR_ARG;
+  if (out_len == 0) return AIP_OK;
+  const int nf = (int)istft_used_frames(T, desc->n_fft, desc->hop, desc->center, length);
+  inv_wss_kernel<<<ew_grid(out_len, di.sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      desc->window, desc->n_fft, desc->hop, desc->center ? desc->n_fft / 2 : 0, nf, inv_wss, (int)out_len);
+  return (int)cudaGetLastError();
+}
+
+int aip_griffinlim_f32(const aip_stft_desc* desc, const float* mag, float* angles, float* tprev, int64_t B,
+                       int64_t T, int32_t n_iter, float momentum, const float* inv_wss, float* wave_out,
+                       int64_t out_pitch, void* workspace, size_t workspace_bytes, void* stream) {
+  const DevInfo di = dev_info();
+  if (!di.ok) return AIP_ERR_DEVICE;
+  if (!desc || !mag || !angles || !tprev || !wave_out || n_iter < 0 || momentum < 0.0f) return AIP_ERR_ARG;
+  if (B > 0x7fffffffLL || T > 0x7fffffffLL || B < 0 || T < 1) return AIP_ERR_ARG;
+  if (B == 0) return AIP_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long F = desc->n_fft / 2 + 1;
+  const long long n = (long long)B * F * T;
+  const long long out_len = istft_length(T, desc->n_fft, desc->hop, desc->center, 0);
+  if (num_frames(out_len, desc->n_fft, desc->hop, desc->center) != T) return AIP_ERR_UNSUPPORTED;
+  scale_angles_kernel<<<ew_grid(n, di.sms), 256, 0, st>>>(reinterpret_cast<float2*>(angles), mag, n);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  InvParams I{};
+  I.spec = reinterpret_cast<const float2*>(angles); I.B = (int)B; I.T = (int)T; I.inv_wss = inv_wss;
+  I.out = wave_out; I.out_pitch = out_pitch;
+  for (int it = 0; it < n_iter; ++it) {
+    int rc = run_inv(desc, I, 0, workspace, workspace_bytes, st);
+    if (rc != AIP_OK) return rc;
+    FwdParams P{};
+    P.wave = wave_out; P.wave_pitch = out_pitch; P.B = (int)B; P.L = (int)out_len;
+    P.mag_kind = MAG_NONE;
+    P.spec = reinterpret_cast<float2*>(angles);
+    P.gl_mag = mag; P.gl_tprev = reinterpret_cast<float2*>(tprev);
+    P.gl_has_prev = it > 0; P.gl_alpha = momentum / (1.0f + momentum);
+    rc = run_fwd(desc, P, T, st);
+    if (rc != AIP_OK) return rc;
+  }
+  return run_inv(desc, I, 0, workspace, workspace_bytes, st);
+}
+
+int aip_db_heuristic_f32(const float* x, int64_t B, int64_t n, int32_t* flags, void* stream) {
+  const DevInfo di = dev_info();
+  if (!di.ok) return AIP_ERR_DEVICE;
+  if (!x || !flags || B < 0 || n < 1 || B > 0x7fffffffLL) return AIP_ERR_ARG;
+  if (B == 0) return AIP_OK;
+  db_heuristic_kernel<<<(unsigned)B, 1024, 0, static_cast<cudaStream_t>(stream)>>>(x, n, flags);
+  return (int)cudaGetLastError();
+}
+
+int aip_gap_zero_f32(const float* in, int64_t in_pitch, float* out, int64_t out_pitch, int64_t B, int64_t L,
+                     const int32_t* gap_samples, void* stream) {
+  const DevInfo di = dev_info();
+  if (!di.ok) return AIP_ERR_DEVICE;
+  if (!in || !out || B < 0 || L < 0 || in_pitch < L || out_pitch < L) return AIP_ERR_ARG;
+  if (B * L == 0) return AIP_OK;
+  gap_zero_kernel<<<ew_grid(B * L, di.sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, in_pitch, out, out_pitch, B, L, gap_samples);
+  return (int)cudaGetLastError();
+}
+
+int aip_gap_mask_f32(float* mask, int64_t pitch, int64_t B, int64_t L, const int32_t* gap_samples, void* stream) {
+  const DevInfo di = dev_info();
+  if (!di.ok) return AIP_ERR_DEVICE;
+  if (!mask || B < 0 || L < 0 || pitch < L) return AIP_ERR_ARG;
+  if (B * L == 0) return AIP_OK;
+  gap_mask_kernel<<<ew_grid(B * L, di.sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, pitch, B, L, gap_samples);
+  return (int)cudaGetLastError();
+}
+
+int aip_frame_mask_f32(float* mask, int64_t B, int64_t F, int64_t T, const int32_t* mask_frames,
+                       int32_t mask_in_gap_is_one, void* stream) {
+  const DevInfo di = dev_info();
+  if (!di.ok) return AIP_ERR_DEVICE;
+  if (!mask || B < 0 || F < 0 || T < 0) return AIP_ERR_ARG;
+  if (B * F * T == 0) return AIP_OK;
+  frame_mask_kernel<<<ew_grid(B * F * T, di.sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      mask, B, F, T, mask_frames, mask_in_gap_is_one);
+  return (int)cudaGetLastError();
+}
+
+int aip_peak_normalize_f32(const float* in, int64_t in_pitch, float* out, int64_t out_pitch, int64_t B,
+                           int64_t L, float* peaks, void* stream) {
+  const DevInfo di = dev_info();
+  if (!di.ok) return AIP_ERR_DEVICE;
+  if (!in || !out || !peaks || B < 0 || L < 0 || in_pitch < L || out_pitch < L || B > 65535) return AIP_ERR_ARG;
+  if (B * L == 0) return AIP_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(peaks, 0, (size_t)B * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  long long gx = (L + 256 * 8 - 1) / (256 * 8);
+  if (gx < 1) gx = 1;
+  if (gx > 64) gx = 64;
+  peak_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, st>>>(in, in_pitch, L, peaks);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  peak_scale_kernel<<<ew_grid(B * L, di.sms), 256, 0, st>>>(in, in_pitch, out, out_pitch, B, L, peaks);
+  return (int)cudaGetLastError();
+}
+
+const char* aip_status_string(int status) {
+  switch (status) {
+    case AIP_OK: return "ok";
+    case AIP_ERR_ARG: return "invalid argument";
+    case AIP_ERR_UNSUPPORTED: return "unsupported parameter combination";
+    case AIP_ERR_DEVICE: return "current CUDA device is not sm_100 (B200); there is no fallback path";
+    case AIP_ERR_WORKSPACE: return "workspace missing or too small";
+    default: return status > 0 ? cudaGetErrorString(static_cast<cudaError_t>(status)) : "unknown status";
+  }
+}
+
+const char* aip_version(void) { return "aip_b200 0.1.0 sm_100a"; }
+
+int aip_device_supported(void) { return dev_info().ok; }
+
+}  // extern "C"

@@ -1,0 +1,250 @@
+// Tile-level bodies of the n_fft = 512 kernels, written as "phase functions": a kernel is
+//     for (tile ...) { phase0(tid); sync; phase1(tid); sync; phase2(tid); sync; }
+// so that csrc/aip_emul.cpp can replay exactly the same code on the host, thread by thread
+// (for phase: for tid: body), and the CPU test-suite can check indexing and arithmetic against
+// the oracle without a GPU.  See aip_core.cuh for the algorithm.
+#pragma once
+#include "aip_core.cuh"
+
+namespace aip {
+
+constexpr int kThreads = 256;              // 8 warps: stage 2 has 8 pair-jobs per frame
+constexpr float kLog10of2 = 0.30102999566398120f;
+constexpr float kLog2of10 = 3.32192809488736235f;
+constexpr float kFltMin = 1.17549435e-38f; // np.finfo(float32).tiny
+
+#if defined(__CUDACC__)
+AIP_HD float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+AIP_HD float fast_log2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+AIP_HD float fast_exp2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+AIP_HD void fast_sincos(float a, float& s, float& c) { __sincosf(a, &s, &c); }
+#else
+AIP_HD float fast_sqrt(float x) { return sqrtf(x); }
+AIP_HD float fast_log2(float x) { return log2f(x); }
+AIP_HD float fast_exp2(float x) { return exp2f(x); }
+AIP_HD void fast_sincos(float a, float& s, float& c) { s = sinf(a); c = cosf(a); }
+#endif
+
+// ===================================================================================================
+// Forward
+// ===================================================================================================
+struct FwdParams {
+  const float* wave;        // [B, L], row pitch wave_pitch (elements)
+  long long wave_pitch;
+  int B, L;
+  int hop, pad;             // pad = n_fft/2 when center else 0  (librosa.stft zero padding)
+  int T;                    // frames per clip = 1 + (L + 2 pad - 512) / hop
+  int T_out;                // frames written (crop, models/CNNBLSTM/dataset.py:109-111), <= T
+  const float* window;      // [512] centre-padded analysis window
+  const int* gap_samples;   // [B,2] or null: zero samples [g0,g1) before the transform (utils.py:141-142,180-183)
+  const int* zero_frames;   // [B,2] or null: zero the SPECTRUM on frames [f0,f1) (models/model_eval.py:154)
+  const int* mask_frames;   // [B,2] or null: frame range of the dense mask
+  int mask_in_gap_is_one;   // 1: CNNBLSTM convention (dataset.py:115-118); 0: GAN convention (GAN/dataset.py:150-152)
+  int mag_kind;
+  float eps, power;
+  float2* spec;             // [B,257,T_out] or null
+  float* mag;               // [B,257,T_out] or null
+  float* phase;             // [B,257,T_out] or null
+  float* mask;              // [B,257,T_out] or null
+  // Griffin-Lim update fused into the epilogue (librosa.griffinlim loop body, utils.py:330-332):
+  const float* gl_mag;      // [B,257,T_out] or null
+  float2* gl_tprev;         // [B,257,T_out] read (if gl_has_prev) then overwritten with the rebuilt spectrum
+  int gl_has_prev;
+  float gl_alpha;           // momentum / (1 + momentum)
+  int tiles_per_clip;
+  long long n_tiles;
+  int tile_floats;          // staged samples per tile, rounded up to a multiple of 4
+  int vec_ok;               // 16-byte vector loads of the waveform are legal
+};
+
+AIP_HDX int fwd_tile_len(int hop) { return (kFR - 1) * hop + kNfft; }
+
+// phase 0: stage the tile's samples (zero padding outside [0, L), gap zeroing)
+AIP_HD void fwd_phase0(const FwdParams& P, int tid, long long tix, float* tile) {
+  const int b = (int)(tix / P.tiles_per_clip);
+  const int t0 = (int)(tix % P.tiles_per_clip) * kFR;
+  const int len = fwd_tile_len(P.hop);
+  const long long g0 = (long long)t0 * P.hop - P.pad;
+  const float* src = P.wave + (long long)b * P.wave_pitch;
+  int gs = 0, ge = 0;
+  if (P.gap_samples) { gs = P.gap_samples[2 * b]; ge = P.gap_samples[2 * b + 1]; }
+  for (int i = tid * 4; i < len; i += kThreads * 4) {
+    const long long g = g0 + i;
+    float v[4];
+    if (P.vec_ok && g >= 0 && g + 3 < P.L && i + 3 < len) {
+      const float4 q = *reinterpret_cast<const float4*>(src + g);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const long long ge_ = g + e;
+        v[e] = (ge_ >= 0 && ge_ < P.L) ? src[ge_] : 0.0f;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const long long ge_ = g + e;
+      if (ge_ >= gs && ge_ < ge) v[e] = 0.0f;
+      if (i + e < len) tile[i + e] = v[e];
+    }
+  }
+}
+
+// phase 1: stage 1 of the FFT, lane = n1, two frames per warp pass
+AIP_HD void fwd_phase1(const FwdParams& P, int tid, const float* tile, float2* exch, const LaneConst& lc) {
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll 1
+  for (int it = 0; it < 2; ++it) {
+    const int f = 2 * (warp + 8 * it) + (lane >> 4);
+    fwd_stage1(tile, exch, P.hop, f, lane & 15, lc);
+  }
+}
+
+template <int kMag, bool kExtra>
+struct FwdEmit {
+  const FwdParams& P;
+  long long base;           // b*257*T_out + t
+  bool active, zero;
+  float maskv;
+  AIP_HM void operator()(int k, float xr, float xi) const {
+    if (!active) return;
+    const long long idx = base + (long long)k * P.T_out;
+    if (kExtra) {
+      if (zero) { xr = 0.0f; xi = 0.0f; }
+      if (P.gl_mag) {
+        // angles = rebuilt - alpha * tprev ; angles /= |angles| + tiny ; angles *= S ; tprev = rebuilt
+        float ar = xr, ai = xi;
+        if (P.gl_has_prev) { const float2 tp = P.gl_tprev[idx]; ar -= P.gl_alpha * tp.x; ai -= P.gl_alpha * tp.y; }
+        P.gl_tprev[idx] = make_float2(xr, xi);
+        const float s = P.gl_mag[idx] / (sqrtf(ar * ar + ai * ai) + kFltMin);
+        xr = ar * s; xi = ai * s;
+      }
+      if (P.spec) P.spec[idx] = make_float2(xr, xi);
+      if (P.phase) P.phase[idx] = atan2f(xi, xr);
+      if (P.mask) P.mask[idx] = maskv;
+    }
+    const int mk = kExtra ? P.mag_kind : kMag;
+    if (mk != MAG_NONE) {
+      const float m = fast_sqrt(xr * xr + xi * xi);
+      float v;
+      if (mk == MAG_ABS) v = m;
+      else if (mk == MAG_LOG10_EPS) v = fast_log2(m + P.eps) * kLog10of2;
+      else {
+        const float mp = (P.power == 1.0f) ? m : powf(m, P.power);
+        v = (mk == MAG_LOG1P_POW) ? log1pf(mp) : mp;
+      }
+      P.mag[idx] = v;
+    }
+  }
+};
+
+// phase 2: stage 2 + split pass + epilogue, lane = frame, warp = pair-job
+template <int kMag, bool kExtra>
+AIP_HD void fwd_phase2(const FwdParams& P, int tid, long long tix, const float2* exch) {
+  const int warp = tid >> 5, lane = tid & 31;
+  const int b = (int)(tix / P.tiles_per_clip);
+  const int t = (int)(tix % P.tiles_per_clip) * kFR + lane;
+  FwdEmit<kMag, kExtra> emit{P, (long long)b * kBins * P.T_out + t, t < P.T_out, false, 0.0f};
+  if (kExtra) {
+    if (P.zero_frames) emit.zero = (t >= P.zero_frames[2 * b] && t < P.zero_frames[2 * b + 1]);
+    if (P.mask) {
+      bool in = false;
+      if (P.mask_frames) in = (t >= P.mask_frames[2 * b] && t < P.mask_frames[2 * b + 1]);
+      emit.maskv = (in == (P.mask_in_gap_is_one != 0)) ? 1.0f : 0.0f;
+    }
+  }
+  fwd_stage2(exch, lane, warp, emit);
+}
+
+// ===================================================================================================
+// Inverse
+// ===================================================================================================
+struct InvParams {
+  const float2* spec;       // [B,257,T] complex, or null
+  const float* mag;         // [B,257,T] magnitude (with mag_domain), used when spec is null
+  const float* phase;       // [B,257,T] or null (zero phase)
+  int mag_domain;
+  const int* db_flags;      // [B] or null: per clip, non-zero => treat mag as dB (utils.py:313-314 heuristic)
+  int B, T;                 // T = frames per clip in the input (row pitch)
+  int n_frames;             // frames used (librosa.istft: min(T, ceil(padded_length / hop)) when length given)
+  int hop, pad;
+  const float* window;      // [512] synthesis window
+  const float* inv_wss;     // [out_len]: 1/window_sumsquare where > tiny else 1 (librosa.istft normalisation)
+  int out_len;
+  float* out;               // [B, out_len], row pitch out_pitch
+  long long out_pitch;
+  int vec_ok;               // float2 stores legal
+  int tiles_per_clip;
+  long long n_tiles;
+  InvGeom g;
+};
+
+struct InvLoad {
+  const InvParams& P;
+  long long base;           // b*257*T + t
+  bool db;
+  AIP_HM void operator()(int k, float& xr, float& xi) const {
+    const long long idx = base + (long long)k * P.T;
+    if (P.spec) {
+      const float2 v = P.spec[idx];
+      xr = v.x; xi = v.y;
+    } else {
+      float m = P.mag[idx];
+      const int dom = db ? (int)DOM_DB : P.mag_domain;
+      if (dom == DOM_POW10) m = fast_exp2(m * kLog2of10);
+      else if (dom == DOM_DB) m = fast_exp2(m * (kLog2of10 * 0.05f));
+      else if (dom == DOM_EXPM1) m = expm1f(m);
+      if (P.phase) {
+        float s, c;
+        fast_sincos(P.phase[idx], s, c);
+        xr = m * c; xi = m * s;
+      } else { xr = m; xi = 0.0f; }
+    }
+  }
+};
+
+// phase 0: stage A, lane = frame, warp = pair-job
+AIP_HD void inv_phase0(const InvParams& P, int tid, long long tix, float2* exch) {
+  const int warp = tid >> 5, lane = tid & 31;
+  const int b = (int)(tix / P.tiles_per_clip);
+  const int j = (int)(tix % P.tiles_per_clip);
+  const int t = j * P.g.FO - P.g.HL + lane;
+  const bool live = (t >= 0 && t < P.n_frames);
+  InvLoad load{P, (long long)b * kBins * P.T + t, P.db_flags ? (P.db_flags[b] != 0) : false};
+  inv_stageA(exch, lane, warp, live, load);
+}
+
+// phase 1: stage B, lane = n1
+AIP_HD void inv_phase1(const InvParams& P, int tid, float2* exch, const LaneConst& lc) {
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll 1
+  for (int it = 0; it < 2; ++it) {
+    const int f = 2 * (warp + 8 * it) + (lane >> 4);
+    inv_stageB(exch, f, lane & 15, lc);
+  }
+}
+
+// phase 2: overlap-add + window-sum-square normalisation + store
+AIP_HD void inv_phase2(const InvParams& P, int tid, long long tix, const float2* fbuf) {
+  const int b = (int)(tix / P.tiles_per_clip);
+  const int j = (int)(tix % P.tiles_per_clip);
+  const int f_first = j * P.g.FO - P.g.HL;
+  const int s0 = j * P.g.FO * P.hop;
+  const int n_pairs = (P.g.FO * P.hop) >> 1;
+  float* dst = P.out + (long long)b * P.out_pitch;
+  for (int q = tid; q < n_pairs; q += kThreads) {
+    const int s = s0 + 2 * q;
+    if (s >= P.out_len) break;
+    float2 v = ola_pair(fbuf, s + P.pad, P.hop, f_first, P.n_frames);
+    v.x *= P.inv_wss[s];
+    if (s + 1 < P.out_len) {
+      v.y *= P.inv_wss[s + 1];
+      if (P.vec_ok) *reinterpret_cast<float2*>(dst + s) = v;
+      else { dst[s] = v.x; dst[s + 1] = v.y; }
+    } else {
+      dst[s] = v.x;
+    }
+  }
+}
+
+}  // namespace aip
