@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""Benchmark of the spectrogram hot path (BASELINE.json metric: audio-seconds per second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--clips B]
+
+A *step* is one pass of the forward hot path over one batch of synthetic 16 kHz audio:
+BASELINE.json configs[1] -- "batched STFT log-magnitude + gap masking, 4096 synthetic 16 kHz 10 s
+clips" at the reference's parameters (n_fft 512 / win 384 / hop 192, gap 0.2 s, log10(|S|+1e-9)).
+One step = ONE launch of ``stft512_fwd_kernel`` per rank.  The JSON line also carries the inverse
+leg (configs[2]: iSTFT overlap-add, batch 1024) and the round trip under ``"legs"``.
+
+  value     whole-job audio-s/s, inputs resident in HBM, CUDA events, max over ranks
+  e2e       same metric through ``frontend.logmag_gap_host`` (pinned HOST buffers in, HOST buffers
+            out; H2D + kernel + D2H inside the timed region, chunked over 3 streams)
+  roofline  algorithmic bytes (4 L + 4 F T per clip) / kernel time vs MEASURED_PEAKS.json
+  cpu_baseline  the numpy/scipy oracle port of the same step on the host cores (bounded sample)
+
+``--impl reference`` times only that CPU port (the reference's own librosa path cannot be
+installed here: librosa/soundfile are absent from the image and the wheelhouse).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+SR, N_FFT, WIN, HOP = 16000, 512, 384, 192
+CLIP_S = 10.0
+GAP_S = 0.2
+EPS = 1e-9
+METRIC = "audio-seconds/sec (STFT->mask->iSTFT)"
+
+
+# ----------------------------------------------------------------------------------------------- CPU
+def _cpu_worker(args):
+    """Oracle port of one step on `n` clips: gap zeroing -> librosa.stft -> log10(|S| + 1e-9)."""
+    seed, n, L = args
+    from oracle import librosa_port as lr          # bench.py's cpu_baseline / reference arm only
+    rng = np.random.default_rng(seed)
+    g = int(GAP_S * SR)
+    t0 = time.perf_counter()
+    acc = 0.0
+    for _ in range(n):
+        x = np.clip(0.1 * rng.standard_normal(L), -1, 1).astype(np.float32)
+        s = int(rng.integers(0, L - g))
+        x[s:s + g] = 0.0
+        S = lr.stft(x, n_fft=N_FFT, hop_length=HOP, win_length=WIN)
+        m = np.log10(np.abs(S) + EPS).astype(np.float32)
+        acc += float(m[0, 0])
+    return time.perf_counter() - t0, acc
+
+
+def cpu_pass(pool, workers: int, clips_per_worker: int, L: int, seed: int = 0):
+    """Returns (audio-s/s, wall seconds) of the CPU port over workers*clips_per_worker clips."""
+    t0 = time.perf_counter()
+    jobs = [(seed * 1000 + w, clips_per_worker, L) for w in range(workers)]
+    if pool is None:
+        [_cpu_worker(j) for j in jobs]
+    else:
+        pool.map(_cpu_worker, jobs)
+    dt = time.perf_counter() - t0
+    return workers * clips_per_worker * (L / SR) / dt, dt
+
+
+def make_pool(workers: int):
+    if workers <= 1:
+        return None
+    import multiprocessing as mp
+    return mp.get_context("fork").Pool(workers)     # forked BEFORE CUDA is initialised
+
+
+# -------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [q.strip() for q in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------- helpers
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(kernel: str):
+    """dram bytes per launch from the committed ncu --set full capture (profiles/traffic.json), or None."""
+    p = ROOT / "profiles" / "traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+def reference_arm(args, rank: int):
+    """The CPU implementation of the same step, all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    L = int(CLIP_S * SR)
+    workers = os.cpu_count() or 1
+    pool = make_pool(workers)
+    per = max(1, args.ref_clips // workers)
+    for _ in range(args.warmup):
+        cpu_pass(pool, workers, max(1, per // 4), L, seed=99)
+    t = []
+    for k in range(args.steps):
+        _, dt = cpu_pass(pool, workers, per, L, seed=k)
+        t.append(dt)
+    if pool is not None:
+        pool.close()
+    ms = 1e3 * float(np.mean(t))
+    value = workers * per * CLIP_S / (ms * 1e-3)
+    sample = f"{workers * per} clips x {CLIP_S:g} s per step ({workers} processes x {per} clips), oracle port (numpy + scipy.fft)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_fft": N_FFT, "win_length": WIN, "hop_length": HOP,
+                   "sample_rate": SR, "clip_seconds": CLIP_S, "gap_seconds": GAP_S,
+                   "note": "librosa is not installable here; the CPU arm is the oracle restatement of the same path"},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+WORKLOAD = ("configs[1]: batched STFT log-magnitude + gap masking, 4096 synthetic 16 kHz 10 s clips per GPU "
+            "(n_fft 512 / win 384 / hop 192, gap 0.2 s, log10(|S|+1e-9))")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=4096, help="clips per GPU (configs[1]: 4096)")
+    ap.add_argument("--inv-clips", type=int, default=1024, help="clips per GPU of the iSTFT leg (configs[2]: 1024)")
+    ap.add_argument("--ref-clips", type=int, default=256, help="clips per step of the CPU arm")
+    ap.add_argument("--cpu-clips", type=int, default=512, help="clips of the cpu_baseline sample (rank 0, N=1)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    L = int(CLIP_S * SR)
+    # ---- CPU baseline first: the worker pool is forked before this process touches CUDA
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        workers = os.cpu_count() or 1
+        pool = make_pool(workers)
+        per = max(1, args.cpu_clips // workers)
+        cpu_pass(pool, workers, 1, L, seed=7)                      # warm the workers
+        v, dt = cpu_pass(pool, workers, per, L, seed=1)
+        if pool is not None:
+            pool.close()
+        cpu_baseline = {"value": v, "unit": "audio-s/s", "cores": workers, "kind": "port",
+                        "sample": f"{workers * per} clips x {CLIP_S:g} s of the same step ({dt:.1f} s wall), "
+                                  "oracle port (numpy + scipy.fft pocketfft, one process per core)"}
+
+    import torch
+    import torch.distributed as dist
+    from ml_audio_inpainting_b200 import frontend, gaps, spectral as sp
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.clips
+    plan = sp.get_plan(N_FFT, HOP, WIN, "hann", True, dev)
+    T = plan.num_frames(L)
+    F = plan.n_bins
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    wave = (0.1 * torch.randn((B, L), generator=gen, device=dev, dtype=torch.float32)).clamp_(-1, 1)
+    g = gaps.gap_len_samples(GAP_S, SR)
+    np.random.seed(rank)
+    starts = gaps.draw_starts_exclusive(L, g, B)                     # utils.add_random_gap's draw
+    gap_dev = torch.as_tensor(np.stack([starts, starts + g], 1).astype(np.int32), device=dev)
+    out = {"mag": torch.empty((B, F, T), dtype=torch.float32, device=dev)}
+
+    def step():
+        sp.stft(wave, plan, gap_samples=gap_dev, mag_kind=sp.MAG_LOG10_EPS, eps=EPS, want_spec=False, out=out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record()
+        for k in range(steps):
+            fn()
+            ev[k + 1].record()
+        barrier()
+        per = [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
+        total = ev[0].elapsed_time(ev[steps])
+        if world > 1:
+            t = torch.tensor([total], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total = float(t.item())
+        return total / steps, per
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, per = timed(step, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * CLIP_S / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (one launch per step => kernel time = step time on the stream)
+    peak, peak_src = measured_peak()
+    alg_bytes = B * (4 * L + 4 * F * T)
+    kernel_ms = float(np.mean(per))
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": recorded_traffic("stft512_fwd_kernel"), "kernel": "stft512_fwd_kernel<LOG10_EPS>",
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms, "peak_source": peak_src,
+                "frac_of_8TBps_nominal": achieved / 8000.0}
+
+    # ---- inverse leg (configs[2]) and round trip, reported beside the headline
+    legs = {}
+    Bi = min(args.inv_clips, B)
+    spec = sp.stft(wave[:Bi], plan, gap_samples=gap_dev[:Bi])["spec"]
+    yout = torch.empty((Bi, plan.istft_length(T)), dtype=torch.float32, device=dev)
+    ms_i, per_i = timed(lambda: sp.istft(plan, spec=spec, out=yout), args.steps, args.warmup)
+    inv_bytes = Bi * (8 * F * T + 4 * yout.shape[1])
+    legs["istft"] = {"workload": f"configs[2]: iSTFT overlap-add of masked complex spectrograms, batch {Bi} per GPU",
+                     "value": world * Bi * CLIP_S / (ms_i * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_i,
+                     "roofline": {"bound": "hbm", "achieved": inv_bytes / (np.mean(per_i) * 1e-3) / 1e9, "peak": peak,
+                                  "unit": "GB/s", "frac": inv_bytes / (np.mean(per_i) * 1e-3) / 1e9 / peak,
+                                  "traffic": recorded_traffic("istft512_kernel"),
+                                  "algorithmic_bytes_per_launch": inv_bytes}}
+    sout = {"spec": spec}
+
+    def roundtrip():
+        sp.stft(wave[:Bi], plan, gap_samples=gap_dev[:Bi], out=sout)
+        sp.istft(plan, spec=spec, out=yout)
+
+    ms_r, _ = timed(roundtrip, args.steps, args.warmup)
+    legs["roundtrip"] = {"workload": f"STFT(complex)+gap -> iSTFT, batch {Bi} per GPU",
+                         "value": world * Bi * CLIP_S / (ms_r * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_r}
+    del spec, yout, sout
+
+    # ---- end to end through the host-buffer API
+    e2e = None
+    if not args.no_e2e:
+        h_wave = torch.empty((B, L), dtype=torch.float32, pin_memory=True)
+        h_wave.copy_(wave)
+        h_out = torch.empty((B, F, T), dtype=torch.float32, pin_memory=True)
+        gaps_np = np.stack([starts, starts + g], 1).astype(np.int32)
+        pipe = frontend.HostPipeline(plan, B, L, chunk=256)
+
+        def e2e_step():
+            pipe.logmag_gap(h_wave, gaps_np, h_out, eps=EPS)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(3, min(args.steps, 5))
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * B * CLIP_S / dt, "unit": "audio-s/s", "h2d_bytes_per_step": int(B * L * 4 + B * 8),
+               "d2h_bytes_per_step": int(B * F * T * 4), "ms_per_step": dt * 1e3, "steps": n_e2e,
+               "api": "ml_audio_inpainting_b200.frontend.HostPipeline.logmag_gap (pinned host in/out, 3 streams)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "clips_per_gpu": B, "n_fft": N_FFT, "win_length": WIN, "hop_length": HOP,
+                       "sample_rate": SR, "clip_seconds": CLIP_S, "gap_seconds": GAP_S, "frames": T,
+                       "outputs": "log10(|S|+1e-9) f32 [B,257,T]", "sharding": f"by clip, {world} rank(s), no collective",
+                       "l2": "inputs (2.6 GB) and outputs (3.5 GB) per step exceed the 126 MB L2; no flush needed"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": args.steps,
+            "clocks": clocks, "legs": legs,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

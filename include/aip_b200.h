@@ -90,14 +90,15 @@ int aip_stft_fwd_f32(const aip_stft_desc* desc,
  * (row length) of the inputs; `length` = 0 for librosa's natural length hop*(T-1) (center) else the
  * requested length.  inv_wss: device [out_len] from aip_inv_window_sumsquare_f32.
  * db_flags: [B] int32 or null; non-zero entries force the dB prologue for that clip.
- * workspace: only needed when n_fft != 512 (aip_istft_workspace_bytes).                            */
+ * workspace: only needed off the fused n_fft = 512 path (aip_istft_workspace_bytes).              */
 int aip_istft_f32(const aip_stft_desc* desc,
                   const float* spec, const float* mag, const float* phase, int32_t mag_domain,
                   const int32_t* db_flags,
                   int64_t B, int64_t T, int64_t length, const float* inv_wss,
                   float* wave_out, int64_t out_pitch,
                   void* workspace, size_t workspace_bytes, void* stream);
-size_t aip_istft_workspace_bytes(int64_t B, int64_t T, int32_t n_fft);
+/* 0 when the (n_fft, hop, center) combination runs the fused n_fft = 512 kernel. */
+size_t aip_istft_workspace_bytes(const aip_stft_desc* desc, int64_t B, int64_t T);
 
 /* 1 / window_sumsquare (where > FLT_MIN, else 1), accumulated in float32 frame by frame exactly as
  * librosa.filters.window_sumsquare does; written to inv_wss[out_len].                              */

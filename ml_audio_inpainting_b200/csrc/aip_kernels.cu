@@ -455,7 +455,7 @@ static int run_inv(const aip_stft_desc* desc, InvParams P, long long length, voi
     istft512_kernel<<<(unsigned)grid, kThreads, smem, st>>>(P);
     e = cudaGetLastError();
   } else {
-    const size_t need = aip_istft_workspace_bytes(P.B, P.T, desc->n_fft);
+    const size_t need = aip_istft_workspace_bytes(desc, P.B, P.T);
     if (!workspace || workspace_bytes < need) return AIP_ERR_WORKSPACE;
     GenericInvParams G;
     G.N = desc->n_fft; G.logN = ilog2(desc->n_fft); G.F = desc->n_fft / 2 + 1;
@@ -508,9 +508,9 @@ int aip_stft_fwd_f32(const aip_stft_desc* desc, const float* wave, int64_t B, in
   return run_fwd(desc, P, T_out, static_cast<cudaStream_t>(stream));
 }
 
-size_t aip_istft_workspace_bytes(int64_t B, int64_t T, int32_t n_fft) {
-  if (n_fft == 512 || B <= 0 || T <= 0) return n_fft == 512 ? 0 : 0;
-  return (size_t)B * (size_t)T * (size_t)n_fft * sizeof(float);
+size_t aip_istft_workspace_bytes(const aip_stft_desc* desc, int64_t B, int64_t T) {
+  if (!desc || B <= 0 || T <= 0 || desc->n_fft <= 0 || inv_fast_ok(desc)) return 0;
+  return (size_t)B * (size_t)T * (size_t)desc->n_fft * sizeof(float);
 }
 
 int aip_istft_f32(const aip_stft_desc* desc, const float* spec, const float* mag, const float* phase,

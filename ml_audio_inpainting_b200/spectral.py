@@ -1,0 +1,299 @@
+"""Batched, device-resident STFT / iSTFT / Griffin-Lim on B200 (host side of the C ABI).
+
+Tensors in, tensors out, all on one CUDA device; torch is used for memory and streams only --
+every number is produced by the sm_100a kernels of ``csrc/aip_kernels.cu`` through
+``include/aip_b200.h``.  Semantics follow librosa >= 0.10 as the reference calls it:
+
+  stft        librosa.stft      via utils.extract_spectrogram   (reference utils.py:192-234)
+  istft       librosa.istft     via utils.spectrogram_to_audio  (reference utils.py:316-327)
+  griffinlim  librosa.griffinlim                                (reference utils.py:328-332)
+
+Layout: waveforms ``[B, L]`` float32, spectrograms ``[B, F, T]`` (T contiguous, like librosa's
+``[F, T]`` per clip), complex spectrograms as ``torch.complex64``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import scipy.signal
+import torch
+
+from . import _cabi
+from ._cabi import (DOM_DB, DOM_EXPM1, DOM_LINEAR, DOM_POW10, MAG_ABS, MAG_LOG10_EPS, MAG_LOG1P_POW,
+                    MAG_NONE, MAG_POW, StftDesc, check)
+
+__all__ = ["StftPlan", "get_plan", "stft", "istft", "griffinlim", "db_heuristic", "fft_window",
+           "MAG_NONE", "MAG_ABS", "MAG_LOG10_EPS", "MAG_LOG1P_POW", "MAG_POW",
+           "DOM_LINEAR", "DOM_POW10", "DOM_DB", "DOM_EXPM1"]
+
+
+def fft_window(window, win_length: int, n_fft: int) -> np.ndarray:
+    """librosa.filters.get_window(window, win_length, fftbins=True) centre-padded to n_fft (float64)."""
+    if callable(window):
+        w = np.asarray(window(win_length), dtype=np.float64)
+    elif isinstance(window, (str, tuple)) or np.isscalar(window):
+        w = np.asarray(scipy.signal.get_window(window, win_length, fftbins=True), dtype=np.float64)
+    else:
+        w = np.asarray(window, dtype=np.float64)
+        if w.shape[0] != win_length:
+            raise ValueError(f"Window size mismatch: {w.shape[0]} != {win_length}")
+    if win_length > n_fft:
+        raise ValueError(f"Target size ({n_fft}) must be at least input size ({win_length})")
+    lpad = (n_fft - win_length) // 2
+    return np.pad(w, (lpad, n_fft - win_length - lpad))
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: ml_audio_inpainting_b200 has no CPU path")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _pairs(x, B: int, device) -> Optional[torch.Tensor]:
+    """[B,2] int32 device tensor from None / numpy / tensor / a single (a, b) pair."""
+    if x is None:
+        return None
+    if isinstance(x, torch.Tensor):
+        t = x.to(device=device, dtype=torch.int32)
+    else:
+        t = torch.as_tensor(np.asarray(x, dtype=np.int64).astype(np.int32), device=device)
+    if t.ndim == 1:
+        t = t.reshape(1, 2).expand(B, 2)
+    if tuple(t.shape) != (B, 2):
+        raise ValueError(f"expected a [{B}, 2] index array, got {tuple(t.shape)}")
+    return t.contiguous()
+
+
+@dataclass
+class StftPlan:
+    """Transform parameters + the device-resident window (and cached 1/window-sum-square tables)."""
+    n_fft: int
+    hop_length: int
+    win_length: int
+    window: object
+    center: bool
+    device: torch.device
+    window_dev: torch.Tensor = field(repr=False, default=None)
+    desc: StftDesc = field(repr=False, default=None)
+    _inv_wss: Dict[Tuple[int, int], torch.Tensor] = field(repr=False, default_factory=dict)
+
+    @property
+    def n_bins(self) -> int:
+        return self.n_fft // 2 + 1
+
+    def num_frames(self, n_samples: int) -> int:
+        T = _cabi.load().aip_num_frames(n_samples, self.n_fft, self.hop_length, int(self.center))
+        if T < 1:
+            raise ValueError(f"n_fft={self.n_fft} is too large for input signal of length={n_samples}")
+        return int(T)
+
+    def istft_length(self, n_frames: int, length: Optional[int] = None) -> int:
+        return int(_cabi.load().aip_istft_length(n_frames, self.n_fft, self.hop_length, int(self.center),
+                                                 int(length or 0)))
+
+    def inv_wss(self, n_frames: int, length: Optional[int] = None) -> torch.Tensor:
+        key = (int(n_frames), int(length or 0))
+        t = self._inv_wss.get(key)
+        if t is None:
+            out_len = self.istft_length(n_frames, length)
+            t = torch.empty(out_len, dtype=torch.float32, device=self.device)
+            check(_cabi.load().aip_inv_window_sumsquare_f32(C.byref(self.desc), key[0], key[1], _ptr(t),
+                                                            out_len, _stream()), "aip_inv_window_sumsquare_f32")
+            if len(self._inv_wss) > 64:
+                self._inv_wss.clear()
+            self._inv_wss[key] = t
+        return t
+
+
+_plans: Dict[tuple, StftPlan] = {}
+
+
+def get_plan(n_fft: int, hop_length: Optional[int] = None, win_length: Optional[int] = None, window="hann",
+             center: bool = True, device=None) -> StftPlan:
+    """Cached plan.  Defaults follow librosa: win_length = n_fft, hop_length = win_length // 4."""
+    lib = _cabi.load()
+    device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    if device.type != "cuda":
+        raise RuntimeError("ml_audio_inpainting_b200 runs on CUDA devices only (no CPU fallback)")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    n_fft = int(n_fft)
+    win_length = int(win_length) if win_length is not None else n_fft
+    hop_length = int(hop_length) if hop_length is not None else win_length // 4
+    if hop_length <= 0:
+        raise ValueError(f"hop_length={hop_length} must be a positive integer")
+    if n_fft < 32 or n_fft > 4096 or (n_fft & (n_fft - 1)):
+        raise NotImplementedError(f"n_fft={n_fft}: the CUDA kernels cover powers of two in [32, 4096]")
+    wkey = window if isinstance(window, (str, tuple, float, int)) else ("array", np.asarray(window).tobytes())
+    key = (n_fft, hop_length, win_length, wkey, bool(center), device.index)
+    plan = _plans.get(key)
+    if plan is None:
+        with torch.cuda.device(device):
+            if not lib.aip_device_supported():
+                raise RuntimeError(f"{torch.cuda.get_device_name(device)} is not an sm_100 (B200) device; "
+                                   "the kernels are built for sm_100a only and there is no fallback")
+        w = fft_window(window, win_length, n_fft).astype(np.float32)
+        wd = torch.from_numpy(w).to(device)
+        desc = StftDesc(n_fft, hop_length, int(bool(center)), 0, wd.data_ptr())
+        plan = StftPlan(n_fft, hop_length, win_length, window, bool(center), device, wd, desc)
+        _plans[key] = plan
+    return plan
+
+
+def stft(wave: torch.Tensor, plan: StftPlan, *, gap_samples=None, zero_frames=None, mask_frames=None,
+         mask_in_gap_is_one: bool = True, mag_kind: int = MAG_NONE, eps: float = 1e-9, power: float = 1.0,
+         t_out: Optional[int] = None, want_spec: bool = True, want_phase: bool = False,
+         want_mask: bool = False, out: Optional[dict] = None) -> dict:
+    """Forward transform with fused epilogues.  Returns a dict with the requested outputs among
+    ``spec`` (complex64 [B,F,T]), ``mag``, ``phase``, ``mask`` (float32 [B,F,T]).
+
+    ``out`` may carry pre-allocated tensors under the same keys (benchmarks re-use buffers)."""
+    _require_cuda(wave, "wave")
+    if wave.dtype != torch.float32:
+        wave = wave.to(torch.float32)
+    squeeze = wave.ndim == 1
+    if squeeze:
+        wave = wave.unsqueeze(0)
+    if wave.ndim != 2:
+        raise ValueError("wave must be [L] or [B, L]")
+    if wave.stride(1) != 1:
+        wave = wave.contiguous()
+    B, L = wave.shape
+    T = plan.num_frames(L)
+    t_out = T if t_out is None else min(int(t_out), T)
+    F = plan.n_bins
+    dev = wave.device
+    out = dict(out) if out else {}
+
+    def buf(name, dtype):
+        t = out.get(name)
+        if t is None:
+            t = torch.empty((B, F, t_out), dtype=dtype, device=dev)
+        elif tuple(t.shape) != (B, F, t_out) or t.dtype != dtype or not t.is_contiguous():
+            raise ValueError(f"out[{name!r}] has the wrong shape/dtype/layout")
+        return t
+
+    spec = buf("spec", torch.complex64) if want_spec else None
+    mag = buf("mag", torch.float32) if mag_kind != MAG_NONE else None
+    phase = buf("phase", torch.float32) if want_phase else None
+    mask = buf("mask", torch.float32) if want_mask else None
+    gaps = _pairs(gap_samples, B, dev)
+    zf = _pairs(zero_frames, B, dev)
+    mf = _pairs(mask_frames, B, dev)
+    with torch.cuda.device(dev):
+        check(_cabi.load().aip_stft_fwd_f32(
+            C.byref(plan.desc), _ptr(wave), B, L, wave.stride(0), _ptr(gaps), _ptr(zf), _ptr(mf),
+            int(bool(mask_in_gap_is_one)), int(mag_kind), float(eps), float(power), t_out,
+            _ptr(spec), _ptr(mag), _ptr(phase), _ptr(mask), _stream()), "aip_stft_fwd_f32")
+    res = {}
+    for name, t in (("spec", spec), ("mag", mag), ("phase", phase), ("mask", mask)):
+        if t is not None:
+            res[name] = t[0] if squeeze else t
+    return res
+
+
+def db_heuristic(x: torch.Tensor) -> torch.Tensor:
+    """Per clip: (max < 0 and mean < 0), the test utils.spectrogram_to_audio applies (utils.py:313-314)."""
+    _require_cuda(x, "x")
+    x = x.contiguous().to(torch.float32)
+    B = x.shape[0]
+    flags = torch.empty(B, dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_cabi.load().aip_db_heuristic_f32(_ptr(x), B, x[0].numel(), _ptr(flags), _stream()),
+              "aip_db_heuristic_f32")
+    return flags
+
+
+def istft(plan: StftPlan, spec: Optional[torch.Tensor] = None, mag: Optional[torch.Tensor] = None,
+          phase: Optional[torch.Tensor] = None, mag_domain: int = DOM_LINEAR, db_auto: bool = False,
+          length: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Inverse transform: complex ``spec`` or ``mag`` (+ ``phase``) -> waveform [B, out_len] float32.
+
+    ``db_auto`` applies the reference's per-clip dB test to ``mag`` on the device (no host sync)."""
+    src = spec if spec is not None else mag
+    if src is None:
+        raise ValueError("istft needs spec or mag")
+    _require_cuda(src, "spectrogram")
+    squeeze = src.ndim == 2
+    lib = _cabi.load()
+
+    def prep(t, dtype):
+        if t is None:
+            return None
+        if t.ndim == 2:
+            t = t.unsqueeze(0)
+        return t.to(dtype).contiguous()
+
+    spec = prep(spec, torch.complex64)
+    mag = prep(mag, torch.float32) if spec is None else None
+    phase = prep(phase, torch.float32) if spec is None else None
+    ref = spec if spec is not None else mag
+    B, F, T = ref.shape
+    if F != plan.n_bins:
+        raise ValueError(f"expected {plan.n_bins} frequency bins for n_fft={plan.n_fft}, got {F}")
+    dev = ref.device
+    out_len = plan.istft_length(T, length)
+    if out is None:
+        out = torch.empty((B, out_len), dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != (B, out_len) or out.dtype != torch.float32 or out.stride(1) != 1:
+        raise ValueError("out has the wrong shape/dtype/layout")
+    inv = plan.inv_wss(T, length)
+    flags = db_heuristic(mag) if (db_auto and mag is not None) else None
+    ws_bytes = int(lib.aip_istft_workspace_bytes(C.byref(plan.desc), B, T))
+    ws = torch.empty(max(ws_bytes, 4) // 4, dtype=torch.float32, device=dev) if ws_bytes else None
+    with torch.cuda.device(dev):
+        check(lib.aip_istft_f32(C.byref(plan.desc), _ptr(spec.view(torch.float32) if spec is not None else None),
+                                _ptr(mag), _ptr(phase), int(mag_domain), _ptr(flags), B, T, int(length or 0),
+                                _ptr(inv), _ptr(out), out.stride(0), _ptr(ws), ws_bytes, _stream()),
+              "aip_istft_f32")
+    return out[0] if squeeze else out
+
+
+def griffinlim(plan: StftPlan, mag: torch.Tensor, n_iter: int = 32, momentum: float = 0.99,
+               init_angles: Optional[torch.Tensor] = None, generator: Optional[torch.Generator] = None,
+               init: Optional[str] = "random") -> torch.Tensor:
+    """librosa.griffinlim: ``init_angles`` (unit phasors, complex64 [B,F,T]) makes it deterministic;
+    otherwise uniform random phases are drawn on the device (``init='random'``) or all ones (``None``)."""
+    _require_cuda(mag, "mag")
+    if momentum < 0:
+        raise ValueError(f"griffinlim() called with momentum={momentum} < 0")
+    squeeze = mag.ndim == 2
+    if squeeze:
+        mag = mag.unsqueeze(0)
+    if torch.is_complex(mag):
+        raise NotImplementedError("griffinlim on a complex 'magnitude' is not implemented on the GPU path")
+    mag = mag.to(torch.float32).contiguous()
+    B, F, T = mag.shape
+    dev = mag.device
+    if init_angles is not None:
+        ang = init_angles.to(device=dev, dtype=torch.complex64).reshape(B, F, T).contiguous().clone()
+    elif init == "random":
+        u = torch.rand((B, F, T), dtype=torch.float32, device=dev, generator=generator)
+        ang = torch.polar(torch.ones_like(u), 2 * np.pi * u)
+    elif init is None:
+        ang = torch.ones((B, F, T), dtype=torch.complex64, device=dev)
+    else:
+        raise ValueError(f"init={init} must either None or 'random'")
+    tprev = torch.empty_like(ang)
+    out_len = plan.istft_length(T)
+    out = torch.empty((B, out_len), dtype=torch.float32, device=dev)
+    inv = plan.inv_wss(T)
+    lib = _cabi.load()
+    ws_bytes = int(lib.aip_istft_workspace_bytes(C.byref(plan.desc), B, T))
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
+    with torch.cuda.device(dev):
+        check(lib.aip_griffinlim_f32(C.byref(plan.desc), _ptr(mag), _ptr(ang.view(torch.float32)),
+                                     _ptr(tprev.view(torch.float32)), B, T, int(n_iter), float(momentum),
+                                     _ptr(inv), _ptr(out), out.stride(0), _ptr(ws), ws_bytes, _stream()),
+              "aip_griffinlim_f32")
+    return out[0] if squeeze else out

@@ -1,0 +1,244 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerances (BASELINE.json north_star): index work bit-exact; spectra / magnitudes / waveforms within
+1e-4 relative max-abs (max|a-b| / max|b|) in fp32; STFT->iSTFT round trip SNR >= 100 dB.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import callers_port as cp          # noqa: E402  (checker)
+from oracle import librosa_port as lr          # noqa: E402
+from oracle import utils_port as up            # noqa: E402
+
+TOL = 1e-4
+P1 = dict(n_fft=512, hop=192, win=384)
+P2 = dict(n_fft=512, hop=128, win=512)
+
+
+def relerr(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def snr_db(ref, x):
+    return float(10 * np.log10((ref.astype(np.float64) ** 2).sum() / max(((ref - x).astype(np.float64) ** 2).sum(), 1e-300)))
+
+
+@pytest.fixture(scope="module")
+def sp():
+    from ml_audio_inpainting_b200 import spectral
+    return spectral
+
+
+def _noise(B, L, seed=0):
+    rng = np.random.default_rng(seed)
+    return np.clip(0.1 * rng.standard_normal((B, L)), -1, 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("par", [P1, P2], ids=["P1", "P2"])
+@pytest.mark.parametrize("L", [80000, 16000, 5000, 777, 512])
+def test_stft_complex_matches_oracle(sp, par, L):
+    x = _noise(3, L, seed=L)
+    plan = sp.get_plan(par["n_fft"], par["hop"], par["win"], "hann", True, "cuda:0")
+    S = sp.stft(torch.from_numpy(x).cuda(), plan)["spec"].cpu().numpy()
+    for b in range(3):
+        ref = lr.stft(x[b], n_fft=par["n_fft"], hop_length=par["hop"], win_length=par["win"])
+        assert S[b].shape == ref.shape
+        assert relerr(S[b], ref) < TOL
+
+
+@pytest.mark.parametrize("par", [P1, P2], ids=["P1", "P2"])
+def test_istft_matches_oracle_and_round_trip(sp, par):
+    L = 80000
+    x = _noise(2, L, seed=5)
+    plan = sp.get_plan(par["n_fft"], par["hop"], par["win"], "hann", True, "cuda:0")
+    xd = torch.from_numpy(x).cuda()
+    S = sp.stft(xd, plan)["spec"]
+    y = sp.istft(plan, spec=S).cpu().numpy()
+    for b in range(2):
+        ref_S = lr.stft(x[b], n_fft=par["n_fft"], hop_length=par["hop"], win_length=par["win"])
+        ref_y = lr.istft(ref_S, hop_length=par["hop"], win_length=par["win"], n_fft=par["n_fft"])
+        assert y[b].shape == ref_y.shape == (par["hop"] * (ref_S.shape[1] - 1),)
+        assert relerr(y[b], ref_y) < TOL
+        # the first and last half-windows are not perfectly reconstructible; compare the interior
+        n = len(ref_y)
+        assert snr_db(x[b, 512:n - 512], y[b, 512:n - 512]) >= 100.0
+
+
+def test_logmag_gap_epilogue(sp):
+    L, B = 80000, 4
+    x = _noise(B, L, seed=11)
+    g = 3200
+    starts = np.array([0, 12345, 64320, L - g - 1])
+    gaps = np.stack([starts, starts + g], 1)
+    plan = sp.get_plan(512, 192, 384, "hann", True, "cuda:0")
+    res = sp.stft(torch.from_numpy(x).cuda(), plan, gap_samples=gaps, mag_kind=sp.MAG_LOG10_EPS, eps=1e-9,
+                  want_spec=False)
+    mag = res["mag"].cpu().numpy()
+    for b in range(B):
+        xg = x[b].copy()
+        xg[gaps[b, 0]:gaps[b, 1]] = 0
+        ref = np.abs(lr.stft(xg, n_fft=512, hop_length=192, win_length=384))
+        # compare in the linear domain (log10 is ill-conditioned at the 1e-9 floor)
+        assert relerr(10.0 ** mag[b].astype(np.float64), ref + 1e-9) < TOL
+        zero = ref == 0
+        assert zero.any() and np.all(mag[b][zero] == np.float32(-9.0))
+
+
+def test_cnnblstm_frontend_bit_exact_masks(sp):
+    from ml_audio_inpainting_b200 import frontend
+    L, B = 80000, 6
+    x = _noise(1, L, seed=3)[0]
+    np.random.seed(42)
+    ref = [cp.cnnblstm_item(x) for _ in range(B)]
+    np.random.seed(42)
+    out = frontend.cnnblstm_batch(torch.from_numpy(np.tile(x, (B, 1))).cuda())
+    mask = out["gap_mask"].cpu().numpy()
+    mag = out["spectrogram_gap"].cpu().numpy()
+    tgt = out["spectrogram_target_phase"].cpu().numpy()
+    for b in range(B):
+        assert tuple(out["gap_frames"][b]) == ref[b]["gap_frames"]
+        assert np.array_equal(mask[b], ref[b]["gap_mask"])
+        assert np.array_equal(out["gap_int_s"][b], ref[b]["gap_int_s"])
+        assert relerr(tgt[b], ref[b]["spectrogram_target_phase"]) < TOL
+        assert relerr(10.0 ** mag[b].astype(np.float64), 10.0 ** ref[b]["spectrogram_gap"].astype(np.float64)) < TOL
+
+
+def test_gan_frontend(sp):
+    from ml_audio_inpainting_b200 import frontend
+    L, B = 80000, 4
+    x = _noise(B, L, seed=8)
+    np.random.seed(7)
+    ref = [cp.gan_item(x[b]) for b in range(B)]
+    np.random.seed(7)
+    out = frontend.gan_batch(torch.from_numpy(x).cuda())
+    for b in range(B):
+        assert tuple(out["gap_samples"][b]) == ref[b]["gap_samples"]
+        assert np.array_equal(out["mask"][b].cpu().numpy(), ref[b]["mask"])
+        assert relerr(np.expm1(out["original_magnitude"][b].cpu().numpy().astype(np.float64)),
+                      np.expm1(ref[b]["original_magnitude"].astype(np.float64))) < TOL
+        assert relerr(np.expm1(out["impaired_magnitude"][b].cpu().numpy().astype(np.float64)),
+                      np.expm1(ref[b]["impaired_magnitude"].astype(np.float64))) < TOL
+        ph, rph = out["original_phase"][b].cpu().numpy(), ref[b]["original_phase"]
+        w = np.expm1(ref[b]["original_magnitude"].astype(np.float64))
+        w = w / w.max()
+        # phase of near-zero bins is arbitrary: weight the phasor error by the magnitude
+        assert float((np.abs(np.exp(1j * ph) - np.exp(1j * rph)) * w).max()) < TOL
+
+
+def test_backend_mag_phase(sp):
+    L = 80000
+    x = _noise(2, L, seed=21)
+    plan = sp.get_plan(512, 192, 384, "hann", True, "cuda:0")
+    r = sp.stft(torch.from_numpy(x).cuda(), plan, mag_kind=sp.MAG_ABS, want_spec=False, want_phase=True)
+    y = sp.istft(plan, mag=r["mag"], phase=r["phase"]).cpu().numpy()
+    for b in range(2):
+        S = lr.stft(x[b], n_fft=512, hop_length=192, win_length=384)
+        ref = up.spectrogram_to_audio(np.abs(S), phase=np.angle(S), n_fft=512, hop_length=192, win_length=384)
+        assert relerr(y[b], ref) < TOL
+
+
+def test_griffinlim_injected_angles(sp):
+    L = 16000
+    x = _noise(2, L, seed=33)
+    plan = sp.get_plan(512, 192, 384, "hann", True, "cuda:0")
+    mag = sp.stft(torch.from_numpy(x).cuda(), plan, mag_kind=sp.MAG_ABS, want_spec=False)["mag"]
+    rng = np.random.default_rng(1)
+    ang = np.exp(2j * np.pi * rng.random(mag.shape)).astype(np.complex64)
+    m = mag.cpu().numpy()
+    for n_iter, tol in [(0, 1e-4), (1, 1e-4), (2, 2e-4), (8, 5e-3)]:
+        y = sp.griffinlim(plan, mag, n_iter=n_iter, init_angles=torch.from_numpy(ang).cuda()).cpu().numpy()
+        for b in range(2):
+            ref = lr.griffinlim(m[b], n_iter=n_iter, hop_length=192, win_length=384, n_fft=512, init_angles=ang[b])
+            assert relerr(y[b], ref) < tol, (n_iter, relerr(y[b], ref))
+
+
+@pytest.mark.parametrize("n_fft,hop,win", [(2048, 512, 2048), (1024, 256, 1024), (256, 64, 256), (512, 191, 384)])
+def test_generic_sizes(sp, n_fft, hop, win):
+    L = 22050
+    x = _noise(2, L, seed=n_fft)
+    plan = sp.get_plan(n_fft, hop, win, "hann", True, "cuda:0")
+    S = sp.stft(torch.from_numpy(x).cuda(), plan)["spec"]
+    y = sp.istft(plan, spec=S).cpu().numpy()
+    S = S.cpu().numpy()
+    for b in range(2):
+        ref = lr.stft(x[b], n_fft=n_fft, hop_length=hop, win_length=win)
+        assert relerr(S[b], ref) < TOL
+        ry = lr.istft(ref, hop_length=hop, win_length=win, n_fft=n_fft)
+        assert relerr(y[b], ry) < TOL
+
+
+def test_mismatched_hop_wss_guard(sp):
+    """CNNBLSTM/train.py:181-183 calls spectrogram_to_audio with hop 512 on a hop-192 spectrogram:
+    window-sum-square has exact zeros; those samples stay un-normalised (librosa's > tiny guard)."""
+    L = 40000
+    x = _noise(1, L, seed=2)
+    plan_a = sp.get_plan(512, 192, 384, "hann", True, "cuda:0")
+    S = sp.stft(torch.from_numpy(x).cuda(), plan_a)["spec"]
+    plan_b = sp.get_plan(512, 512, 512, "hann", True, "cuda:0")
+    y = sp.istft(plan_b, spec=S).cpu().numpy()[0]
+    ref = lr.istft(S.cpu().numpy()[0], hop_length=512, win_length=512, n_fft=512)
+    assert y.shape == ref.shape
+    assert np.all(np.isfinite(y)) and relerr(y, ref) < TOL
+
+
+def test_small_kernels(sp):
+    import ctypes as C
+    from ml_audio_inpainting_b200 import _cabi
+    lib = _cabi.load()
+    B, L = 5, 12345
+    x = torch.from_numpy(_noise(B, L, seed=1)).cuda()
+    gaps = torch.tensor([[0, 10], [100, 100], [12000, 12345], [5, 6], [0, 12345]], dtype=torch.int32, device="cuda")
+    out = torch.empty_like(x)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _cabi.check(lib.aip_gap_zero_f32(x.data_ptr(), L, out.data_ptr(), L, B, L, gaps.data_ptr(), st), "gap_zero")
+    mask = torch.empty_like(x)
+    _cabi.check(lib.aip_gap_mask_f32(mask.data_ptr(), L, B, L, gaps.data_ptr(), st), "gap_mask")
+    xr, g = x.cpu().numpy(), gaps.cpu().numpy()
+    for b in range(B):
+        m = np.ones(L, np.float32); m[g[b, 0]:g[b, 1]] = 0
+        assert np.array_equal(mask[b].cpu().numpy(), m)
+        assert np.array_equal(out[b].cpu().numpy(), xr[b] * m)
+    peaks = torch.empty(B, device="cuda")
+    x[4] = 0
+    _cabi.check(lib.aip_peak_normalize_f32(x.data_ptr(), L, out.data_ptr(), L, B, L, peaks.data_ptr(), st), "peak")
+    xr = x.cpu().numpy()
+    for b in range(B):
+        assert np.array_equal(out[b].cpu().numpy(), lr.normalize(xr[b]))
+    flags = sp.db_heuristic(torch.stack([-torch.rand(100, device="cuda") - 0.1, torch.rand(100, device="cuda")]))
+    assert flags.cpu().tolist() == [1, 0]
+
+
+def test_config1_reference_clips_round_trip(sp, golden_clips):
+    """BASELINE.json configs[0]: STFT -> add gap -> iSTFT on the 9 test_samples clips (model_eval.py shape)."""
+    import json
+    from pathlib import Path
+    from ml_audio_inpainting_b200 import frontend
+    anchors = json.loads((Path(__file__).parent / "golden" / "anchors.json").read_text())
+    names = sorted(golden_clips)
+    x = np.stack([golden_clips[n] for n in names])
+    xd = torch.from_numpy(x).cuda()
+    ev = frontend.eval_cnnlstm_batch(xd)
+    gan = frontend.eval_gan_batch(xd)
+    y = frontend.backend_batch(ev["original_spectrogram"].abs(), ev["original_phase"]).cpu().numpy()
+    for b, n in enumerate(names):
+        a = anchors[n]
+        ref = cp.eval_frontend_cnnlstm(x[b])
+        assert list(ev["gap_frames"][b]) == a["cnnlstm_gap_frames"] == [166, 173]
+        assert list(gan["gap_frames"][b]) == a["gan_gap_frames"] == [250, 260]
+        assert list(gan["gap_samples"][b]) == a["gap_samples"] == [32000, 33280]
+        S = ev["original_spectrogram"][b].cpu().numpy()
+        assert list(S.shape) == a["shape"]
+        assert relerr(S, ref["original_spectrogram"]) < TOL
+        assert abs(np.abs(S).max() - a["max_abs_S"]) / a["max_abs_S"] < TOL
+        assert abs(np.abs(S).astype(np.float64).sum() - a["sum_abs_S"]) / a["sum_abs_S"] < TOL
+        assert np.array_equal(ev["mask"][b].cpu().numpy(), ref["mask"])
+        lm = ev["log_impaired_magnitude"][b].cpu().numpy()
+        assert lm.min() == np.float32(-9.0) and np.all(lm[:, 166:173] == np.float32(-9.0))
+        assert relerr(10.0 ** lm.astype(np.float64), 10.0 ** ref["log_impaired_magnitude"].astype(np.float64)) < TOL
+        ry = cp.eval_backend(np.abs(ref["original_spectrogram"]), ref["original_phase"])
+        assert y[b].shape == ry.shape == (a["istft_len"],)
+        assert relerr(y[b], ry) < TOL
+        assert snr_db(x[b, 512:79872 - 512], y[b, 512:79872 - 512]) >= 100.0
