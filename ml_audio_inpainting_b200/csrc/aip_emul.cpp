@@ -41,7 +41,9 @@ int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, 
   for (int tid = 0; tid < kThreads; ++tid) lane_const_init(lc[tid], window, tid & 15, 0.5f);
   const bool extra = spec || phase || mask || zero_frames || !(mag_kind == MAG_ABS || mag_kind == MAG_LOG10_EPS);
   for (long long tix = 0; tix < P.n_tiles; ++tix) {
-    for (int tid = 0; tid < kThreads; ++tid) fwd_phase0(P, tid, tix, tile.data());
+    const FwdTilePlan q = fwd_tile_plan(P, tix);
+    if (q.n_bulk > 0) memcpy(tile.data() + q.v_lo, q.src + q.g0 + q.v_lo, (size_t)q.n_bulk * 4);   // the TMA bulk copy
+    for (int tid = 0; tid < kThreads; ++tid) fwd_fixup(q, tid, tile.data());
     for (int tid = 0; tid < kThreads; ++tid) fwd_phase1(P, tid, tile.data(), exch.data(), lc[tid]);
     for (int tid = 0; tid < kThreads; ++tid) {
       if (extra) fwd_phase2<MAG_NONE, true>(P, tid, tix, exch.data());

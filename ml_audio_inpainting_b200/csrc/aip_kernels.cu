@@ -23,21 +23,81 @@ namespace aip {
 // ---------------------------------------------------------------------------------------------------
 // n_fft = 512 kernels
 // ---------------------------------------------------------------------------------------------------
+// ---- TMA (1-D bulk copy) + mbarrier plumbing --------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\n"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// global -> shared bulk copy, completion signalled on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void fwd_issue_tile(const FwdTilePlan& q, float* tile, uint64_t* bar) {
+  if (q.n_bulk > 0) {
+    const uint32_t bytes = (uint32_t)q.n_bulk * 4u;
+    mbar_expect_tx(bar, bytes);
+    tma_load_1d(tile + q.v_lo, q.src + q.g0 + q.v_lo, bytes, bar);
+  }
+}
+
+// Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ...  Per tile:
+//   wait for the TMA copy of this tile's samples (issued one phase-2 earlier) -> patch edges / gap
+//   -> sync -> stage 1 (tile -> exchange) -> sync -> issue the NEXT tile's TMA copy into the now free
+//   tile buffer -> stage 2 + epilogue (exchange -> HBM) while that copy is in flight.
 template <int kMag, bool kExtra>
 __global__ void __launch_bounds__(kThreads, 2) stft512_fwd_kernel(const FwdParams P) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bar;
   float* tile = smem;
   float2* exch = reinterpret_cast<float2*>(smem + P.tile_floats);
   const int tid = threadIdx.x;
   LaneConst lc;
   lane_const_init(lc, P.window, tid & 15, 0.5f);
-  for (long long tix = blockIdx.x; tix < P.n_tiles; tix += gridDim.x) {
-    fwd_phase0(P, tid, tix, tile);
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  long long tix = blockIdx.x;
+  FwdTilePlan q = fwd_tile_plan(P, tix);
+  if (tid == 0) fwd_issue_tile(q, tile, &bar);
+  uint32_t parity = 0;
+  while (true) {
+    if (q.n_bulk > 0) { mbar_wait(&bar, parity); parity ^= 1u; }
+    fwd_fixup(q, tid, tile);
     __syncthreads();
     fwd_phase1(P, tid, tile, exch, lc);
+    fence_proxy_async();
     __syncthreads();
-    fwd_phase2<kMag, kExtra>(P, tid, tix, exch);
-    __syncthreads();
+    const long long cur = tix;
+    tix += gridDim.x;
+    const bool more = tix < P.n_tiles;
+    if (more) {
+      q = fwd_tile_plan(P, tix);
+      if (tid == 0) fwd_issue_tile(q, tile, &bar);
+    }
+    fwd_phase2<kMag, kExtra>(P, tid, cur, exch);
+    if (!more) break;
   }
 }
 

@@ -54,40 +54,51 @@ struct FwdParams {
   int tiles_per_clip;
   long long n_tiles;
   int tile_floats;          // staged samples per tile, rounded up to a multiple of 4
-  int vec_ok;               // 16-byte vector loads of the waveform are legal
+  int vec_ok;               // 16-byte bulk copies of the waveform are legal (alignment)
 };
 
 AIP_HDX int fwd_tile_len(int hop) { return (kFR - 1) * hop + kNfft; }
 
-// phase 0: stage the tile's samples (zero padding outside [0, L), gap zeroing)
-AIP_HD void fwd_phase0(const FwdParams& P, int tid, long long tix, float* tile) {
+// Where a tile's samples come from.  Tile element i <-> clip sample g0 + i.  Elements
+// [v_lo, v_lo + n_bulk) are moved by ONE 1-D TMA bulk copy (cp.async.bulk, 16-byte granules) issued a
+// whole phase ahead; the rest (zero padding outside [0, L), a <= 3 element ragged tail, the gap range)
+// is patched by the threads once the copy has landed (fwd_fixup).
+struct FwdTilePlan {
+  const float* src;     // clip base
+  long long g0;         // clip sample of tile element 0 (may be negative: centre padding)
+  int len;              // tile elements
+  int v_lo, v_hi;       // tile elements that map to real samples: [v_lo, v_hi)
+  int n_bulk;           // elements moved by the bulk copy (multiple of 4), starting at v_lo
+  int gs, ge;           // gap range in clip samples
+};
+
+AIP_HD FwdTilePlan fwd_tile_plan(const FwdParams& P, long long tix) {
+  FwdTilePlan q;
   const int b = (int)(tix / P.tiles_per_clip);
   const int t0 = (int)(tix % P.tiles_per_clip) * kFR;
-  const int len = fwd_tile_len(P.hop);
-  const long long g0 = (long long)t0 * P.hop - P.pad;
-  const float* src = P.wave + (long long)b * P.wave_pitch;
-  int gs = 0, ge = 0;
-  if (P.gap_samples) { gs = P.gap_samples[2 * b]; ge = P.gap_samples[2 * b + 1]; }
-  for (int i = tid * 4; i < len; i += kThreads * 4) {
-    const long long g = g0 + i;
-    float v[4];
-    if (P.vec_ok && g >= 0 && g + 3 < P.L && i + 3 < len) {
-      const float4 q = *reinterpret_cast<const float4*>(src + g);
-      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-    } else {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const long long ge_ = g + e;
-        v[e] = (ge_ >= 0 && ge_ < P.L) ? src[ge_] : 0.0f;
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const long long ge_ = g + e;
-      if (ge_ >= gs && ge_ < ge) v[e] = 0.0f;
-      if (i + e < len) tile[i + e] = v[e];
-    }
-  }
+  q.len = fwd_tile_len(P.hop);
+  q.g0 = (long long)t0 * P.hop - P.pad;
+  q.src = P.wave + (long long)b * P.wave_pitch;
+  q.v_lo = q.g0 < 0 ? (int)(-q.g0) : 0;
+  const long long hi = (long long)P.L - q.g0;
+  q.v_hi = hi < q.len ? (int)(hi > 0 ? hi : 0) : q.len;
+  if (q.v_lo > q.v_hi) q.v_lo = q.v_hi;
+  q.n_bulk = P.vec_ok ? ((q.v_hi - q.v_lo) & ~3) : 0;
+  q.gs = q.ge = 0;
+  if (P.gap_samples) { q.gs = P.gap_samples[2 * b]; q.ge = P.gap_samples[2 * b + 1]; }
+  return q;
+}
+
+// everything of the tile that the bulk copy does not deliver
+AIP_HD void fwd_fixup(const FwdTilePlan& q, int tid, float* tile) {
+  for (int i = tid; i < q.v_lo; i += kThreads) tile[i] = 0.0f;
+  for (int i = q.v_lo + q.n_bulk + tid; i < q.v_hi; i += kThreads) tile[i] = q.src[q.g0 + i];
+  for (int i = q.v_hi + tid; i < q.len; i += kThreads) tile[i] = 0.0f;
+  // gap zeroing (utils.py:141-142, :180-183) on the staged samples
+  long long a = (long long)q.gs - q.g0, e = (long long)q.ge - q.g0;
+  if (a < 0) a = 0;
+  if (e > q.len) e = q.len;
+  for (long long i = a + tid; i < e; i += kThreads) tile[i] = 0.0f;
 }
 
 // phase 1: stage 1 of the FFT, lane = n1, two frames per warp pass

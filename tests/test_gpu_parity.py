@@ -180,8 +180,15 @@ def test_mismatched_hop_wss_guard(sp):
     plan_b = sp.get_plan(512, 512, 512, "hann", True, "cuda:0")
     y = sp.istft(plan_b, spec=S).cpu().numpy()[0]
     ref = lr.istft(S.cpu().numpy()[0], hop_length=512, win_length=512, n_fft=512)
-    assert y.shape == ref.shape
-    assert np.all(np.isfinite(y)) and relerr(y, ref) < TOL
+    assert y.shape == ref.shape and np.all(np.isfinite(y))
+    # where window-sum-square is tiny (hann taps next to the exact zeros) y = (w x) / w^2 amplifies the fp32
+    # round-off of x by 1/w in the reference as well: compare where wss is well conditioned, and require the
+    # un-normalised samples (wss <= tiny, every 512th) to match as they are.
+    wss = lr.window_sumsquare("hann", S.shape[-1], hop_length=512, win_length=512, n_fft=512, dtype=np.float32)[256:256 + len(ref)]
+    good = wss > 1e-2
+    assert good.mean() > 0.8 and relerr(y[good], ref[good]) < TOL
+    dead = ~(wss > np.finfo(np.float32).tiny)
+    assert dead.sum() >= len(ref) // 512 and np.abs(y[dead] - ref[dead]).max() < 1e-6
 
 
 def test_small_kernels(sp):
