@@ -158,25 +158,26 @@ AIP_HD void fwd_stage1(const float* tile, float2* exch, int hop, int f, int n1, 
   }
 }
 
-// split pass for one (k, 256-k) pair: Zk = Zc[k], Zn = Zc[256-k]
+// split pass for one (k, 256-k) pair: Zk = Zc[k], Zn = Zc[256-k], w = W512^k.
+// Output rows are addressed through the emitter's two cursors: lo(j) = bin k_lo + 16 j, hi(j) = bin k_hi - 16 j.
 template <class Emit>
-AIP_HD void fwd_pair(float zkr, float zki, float znr, float zni, int k, Emit& emit) {
+AIP_HD void fwd_pair(float zkr, float zki, float znr, float zni, float2 w, int j, Emit& emit) {
   const float er = zkr + znr, ei = zki - zni;
   const float orr = zkr - znr, oi = zki + zni;
-  const float2 w = kTw512[k];
   const float tr = orr * w.x - oi * w.y;
   const float ti = orr * w.y + oi * w.x;
-  emit(k, er + ti, ei - tr);
-  emit(256 - k, er - ti, -(ei + tr));
+  emit.lo(j, er + ti, ei - tr);
+  emit.hi(j, er - ti, -(ei + tr));
 }
 
 // ---------------------------------------------------------------------------------------------------
 // Forward, stage 2.  One call = one (frame f, pair-job p) job, p = 0..7: two 16-point DFTs over n1
-// (jobs p and 16-p, or 0 and 8), the split pass, and emit(k, re, im) for the 32 (p>0) or 33 (p=0)
-// bins this job owns.
+// (jobs p and 16-p, or 0 and 8), the split pass, and the 32 (p>0) or 33 (p=0) bins this job owns
+// handed to the emitter.  tw = W512^k table (shared memory on the device: the index is warp-uniform
+// but not a compile-time constant, and indexed constant-bank loads throttle the MIO pipe).
 // ---------------------------------------------------------------------------------------------------
 template <class Emit>
-AIP_HD void fwd_stage2(const float2* exch, int f, int p, Emit& emit) {
+AIP_HD void fwd_stage2(const float2* exch, const float2* tw, int f, int p, Emit& emit) {
   float ar[16], ai[16], br[16], bi[16];
   const int ja = p, jb = (p == 0) ? 8 : 16 - p;
   const float2* sa = exch + ja * 16 * kXP + f;
@@ -190,34 +191,38 @@ AIP_HD void fwd_stage2(const float2* exch, int f, int p, Emit& emit) {
   fft16(ar, ai);
   fft16(br, bi);
   if (p != 0) {
+    emit.rows(p, 256 - p);
+    const float2* twp = tw + p;
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1)
-      fwd_pair(ar[perm16(k1)], ai[perm16(k1)], br[perm16(15 - k1)], bi[perm16(15 - k1)], p + 16 * k1, emit);
+      fwd_pair(ar[perm16(k1)], ai[perm16(k1)], br[perm16(15 - k1)], bi[perm16(15 - k1)], twp[16 * k1], k1, emit);
   } else {
+    emit.rows(0, 256);
     const float z0r = ar[perm16(0)], z0i = ai[perm16(0)];
-    emit(0, 2.0f * (z0r + z0i), 0.0f);
-    emit(256, 2.0f * (z0r - z0i), 0.0f);
+    emit.lo(0, 2.0f * (z0r + z0i), 0.0f);
+    emit.hi(0, 2.0f * (z0r - z0i), 0.0f);
 #pragma unroll
     for (int k1 = 1; k1 < 8; ++k1)
-      fwd_pair(ar[perm16(k1)], ai[perm16(k1)], ar[perm16(16 - k1)], ai[perm16(16 - k1)], 16 * k1, emit);
-    emit(128, 2.0f * ar[perm16(8)], -2.0f * ai[perm16(8)]);
+      fwd_pair(ar[perm16(k1)], ai[perm16(k1)], ar[perm16(16 - k1)], ai[perm16(16 - k1)], tw[16 * k1], k1, emit);
+    emit.lo(8, 2.0f * ar[perm16(8)], -2.0f * ai[perm16(8)]);
+    emit.rows(8, 248);
 #pragma unroll
     for (int k1 = 0; k1 < 8; ++k1)
-      fwd_pair(br[perm16(k1)], bi[perm16(k1)], br[perm16(15 - k1)], bi[perm16(15 - k1)], 8 + 16 * k1, emit);
+      fwd_pair(br[perm16(k1)], bi[perm16(k1)], br[perm16(15 - k1)], bi[perm16(15 - k1)], tw[8 + 16 * k1], k1, emit);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Inverse, stage A.  One call = one (frame f, pair-job p) job: load(k, re, im) the bins it owns,
-// undo the split pass, two inverse 16-point DFTs over k1, raw results to the exchange buffer
-// (index (k2*16 + n1)*33 + f).  scipy.fft.irfft drops imag(DC) and imag(Nyquist); so do we.
+// Inverse, stage A.  One call = one (frame f, pair-job p) job: fetch the bins it owns through the
+// loader's cursors (lo(j) = bin k_lo + 16 j, hi(j) = bin k_hi - 16 j), undo the split pass, two inverse
+// 16-point DFTs over k1, raw results to the exchange buffer (index (k2*16 + n1)*33 + f).
+// scipy.fft.irfft drops imag(DC) and imag(Nyquist); so do we.
 // ---------------------------------------------------------------------------------------------------
-AIP_HD void inv_pair(float akr, float aki, float bkr, float bki, int k,
+AIP_HD void inv_pair(float akr, float aki, float bkr, float bki, float2 w,
                      float& zkr, float& zki, float& znr, float& zni) {
-  // A = X[k], B = X[256-k]
+  // A = X[k], B = X[256-k], w = W512^k
   const float er = akr + bkr, ei = aki - bki;
   const float orr = akr - bkr, oi = aki + bki;
-  const float2 w = kTw512[k];
   const float tr = orr * w.x + oi * w.y;       // conj(W) * O
   const float ti = oi * w.x - orr * w.y;
   zkr = er - ti; zki = ei + tr;
@@ -225,37 +230,40 @@ AIP_HD void inv_pair(float akr, float aki, float bkr, float bki, int k,
 }
 
 template <class Load>
-AIP_HD void inv_stageA(float2* exch, int f, int p, bool live, Load& load) {
+AIP_HD void inv_stageA(float2* exch, const float2* tw, int f, int p, bool live, Load& load) {
   float ar[16], ai[16], br[16], bi[16];
   const int ja = p, jb = (p == 0) ? 8 : 16 - p;
   if (live) {
     if (p != 0) {
+      load.rows(p, 256 - p);
+      const float2* twp = tw + p;
 #pragma unroll
       for (int k1 = 0; k1 < 16; ++k1) {
         float xr, xi, yr, yi;
-        const int k = p + 16 * k1;
-        load(k, xr, xi);
-        load(256 - k, yr, yi);
-        inv_pair(xr, xi, yr, yi, k, ar[k1], ai[k1], br[15 - k1], bi[15 - k1]);
+        load.lo(k1, xr, xi);
+        load.hi(k1, yr, yi);
+        inv_pair(xr, xi, yr, yi, twp[16 * k1], ar[k1], ai[k1], br[15 - k1], bi[15 - k1]);
       }
     } else {
       float xr, xi, yr, yi;
-      load(0, xr, xi);
-      load(256, yr, yi);
+      load.rows(0, 256);
+      load.lo(0, xr, xi);
+      load.hi(0, yr, yi);
       ar[0] = xr + yr; ai[0] = xr - yr;
 #pragma unroll
       for (int k1 = 1; k1 < 8; ++k1) {
-        load(16 * k1, xr, xi);
-        load(256 - 16 * k1, yr, yi);
-        inv_pair(xr, xi, yr, yi, 16 * k1, ar[k1], ai[k1], ar[16 - k1], ai[16 - k1]);
+        load.lo(k1, xr, xi);
+        load.hi(k1, yr, yi);
+        inv_pair(xr, xi, yr, yi, tw[16 * k1], ar[k1], ai[k1], ar[16 - k1], ai[16 - k1]);
       }
-      load(128, xr, xi);
+      load.lo(8, xr, xi);
       ar[8] = 2.0f * xr; ai[8] = -2.0f * xi;
+      load.rows(8, 248);
 #pragma unroll
       for (int k1 = 0; k1 < 8; ++k1) {
-        load(8 + 16 * k1, xr, xi);
-        load(248 - 16 * k1, yr, yi);
-        inv_pair(xr, xi, yr, yi, 8 + 16 * k1, br[k1], bi[k1], br[15 - k1], bi[15 - k1]);
+        load.lo(k1, xr, xi);
+        load.hi(k1, yr, yi);
+        inv_pair(xr, xi, yr, yi, tw[8 + 16 * k1], br[k1], bi[k1], br[15 - k1], bi[15 - k1]);
       }
     }
     fft16(ai, ar);      // inverse transform: swapped roles

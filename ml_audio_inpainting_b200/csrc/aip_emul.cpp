@@ -46,9 +46,9 @@ int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, 
     for (int tid = 0; tid < kThreads; ++tid) fwd_fixup(q, tid, tile.data());
     for (int tid = 0; tid < kThreads; ++tid) fwd_phase1(P, tid, tile.data(), exch.data(), lc[tid]);
     for (int tid = 0; tid < kThreads; ++tid) {
-      if (extra) fwd_phase2<MAG_NONE, true>(P, tid, tix, exch.data());
-      else if (mag_kind == MAG_ABS) fwd_phase2<MAG_ABS, false>(P, tid, tix, exch.data());
-      else fwd_phase2<MAG_LOG10_EPS, false>(P, tid, tix, exch.data());
+      if (extra) fwd_phase2<MAG_NONE, true>(P, tid, tix, exch.data(), kTw512);
+      else if (mag_kind == MAG_ABS) fwd_phase2<MAG_ABS, false>(P, tid, tix, exch.data(), kTw512);
+      else fwd_phase2<MAG_LOG10_EPS, false>(P, tid, tix, exch.data(), kTw512);
     }
   }
   return 0;
@@ -81,7 +81,7 @@ int emul_istft512(const float* spec, const float* mag, const float* phase, int m
   std::vector<LaneConst> lc(kThreads);
   for (int tid = 0; tid < kThreads; ++tid) lane_const_init(lc[tid], window, tid & 15, 1.0f / 512.0f);
   for (long long tix = 0; tix < P.n_tiles; ++tix) {
-    for (int tid = 0; tid < kThreads; ++tid) inv_phase0(P, tid, tix, exch.data());
+    for (int tid = 0; tid < kThreads; ++tid) inv_phase0(P, tid, tix, exch.data(), kTw512);
     for (int tid = 0; tid < kThreads; ++tid) inv_phase1(P, tid, exch.data(), lc[tid]);
     for (int tid = 0; tid < kThreads; ++tid) inv_phase2(P, tid, tix, exch.data());
   }

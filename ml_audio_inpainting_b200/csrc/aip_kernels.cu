@@ -71,12 +71,14 @@ template <int kMag, bool kExtra>
 __global__ void __launch_bounds__(kThreads, 2) stft512_fwd_kernel(const FwdParams P) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ float2 tw[kBins];
   float* tile = smem;
   float2* exch = reinterpret_cast<float2*>(smem + P.tile_floats);
   const int tid = threadIdx.x;
   LaneConst lc;
   lane_const_init(lc, P.window, tid & 15, 0.5f);
   if (tid == 0) mbar_init(&bar, 1);
+  for (int k = tid; k < kBins; k += kThreads) tw[k] = kTw512[k];
   __syncthreads();
   long long tix = blockIdx.x;
   FwdTilePlan q = fwd_tile_plan(P, tix);
@@ -96,19 +98,22 @@ __global__ void __launch_bounds__(kThreads, 2) stft512_fwd_kernel(const FwdParam
       q = fwd_tile_plan(P, tix);
       if (tid == 0) fwd_issue_tile(q, tile, &bar);
     }
-    fwd_phase2<kMag, kExtra>(P, tid, cur, exch);
+    fwd_phase2<kMag, kExtra>(P, tid, cur, exch, tw);
     if (!more) break;
   }
 }
 
 __global__ void __launch_bounds__(kThreads, 2) istft512_kernel(const InvParams P) {
   extern __shared__ __align__(16) float smem[];
+  __shared__ float2 tw[kBins];
   float2* exch = reinterpret_cast<float2*>(smem);
   const int tid = threadIdx.x;
   LaneConst lc;
   lane_const_init(lc, P.window, tid & 15, 1.0f / 512.0f);
+  for (int k = tid; k < kBins; k += kThreads) tw[k] = kTw512[k];
+  __syncthreads();
   for (long long tix = blockIdx.x; tix < P.n_tiles; tix += gridDim.x) {
-    inv_phase0(P, tid, tix, exch);
+    inv_phase0(P, tid, tix, exch, tw);
     __syncthreads();
     inv_phase1(P, tid, exch, lc);
     __syncthreads();
@@ -166,16 +171,11 @@ __global__ void __launch_bounds__(256) stft_generic_fwd_kernel(const GenericFwdP
     }
     __syncthreads();
     smem_fft(buf, N, G.logN, false);
-    FwdEmit<MAG_NONE, true> emit{P, (long long)b * G.F * P.T_out + t, true, false, 0.0f};
-    if (P.zero_frames) emit.zero = (t >= P.zero_frames[2 * b] && t < P.zero_frames[2 * b + 1]);
-    if (P.mask) {
-      bool in = false;
-      if (P.mask_frames) in = (t >= P.mask_frames[2 * b] && t < P.mask_frames[2 * b + 1]);
-      emit.maskv = (in == (P.mask_in_gap_is_one != 0)) ? 1.0f : 0.0f;
-    }
+    FwdEmit<MAG_NONE, true> emit = fwd_make_emit<MAG_NONE, true>(P, b, t, G.F);
     for (int k = threadIdx.x; k < G.F; k += blockDim.x) {
       const float2 x = buf[k];
-      emit(k, x.x, (k == 0 || k == N / 2) ? 0.0f : x.y);
+      emit.rows(k, k);
+      emit.lo(0, x.x, (k == 0 || k == N / 2) ? 0.0f : x.y);
     }
     __syncthreads();
   }
@@ -195,10 +195,11 @@ __global__ void __launch_bounds__(256) istft_generic_frames_kernel(const Generic
   for (long long fix = blockIdx.x; fix < P.n_tiles; fix += gridDim.x) {
     const int b = (int)(fix / P.n_frames);
     const int t = (int)(fix % P.n_frames);
-    InvLoad load{P, (long long)b * G.F * P.T + t, P.db_flags ? (P.db_flags[b] != 0) : false};
+    InvLoad load{P, (long long)b * G.F * P.T + t, P.db_flags ? (P.db_flags[b] != 0) : false, 0, 0, 0};
     for (int k = threadIdx.x; k < G.F; k += blockDim.x) {
       float xr, xi;
-      load(k, xr, xi);
+      load.rows(k, k);
+      load.lo(0, xr, xi);
       if (k == 0 || k == N / 2) xi = 0.0f;
       buf[__brev((unsigned)k) >> (32 - G.logN)] = make_float2(xr, xi);
       if (k != 0 && k != N / 2) buf[__brev((unsigned)(N - k)) >> (32 - G.logN)] = make_float2(xr, -xi);

@@ -111,16 +111,28 @@ AIP_HD void fwd_phase1(const FwdParams& P, int tid, const float* tile, float2* e
   }
 }
 
+// Epilogue.  A stage-2 thread writes bins k_lo + 16 j and k_hi - 16 j of ONE frame (its lane): the two
+// row cursors are set once per job (rows()), each store is then base + j * (16 T) -- and, the lane being the
+// frame index, a warp's store of one bin is 32 consecutive floats of that row.  Inactive lanes (frames past
+// T_out in the last tile of a clip) run the arithmetic and skip the stores (predication, no branches).
 template <int kMag, bool kExtra>
 struct FwdEmit {
   const FwdParams& P;
-  long long base;           // b*257*T_out + t
+  long long base;           // b*F*T_out + t
   bool active, zero;
   float maskv;
-  AIP_HM void operator()(int k, float xr, float xi) const {
-    if (!active) return;
-    const long long idx = base + (long long)k * P.T_out;
+  long long off_lo, off_hi; // element offsets of the two row cursors
+  int s16;                  // 16 * T_out
+  AIP_HM void rows(int k_lo, int k_hi) {
+    off_lo = base + (long long)k_lo * P.T_out;
+    off_hi = base + (long long)k_hi * P.T_out;
+    s16 = 16 * P.T_out;
+  }
+  AIP_HM void lo(int j, float xr, float xi) const { put(off_lo + j * s16, xr, xi); }
+  AIP_HM void hi(int j, float xr, float xi) const { put(off_hi - j * s16, xr, xi); }
+  AIP_HM void put(long long idx, float xr, float xi) const {
     if (kExtra) {
+      if (!active) return;
       if (zero) { xr = 0.0f; xi = 0.0f; }
       if (P.gl_mag) {
         // angles = rebuilt - alpha * tprev ; angles /= |angles| + tiny ; angles *= S ; tprev = rebuilt
@@ -144,18 +156,14 @@ struct FwdEmit {
         const float mp = (P.power == 1.0f) ? m : powf(m, P.power);
         v = (mk == MAG_LOG1P_POW) ? log1pf(mp) : mp;
       }
-      P.mag[idx] = v;
+      if (active) P.mag[idx] = v;
     }
   }
 };
 
-// phase 2: stage 2 + split pass + epilogue, lane = frame, warp = pair-job
 template <int kMag, bool kExtra>
-AIP_HD void fwd_phase2(const FwdParams& P, int tid, long long tix, const float2* exch) {
-  const int warp = tid >> 5, lane = tid & 31;
-  const int b = (int)(tix / P.tiles_per_clip);
-  const int t = (int)(tix % P.tiles_per_clip) * kFR + lane;
-  FwdEmit<kMag, kExtra> emit{P, (long long)b * kBins * P.T_out + t, t < P.T_out, false, 0.0f};
+AIP_HD FwdEmit<kMag, kExtra> fwd_make_emit(const FwdParams& P, int b, int t, int n_bins) {
+  FwdEmit<kMag, kExtra> emit{P, (long long)b * n_bins * P.T_out + t, t < P.T_out, false, 0.0f, 0, 0, 0};
   if (kExtra) {
     if (P.zero_frames) emit.zero = (t >= P.zero_frames[2 * b] && t < P.zero_frames[2 * b + 1]);
     if (P.mask) {
@@ -164,7 +172,17 @@ AIP_HD void fwd_phase2(const FwdParams& P, int tid, long long tix, const float2*
       emit.maskv = (in == (P.mask_in_gap_is_one != 0)) ? 1.0f : 0.0f;
     }
   }
-  fwd_stage2(exch, lane, warp, emit);
+  return emit;
+}
+
+// phase 2: stage 2 + split pass + epilogue, lane = frame, warp = pair-job
+template <int kMag, bool kExtra>
+AIP_HD void fwd_phase2(const FwdParams& P, int tid, long long tix, const float2* exch, const float2* tw) {
+  const int warp = tid >> 5, lane = tid & 31;
+  const int b = (int)(tix / P.tiles_per_clip);
+  const int t = (int)(tix % P.tiles_per_clip) * kFR + lane;
+  FwdEmit<kMag, kExtra> emit = fwd_make_emit<kMag, kExtra>(P, b, t, kBins);
+  fwd_stage2(exch, tw, lane, warp, emit);
 }
 
 // ===================================================================================================
@@ -192,10 +210,18 @@ struct InvParams {
 
 struct InvLoad {
   const InvParams& P;
-  long long base;           // b*257*T + t
+  long long base;           // b*F*T + t
   bool db;
-  AIP_HM void operator()(int k, float& xr, float& xi) const {
-    const long long idx = base + (long long)k * P.T;
+  long long off_lo, off_hi;
+  int s16;
+  AIP_HM void rows(int k_lo, int k_hi) {
+    off_lo = base + (long long)k_lo * P.T;
+    off_hi = base + (long long)k_hi * P.T;
+    s16 = 16 * P.T;
+  }
+  AIP_HM void lo(int j, float& xr, float& xi) const { get(off_lo + j * s16, xr, xi); }
+  AIP_HM void hi(int j, float& xr, float& xi) const { get(off_hi - j * s16, xr, xi); }
+  AIP_HM void get(long long idx, float& xr, float& xi) const {
     if (P.spec) {
       const float2 v = P.spec[idx];
       xr = v.x; xi = v.y;
@@ -215,14 +241,14 @@ struct InvLoad {
 };
 
 // phase 0: stage A, lane = frame, warp = pair-job
-AIP_HD void inv_phase0(const InvParams& P, int tid, long long tix, float2* exch) {
+AIP_HD void inv_phase0(const InvParams& P, int tid, long long tix, float2* exch, const float2* tw) {
   const int warp = tid >> 5, lane = tid & 31;
   const int b = (int)(tix / P.tiles_per_clip);
   const int j = (int)(tix % P.tiles_per_clip);
   const int t = j * P.g.FO - P.g.HL + lane;
   const bool live = (t >= 0 && t < P.n_frames);
-  InvLoad load{P, (long long)b * kBins * P.T + t, P.db_flags ? (P.db_flags[b] != 0) : false};
-  inv_stageA(exch, lane, warp, live, load);
+  InvLoad load{P, (long long)b * kBins * P.T + t, P.db_flags ? (P.db_flags[b] != 0) : false, 0, 0, 0};
+  inv_stageA(exch, tw, lane, warp, live, load);
 }
 
 // phase 1: stage B, lane = n1
