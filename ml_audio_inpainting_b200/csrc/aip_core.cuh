@@ -158,27 +158,43 @@ AIP_HD void fwd_stage1(const float* tile, float2* exch, int hop, int f, int n1, 
   }
 }
 
-// split pass for one (k, 256-k) pair: Zk = Zc[k], Zn = Zc[256-k], w = W512^k.
+// Split-pass twiddles of one pair-job, register resident (a stage-2 / stage-A warp keeps its job p for
+// the whole kernel).  p > 0: w[k1] = W512^(p + 16 k1).  p = 0: w[k1] = W512^(8 + 16 k1) for k1 < 8 (job 8)
+// and w[8 + k1] = W512^(16 k1), k1 = 1..7 (job 0).
+struct PairTw {
+  float wr[16], wi[16];
+};
+
+AIP_HD void pair_tw_init(PairTw& w, int p) {
+#pragma unroll
+  for (int k1 = 0; k1 < 16; ++k1) {
+    const int k = (p != 0) ? p + 16 * k1 : (k1 < 8 ? 8 + 16 * k1 : 16 * (k1 - 8));
+    const float2 t = kTw512[k];
+    w.wr[k1] = t.x;
+    w.wi[k1] = t.y;
+  }
+}
+
+// split pass for one (k, 256-k) pair: Zk = Zc[k], Zn = Zc[256-k], (wr, wi) = W512^k.
 // Output rows are addressed through the emitter's two cursors: lo(j) = bin k_lo + 16 j, hi(j) = bin k_hi - 16 j.
 template <class Emit>
-AIP_HD void fwd_pair(float zkr, float zki, float znr, float zni, float2 w, int j, Emit& emit) {
+AIP_HD void fwd_pair(float zkr, float zki, float znr, float zni, float wr, float wi, int j, Emit& emit) {
   const float er = zkr + znr, ei = zki - zni;
   const float orr = zkr - znr, oi = zki + zni;
-  const float tr = orr * w.x - oi * w.y;
-  const float ti = orr * w.y + oi * w.x;
+  const float tr = orr * wr - oi * wi;
+  const float ti = orr * wi + oi * wr;
   emit.lo(j, er + ti, ei - tr);
   emit.hi(j, er - ti, -(ei + tr));
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Forward, stage 2.  One call = one (frame f, pair-job p) job, p = 0..7: two 16-point DFTs over n1
-// (jobs p and 16-p, or 0 and 8), the split pass, and the 32 (p>0) or 33 (p=0) bins this job owns
-// handed to the emitter.  tw = W512^k table (shared memory on the device: the index is warp-uniform
-// but not a compile-time constant, and indexed constant-bank loads throttle the MIO pipe).
+// Forward, stage 2.  One (frame f, pair-job p) job, p = 0..7, in two steps so that the exchange buffer
+// can be handed back to the stage-1 warps as soon as it has been read:
+//   fwd_stage2_load     32 float2 of jobs (p, 16-p) or (0, 8) -> registers
+//   fwd_stage2_compute  two 16-point DFTs over n1, the split pass, 32 (p>0) / 33 (p=0) bins to the emitter
 // ---------------------------------------------------------------------------------------------------
-template <class Emit>
-AIP_HD void fwd_stage2(const float2* exch, const float2* tw, int f, int p, Emit& emit) {
-  float ar[16], ai[16], br[16], bi[16];
+AIP_HD void fwd_stage2_load(const float2* exch, int f, int p, float (&ar)[16], float (&ai)[16],
+                            float (&br)[16], float (&bi)[16]) {
   const int ja = p, jb = (p == 0) ? 8 : 16 - p;
   const float2* sa = exch + ja * 16 * kXP + f;
   const float2* sb = exch + jb * 16 * kXP + f;
@@ -188,14 +204,18 @@ AIP_HD void fwd_stage2(const float2* exch, const float2* tw, int f, int p, Emit&
     const float2 b = sb[n1 * kXP];
     ar[n1] = a.x; ai[n1] = a.y; br[n1] = b.x; bi[n1] = b.y;
   }
+}
+
+template <class Emit>
+AIP_HD void fwd_stage2_compute(float (&ar)[16], float (&ai)[16], float (&br)[16], float (&bi)[16],
+                               const PairTw& w, int p, Emit& emit) {
   fft16(ar, ai);
   fft16(br, bi);
   if (p != 0) {
     emit.rows(p, 256 - p);
-    const float2* twp = tw + p;
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1)
-      fwd_pair(ar[perm16(k1)], ai[perm16(k1)], br[perm16(15 - k1)], bi[perm16(15 - k1)], twp[16 * k1], k1, emit);
+      fwd_pair(ar[perm16(k1)], ai[perm16(k1)], br[perm16(15 - k1)], bi[perm16(15 - k1)], w.wr[k1], w.wi[k1], k1, emit);
   } else {
     emit.rows(0, 256);
     const float z0r = ar[perm16(0)], z0i = ai[perm16(0)];
@@ -203,12 +223,12 @@ AIP_HD void fwd_stage2(const float2* exch, const float2* tw, int f, int p, Emit&
     emit.hi(0, 2.0f * (z0r - z0i), 0.0f);
 #pragma unroll
     for (int k1 = 1; k1 < 8; ++k1)
-      fwd_pair(ar[perm16(k1)], ai[perm16(k1)], ar[perm16(16 - k1)], ai[perm16(16 - k1)], tw[16 * k1], k1, emit);
+      fwd_pair(ar[perm16(k1)], ai[perm16(k1)], ar[perm16(16 - k1)], ai[perm16(16 - k1)], w.wr[8 + k1], w.wi[8 + k1], k1, emit);
     emit.lo(8, 2.0f * ar[perm16(8)], -2.0f * ai[perm16(8)]);
     emit.rows(8, 248);
 #pragma unroll
     for (int k1 = 0; k1 < 8; ++k1)
-      fwd_pair(br[perm16(k1)], bi[perm16(k1)], br[perm16(15 - k1)], bi[perm16(15 - k1)], tw[8 + 16 * k1], k1, emit);
+      fwd_pair(br[perm16(k1)], bi[perm16(k1)], br[perm16(15 - k1)], bi[perm16(15 - k1)], w.wr[k1], w.wi[k1], k1, emit);
   }
 }
 

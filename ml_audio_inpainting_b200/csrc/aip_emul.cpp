@@ -32,23 +32,29 @@ int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, 
   P.mag_kind = mag_kind; P.eps = eps; P.power = power;
   P.spec = reinterpret_cast<float2*>(spec); P.mag = mag; P.phase = phase; P.mask = mask;
   P.tiles_per_clip = (T_out + kFR - 1) / kFR;
-  P.n_tiles = (long long)B * P.tiles_per_clip;
-  P.tile_floats = (fwd_tile_len(hop) + 3) & ~3;
+  P.n_tiles = B * P.tiles_per_clip;
+  P.tile_floats = (fwd_tile_len(hop) + 31) & ~31;
+  P.n_tile_bufs = 1;
   P.vec_ok = vec_ok && ((hop & 3) == 0) && ((pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(wave) & 15) == 0);
   std::vector<float> tile(P.tile_floats);
   std::vector<float2> exch(kExch);
   std::vector<LaneConst> lc(kThreads);
-  for (int tid = 0; tid < kThreads; ++tid) lane_const_init(lc[tid], window, tid & 15, 0.5f);
+  std::vector<PairTw> pw(kThreads);
+  for (int tid = 0; tid < kThreads; ++tid) {
+    lane_const_init(lc[tid], window, tid & 15, 0.5f);
+    pair_tw_init(pw[tid], tid >> 5);
+  }
+  NoRelease rel;
   const bool extra = spec || phase || mask || zero_frames || !(mag_kind == MAG_ABS || mag_kind == MAG_LOG10_EPS);
-  for (long long tix = 0; tix < P.n_tiles; ++tix) {
+  for (int tix = 0; tix < P.n_tiles; ++tix) {
     const FwdTilePlan q = fwd_tile_plan(P, tix);
     if (q.n_bulk > 0) memcpy(tile.data() + q.v_lo, q.src + q.g0 + q.v_lo, (size_t)q.n_bulk * 4);   // the TMA bulk copy
-    for (int tid = 0; tid < kThreads; ++tid) fwd_fixup(q, tid, tile.data());
+    if (fwd_needs_fixup(q)) for (int tid = 0; tid < kThreads; ++tid) fwd_fixup(q, tid, tile.data());
     for (int tid = 0; tid < kThreads; ++tid) fwd_phase1(P, tid, tile.data(), exch.data(), lc[tid]);
     for (int tid = 0; tid < kThreads; ++tid) {
-      if (extra) fwd_phase2<MAG_NONE, true>(P, tid, tix, exch.data(), kTw512);
-      else if (mag_kind == MAG_ABS) fwd_phase2<MAG_ABS, false>(P, tid, tix, exch.data(), kTw512);
-      else fwd_phase2<MAG_LOG10_EPS, false>(P, tid, tix, exch.data(), kTw512);
+      if (extra) fwd_phase2<MAG_NONE, true>(P, tid, tix, exch.data(), pw[tid], rel);
+      else if (mag_kind == MAG_ABS) fwd_phase2<MAG_ABS, false>(P, tid, tix, exch.data(), pw[tid], rel);
+      else fwd_phase2<MAG_LOG10_EPS, false>(P, tid, tix, exch.data(), pw[tid], rel);
     }
   }
   return 0;

@@ -55,51 +55,105 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// one elected thread: start the bulk copy of a tile's in-range samples (or just complete the phase)
 __device__ __forceinline__ void fwd_issue_tile(const FwdTilePlan& q, float* tile, uint64_t* bar) {
   if (q.n_bulk > 0) {
     const uint32_t bytes = (uint32_t)q.n_bulk * 4u;
     mbar_expect_tx(bar, bytes);
     tma_load_1d(tile + q.v_lo, q.src + q.g0 + q.v_lo, bytes, bar);
+  } else {
+    mbar_arrive(bar);
   }
 }
 
-// Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ...  Per tile:
-//   wait for the TMA copy of this tile's samples (issued one phase-2 earlier) -> patch edges / gap
-//   -> sync -> stage 1 (tile -> exchange) -> sync -> issue the NEXT tile's TMA copy into the now free
-//   tile buffer -> stage 2 + epilogue (exchange -> HBM) while that copy is in flight.
+struct ArriveRelease {
+  uint64_t* bar;
+  __device__ __forceinline__ void operator()() const { mbar_arrive(bar); }
+};
+
+constexpr int kFwdThreads = 2 * kThreads;   // 8 stage-2 (consumer) warps + 8 stage-1 (producer) warps
+
+// Warp-specialised, persistent, one CTA per SM.  Tiles blockIdx.x, +gridDim.x, ... flow through
+//   TMA bulk copy -> tile[slot] -> stage-1 warps (lane = n1; window, 16-pt DFT, twiddle) -> exch[es]
+//   -> stage-2 warps (lane = frame; 2 x 16-pt DFT, split pass, |.|/log epilogue) -> HBM
+// with mbarrier hand-offs (tile_full / tile_empty / exch_full / exch_empty), so the copy of tile i+1,
+// stage 1 of tile i+1 and stage 2 of tile i overlap, and each role keeps ITS constants in registers
+// (stage 1: 32 window taps + 16 W256 twiddles per lane; stage 2: 16 W512 twiddles per warp).
 template <int kMag, bool kExtra>
-__global__ void __launch_bounds__(kThreads, 2) stft512_fwd_kernel(const FwdParams P) {
+__global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdParams P) {
   extern __shared__ __align__(128) float smem[];
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ float2 tw[kBins];
-  float* tile = smem;
-  float2* exch = reinterpret_cast<float2*>(smem + P.tile_floats);
+  __shared__ __align__(8) uint64_t bars[8];
+  uint64_t* tile_full = bars;        // [2] count 1 (+ tx bytes)
+  uint64_t* tile_empty = bars + 2;   // [2] count 256 (stage-1 threads)
+  uint64_t* exch_full = bars + 4;    // [2] count 256 (stage-1 threads)
+  uint64_t* exch_empty = bars + 6;   // [2] count 256 (stage-2 threads)
+  const int ntb = P.n_tile_bufs;
+  float2* exch0 = reinterpret_cast<float2*>(smem + ntb * P.tile_floats);
   const int tid = threadIdx.x;
-  LaneConst lc;
-  lane_const_init(lc, P.window, tid & 15, 0.5f);
-  if (tid == 0) mbar_init(&bar, 1);
-  for (int k = tid; k < kBins; k += kThreads) tw[k] = kTw512[k];
-  __syncthreads();
-  long long tix = blockIdx.x;
-  FwdTilePlan q = fwd_tile_plan(P, tix);
-  if (tid == 0) fwd_issue_tile(q, tile, &bar);
-  uint32_t parity = 0;
-  while (true) {
-    if (q.n_bulk > 0) { mbar_wait(&bar, parity); parity ^= 1u; }
-    fwd_fixup(q, tid, tile);
-    __syncthreads();
-    fwd_phase1(P, tid, tile, exch, lc);
-    fence_proxy_async();
-    __syncthreads();
-    const long long cur = tix;
-    tix += gridDim.x;
-    const bool more = tix < P.n_tiles;
-    if (more) {
-      q = fwd_tile_plan(P, tix);
-      if (tid == 0) fwd_issue_tile(q, tile, &bar);
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tile_full + i, 1);
+      mbar_init(tile_empty + i, kThreads);
+      mbar_init(exch_full + i, kThreads);
+      mbar_init(exch_empty + i, kThreads);
     }
-    fwd_phase2<kMag, kExtra>(P, tid, cur, exch, tw);
-    if (!more) break;
+  }
+  __syncthreads();
+  const int stride = gridDim.x;
+  if (tid >= kThreads) {
+    // ------------------------------------------------------------------ producers: stage 1
+    const int ptid = tid - kThreads;
+    LaneConst lc;
+    lane_const_init(lc, P.window, ptid & 15, 0.5f);
+    int tix = blockIdx.x;
+    if (ptid == 0 && tix < P.n_tiles) fwd_issue_tile(fwd_tile_plan(P, tix), smem, tile_full);
+#pragma unroll 1
+    for (int i = 0; tix < P.n_tiles; tix += stride, ++i) {
+      const int slot = (ntb == 2) ? (i & 1) : 0;
+      const int use = (ntb == 2) ? (i >> 1) : i;
+      float* tile = smem + slot * P.tile_floats;
+      const FwdTilePlan q = fwd_tile_plan(P, tix);
+      if (ntb == 2 && ptid == 0 && tix + stride < P.n_tiles) {
+        // the other slot was last read by tile i-1
+        if (i >= 1) mbar_wait(tile_empty + (slot ^ 1), (uint32_t)(((i - 1) >> 1) & 1));
+        fwd_issue_tile(fwd_tile_plan(P, tix + stride), smem + (slot ^ 1) * P.tile_floats, tile_full + (slot ^ 1));
+      }
+      mbar_wait(tile_full + slot, (uint32_t)(use & 1));
+      if (fwd_needs_fixup(q)) {
+        fwd_fixup(q, ptid, tile);
+        named_bar_sync(1, kThreads);
+      }
+      const int es = i & 1;
+      if (i >= 2) mbar_wait(exch_empty + es, (uint32_t)(((i >> 1) - 1) & 1));
+      fwd_phase1(P, ptid, tile, exch0 + es * kExch, lc);
+      mbar_arrive(exch_full + es);
+      fence_proxy_async();
+      mbar_arrive(tile_empty + slot);
+      if (ntb == 1 && ptid == 0 && tix + stride < P.n_tiles) {
+        mbar_wait(tile_empty, (uint32_t)(i & 1));
+        fwd_issue_tile(fwd_tile_plan(P, tix + stride), smem, tile_full);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ consumers: stage 2 + epilogue
+    PairTw w;
+    pair_tw_init(w, tid >> 5);
+    int i = 0;
+#pragma unroll 1
+    for (int tix = blockIdx.x; tix < P.n_tiles; tix += stride, ++i) {
+      const int es = i & 1;
+      mbar_wait(exch_full + es, (uint32_t)((i >> 1) & 1));
+      ArriveRelease rel{exch_empty + es};
+      fwd_phase2<kMag, kExtra>(P, tid, tix, exch0 + es * kExch, w, rel);
+    }
   }
 }
 
@@ -156,7 +210,7 @@ __global__ void __launch_bounds__(256) stft_generic_fwd_kernel(const GenericFwdP
   float2* buf = reinterpret_cast<float2*>(smem);
   const FwdParams& P = G.P;
   const int N = G.N;
-  for (long long fix = blockIdx.x; fix < P.n_tiles; fix += gridDim.x) {
+  for (int fix = blockIdx.x; fix < P.n_tiles; fix += gridDim.x) {
     const int b = (int)(fix / P.T_out);
     const int t = (int)(fix % P.T_out);
     const float* src = P.wave + (long long)b * P.wave_pitch;
@@ -171,7 +225,7 @@ __global__ void __launch_bounds__(256) stft_generic_fwd_kernel(const GenericFwdP
     }
     __syncthreads();
     smem_fft(buf, N, G.logN, false);
-    FwdEmit<MAG_NONE, true> emit = fwd_make_emit<MAG_NONE, true>(P, b, t, G.F);
+    FwdEmitFull emit = fwd_make_emit_full(P, b, t, G.F, true);
     for (int k = threadIdx.x; k < G.F; k += blockDim.x) {
       const float2 x = buf[k];
       emit.rows(k, k);
@@ -401,11 +455,19 @@ static long long istft_used_frames(long long T, int n_fft, int hop, int center, 
   return nf < T ? nf : T;
 }
 
-static bool fwd_fast_ok(const aip_stft_desc* d, const DevInfo& di) {
-  if (d->n_fft != 512 || (d->hop & 1)) return false;
-  const size_t smem = ((size_t)((fwd_tile_len(d->hop) + 3) & ~3) + 2 * (size_t)kExch) * sizeof(float);
-  return smem <= (size_t)di.max_smem;
+// shared memory of the forward kernel: n_tile_bufs staged-waveform buffers + 2 exchange buffers
+static size_t fwd_smem_bytes(int hop, int n_tile_bufs) {
+  return ((size_t)n_tile_bufs * (size_t)((fwd_tile_len(hop) + 31) & ~31) + 4 * (size_t)kExch) * sizeof(float);
 }
+
+static int fwd_tile_bufs(const aip_stft_desc* d, const DevInfo& di) {
+  if (d->n_fft != 512 || (d->hop & 1)) return 0;
+  if (fwd_smem_bytes(d->hop, 2) + 1024 <= (size_t)di.max_smem) return 2;
+  if (fwd_smem_bytes(d->hop, 1) + 1024 <= (size_t)di.max_smem) return 1;
+  return 0;
+}
+
+static bool fwd_fast_ok(const aip_stft_desc* d, const DevInfo& di) { return fwd_tile_bufs(d, di) > 0; }
 
 static bool inv_fast_ok(const aip_stft_desc* d) {
   if (d->n_fft != 512 || (d->hop & 1)) return false;
@@ -415,16 +477,12 @@ static bool inv_fast_ok(const aip_stft_desc* d) {
 template <int kMag, bool kExtra>
 static cudaError_t launch_fwd512_t(const FwdParams& P, const DevInfo& di, cudaStream_t st) {
   auto kern = stft512_fwd_kernel<kMag, kExtra>;
-  const size_t smem = ((size_t)P.tile_floats + 2 * (size_t)kExch) * sizeof(float);
+  const size_t smem = fwd_smem_bytes(P.hop, P.n_tile_bufs);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  int occ = 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem);
-  if (e != cudaSuccess) return e;
-  if (occ < 1) occ = 1;
-  long long grid = (long long)di.sms * occ;
+  int grid = di.sms;                    // persistent: one CTA per SM
   if (grid > P.n_tiles) grid = P.n_tiles;
-  kern<<<(unsigned)grid, kThreads, smem, st>>>(P);
+  kern<<<(unsigned)grid, kFwdThreads, smem, st>>>(P);
   return cudaGetLastError();
 }
 
@@ -439,7 +497,8 @@ static cudaError_t launch_fwd512(const FwdParams& P, const DevInfo& di, cudaStre
 static cudaError_t launch_fwd_generic(FwdParams P, int n_fft, const DevInfo& di, cudaStream_t st) {
   GenericFwdParams G;
   G.N = n_fft; G.logN = ilog2(n_fft); G.F = n_fft / 2 + 1;
-  P.n_tiles = (long long)P.B * P.T_out;
+  if ((long long)P.B * P.T_out > 0x7fffffffLL) return cudaErrorInvalidValue;
+  P.n_tiles = (int)((long long)P.B * P.T_out);
   G.P = P;
   const size_t smem = (size_t)n_fft * sizeof(float2);
   cudaError_t e = cudaFuncSetAttribute(stft_generic_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -470,8 +529,10 @@ static int run_fwd(const aip_stft_desc* desc, FwdParams P, long long T_out, cuda
   cudaError_t e;
   if (fwd_fast_ok(desc, di)) {
     P.tiles_per_clip = (int)((T_out + kFR - 1) / kFR);
-    P.n_tiles = (long long)P.B * P.tiles_per_clip;
-    P.tile_floats = (fwd_tile_len(P.hop) + 3) & ~3;
+    if ((long long)P.B * P.tiles_per_clip > 0x7fffffffLL || T_out > (1 << 22)) return AIP_ERR_UNSUPPORTED;
+    P.n_tiles = (int)((long long)P.B * P.tiles_per_clip);
+    P.tile_floats = (fwd_tile_len(P.hop) + 31) & ~31;
+    P.n_tile_bufs = fwd_tile_bufs(desc, di);
     P.vec_ok = ((P.hop & 3) == 0) && ((P.pad & 3) == 0) && ((P.wave_pitch & 3) == 0) &&
                ((reinterpret_cast<uintptr_t>(P.wave) & 15) == 0);
     e = launch_fwd512(P, di, st);

@@ -52,8 +52,9 @@ struct FwdParams {
   int gl_has_prev;
   float gl_alpha;           // momentum / (1 + momentum)
   int tiles_per_clip;
-  long long n_tiles;
-  int tile_floats;          // staged samples per tile, rounded up to a multiple of 4
+  int n_tiles;              // B * tiles_per_clip (< 2^31)
+  int tile_floats;          // floats per staged-waveform buffer (tile length rounded up to 128 B)
+  int n_tile_bufs;          // 2: the next tile's copy overlaps stage 1; 1: large hops
   int vec_ok;               // 16-byte bulk copies of the waveform are legal (alignment)
 };
 
@@ -72,10 +73,10 @@ struct FwdTilePlan {
   int gs, ge;           // gap range in clip samples
 };
 
-AIP_HD FwdTilePlan fwd_tile_plan(const FwdParams& P, long long tix) {
+AIP_HD FwdTilePlan fwd_tile_plan(const FwdParams& P, int tix) {
   FwdTilePlan q;
-  const int b = (int)(tix / P.tiles_per_clip);
-  const int t0 = (int)(tix % P.tiles_per_clip) * kFR;
+  const int b = tix / P.tiles_per_clip;
+  const int t0 = (tix - b * P.tiles_per_clip) * kFR;
   q.len = fwd_tile_len(P.hop);
   q.g0 = (long long)t0 * P.hop - P.pad;
   q.src = P.wave + (long long)b * P.wave_pitch;
@@ -87,6 +88,10 @@ AIP_HD FwdTilePlan fwd_tile_plan(const FwdParams& P, long long tix) {
   q.gs = q.ge = 0;
   if (P.gap_samples) { q.gs = P.gap_samples[2 * b]; q.ge = P.gap_samples[2 * b + 1]; }
   return q;
+}
+
+AIP_HD bool fwd_needs_fixup(const FwdTilePlan& q) {
+  return q.v_lo > 0 || q.v_lo + q.n_bulk < q.len || ((long long)q.ge > q.g0 && (long long)q.gs < q.g0 + q.len && q.ge > q.gs);
 }
 
 // everything of the tile that the bulk copy does not deliver
@@ -101,7 +106,7 @@ AIP_HD void fwd_fixup(const FwdTilePlan& q, int tid, float* tile) {
   for (long long i = a + tid; i < e; i += kThreads) tile[i] = 0.0f;
 }
 
-// phase 1: stage 1 of the FFT, lane = n1, two frames per warp pass
+// stage 1 of the FFT for one tile: 256 threads, lane = n1 (16 lanes per frame), two frames per warp pass
 AIP_HD void fwd_phase1(const FwdParams& P, int tid, const float* tile, float2* exch, const LaneConst& lc) {
   const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll 1
@@ -111,12 +116,37 @@ AIP_HD void fwd_phase1(const FwdParams& P, int tid, const float* tile, float2* e
   }
 }
 
-// Epilogue.  A stage-2 thread writes bins k_lo + 16 j and k_hi - 16 j of ONE frame (its lane): the two
-// row cursors are set once per job (rows()), each store is then base + j * (16 T) -- and, the lane being the
-// frame index, a warp's store of one bin is 32 consecutive floats of that row.  Inactive lanes (frames past
-// T_out in the last tile of a clip) run the arithmetic and skip the stores (predication, no branches).
-template <int kMag, bool kExtra>
-struct FwdEmit {
+AIP_HD float mag_value(int mk, float xr, float xi, float eps, float power) {
+  const float m = fast_sqrt(xr * xr + xi * xi);
+  if (mk == MAG_ABS) return m;
+  if (mk == MAG_LOG10_EPS) return fast_log2(m + eps) * kLog10of2;
+  const float mp = (power == 1.0f) ? m : powf(m, power);
+  return (mk == MAG_LOG1P_POW) ? log1pf(mp) : mp;
+}
+
+// Epilogue, magnitude-only fast path.  A stage-2 thread writes bins k_lo + 16 j and k_hi - 16 j of ONE frame
+// (its lane): two row pointers are set per job (rows()), each store is then pointer + j * (16 T) -- and, the
+// lane being the frame index, a warp's store of one bin is 32 consecutive floats of that row.  No predicates:
+// in the last tile of a clip the lanes past T_out recompute the last valid frame and store the same values.
+template <int kMag>
+struct FwdEmitFast {
+  float* col;               // mag + b*F*T_out + t
+  int T;                    // T_out
+  float eps, power;
+  float* plo;
+  float* phi;
+  int s16;
+  AIP_HM void rows(int k_lo, int k_hi) {
+    plo = col + k_lo * T;
+    phi = col + k_hi * T;
+    s16 = 16 * T;
+  }
+  AIP_HM void lo(int j, float xr, float xi) const { plo[j * s16] = mag_value(kMag, xr, xi, eps, power); }
+  AIP_HM void hi(int j, float xr, float xi) const { phi[-(j * s16)] = mag_value(kMag, xr, xi, eps, power); }
+};
+
+// Epilogue, general path: complex / phase / mask outputs, spectrum-domain gap, Griffin-Lim update.
+struct FwdEmitFull {
   const FwdParams& P;
   long long base;           // b*F*T_out + t
   bool active, zero;
@@ -131,58 +161,55 @@ struct FwdEmit {
   AIP_HM void lo(int j, float xr, float xi) const { put(off_lo + j * s16, xr, xi); }
   AIP_HM void hi(int j, float xr, float xi) const { put(off_hi - j * s16, xr, xi); }
   AIP_HM void put(long long idx, float xr, float xi) const {
-    if (kExtra) {
-      if (!active) return;
-      if (zero) { xr = 0.0f; xi = 0.0f; }
-      if (P.gl_mag) {
-        // angles = rebuilt - alpha * tprev ; angles /= |angles| + tiny ; angles *= S ; tprev = rebuilt
-        float ar = xr, ai = xi;
-        if (P.gl_has_prev) { const float2 tp = P.gl_tprev[idx]; ar -= P.gl_alpha * tp.x; ai -= P.gl_alpha * tp.y; }
-        P.gl_tprev[idx] = make_float2(xr, xi);
-        const float s = P.gl_mag[idx] / (sqrtf(ar * ar + ai * ai) + kFltMin);
-        xr = ar * s; xi = ai * s;
-      }
-      if (P.spec) P.spec[idx] = make_float2(xr, xi);
-      if (P.phase) P.phase[idx] = atan2f(xi, xr);
-      if (P.mask) P.mask[idx] = maskv;
+    if (!active) return;
+    if (zero) { xr = 0.0f; xi = 0.0f; }
+    if (P.gl_mag) {
+      // angles = rebuilt - alpha * tprev ; angles /= |angles| + tiny ; angles *= S ; tprev = rebuilt
+      float ar = xr, ai = xi;
+      if (P.gl_has_prev) { const float2 tp = P.gl_tprev[idx]; ar -= P.gl_alpha * tp.x; ai -= P.gl_alpha * tp.y; }
+      P.gl_tprev[idx] = make_float2(xr, xi);
+      const float s = P.gl_mag[idx] / (sqrtf(ar * ar + ai * ai) + kFltMin);
+      xr = ar * s; xi = ai * s;
     }
-    const int mk = kExtra ? P.mag_kind : kMag;
-    if (mk != MAG_NONE) {
-      const float m = fast_sqrt(xr * xr + xi * xi);
-      float v;
-      if (mk == MAG_ABS) v = m;
-      else if (mk == MAG_LOG10_EPS) v = fast_log2(m + P.eps) * kLog10of2;
-      else {
-        const float mp = (P.power == 1.0f) ? m : powf(m, P.power);
-        v = (mk == MAG_LOG1P_POW) ? log1pf(mp) : mp;
-      }
-      if (active) P.mag[idx] = v;
-    }
+    if (P.spec) P.spec[idx] = make_float2(xr, xi);
+    if (P.phase) P.phase[idx] = atan2f(xi, xr);
+    if (P.mask) P.mask[idx] = maskv;
+    if (P.mag_kind != MAG_NONE) P.mag[idx] = mag_value(P.mag_kind, xr, xi, P.eps, P.power);
   }
 };
 
-template <int kMag, bool kExtra>
-AIP_HD FwdEmit<kMag, kExtra> fwd_make_emit(const FwdParams& P, int b, int t, int n_bins) {
-  FwdEmit<kMag, kExtra> emit{P, (long long)b * n_bins * P.T_out + t, t < P.T_out, false, 0.0f, 0, 0, 0};
-  if (kExtra) {
-    if (P.zero_frames) emit.zero = (t >= P.zero_frames[2 * b] && t < P.zero_frames[2 * b + 1]);
-    if (P.mask) {
-      bool in = false;
-      if (P.mask_frames) in = (t >= P.mask_frames[2 * b] && t < P.mask_frames[2 * b + 1]);
-      emit.maskv = (in == (P.mask_in_gap_is_one != 0)) ? 1.0f : 0.0f;
-    }
+AIP_HD FwdEmitFull fwd_make_emit_full(const FwdParams& P, int b, int t, int n_bins, bool active) {
+  FwdEmitFull emit{P, (long long)b * n_bins * P.T_out + t, active, false, 0.0f, 0, 0, 0};
+  if (P.zero_frames) emit.zero = (t >= P.zero_frames[2 * b] && t < P.zero_frames[2 * b + 1]);
+  if (P.mask) {
+    bool in = false;
+    if (P.mask_frames) in = (t >= P.mask_frames[2 * b] && t < P.mask_frames[2 * b + 1]);
+    emit.maskv = (in == (P.mask_in_gap_is_one != 0)) ? 1.0f : 0.0f;
   }
   return emit;
 }
 
-// phase 2: stage 2 + split pass + epilogue, lane = frame, warp = pair-job
-template <int kMag, bool kExtra>
-AIP_HD void fwd_phase2(const FwdParams& P, int tid, long long tix, const float2* exch, const float2* tw) {
-  const int warp = tid >> 5, lane = tid & 31;
-  const int b = (int)(tix / P.tiles_per_clip);
-  const int t = (int)(tix % P.tiles_per_clip) * kFR + lane;
-  FwdEmit<kMag, kExtra> emit = fwd_make_emit<kMag, kExtra>(P, b, t, kBins);
-  fwd_stage2(exch, tw, lane, warp, emit);
+struct NoRelease { AIP_HM void operator()() const {} };
+
+// stage 2 + split pass + epilogue for one tile: 256 threads, lane = frame, warp = pair-job.
+// `release` runs once the exchange buffer has been read into registers.
+template <int kMag, bool kExtra, class Release>
+AIP_HD void fwd_phase2(const FwdParams& P, int tid, int tix, const float2* exch, const PairTw& w, Release& release) {
+  const int p = tid >> 5, lane = tid & 31;
+  const int b = tix / P.tiles_per_clip;
+  const int t0 = (tix - b * P.tiles_per_clip) * kFR;
+  const int n_valid = (P.T_out - t0) < kFR ? (P.T_out - t0) : kFR;
+  const int fr = lane < n_valid ? lane : n_valid - 1;     // lanes past the end replay the last valid frame
+  float ar[16], ai[16], br[16], bi[16];
+  fwd_stage2_load(exch, fr, p, ar, ai, br, bi);
+  release();
+  if (kExtra) {
+    FwdEmitFull emit = fwd_make_emit_full(P, b, t0 + fr, kBins, lane < n_valid);
+    fwd_stage2_compute(ar, ai, br, bi, w, p, emit);
+  } else {
+    FwdEmitFast<kMag> emit{P.mag + ((long long)b * kBins * P.T_out + t0 + fr), P.T_out, P.eps, P.power, nullptr, nullptr, 0};
+    fwd_stage2_compute(ar, ai, br, bi, w, p, emit);
+  }
 }
 
 // ===================================================================================================
