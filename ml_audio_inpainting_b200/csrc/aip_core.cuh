@@ -238,31 +238,30 @@ AIP_HD void fwd_stage2_compute(float (&ar)[16], float (&ai)[16], float (&br)[16]
 // 16-point DFTs over k1, raw results to the exchange buffer (index (k2*16 + n1)*33 + f).
 // scipy.fft.irfft drops imag(DC) and imag(Nyquist); so do we.
 // ---------------------------------------------------------------------------------------------------
-AIP_HD void inv_pair(float akr, float aki, float bkr, float bki, float2 w,
+AIP_HD void inv_pair(float akr, float aki, float bkr, float bki, float wr, float wi,
                      float& zkr, float& zki, float& znr, float& zni) {
-  // A = X[k], B = X[256-k], w = W512^k
+  // A = X[k], B = X[256-k], (wr, wi) = W512^k
   const float er = akr + bkr, ei = aki - bki;
   const float orr = akr - bkr, oi = aki + bki;
-  const float tr = orr * w.x + oi * w.y;       // conj(W) * O
-  const float ti = oi * w.x - orr * w.y;
+  const float tr = orr * wr + oi * wi;       // conj(W) * O
+  const float ti = oi * wr - orr * wi;
   zkr = er - ti; zki = ei + tr;
   znr = er + ti; zni = tr - ei;
 }
 
 template <class Load>
-AIP_HD void inv_stageA(float2* exch, const float2* tw, int f, int p, bool live, Load& load) {
+AIP_HD void inv_stageA(float2* exch, const PairTw& w, int f, int p, bool live, Load& load) {
   float ar[16], ai[16], br[16], bi[16];
   const int ja = p, jb = (p == 0) ? 8 : 16 - p;
   if (live) {
     if (p != 0) {
       load.rows(p, 256 - p);
-      const float2* twp = tw + p;
 #pragma unroll
       for (int k1 = 0; k1 < 16; ++k1) {
         float xr, xi, yr, yi;
         load.lo(k1, xr, xi);
         load.hi(k1, yr, yi);
-        inv_pair(xr, xi, yr, yi, twp[16 * k1], ar[k1], ai[k1], br[15 - k1], bi[15 - k1]);
+        inv_pair(xr, xi, yr, yi, w.wr[k1], w.wi[k1], ar[k1], ai[k1], br[15 - k1], bi[15 - k1]);
       }
     } else {
       float xr, xi, yr, yi;
@@ -274,7 +273,7 @@ AIP_HD void inv_stageA(float2* exch, const float2* tw, int f, int p, bool live, 
       for (int k1 = 1; k1 < 8; ++k1) {
         load.lo(k1, xr, xi);
         load.hi(k1, yr, yi);
-        inv_pair(xr, xi, yr, yi, tw[16 * k1], ar[k1], ai[k1], ar[16 - k1], ai[16 - k1]);
+        inv_pair(xr, xi, yr, yi, w.wr[8 + k1], w.wi[8 + k1], ar[k1], ai[k1], ar[16 - k1], ai[16 - k1]);
       }
       load.lo(8, xr, xi);
       ar[8] = 2.0f * xr; ai[8] = -2.0f * xi;
@@ -283,7 +282,7 @@ AIP_HD void inv_stageA(float2* exch, const float2* tw, int f, int p, bool live, 
       for (int k1 = 0; k1 < 8; ++k1) {
         load.lo(k1, xr, xi);
         load.hi(k1, yr, yi);
-        inv_pair(xr, xi, yr, yi, tw[8 + 16 * k1], br[k1], bi[k1], br[15 - k1], bi[15 - k1]);
+        inv_pair(xr, xi, yr, yi, w.wr[k1], w.wi[k1], br[k1], bi[k1], br[15 - k1], bi[15 - k1]);
       }
     }
     fft16(ai, ar);      // inverse transform: swapped roles

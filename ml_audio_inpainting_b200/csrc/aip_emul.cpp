@@ -45,17 +45,23 @@ int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, 
     pair_tw_init(pw[tid], tid >> 5);
   }
   NoRelease rel;
-  const bool extra = spec || phase || mask || zero_frames || !(mag_kind == MAG_ABS || mag_kind == MAG_LOG10_EPS);
+  const int mode = fwd_mode_of(P);
+  TileCursor c = tile_cursor(0, P.tiles_per_clip);
   for (int tix = 0; tix < P.n_tiles; ++tix) {
-    const FwdTilePlan q = fwd_tile_plan(P, tix);
+    const FwdTilePlan q = fwd_tile_plan(P, c);
     if (q.n_bulk > 0) memcpy(tile.data() + q.v_lo, q.src + q.g0 + q.v_lo, (size_t)q.n_bulk * 4);   // the TMA bulk copy
     if (fwd_needs_fixup(q)) for (int tid = 0; tid < kThreads; ++tid) fwd_fixup(q, tid, tile.data());
     for (int tid = 0; tid < kThreads; ++tid) fwd_phase1(P, tid, tile.data(), exch.data(), lc[tid]);
     for (int tid = 0; tid < kThreads; ++tid) {
-      if (extra) fwd_phase2<MAG_NONE, true>(P, tid, tix, exch.data(), pw[tid], rel);
-      else if (mag_kind == MAG_ABS) fwd_phase2<MAG_ABS, false>(P, tid, tix, exch.data(), pw[tid], rel);
-      else fwd_phase2<MAG_LOG10_EPS, false>(P, tid, tix, exch.data(), pw[tid], rel);
+      switch (mode) {
+        case FWD_MAG_ABS: fwd_phase2<FWD_MAG_ABS>(P, tid, c, exch.data(), pw[tid], rel); break;
+        case FWD_MAG_LOG10: fwd_phase2<FWD_MAG_LOG10>(P, tid, c, exch.data(), pw[tid], rel); break;
+        case FWD_SPEC: fwd_phase2<FWD_SPEC>(P, tid, c, exch.data(), pw[tid], rel); break;
+        case FWD_GL: fwd_phase2<FWD_GL>(P, tid, c, exch.data(), pw[tid], rel); break;
+        default: fwd_phase2<FWD_FULL>(P, tid, c, exch.data(), pw[tid], rel); break;
+      }
     }
+    tile_advance(c, P.tiles_per_clip);
   }
   return 0;
 }
@@ -82,14 +88,23 @@ int emul_istft512(const float* spec, const float* mag, const float* phase, int m
   P.vec_ok = ((out_pitch & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
   const long long span = (long long)P.g.FO * hop;
   P.tiles_per_clip = (int)((out_len + span - 1) / span);
-  P.n_tiles = (long long)B * P.tiles_per_clip;
+  P.n_tiles = B * P.tiles_per_clip;
   std::vector<float2> exch(kExch);
   std::vector<LaneConst> lc(kThreads);
-  for (int tid = 0; tid < kThreads; ++tid) lane_const_init(lc[tid], window, tid & 15, 1.0f / 512.0f);
-  for (long long tix = 0; tix < P.n_tiles; ++tix) {
-    for (int tid = 0; tid < kThreads; ++tid) inv_phase0(P, tid, tix, exch.data(), kTw512);
+  std::vector<PairTw> pw(kThreads);
+  for (int tid = 0; tid < kThreads; ++tid) {
+    lane_const_init(lc[tid], window, tid & 15, 1.0f / 512.0f);
+    pair_tw_init(pw[tid], tid >> 5);
+  }
+  TileCursor c = tile_cursor(0, P.tiles_per_clip);
+  for (int tix = 0; tix < P.n_tiles; ++tix) {
+    for (int tid = 0; tid < kThreads; ++tid) {
+      if (spec) inv_phase0<true>(P, tid, c, exch.data(), pw[tid]);
+      else inv_phase0<false>(P, tid, c, exch.data(), pw[tid]);
+    }
     for (int tid = 0; tid < kThreads; ++tid) inv_phase1(P, tid, exch.data(), lc[tid]);
-    for (int tid = 0; tid < kThreads; ++tid) inv_phase2(P, tid, tix, exch.data());
+    for (int tid = 0; tid < kThreads; ++tid) inv_phase2(P, tid, c, exch.data());
+    tile_advance(c, P.tiles_per_clip);
   }
   return 0;
 }

@@ -35,16 +35,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
+// blocks until the phase with the given parity has completed; the suspend-time hint lets the hardware
+// park the warp instead of spinning through issue slots the compute warps need
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra LAB_DONE;\n"
       "bra LAB_WAIT;\n"
       "LAB_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
 }
 
 // global -> shared bulk copy, completion signalled on the mbarrier (SASS: UBLKCP)
@@ -87,7 +89,7 @@ constexpr int kFwdThreads = 2 * kThreads;   // 8 stage-2 (consumer) warps + 8 st
 // with mbarrier hand-offs (tile_full / tile_empty / exch_full / exch_empty), so the copy of tile i+1,
 // stage 1 of tile i+1 and stage 2 of tile i overlap, and each role keeps ITS constants in registers
 // (stage 1: 32 window taps + 16 W256 twiddles per lane; stage 2: 16 W512 twiddles per warp).
-template <int kMag, bool kExtra>
+template <int kMode>
 __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdParams P) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bars[8];
@@ -107,24 +109,29 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
     }
   }
   __syncthreads();
-  const int stride = gridDim.x;
+  const int first = blockIdx.x * P.tiles_per_cta;
+  int n = P.n_tiles - first;
+  if (n > P.tiles_per_cta) n = P.tiles_per_cta;      // this CTA's run: tiles [first, first + n)
+  if (n <= 0) return;
+  TileCursor c = tile_cursor(first, P.tiles_per_clip);
   if (tid >= kThreads) {
     // ------------------------------------------------------------------ producers: stage 1
     const int ptid = tid - kThreads;
     LaneConst lc;
     lane_const_init(lc, P.window, ptid & 15, 0.5f);
-    int tix = blockIdx.x;
-    if (ptid == 0 && tix < P.n_tiles) fwd_issue_tile(fwd_tile_plan(P, tix), smem, tile_full);
+    FwdTilePlan q = fwd_tile_plan(P, c);
+    if (ptid == 0) fwd_issue_tile(q, smem, tile_full);
 #pragma unroll 1
-    for (int i = 0; tix < P.n_tiles; tix += stride, ++i) {
+    for (int i = 0; i < n; ++i) {
       const int slot = (ntb == 2) ? (i & 1) : 0;
       const int use = (ntb == 2) ? (i >> 1) : i;
       float* tile = smem + slot * P.tile_floats;
-      const FwdTilePlan q = fwd_tile_plan(P, tix);
-      if (ntb == 2 && ptid == 0 && tix + stride < P.n_tiles) {
+      tile_advance(c, P.tiles_per_clip);
+      const FwdTilePlan qn = fwd_tile_plan(P, c);      // next tile (unused when i + 1 == n)
+      if (ntb == 2 && ptid == 0 && i + 1 < n) {
         // the other slot was last read by tile i-1
         if (i >= 1) mbar_wait(tile_empty + (slot ^ 1), (uint32_t)(((i - 1) >> 1) & 1));
-        fwd_issue_tile(fwd_tile_plan(P, tix + stride), smem + (slot ^ 1) * P.tile_floats, tile_full + (slot ^ 1));
+        fwd_issue_tile(qn, smem + (slot ^ 1) * P.tile_floats, tile_full + (slot ^ 1));
       }
       mbar_wait(tile_full + slot, (uint32_t)(use & 1));
       if (fwd_needs_fixup(q)) {
@@ -137,42 +144,78 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
       mbar_arrive(exch_full + es);
       fence_proxy_async();
       mbar_arrive(tile_empty + slot);
-      if (ntb == 1 && ptid == 0 && tix + stride < P.n_tiles) {
+      if (ntb == 1 && ptid == 0 && i + 1 < n) {
         mbar_wait(tile_empty, (uint32_t)(i & 1));
-        fwd_issue_tile(fwd_tile_plan(P, tix + stride), smem, tile_full);
+        fwd_issue_tile(qn, smem, tile_full);
       }
+      q = qn;
     }
   } else {
     // ------------------------------------------------------------------ consumers: stage 2 + epilogue
     PairTw w;
     pair_tw_init(w, tid >> 5);
-    int i = 0;
 #pragma unroll 1
-    for (int tix = blockIdx.x; tix < P.n_tiles; tix += stride, ++i) {
+    for (int i = 0; i < n; ++i) {
       const int es = i & 1;
       mbar_wait(exch_full + es, (uint32_t)((i >> 1) & 1));
       ArriveRelease rel{exch_empty + es};
-      fwd_phase2<kMag, kExtra>(P, tid, tix, exch0 + es * kExch, w, rel);
+      fwd_phase2<kMode>(P, tid, c, exch0 + es * kExch, w, rel);
+      tile_advance(c, P.tiles_per_clip);
     }
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 2) istft512_kernel(const InvParams P) {
-  extern __shared__ __align__(16) float smem[];
-  __shared__ float2 tw[kBins];
-  float2* exch = reinterpret_cast<float2*>(smem);
+// Warp-specialised, persistent, one CTA per SM (same plumbing as the forward kernel):
+//   stage-A warps (lane = frame): HBM -> registers, split-pass prologue, 2 x inverse 16-pt DFT -> exch[es]
+//   stage-B warps (lane = n1): twiddle, inverse 16-pt DFT, synthesis window (in place: exch[es] becomes the
+//   frame buffer) -> named barrier -> overlap-add + 1/window-sum-square -> HBM -> release exch[es]
+// The stage-A warps run up to two tiles ahead, so their global-load latency hides behind stage B.
+template <bool kSpecOnly>
+__global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParams P) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bars[4];
+  uint64_t* exch_full = bars;        // [2] count 256 (stage-A threads)
+  uint64_t* exch_empty = bars + 2;   // [2] count 256 (stage-B threads)
+  float2* exch0 = reinterpret_cast<float2*>(smem);
   const int tid = threadIdx.x;
-  LaneConst lc;
-  lane_const_init(lc, P.window, tid & 15, 1.0f / 512.0f);
-  for (int k = tid; k < kBins; k += kThreads) tw[k] = kTw512[k];
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(exch_full + i, kThreads);
+      mbar_init(exch_empty + i, kThreads);
+    }
+  }
   __syncthreads();
-  for (long long tix = blockIdx.x; tix < P.n_tiles; tix += gridDim.x) {
-    inv_phase0(P, tid, tix, exch, tw);
-    __syncthreads();
-    inv_phase1(P, tid, exch, lc);
-    __syncthreads();
-    inv_phase2(P, tid, tix, exch);
-    __syncthreads();
+  const int first = blockIdx.x * P.tiles_per_cta;
+  int n = P.n_tiles - first;
+  if (n > P.tiles_per_cta) n = P.tiles_per_cta;
+  if (n <= 0) return;
+  TileCursor c = tile_cursor(first, P.tiles_per_clip);
+  if (tid < kThreads) {
+    PairTw w;
+    pair_tw_init(w, tid >> 5);
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+      const int es = i & 1;
+      if (i >= 2) mbar_wait(exch_empty + es, (uint32_t)(((i >> 1) - 1) & 1));
+      inv_phase0<kSpecOnly>(P, tid, c, exch0 + es * kExch, w);
+      mbar_arrive(exch_full + es);
+      tile_advance(c, P.tiles_per_clip);
+    }
+  } else {
+    const int btid = tid - kThreads;
+    LaneConst lc;
+    lane_const_init(lc, P.window, btid & 15, 1.0f / 512.0f);
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+      const int es = i & 1;
+      float2* exch = exch0 + es * kExch;
+      mbar_wait(exch_full + es, (uint32_t)((i >> 1) & 1));
+      inv_phase1(P, btid, exch, lc);
+      named_bar_sync(1, kThreads);
+      inv_phase2(P, btid, c, exch);
+      mbar_arrive(exch_empty + es);
+      tile_advance(c, P.tiles_per_clip);
+    }
   }
 }
 
@@ -206,7 +249,7 @@ struct GenericFwdParams {
 };
 
 __global__ void __launch_bounds__(256) stft_generic_fwd_kernel(const GenericFwdParams G) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   float2* buf = reinterpret_cast<float2*>(smem);
   const FwdParams& P = G.P;
   const int N = G.N;
@@ -242,14 +285,14 @@ struct GenericInvParams {
 };
 
 __global__ void __launch_bounds__(256) istft_generic_frames_kernel(const GenericInvParams G) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   float2* buf = reinterpret_cast<float2*>(smem);
   const InvParams& P = G.P;
   const int N = G.N;
-  for (long long fix = blockIdx.x; fix < P.n_tiles; fix += gridDim.x) {
+  for (int fix = blockIdx.x; fix < P.n_tiles; fix += gridDim.x) {
     const int b = (int)(fix / P.n_frames);
     const int t = (int)(fix % P.n_frames);
-    InvLoad load{P, (long long)b * G.F * P.T + t, P.db_flags ? (P.db_flags[b] != 0) : false, 0, 0, 0};
+    InvLoadFull load{P, (long long)b * G.F * P.T + t, P.db_flags ? (P.db_flags[b] != 0) : false, 0, 0, 0};
     for (int k = threadIdx.x; k < G.F; k += blockDim.x) {
       float xr, xi;
       load.rows(k, k);
@@ -474,24 +517,28 @@ static bool inv_fast_ok(const aip_stft_desc* d) {
   return inv_geom(d->hop, d->center ? 256 : 0).FO >= 4;
 }
 
-template <int kMag, bool kExtra>
-static cudaError_t launch_fwd512_t(const FwdParams& P, const DevInfo& di, cudaStream_t st) {
-  auto kern = stft512_fwd_kernel<kMag, kExtra>;
+template <int kMode>
+static cudaError_t launch_fwd512_t(FwdParams P, const DevInfo& di, cudaStream_t st) {
+  auto kern = stft512_fwd_kernel<kMode>;
   const size_t smem = fwd_smem_bytes(P.hop, P.n_tile_bufs);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  int grid = di.sms;                    // persistent: one CTA per SM
+  int grid = di.sms;                    // persistent: one CTA per SM, a contiguous run of tiles each
   if (grid > P.n_tiles) grid = P.n_tiles;
+  P.tiles_per_cta = (P.n_tiles + grid - 1) / grid;
+  grid = (P.n_tiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
   kern<<<(unsigned)grid, kFwdThreads, smem, st>>>(P);
   return cudaGetLastError();
 }
 
 static cudaError_t launch_fwd512(const FwdParams& P, const DevInfo& di, cudaStream_t st) {
-  const bool extra = P.spec || P.phase || P.mask || P.zero_frames || P.gl_mag ||
-                     !(P.mag_kind == MAG_ABS || P.mag_kind == MAG_LOG10_EPS);
-  if (!extra && P.mag_kind == MAG_ABS) return launch_fwd512_t<MAG_ABS, false>(P, di, st);
-  if (!extra && P.mag_kind == MAG_LOG10_EPS) return launch_fwd512_t<MAG_LOG10_EPS, false>(P, di, st);
-  return launch_fwd512_t<MAG_NONE, true>(P, di, st);
+  switch (fwd_mode_of(P)) {
+    case FWD_MAG_ABS: return launch_fwd512_t<FWD_MAG_ABS>(P, di, st);
+    case FWD_MAG_LOG10: return launch_fwd512_t<FWD_MAG_LOG10>(P, di, st);
+    case FWD_SPEC: return launch_fwd512_t<FWD_SPEC>(P, di, st);
+    case FWD_GL: return launch_fwd512_t<FWD_GL>(P, di, st);
+    default: return launch_fwd512_t<FWD_FULL>(P, di, st);
+  }
 }
 
 static cudaError_t launch_fwd_generic(FwdParams P, int n_fft, const DevInfo& di, cudaStream_t st) {
@@ -563,18 +610,19 @@ static int run_inv(const aip_stft_desc* desc, InvParams P, long long length, voi
     P.g = inv_geom(P.hop, P.pad);
     const long long span = (long long)P.g.FO * P.hop;
     P.tiles_per_clip = (int)((out_len + span - 1) / span);
-    P.n_tiles = (long long)P.B * P.tiles_per_clip;
+    if ((long long)P.B * P.tiles_per_clip > 0x7fffffffLL || P.T > (1 << 22)) return AIP_ERR_UNSUPPORTED;
+    P.n_tiles = (int)((long long)P.B * P.tiles_per_clip);
     P.vec_ok = ((P.out_pitch & 1) == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 7) == 0);
-    const size_t smem = (size_t)kExch * sizeof(float2);
-    e = cudaFuncSetAttribute(istft512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    int occ = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, istft512_kernel, kThreads, smem);
-    if (e != cudaSuccess) return (int)e;
-    if (occ < 1) occ = 1;
-    long long grid = (long long)di.sms * occ;
+    const size_t smem = 2 * (size_t)kExch * sizeof(float2);
+    int grid = di.sms;
     if (grid > P.n_tiles) grid = P.n_tiles;
-    istft512_kernel<<<(unsigned)grid, kThreads, smem, st>>>(P);
+    P.tiles_per_cta = (P.n_tiles + grid - 1) / grid;
+    grid = (P.n_tiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
+    const bool spec_only = P.spec != nullptr;
+    auto kern = spec_only ? istft512_kernel<true> : istft512_kernel<false>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<(unsigned)grid, kFwdThreads, smem, st>>>(P);
     e = cudaGetLastError();
   } else {
     const size_t need = aip_istft_workspace_bytes(desc, P.B, P.T);
@@ -582,7 +630,8 @@ static int run_inv(const aip_stft_desc* desc, InvParams P, long long length, voi
     GenericInvParams G;
     G.N = desc->n_fft; G.logN = ilog2(desc->n_fft); G.F = desc->n_fft / 2 + 1;
     G.frames = static_cast<float*>(workspace);
-    P.n_tiles = (long long)P.B * P.n_frames;
+    if ((long long)P.B * P.n_frames > 0x7fffffffLL) return AIP_ERR_UNSUPPORTED;
+    P.n_tiles = (int)((long long)P.B * P.n_frames);
     G.P = P;
     const size_t smem = (size_t)desc->n_fft * sizeof(float2);
     e = cudaFuncSetAttribute(istft_generic_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

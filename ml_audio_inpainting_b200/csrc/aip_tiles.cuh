@@ -55,6 +55,7 @@ struct FwdParams {
   int n_tiles;              // B * tiles_per_clip (< 2^31)
   int tile_floats;          // floats per staged-waveform buffer (tile length rounded up to 128 B)
   int n_tile_bufs;          // 2: the next tile's copy overlaps stage 1; 1: large hops
+  int tiles_per_cta;        // contiguous run of tiles per CTA
   int vec_ok;               // 16-byte bulk copies of the waveform are legal (alignment)
 };
 
@@ -66,32 +67,44 @@ AIP_HDX int fwd_tile_len(int hop) { return (kFR - 1) * hop + kNfft; }
 // is patched by the threads once the copy has landed (fwd_fixup).
 struct FwdTilePlan {
   const float* src;     // clip base
-  long long g0;         // clip sample of tile element 0 (may be negative: centre padding)
+  int g0;               // clip sample of tile element 0 (may be negative: centre padding)
   int len;              // tile elements
   int v_lo, v_hi;       // tile elements that map to real samples: [v_lo, v_hi)
   int n_bulk;           // elements moved by the bulk copy (multiple of 4), starting at v_lo
   int gs, ge;           // gap range in clip samples
 };
 
-AIP_HD FwdTilePlan fwd_tile_plan(const FwdParams& P, int tix) {
+// A CTA owns a contiguous run of tiles; (clip b, tile-in-clip tt) advance without divisions.
+struct TileCursor {
+  int b, tt;
+};
+AIP_HD TileCursor tile_cursor(int tix, int tiles_per_clip) {
+  TileCursor c;
+  c.b = tix / tiles_per_clip;
+  c.tt = tix - c.b * tiles_per_clip;
+  return c;
+}
+AIP_HD void tile_advance(TileCursor& c, int tiles_per_clip) {
+  if (++c.tt == tiles_per_clip) { c.tt = 0; ++c.b; }
+}
+
+AIP_HD FwdTilePlan fwd_tile_plan(const FwdParams& P, const TileCursor& c) {
   FwdTilePlan q;
-  const int b = tix / P.tiles_per_clip;
-  const int t0 = (tix - b * P.tiles_per_clip) * kFR;
   q.len = fwd_tile_len(P.hop);
-  q.g0 = (long long)t0 * P.hop - P.pad;
-  q.src = P.wave + (long long)b * P.wave_pitch;
-  q.v_lo = q.g0 < 0 ? (int)(-q.g0) : 0;
-  const long long hi = (long long)P.L - q.g0;
-  q.v_hi = hi < q.len ? (int)(hi > 0 ? hi : 0) : q.len;
+  q.g0 = c.tt * kFR * P.hop - P.pad;
+  q.src = P.wave + (long long)c.b * P.wave_pitch;
+  q.v_lo = q.g0 < 0 ? -q.g0 : 0;
+  const int hi = P.L - q.g0;
+  q.v_hi = hi < q.len ? (hi > 0 ? hi : 0) : q.len;
   if (q.v_lo > q.v_hi) q.v_lo = q.v_hi;
   q.n_bulk = P.vec_ok ? ((q.v_hi - q.v_lo) & ~3) : 0;
   q.gs = q.ge = 0;
-  if (P.gap_samples) { q.gs = P.gap_samples[2 * b]; q.ge = P.gap_samples[2 * b + 1]; }
+  if (P.gap_samples) { q.gs = P.gap_samples[2 * c.b]; q.ge = P.gap_samples[2 * c.b + 1]; }
   return q;
 }
 
 AIP_HD bool fwd_needs_fixup(const FwdTilePlan& q) {
-  return q.v_lo > 0 || q.v_lo + q.n_bulk < q.len || ((long long)q.ge > q.g0 && (long long)q.gs < q.g0 + q.len && q.ge > q.gs);
+  return q.v_lo > 0 || q.v_lo + q.n_bulk < q.len || (q.ge > q.g0 && q.gs < q.g0 + q.len && q.ge > q.gs);
 }
 
 // everything of the tile that the bulk copy does not deliver
@@ -100,10 +113,10 @@ AIP_HD void fwd_fixup(const FwdTilePlan& q, int tid, float* tile) {
   for (int i = q.v_lo + q.n_bulk + tid; i < q.v_hi; i += kThreads) tile[i] = q.src[q.g0 + i];
   for (int i = q.v_hi + tid; i < q.len; i += kThreads) tile[i] = 0.0f;
   // gap zeroing (utils.py:141-142, :180-183) on the staged samples
-  long long a = (long long)q.gs - q.g0, e = (long long)q.ge - q.g0;
+  int a = q.gs - q.g0, e = q.ge - q.g0;
   if (a < 0) a = 0;
   if (e > q.len) e = q.len;
-  for (long long i = a + tid; i < e; i += kThreads) tile[i] = 0.0f;
+  for (int i = a + tid; i < e; i += kThreads) tile[i] = 0.0f;
 }
 
 // stage 1 of the FFT for one tile: 256 threads, lane = n1 (16 lanes per frame), two frames per warp pass
@@ -145,7 +158,46 @@ struct FwdEmitFast {
   AIP_HM void hi(int j, float xr, float xi) const { phi[-(j * s16)] = mag_value(kMag, xr, xi, eps, power); }
 };
 
-// Epilogue, general path: complex / phase / mask outputs, spectrum-domain gap, Griffin-Lim update.
+// Epilogue, complex-only fast path (utils.extract_spectrogram's own output): one float2 store per bin.
+struct FwdEmitSpec {
+  float2* col;              // spec + b*F*T_out + t
+  int T;
+  float2* plo;
+  float2* phi;
+  int s16;
+  AIP_HM void rows(int k_lo, int k_hi) {
+    plo = col + k_lo * T;
+    phi = col + k_hi * T;
+    s16 = 16 * T;
+  }
+  AIP_HM void lo(int j, float xr, float xi) const { plo[j * s16] = make_float2(xr, xi); }
+  AIP_HM void hi(int j, float xr, float xi) const { phi[-(j * s16)] = make_float2(xr, xi); }
+};
+
+// Epilogue, Griffin-Lim update (librosa.griffinlim loop body, utils.py:330-332):
+//   angles = rebuilt - alpha * tprev ; angles /= |angles| + tiny ; angles *= S ; tprev = rebuilt
+struct FwdEmitGL {
+  float2* spec;             // angles out   (+ b*F*T + t)
+  float2* tprev;            // previous rebuilt spectrum, overwritten
+  const float* mag;         // target magnitudes S
+  int T;
+  float alpha;
+  bool has_prev, active;
+  int olo, ohi, s16;
+  AIP_HM void rows(int k_lo, int k_hi) { olo = k_lo * T; ohi = k_hi * T; s16 = 16 * T; }
+  AIP_HM void lo(int j, float xr, float xi) const { put(olo + j * s16, xr, xi); }
+  AIP_HM void hi(int j, float xr, float xi) const { put(ohi - j * s16, xr, xi); }
+  AIP_HM void put(int o, float xr, float xi) const {
+    if (!active) return;
+    float ar = xr, ai = xi;
+    if (has_prev) { const float2 tp = tprev[o]; ar -= alpha * tp.x; ai -= alpha * tp.y; }
+    tprev[o] = make_float2(xr, xi);
+    const float s = mag[o] / (sqrtf(ar * ar + ai * ai) + kFltMin);
+    spec[o] = make_float2(ar * s, ai * s);
+  }
+};
+
+// Epilogue, general path: any mix of complex / magnitude / phase / mask outputs and the spectrum-domain gap.
 struct FwdEmitFull {
   const FwdParams& P;
   long long base;           // b*F*T_out + t
@@ -160,11 +212,13 @@ struct FwdEmitFull {
   }
   AIP_HM void lo(int j, float xr, float xi) const { put(off_lo + j * s16, xr, xi); }
   AIP_HM void hi(int j, float xr, float xi) const { put(off_hi - j * s16, xr, xi); }
-  AIP_HM void put(long long idx, float xr, float xi) const {
+#if defined(__CUDACC__)
+  __device__ __noinline__      // called 65 times per job: keep the kernel inside the instruction cache
+#endif
+  void put(long long idx, float xr, float xi) const {
     if (!active) return;
     if (zero) { xr = 0.0f; xi = 0.0f; }
     if (P.gl_mag) {
-      // angles = rebuilt - alpha * tprev ; angles /= |angles| + tiny ; angles *= S ; tprev = rebuilt
       float ar = xr, ai = xi;
       if (P.gl_has_prev) { const float2 tp = P.gl_tprev[idx]; ar -= P.gl_alpha * tp.x; ai -= P.gl_alpha * tp.y; }
       P.gl_tprev[idx] = make_float2(xr, xi);
@@ -191,23 +245,49 @@ AIP_HD FwdEmitFull fwd_make_emit_full(const FwdParams& P, int b, int t, int n_bi
 
 struct NoRelease { AIP_HM void operator()() const {} };
 
+// kernel variants (template parameter kMode of the forward kernel)
+enum FwdMode : int {
+  FWD_MAG_ABS = 0,      // |S| only
+  FWD_MAG_LOG10 = 1,    // log10(|S| + eps) only
+  FWD_SPEC = 2,         // complex only
+  FWD_GL = 3,           // Griffin-Lim update
+  FWD_FULL = 4          // everything else
+};
+
+AIP_HDX int fwd_mode_of(const FwdParams& P) {
+  const bool plain = !(P.phase || P.mask || P.zero_frames);
+  if (P.gl_mag) return (plain && P.spec && P.gl_tprev && P.mag_kind == MAG_NONE) ? (int)FWD_GL : (int)FWD_FULL;
+  if (plain && !P.spec && P.mag_kind == MAG_ABS) return FWD_MAG_ABS;
+  if (plain && !P.spec && P.mag_kind == MAG_LOG10_EPS) return FWD_MAG_LOG10;
+  if (plain && P.spec && P.mag_kind == MAG_NONE) return FWD_SPEC;
+  return FWD_FULL;
+}
+
 // stage 2 + split pass + epilogue for one tile: 256 threads, lane = frame, warp = pair-job.
 // `release` runs once the exchange buffer has been read into registers.
-template <int kMag, bool kExtra, class Release>
-AIP_HD void fwd_phase2(const FwdParams& P, int tid, int tix, const float2* exch, const PairTw& w, Release& release) {
+template <int kMode, class Release>
+AIP_HD void fwd_phase2(const FwdParams& P, int tid, const TileCursor& c, const float2* exch, const PairTw& w,
+                       Release& release) {
   const int p = tid >> 5, lane = tid & 31;
-  const int b = tix / P.tiles_per_clip;
-  const int t0 = (tix - b * P.tiles_per_clip) * kFR;
+  const int t0 = c.tt * kFR;
   const int n_valid = (P.T_out - t0) < kFR ? (P.T_out - t0) : kFR;
   const int fr = lane < n_valid ? lane : n_valid - 1;     // lanes past the end replay the last valid frame
   float ar[16], ai[16], br[16], bi[16];
   fwd_stage2_load(exch, fr, p, ar, ai, br, bi);
   release();
-  if (kExtra) {
-    FwdEmitFull emit = fwd_make_emit_full(P, b, t0 + fr, kBins, lane < n_valid);
+  const long long col = (long long)c.b * kBins * P.T_out + t0 + fr;
+  if (kMode == FWD_MAG_ABS || kMode == FWD_MAG_LOG10) {
+    FwdEmitFast<(kMode == FWD_MAG_ABS ? (int)MAG_ABS : (int)MAG_LOG10_EPS)> emit{P.mag + col, P.T_out, P.eps, P.power, nullptr, nullptr, 0};
+    fwd_stage2_compute(ar, ai, br, bi, w, p, emit);
+  } else if (kMode == FWD_SPEC) {
+    FwdEmitSpec emit{P.spec + col, P.T_out, nullptr, nullptr, 0};
+    fwd_stage2_compute(ar, ai, br, bi, w, p, emit);
+  } else if (kMode == FWD_GL) {
+    FwdEmitGL emit{P.spec + col, P.gl_tprev + col, P.gl_mag + col, P.T_out, P.gl_alpha, P.gl_has_prev != 0,
+                   lane < n_valid, 0, 0, 0};
     fwd_stage2_compute(ar, ai, br, bi, w, p, emit);
   } else {
-    FwdEmitFast<kMag> emit{P.mag + ((long long)b * kBins * P.T_out + t0 + fr), P.T_out, P.eps, P.power, nullptr, nullptr, 0};
+    FwdEmitFull emit = fwd_make_emit_full(P, c.b, t0 + fr, kBins, lane < n_valid);
     fwd_stage2_compute(ar, ai, br, bi, w, p, emit);
   }
 }
@@ -231,11 +311,25 @@ struct InvParams {
   long long out_pitch;
   int vec_ok;               // float2 stores legal
   int tiles_per_clip;
-  long long n_tiles;
+  int n_tiles;
+  int tiles_per_cta;
   InvGeom g;
 };
 
-struct InvLoad {
+// Prologue loaders.  A stage-A thread reads bins k_lo + 16 j and k_hi - 16 j of ONE frame (its lane), so a
+// warp's load of one bin is 32 consecutive elements of that row of the [F, T] input.
+struct InvLoadSpec {        // complex input
+  const float2* col;        // spec + b*F*T + t
+  int T;
+  const float2* plo;
+  const float2* phi;
+  int s16;
+  AIP_HM void rows(int k_lo, int k_hi) { plo = col + k_lo * T; phi = col + k_hi * T; s16 = 16 * T; }
+  AIP_HM void lo(int j, float& xr, float& xi) const { const float2 v = plo[j * s16]; xr = v.x; xi = v.y; }
+  AIP_HM void hi(int j, float& xr, float& xi) const { const float2 v = phi[-(j * s16)]; xr = v.x; xi = v.y; }
+};
+
+struct InvLoadFull {        // magnitude (+ phase) input with the dB / 10** / expm1 prologue
   const InvParams& P;
   long long base;           // b*F*T + t
   bool db;
@@ -252,33 +346,38 @@ struct InvLoad {
     if (P.spec) {
       const float2 v = P.spec[idx];
       xr = v.x; xi = v.y;
-    } else {
-      float m = P.mag[idx];
-      const int dom = db ? (int)DOM_DB : P.mag_domain;
-      if (dom == DOM_POW10) m = fast_exp2(m * kLog2of10);
-      else if (dom == DOM_DB) m = fast_exp2(m * (kLog2of10 * 0.05f));
-      else if (dom == DOM_EXPM1) m = expm1f(m);
-      if (P.phase) {
-        float s, c;
-        fast_sincos(P.phase[idx], s, c);
-        xr = m * c; xi = m * s;
-      } else { xr = m; xi = 0.0f; }
+      return;
     }
+    float m = P.mag[idx];
+    const int dom = db ? (int)DOM_DB : P.mag_domain;
+    if (dom == DOM_POW10) m = fast_exp2(m * kLog2of10);
+    else if (dom == DOM_DB) m = fast_exp2(m * (kLog2of10 * 0.05f));
+    else if (dom == DOM_EXPM1) m = expm1f(m);
+    if (P.phase) {
+      float s, c;
+      fast_sincos(P.phase[idx], s, c);
+      xr = m * c; xi = m * s;
+    } else { xr = m; xi = 0.0f; }
   }
 };
 
-// phase 0: stage A, lane = frame, warp = pair-job
-AIP_HD void inv_phase0(const InvParams& P, int tid, long long tix, float2* exch, const float2* tw) {
+// stage A for one tile: 256 threads, lane = frame, warp = pair-job
+template <bool kSpecOnly>
+AIP_HD void inv_phase0(const InvParams& P, int tid, const TileCursor& c, float2* exch, const PairTw& w) {
   const int warp = tid >> 5, lane = tid & 31;
-  const int b = (int)(tix / P.tiles_per_clip);
-  const int j = (int)(tix % P.tiles_per_clip);
-  const int t = j * P.g.FO - P.g.HL + lane;
+  const int t = c.tt * P.g.FO - P.g.HL + lane;
   const bool live = (t >= 0 && t < P.n_frames);
-  InvLoad load{P, (long long)b * kBins * P.T + t, P.db_flags ? (P.db_flags[b] != 0) : false, 0, 0, 0};
-  inv_stageA(exch, tw, lane, warp, live, load);
+  const long long col = (long long)c.b * kBins * P.T + t;
+  if (kSpecOnly) {
+    InvLoadSpec load{P.spec + col, P.T, nullptr, nullptr, 0};
+    inv_stageA(exch, w, lane, warp, live, load);
+  } else {
+    InvLoadFull load{P, col, P.db_flags ? (P.db_flags[c.b] != 0) : false, 0, 0, 0};
+    inv_stageA(exch, w, lane, warp, live, load);
+  }
 }
 
-// phase 1: stage B, lane = n1
+// stage B for one tile: 256 threads, lane = n1
 AIP_HD void inv_phase1(const InvParams& P, int tid, float2* exch, const LaneConst& lc) {
   const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll 1
@@ -288,14 +387,12 @@ AIP_HD void inv_phase1(const InvParams& P, int tid, float2* exch, const LaneCons
   }
 }
 
-// phase 2: overlap-add + window-sum-square normalisation + store
-AIP_HD void inv_phase2(const InvParams& P, int tid, long long tix, const float2* fbuf) {
-  const int b = (int)(tix / P.tiles_per_clip);
-  const int j = (int)(tix % P.tiles_per_clip);
-  const int f_first = j * P.g.FO - P.g.HL;
-  const int s0 = j * P.g.FO * P.hop;
+// overlap-add + window-sum-square normalisation + store for one tile (256 threads)
+AIP_HD void inv_phase2(const InvParams& P, int tid, const TileCursor& c, const float2* fbuf) {
+  const int f_first = c.tt * P.g.FO - P.g.HL;
+  const int s0 = c.tt * P.g.FO * P.hop;
   const int n_pairs = (P.g.FO * P.hop) >> 1;
-  float* dst = P.out + (long long)b * P.out_pitch;
+  float* dst = P.out + (long long)c.b * P.out_pitch;
   for (int q = tid; q < n_pairs; q += kThreads) {
     const int s = s0 + 2 * q;
     if (s >= P.out_len) break;
