@@ -336,19 +336,38 @@ AIP_HDX InvGeom inv_geom(int hop, int pad) {
   return g;
 }
 
-// Overlap-add of one output sample PAIR (s, s+1), s even, from the frame buffer.
-// p = s + pad is the position in the padded signal; f_first = first frame held by the tile;
-// n_frames = frames that exist (T').  Returns the un-normalised sums.
-AIP_HD float2 ola_pair(const float2* fbuf, int p, int hop, int f_first, int n_frames) {
-  int f_lo = (p - (kNfft - 1) + hop - 1);
-  f_lo = f_lo > 0 ? f_lo / hop : 0;            // ceil((p-511)/hop) clamped at 0
-  int f_hi = p / hop;
-  if (f_hi > n_frames - 1) f_hi = n_frames - 1;
+// floor(n / d) for 0 <= n < 2^32 / d via a host-precomputed reciprocal m = ceil(2^32 / d)
+AIP_HD int magic_div(int n, unsigned m) {
+#if defined(__CUDACC__)
+  return (int)__umulhi((unsigned)n, m);
+#else
+  return (int)(((unsigned long long)(unsigned)n * m) >> 32);
+#endif
+}
+
+// Overlap-add of one output sample PAIR out of the frame buffer (float2 slot (n/2)*33 + fl holds samples
+// (n, n+1) of local frame fl).  The pair sits at offset r (even) of local frame h, i.e. the frames covering it
+// are fl = h - m with n = r + m*hop < 512, m = 0 .. K-1, K = ceil(512 / hop); only the m = K-1 term can be
+// missing.  librosa adds frames in increasing order = decreasing m.  `edge`: some local frames do not exist
+// (clip start / end), [fl_min, fl_max] are the ones that do.
+AIP_HD float2 ola_pair(const float2* fbuf, int h, int r, int hop, int K, bool edge, int fl_min, int fl_max) {
+  const int step = (hop >> 1) * kXP - 1;            // slot(m) - slot(m-1)
+  int m = K - 1;
+  int n = r + m * hop;
+  const float2* src = fbuf + (n >> 1) * kXP + (h - m);
   float sx = 0.0f, sy = 0.0f;
-  for (int f = f_lo; f <= f_hi; ++f) {
-    const int n = p - f * hop;                 // even, in [0, 510]
-    const float2 v = fbuf[(n >> 1) * kXP + (f - f_first)];
-    sx += v.x; sy += v.y;
+  if (!edge) {
+    if (n < kNfft) { const float2 v = *src; sx += v.x; sy += v.y; }
+    for (--m; m >= 0; --m) {
+      src -= step;
+      const float2 v = *src;
+      sx += v.x; sy += v.y;
+    }
+  } else {
+    for (; m >= 0; --m, n -= hop, src -= step) {
+      const int fl = h - m;
+      if (n < kNfft && fl >= fl_min && fl <= fl_max) { const float2 v = *src; sx += v.x; sy += v.y; }
+    }
   }
   return make_float2(sx, sy);
 }

@@ -85,10 +85,15 @@ int emul_istft512(const float* spec, const float* mag, const float* phase, int m
   }
   P.out_len = out_len;
   P.window = window; P.inv_wss = inv_wss; P.out = out; P.out_pitch = out_pitch;
-  P.vec_ok = ((out_pitch & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
+  P.vec_ok = ((out_pitch & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0) &&
+             ((reinterpret_cast<uintptr_t>(inv_wss) & 7) == 0);
   const long long span = (long long)P.g.FO * hop;
   P.tiles_per_clip = (int)((out_len + span - 1) / span);
   P.n_tiles = B * P.tiles_per_clip;
+  P.hop_magic = (unsigned)((0x100000000ULL + (unsigned)hop - 1) / (unsigned)hop);
+  P.ola_terms = (kNfft + hop - 1) / hop;
+  P.ola_dq = (2 * kThreads) / hop;
+  P.ola_dr = (2 * kThreads) % hop;
   std::vector<float2> exch(kExch);
   std::vector<LaneConst> lc(kThreads);
   std::vector<PairTw> pw(kThreads);

@@ -61,6 +61,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// one arrival per WARP (barrier counts are in warps): every arrival wakes the waiters, so 8 instead of 256
+// arrivals per phase keeps the parked warps parked.  __syncwarp orders the other lanes' shared-memory
+// accesses before lane 0's release.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -78,7 +86,7 @@ __device__ __forceinline__ void fwd_issue_tile(const FwdTilePlan& q, float* tile
 
 struct ArriveRelease {
   uint64_t* bar;
-  __device__ __forceinline__ void operator()() const { mbar_arrive(bar); }
+  __device__ __forceinline__ void operator()() const { mbar_arrive_warp(bar); }
 };
 
 constexpr int kFwdThreads = 2 * kThreads;   // 8 stage-2 (consumer) warps + 8 stage-1 (producer) warps
@@ -94,18 +102,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bars[8];
   uint64_t* tile_full = bars;        // [2] count 1 (+ tx bytes)
-  uint64_t* tile_empty = bars + 2;   // [2] count 256 (stage-1 threads)
-  uint64_t* exch_full = bars + 4;    // [2] count 256 (stage-1 threads)
-  uint64_t* exch_empty = bars + 6;   // [2] count 256 (stage-2 threads)
+  uint64_t* tile_empty = bars + 2;   // [2] count 8 (stage-1 warps)
+  uint64_t* exch_full = bars + 4;    // [2] count 8 (stage-1 warps)
+  uint64_t* exch_empty = bars + 6;   // [2] count 8 (stage-2 warps)
   const int ntb = P.n_tile_bufs;
   float2* exch0 = reinterpret_cast<float2*>(smem + ntb * P.tile_floats);
   const int tid = threadIdx.x;
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(tile_full + i, 1);
-      mbar_init(tile_empty + i, kThreads);
-      mbar_init(exch_full + i, kThreads);
-      mbar_init(exch_empty + i, kThreads);
+      mbar_init(tile_empty + i, kThreads / 32);
+      mbar_init(exch_full + i, kThreads / 32);
+      mbar_init(exch_empty + i, kThreads / 32);
     }
   }
   __syncthreads();
@@ -141,9 +149,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
       const int es = i & 1;
       if (i >= 2) mbar_wait(exch_empty + es, (uint32_t)(((i >> 1) - 1) & 1));
       fwd_phase1(P, ptid, tile, exch0 + es * kExch, lc);
-      mbar_arrive(exch_full + es);
+      mbar_arrive_warp(exch_full + es);
       fence_proxy_async();
-      mbar_arrive(tile_empty + slot);
+      mbar_arrive_warp(tile_empty + slot);
       if (ntb == 1 && ptid == 0 && i + 1 < n) {
         mbar_wait(tile_empty, (uint32_t)(i & 1));
         fwd_issue_tile(qn, smem, tile_full);
@@ -174,14 +182,14 @@ template <bool kSpecOnly>
 __global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParams P) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bars[4];
-  uint64_t* exch_full = bars;        // [2] count 256 (stage-A threads)
-  uint64_t* exch_empty = bars + 2;   // [2] count 256 (stage-B threads)
+  uint64_t* exch_full = bars;        // [2] count 8 (stage-A warps)
+  uint64_t* exch_empty = bars + 2;   // [2] count 8 (stage-B warps)
   float2* exch0 = reinterpret_cast<float2*>(smem);
   const int tid = threadIdx.x;
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(exch_full + i, kThreads);
-      mbar_init(exch_empty + i, kThreads);
+      mbar_init(exch_full + i, kThreads / 32);
+      mbar_init(exch_empty + i, kThreads / 32);
     }
   }
   __syncthreads();
@@ -198,7 +206,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParam
       const int es = i & 1;
       if (i >= 2) mbar_wait(exch_empty + es, (uint32_t)(((i >> 1) - 1) & 1));
       inv_phase0<kSpecOnly>(P, tid, c, exch0 + es * kExch, w);
-      mbar_arrive(exch_full + es);
+      mbar_arrive_warp(exch_full + es);
       tile_advance(c, P.tiles_per_clip);
     }
   } else {
@@ -213,7 +221,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParam
       inv_phase1(P, btid, exch, lc);
       named_bar_sync(1, kThreads);
       inv_phase2(P, btid, c, exch);
-      mbar_arrive(exch_empty + es);
+      mbar_arrive_warp(exch_empty + es);
       tile_advance(c, P.tiles_per_clip);
     }
   }
@@ -512,6 +520,13 @@ static int fwd_tile_bufs(const aip_stft_desc* d, const DevInfo& di) {
 
 static bool fwd_fast_ok(const aip_stft_desc* d, const DevInfo& di) { return fwd_tile_bufs(d, di) > 0; }
 
+static void inv_fill_ola(InvParams& P) {
+  P.hop_magic = (unsigned)((0x100000000ULL + (unsigned)P.hop - 1) / (unsigned)P.hop);
+  P.ola_terms = (kNfft + P.hop - 1) / P.hop;
+  P.ola_dq = (2 * kThreads) / P.hop;
+  P.ola_dr = (2 * kThreads) % P.hop;
+}
+
 static bool inv_fast_ok(const aip_stft_desc* d) {
   if (d->n_fft != 512 || (d->hop & 1)) return false;
   return inv_geom(d->hop, d->center ? 256 : 0).FO >= 4;
@@ -612,7 +627,9 @@ static int run_inv(const aip_stft_desc* desc, InvParams P, long long length, voi
     P.tiles_per_clip = (int)((out_len + span - 1) / span);
     if ((long long)P.B * P.tiles_per_clip > 0x7fffffffLL || P.T > (1 << 22)) return AIP_ERR_UNSUPPORTED;
     P.n_tiles = (int)((long long)P.B * P.tiles_per_clip);
-    P.vec_ok = ((P.out_pitch & 1) == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 7) == 0);
+    P.vec_ok = ((P.out_pitch & 1) == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 7) == 0) &&
+               ((reinterpret_cast<uintptr_t>(P.inv_wss) & 7) == 0);
+    inv_fill_ola(P);
     const size_t smem = 2 * (size_t)kExch * sizeof(float2);
     int grid = di.sms;
     if (grid > P.n_tiles) grid = P.n_tiles;

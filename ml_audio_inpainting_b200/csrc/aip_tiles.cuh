@@ -309,11 +309,15 @@ struct InvParams {
   int out_len;
   float* out;               // [B, out_len], row pitch out_pitch
   long long out_pitch;
-  int vec_ok;               // float2 stores legal
+  int vec_ok;               // float2 loads of inv_wss / stores of the output are legal
   int tiles_per_clip;
   int n_tiles;
   int tiles_per_cta;
   InvGeom g;
+  unsigned hop_magic;       // ceil(2^32 / hop)
+  int ola_terms;            // ceil(512 / hop): frames overlapping one sample
+  int ola_dq, ola_dr;       // (2 * 256) / hop and (2 * 256) % hop: per-iteration advance of a thread's pair
+
 };
 
 // Prologue loaders.  A stage-A thread reads bins k_lo + 16 j and k_hi - 16 j of ONE frame (its lane), so a
@@ -387,24 +391,42 @@ AIP_HD void inv_phase1(const InvParams& P, int tid, float2* exch, const LaneCons
   }
 }
 
-// overlap-add + window-sum-square normalisation + store for one tile (256 threads)
+// overlap-add + window-sum-square normalisation + store for one tile (256 threads): thread q, q + 256, ...
+// owns output pairs (s0 + 2q, s0 + 2q + 1); its (frame, offset) coordinates advance incrementally.
 AIP_HD void inv_phase2(const InvParams& P, int tid, const TileCursor& c, const float2* fbuf) {
+  const int hop = P.hop;
   const int f_first = c.tt * P.g.FO - P.g.HL;
-  const int s0 = c.tt * P.g.FO * P.hop;
-  const int n_pairs = (P.g.FO * P.hop) >> 1;
+  const int s0 = c.tt * P.g.FO * hop;
+  int fl_min = -f_first;
+  if (fl_min < 0) fl_min = 0;
+  int fl_max = P.n_frames - 1 - f_first;
+  if (fl_max > kFR - 1) fl_max = kFR - 1;
+  const bool edge = fl_min > 0 || fl_max < kFR - 1;
+  const int n_pairs = (P.g.FO * hop) >> 1;
   float* dst = P.out + (long long)c.b * P.out_pitch;
+  // position of pair q relative to local frame 0: u = 2q + pad + HL*hop = h*hop + r
+  const int u0 = 2 * tid + P.pad + P.g.HL * hop;
+  int h = magic_div(u0, P.hop_magic);
+  int r = u0 - h * hop;
   for (int q = tid; q < n_pairs; q += kThreads) {
     const int s = s0 + 2 * q;
     if (s >= P.out_len) break;
-    float2 v = ola_pair(fbuf, s + P.pad, P.hop, f_first, P.n_frames);
-    v.x *= P.inv_wss[s];
+    float2 v = ola_pair(fbuf, h, r, hop, P.ola_terms, edge, fl_min, fl_max);
     if (s + 1 < P.out_len) {
-      v.y *= P.inv_wss[s + 1];
-      if (P.vec_ok) *reinterpret_cast<float2*>(dst + s) = v;
-      else { dst[s] = v.x; dst[s + 1] = v.y; }
+      if (P.vec_ok) {
+        const float2 nw = *reinterpret_cast<const float2*>(P.inv_wss + s);
+        v.x *= nw.x; v.y *= nw.y;
+        *reinterpret_cast<float2*>(dst + s) = v;
+      } else {
+        dst[s] = v.x * P.inv_wss[s];
+        dst[s + 1] = v.y * P.inv_wss[s + 1];
+      }
     } else {
-      dst[s] = v.x;
+      dst[s] = v.x * P.inv_wss[s];
     }
+    h += P.ola_dq;
+    r += P.ola_dr;
+    if (r >= hop) { r -= hop; ++h; }
   }
 }
 

@@ -1,0 +1,175 @@
+"""CPU tier: the kernels' own per-thread code (csrc/aip_tiles.cuh compiled by g++, replayed thread by thread)
+against the oracle.  This checks the algorithm, the lane/warp maps, the exchange-buffer layout, the tile edge
+handling and the overlap-add WITHOUT a GPU; the GPU tier (test_gpu_parity.py) checks the real launches."""
+import numpy as np
+import pytest
+
+from oracle import callers_port as cp
+from oracle import librosa_port as lr
+from tests import emul
+
+TOL = 1e-4
+
+
+def relerr(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def noise(B, L, seed):
+    rng = np.random.default_rng(seed)
+    return np.clip(0.1 * rng.standard_normal((B, L)), -1, 1).astype(np.float32)
+
+
+def win(win_length, name="hann"):
+    return lr.fft_window(name, win_length, 512).astype(np.float32)
+
+
+def inv_wss(window_name, win_length, hop, T, out_len, center=True):
+    wss = lr.window_sumsquare(window_name, T, hop_length=hop, win_length=win_length, n_fft=512, dtype=np.float32)
+    start = 256 if center else 0
+    wss = wss[start:start + out_len]
+    if len(wss) < out_len:
+        wss = np.pad(wss, (0, out_len - len(wss)))
+    with np.errstate(divide="ignore"):
+        return np.where(wss > np.finfo(np.float32).tiny, 1.0 / wss, 1.0).astype(np.float32)
+
+
+@pytest.mark.parametrize("hop,wl", [(192, 384), (128, 512), (512, 512), (64, 256), (250, 500)])
+@pytest.mark.parametrize("L", [512, 777, 6001, 16000])
+def test_forward_complex(hop, wl, L):
+    x = noise(2, L, seed=hop + L)
+    S = emul.stft(x, hop, win(wl))["spec"]
+    for b in range(2):
+        ref = lr.stft(x[b], n_fft=512, hop_length=hop, win_length=wl)
+        assert S[b].shape == ref.shape
+        assert relerr(S[b], ref) < TOL
+
+
+@pytest.mark.parametrize("center", [True, False])
+@pytest.mark.parametrize("vec_ok", [True, False])
+def test_forward_center_and_scalar_path(center, vec_ok):
+    x = noise(1, 5003, seed=3)
+    S = emul.stft(x, 192, win(384), center=center, vec_ok=vec_ok)["spec"]
+    ref = lr.stft(x[0], n_fft=512, hop_length=192, win_length=384, center=center)
+    assert S[0].shape == ref.shape and relerr(S[0], ref) < TOL
+
+
+@pytest.mark.parametrize("window", ["hann", "hamming", "blackman"])
+def test_forward_windows(window):
+    x = noise(1, 8000, seed=9)
+    S = emul.stft(x, 128, win(400, window))["spec"]
+    ref = lr.stft(x[0], n_fft=512, hop_length=128, win_length=400, window=window)
+    assert relerr(S[0], ref) < TOL
+
+
+def test_forward_gap_logmag_mask_crop():
+    L, B = 16000, 4
+    x = noise(B, L, seed=1)
+    gaps = np.array([[0, 1600], [7000, 10200], [L - 1600, L], [5000, 5000]])
+    frames = np.array([[0, 9], [36, 54], [75, 84], [10, 10]])
+    out = emul.stft(x, 192, win(384), gap_samples=gaps, mask_frames=frames, mag_kind=2, want_spec=False,
+                    want_mask=True, t_out=80)
+    for b in range(B):
+        xg = x[b].copy()
+        xg[gaps[b, 0]:gaps[b, 1]] = 0
+        ref = np.abs(lr.stft(xg, n_fft=512, hop_length=192, win_length=384))[:, :80]
+        assert out["mag"][b].shape == (257, 80)
+        assert relerr(10.0 ** out["mag"][b].astype(np.float64), ref + 1e-9) < TOL
+        m = np.zeros((257, 80), np.float32)
+        m[:, frames[b, 0]:frames[b, 1]] = 1
+        assert np.array_equal(out["mask"][b], m)
+    # frames that see only zeros are exactly log10(1e-9)
+    assert np.all(out["mag"][1][:, 40:50] == np.float32(-9.0))
+
+
+def test_forward_gan_epilogue_and_spec_gap():
+    L = 16000
+    x = noise(1, L, seed=5)
+    ref = cp.gan_item(x[0], gap_start_s=0.4)
+    s0, s1 = ref["gap_samples"]
+    f0, f1 = ref["gap_frames"]
+    o = emul.stft(x, 128, win(512), mag_kind=3, want_spec=False, want_phase=True, want_mask=True,
+                  mask_frames=np.array([[f0, f1]]), mask_in_gap_is_one=False)
+    assert np.array_equal(o["mask"][0], ref["mask"])
+    assert relerr(np.expm1(o["mag"][0].astype(np.float64)), np.expm1(ref["original_magnitude"].astype(np.float64))) < TOL
+    w = np.expm1(ref["original_magnitude"].astype(np.float64))
+    assert float((np.abs(np.exp(1j * o["phase"][0]) - np.exp(1j * ref["original_phase"])) * w / w.max()).max()) < TOL
+    imp = emul.stft(x, 128, win(512), gap_samples=np.array([[s0, s1]]), mag_kind=3, want_spec=False)
+    assert relerr(np.expm1(imp["mag"][0].astype(np.float64)), np.expm1(ref["impaired_magnitude"].astype(np.float64))) < TOL
+    # model_eval.py:154 spectrum-domain gap
+    ev = cp.eval_frontend_cnnlstm(x[0], t0=0.3, t1=0.38)
+    z = emul.stft(x, 192, win(384), zero_frames=np.array([ev["gap_frames"]]), mag_kind=2, want_spec=False)
+    assert relerr(10.0 ** z["mag"][0].astype(np.float64), 10.0 ** ev["log_impaired_magnitude"].astype(np.float64)) < TOL
+    assert np.all(z["mag"][0][:, ev["gap_frames"][0]:ev["gap_frames"][1]] == np.float32(-9.0))
+
+
+@pytest.mark.parametrize("hop,wl", [(192, 384), (128, 512), (512, 512), (64, 256), (250, 500)])
+@pytest.mark.parametrize("L", [2000, 16000])
+def test_inverse_complex(hop, wl, L):
+    x = noise(2, L, seed=7 * hop + L)
+    S = np.stack([lr.stft(x[b], n_fft=512, hop_length=hop, win_length=wl) for b in range(2)])
+    T = S.shape[2]
+    ref = np.stack([lr.istft(S[b], hop_length=hop, win_length=wl, n_fft=512) for b in range(2)])
+    y = emul.istft(hop, win(wl), inv_wss("hann", wl, hop, T, ref.shape[1]), spec=S)
+    good = np.ones(ref.shape[1], bool)
+    if hop == wl:   # window-sum-square has (near-)zeros: compare where it is well conditioned
+        good = inv_wss("hann", wl, hop, T, ref.shape[1]) < 100.0
+    for b in range(2):
+        assert relerr(y[b][good], ref[b][good]) < TOL
+
+
+@pytest.mark.parametrize("length", [3000, 15872, 16000, 20000])
+def test_inverse_length_argument(length):
+    x = noise(1, 16000, seed=2)
+    S = lr.stft(x[0], n_fft=512, hop_length=192, win_length=384)
+    ref = lr.istft(S, hop_length=192, win_length=384, n_fft=512, length=length)
+    T = S.shape[1]
+    n_frames = min(T, int(np.ceil((length + 512) / 192)))
+    iw = inv_wss("hann", 384, 192, n_frames, length)
+    y = emul.istft(192, win(384), iw, spec=S[None], length=length)
+    assert y.shape[1] == len(ref) == length
+    good = iw < 100.0        # past the last frame's centre the window sum decays to ~0: ill-conditioned in the reference too
+    assert good.sum() >= min(length, 15936) - 8 and relerr(y[0][good], ref[good]) < TOL
+    assert np.all(y[0][16384:] == 0) and np.all(ref[16384:] == 0)
+
+
+def test_inverse_uncentered():
+    x = noise(1, 9000, seed=4)
+    S = lr.stft(x[0], n_fft=512, hop_length=128, win_length=512, center=False)
+    ref = lr.istft(S, hop_length=128, win_length=512, n_fft=512, center=False)
+    y = emul.istft(128, win(512), inv_wss("hann", 512, 128, S.shape[1], len(ref), center=False), spec=S[None], center=False)
+    inner = slice(512, len(ref) - 512)          # the un-centred ends divide by tiny window sums
+    assert relerr(y[0][inner], ref[inner]) < TOL
+
+
+def test_inverse_mag_phase_and_domains():
+    x = noise(1, 8000, seed=6)
+    S = lr.stft(x[0], n_fft=512, hop_length=192, win_length=384)
+    T = S.shape[1]
+    ref = lr.istft((np.abs(S) * np.exp(1j * np.angle(S))).astype(np.complex64), hop_length=192, win_length=384, n_fft=512)
+    iw = inv_wss("hann", 384, 192, T, len(ref))
+    mag, ph = np.abs(S)[None], np.angle(S)[None]
+    assert relerr(emul.istft(192, win(384), iw, mag=mag, phase=ph)[0], ref) < TOL
+    assert relerr(emul.istft(192, win(384), iw, mag=np.log10(mag + 1e-12), phase=ph, mag_domain=1)[0], ref) < 2 * TOL
+    db = 20 * np.log10(mag / mag.max() * 0.5 + 1e-12)
+    ref_db = lr.istft((lr.db_to_amplitude(db[0]) * np.exp(1j * ph[0])).astype(np.complex64), hop_length=192, win_length=384, n_fft=512)
+    assert relerr(emul.istft(192, win(384), iw, mag=db, phase=ph, mag_domain=2)[0], ref_db) < 2 * TOL
+    assert relerr(emul.istft(192, win(384), iw, mag=db, phase=ph, db_flags=np.array([1]))[0], ref_db) < 2 * TOL
+    assert relerr(emul.istft(192, win(384), iw, mag=np.log1p(mag), phase=ph, mag_domain=3)[0], ref) < 2 * TOL
+    # imag(DC) / imag(Nyquist) are ignored, as scipy.fft.irfft does
+    S2 = S.copy()
+    S2[0] += 3j
+    S2[-1] -= 2j
+    assert relerr(emul.istft(192, win(384), iw, spec=S2[None])[0], lr.istft(S, hop_length=192, win_length=384, n_fft=512)) < TOL
+
+
+def test_round_trip_snr(golden_clips):
+    name = sorted(golden_clips)[0]
+    x = golden_clips[name][:32000]
+    S = emul.stft(x[None], 192, win(384))["spec"]
+    T = S.shape[2]
+    y = emul.istft(192, win(384), inv_wss("hann", 384, 192, T, 192 * (T - 1)), spec=S)[0]
+    n = len(y)
+    err = (x[512:n - 512] - y[512:n - 512]).astype(np.float64)
+    snr = 10 * np.log10((x[512:n - 512].astype(np.float64) ** 2).sum() / (err ** 2).sum())
+    assert snr >= 100.0, snr
