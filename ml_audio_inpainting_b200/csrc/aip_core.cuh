@@ -249,8 +249,8 @@ AIP_HD void inv_pair(float akr, float aki, float bkr, float bki, float wr, float
   znr = er + ti; zni = tr - ei;
 }
 
-template <class Load>
-AIP_HD void inv_stageA(float2* exch, const PairTw& w, int f, int p, bool live, Load& load) {
+template <class Load, class BeforeStore>
+AIP_HD void inv_stageA(float2* exch, const PairTw& w, int f, int p, bool live, Load& load, BeforeStore& before_store) {
   float ar[16], ai[16], br[16], bi[16];
   const int ja = p, jb = (p == 0) ? 8 : 16 - p;
   if (live) {
@@ -291,6 +291,7 @@ AIP_HD void inv_stageA(float2* exch, const PairTw& w, int f, int p, bool live, L
 #pragma unroll
     for (int q = 0; q < 16; ++q) { ar[q] = ai[q] = br[q] = bi[q] = 0.0f; }
   }
+  before_store();      // the exchange buffer must have been released by the previous tile's readers
   float2* da = exch + ja * 16 * kXP + f;
   float2* db = exch + jb * 16 * kXP + f;
 #pragma unroll

@@ -35,18 +35,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
-// blocks until the phase with the given parity has completed; the suspend-time hint lets the hardware
-// park the warp instead of spinning through issue slots the compute warps need
+// blocks until the phase with the given parity has completed (try_wait parks the warp for a hardware-
+// defined time per attempt; a longer suspend-time hint measured SLOWER: later wake-ups)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra LAB_DONE;\n"
       "bra LAB_WAIT;\n"
       "LAB_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 // global -> shared bulk copy, completion signalled on the mbarrier (SASS: UBLKCP)
@@ -173,24 +173,42 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
   }
 }
 
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct AsyncCopy8 {
+  __device__ __forceinline__ void operator()(float2* dst, const float2* src) const { cp_async8(dst, src); }
+};
+
+struct WaitBefore {
+  uint64_t* bar;
+  uint32_t parity;
+  bool enabled;
+  __device__ __forceinline__ void operator()() const { if (enabled) mbar_wait(bar, parity); }
+};
+
 // Warp-specialised, persistent, one CTA per SM (same plumbing as the forward kernel):
-//   stage-A warps (lane = frame): HBM -> registers, split-pass prologue, 2 x inverse 16-pt DFT -> exch[es]
-//   stage-B warps (lane = n1): twiddle, inverse 16-pt DFT, synthesis window (in place: exch[es] becomes the
-//   frame buffer) -> named barrier -> overlap-add + 1/window-sum-square -> HBM -> release exch[es]
-// The stage-A warps run up to two tiles ahead, so their global-load latency hides behind stage B.
-template <bool kSpecOnly>
+//   stage-A warps (lane = frame): their bins of tile i+1 stream HBM -> private staging slots (cp.async) while
+//   they run tile i: staging -> registers, split-pass prologue, 2 x inverse 16-pt DFT -> exchange buffer
+//   stage-B warps (lane = n1): twiddle, inverse 16-pt DFT, synthesis window (in place: the exchange buffer
+//   becomes the frame buffer) -> named barrier -> overlap-add + 1/window-sum-square -> HBM -> release
+// Shared memory: 2 staging buffers (2 x 66 KB) + 1 exchange buffer (66 KB).
+template <bool kStaged>
 __global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParams P) {
   extern __shared__ __align__(128) float smem[];
-  __shared__ __align__(8) uint64_t bars[4];
-  uint64_t* exch_full = bars;        // [2] count 8 (stage-A warps)
-  uint64_t* exch_empty = bars + 2;   // [2] count 8 (stage-B warps)
-  float2* exch0 = reinterpret_cast<float2*>(smem);
+  __shared__ __align__(8) uint64_t bars[2];
+  uint64_t* exch_full = bars;        // count 8 (stage-A warps)
+  uint64_t* exch_empty = bars + 1;   // count 8 (stage-B warps)
+  float2* exch = reinterpret_cast<float2*>(smem);
+  float2* stage0 = exch + kExch;
   const int tid = threadIdx.x;
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(exch_full + i, kThreads / 32);
-      mbar_init(exch_empty + i, kThreads / 32);
-    }
+    mbar_init(exch_full, kThreads / 32);
+    mbar_init(exch_empty, kThreads / 32);
   }
   __syncthreads();
   const int first = blockIdx.x * P.tiles_per_cta;
@@ -201,12 +219,23 @@ __global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParam
   if (tid < kThreads) {
     PairTw w;
     pair_tw_init(w, tid >> 5);
+    AsyncCopy8 copy;
+    TileCursor cn = c;
+    if (kStaged) {
+      inv_stage_issue(P, tid, cn, stage0, copy);
+      cp_async_commit();
+    }
 #pragma unroll 1
     for (int i = 0; i < n; ++i) {
-      const int es = i & 1;
-      if (i >= 2) mbar_wait(exch_empty + es, (uint32_t)(((i >> 1) - 1) & 1));
-      inv_phase0<kSpecOnly>(P, tid, c, exch0 + es * kExch, w);
-      mbar_arrive_warp(exch_full + es);
+      if (kStaged) {
+        tile_advance(cn, P.tiles_per_clip);
+        if (i + 1 < n) inv_stage_issue(P, tid, cn, stage0 + ((i + 1) & 1) * kStage, copy);
+        cp_async_commit();
+        cp_async_wait<1>();          // this thread's copies of tile i have landed
+      }
+      WaitBefore wb{exch_empty, (uint32_t)((i - 1) & 1), i >= 1};
+      inv_phase0<kStaged>(P, tid, c, stage0 + (i & 1) * kStage, exch, w, wb);
+      mbar_arrive_warp(exch_full);
       tile_advance(c, P.tiles_per_clip);
     }
   } else {
@@ -215,13 +244,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParam
     lane_const_init(lc, P.window, btid & 15, 1.0f / 512.0f);
 #pragma unroll 1
     for (int i = 0; i < n; ++i) {
-      const int es = i & 1;
-      float2* exch = exch0 + es * kExch;
-      mbar_wait(exch_full + es, (uint32_t)((i >> 1) & 1));
+      mbar_wait(exch_full, (uint32_t)(i & 1));
       inv_phase1(P, btid, exch, lc);
       named_bar_sync(1, kThreads);
       inv_phase2(P, btid, c, exch);
-      mbar_arrive_warp(exch_empty + es);
+      mbar_arrive_warp(exch_empty);
       tile_advance(c, P.tiles_per_clip);
     }
   }
@@ -630,13 +657,13 @@ static int run_inv(const aip_stft_desc* desc, InvParams P, long long length, voi
     P.vec_ok = ((P.out_pitch & 1) == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 7) == 0) &&
                ((reinterpret_cast<uintptr_t>(P.inv_wss) & 7) == 0);
     inv_fill_ola(P);
-    const size_t smem = 2 * (size_t)kExch * sizeof(float2);
+    const bool staged = P.spec != nullptr;
+    const size_t smem = ((size_t)kExch + (staged ? 2 * (size_t)kStage : 0)) * sizeof(float2);
     int grid = di.sms;
     if (grid > P.n_tiles) grid = P.n_tiles;
     P.tiles_per_cta = (P.n_tiles + grid - 1) / grid;
     grid = (P.n_tiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
-    const bool spec_only = P.spec != nullptr;
-    auto kern = spec_only ? istft512_kernel<true> : istft512_kernel<false>;
+    auto kern = staged ? istft512_kernel<true> : istft512_kernel<false>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<(unsigned)grid, kFwdThreads, smem, st>>>(P);

@@ -322,17 +322,6 @@ struct InvParams {
 
 // Prologue loaders.  A stage-A thread reads bins k_lo + 16 j and k_hi - 16 j of ONE frame (its lane), so a
 // warp's load of one bin is 32 consecutive elements of that row of the [F, T] input.
-struct InvLoadSpec {        // complex input
-  const float2* col;        // spec + b*F*T + t
-  int T;
-  const float2* plo;
-  const float2* phi;
-  int s16;
-  AIP_HM void rows(int k_lo, int k_hi) { plo = col + k_lo * T; phi = col + k_hi * T; s16 = 16 * T; }
-  AIP_HM void lo(int j, float& xr, float& xi) const { const float2 v = plo[j * s16]; xr = v.x; xi = v.y; }
-  AIP_HM void hi(int j, float& xr, float& xi) const { const float2 v = phi[-(j * s16)]; xr = v.x; xi = v.y; }
-};
-
 struct InvLoadFull {        // magnitude (+ phase) input with the dB / 10** / expm1 prologue
   const InvParams& P;
   long long base;           // b*F*T + t
@@ -365,19 +354,78 @@ struct InvLoadFull {        // magnitude (+ phase) input with the dB / 10** / ex
   }
 };
 
-// stage A for one tile: 256 threads, lane = frame, warp = pair-job
-template <bool kSpecOnly>
-AIP_HD void inv_phase0(const InvParams& P, int tid, const TileCursor& c, float2* exch, const PairTw& w) {
+// Staging of the complex input.  Each stage-A thread copies the 32 (33 for pair-job 0) bins IT will consume
+// into its private column of a staging buffer (slot idx*256 + tid) with 8-byte async copies, one tile ahead;
+// nobody else touches those slots, so cp.async.wait_group is the only synchronisation needed.
+constexpr int kStageSlots = 33;
+constexpr int kStage = kStageSlots * kThreads;       // float2 elements per staging buffer
+
+// staging order of pair-job p's bins: visit(idx, k)
+template <class V>
+AIP_HD void inv_visit_bins(int p, V& visit) {
+  if (p != 0) {
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) {
+      visit(2 * k1, p + 16 * k1);
+      visit(2 * k1 + 1, 256 - p - 16 * k1);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 9; ++j) visit(j, 16 * j);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) visit(9 + j, 256 - 16 * j);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) visit(17 + j, 8 + 16 * j);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) visit(25 + j, 248 - 16 * j);
+  }
+}
+
+template <class Copy>
+struct InvStageVisitor {
+  float2* st;               // staging buffer + tid
+  const float2* col;        // spec + b*F*T + t
+  int T;
+  Copy& copy;
+  AIP_HM void operator()(int idx, int k) const { copy(st + idx * kThreads, col + k * T); }
+};
+
+// issue the copies of one tile for this thread (nothing for frames that do not exist)
+template <class Copy>
+AIP_HD void inv_stage_issue(const InvParams& P, int tid, const TileCursor& c, float2* stage, Copy& copy) {
+  const int warp = tid >> 5, lane = tid & 31;
+  const int t = c.tt * P.g.FO - P.g.HL + lane;
+  if (t < 0 || t >= P.n_frames) return;
+  InvStageVisitor<Copy> v{stage + tid, P.spec + ((long long)c.b * kBins * P.T + t), P.T, copy};
+  inv_visit_bins(warp, v);
+}
+
+struct InvLoadStaged {      // reads back what inv_stage_issue staged
+  const float2* st;         // staging buffer + tid
+  int blo, bhi, stride;
+  AIP_HM void rows(int k_lo, int k_hi) {
+    if (k_lo == 0 && k_hi == 256) { blo = 0; bhi = 9; stride = 1; }
+    else if (k_lo == 8 && k_hi == 248) { blo = 17; bhi = 25; stride = 1; }
+    else { blo = 0; bhi = 1; stride = 2; }
+  }
+  AIP_HM void lo(int j, float& xr, float& xi) const { const float2 v = st[(blo + j * stride) * kThreads]; xr = v.x; xi = v.y; }
+  AIP_HM void hi(int j, float& xr, float& xi) const { const float2 v = st[(bhi + j * stride) * kThreads]; xr = v.x; xi = v.y; }
+};
+
+// stage A for one tile: 256 threads, lane = frame, warp = pair-job.  kStaged: complex input read from the
+// staging buffer; otherwise magnitude (+ phase) input read straight from HBM with the prologue applied.
+template <bool kStaged, class BeforeStore>
+AIP_HD void inv_phase0(const InvParams& P, int tid, const TileCursor& c, const float2* stage, float2* exch,
+                       const PairTw& w, BeforeStore& before_store) {
   const int warp = tid >> 5, lane = tid & 31;
   const int t = c.tt * P.g.FO - P.g.HL + lane;
   const bool live = (t >= 0 && t < P.n_frames);
-  const long long col = (long long)c.b * kBins * P.T + t;
-  if (kSpecOnly) {
-    InvLoadSpec load{P.spec + col, P.T, nullptr, nullptr, 0};
-    inv_stageA(exch, w, lane, warp, live, load);
+  if (kStaged) {
+    InvLoadStaged load{stage + tid, 0, 0, 0};
+    inv_stageA(exch, w, lane, warp, live, load, before_store);
   } else {
-    InvLoadFull load{P, col, P.db_flags ? (P.db_flags[c.b] != 0) : false, 0, 0, 0};
-    inv_stageA(exch, w, lane, warp, live, load);
+    InvLoadFull load{P, (long long)c.b * kBins * P.T + t, P.db_flags ? (P.db_flags[c.b] != 0) : false, 0, 0, 0};
+    inv_stageA(exch, w, lane, warp, live, load, before_store);
   }
 }
 
