@@ -98,6 +98,15 @@ int emul_istft512(const float* spec, const float* mag, const float* phase, int m
   P.ola_terms = (kNfft + hop - 1) / hop;
   P.ola_dq = (2 * kThreads) / hop;
   P.ola_dr = (2 * kThreads) % hop;
+  {
+    int f_ref = P.ola_terms - 1;
+    const int need = (P.pad + hop - 1) / hop;
+    if (f_ref < need) f_ref = need;
+    const long long s_ref = (long long)f_ref * hop - P.pad;
+    P.wss_ref = (f_ref <= P.n_frames - 1 && s_ref >= 0 && s_ref + hop <= out_len) ? (int)s_ref : -1;
+  }
+  std::vector<float> wtab;
+  if (P.wss_ref >= 0 && hop <= kMaxWtab) wtab.assign(inv_wss + P.wss_ref, inv_wss + P.wss_ref + hop);
   std::vector<float2> exch(kExch);
   std::vector<LaneConst> lc(kThreads);
   std::vector<PairTw> pw(kThreads);
@@ -119,7 +128,7 @@ int emul_istft512(const float* spec, const float* mag, const float* phase, int m
       }
     }
     for (int tid = 0; tid < kThreads; ++tid) inv_phase1(P, tid, exch.data(), lc[tid]);
-    for (int tid = 0; tid < kThreads; ++tid) inv_phase2(P, tid, c, exch.data());
+    for (int tid = 0; tid < kThreads; ++tid) inv_phase2(P, tid, c, exch.data(), wtab.empty() ? nullptr : wtab.data());
     tile_advance(c, P.tiles_per_clip);
   }
   return 0;

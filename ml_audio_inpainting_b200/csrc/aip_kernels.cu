@@ -201,6 +201,10 @@ template <bool kStaged>
 __global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParams P) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bars[2];
+  __shared__ __align__(8) float wtab_s[kMaxWtab];
+  const float* wtab = (P.wss_ref >= 0 && P.hop <= kMaxWtab) ? wtab_s : nullptr;
+  if (wtab)
+    for (int r = threadIdx.x; r < P.hop; r += blockDim.x) wtab_s[r] = P.inv_wss[P.wss_ref + r];
   uint64_t* exch_full = bars;        // count 8 (stage-A warps)
   uint64_t* exch_empty = bars + 1;   // count 8 (stage-B warps)
   float2* exch = reinterpret_cast<float2*>(smem);
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParam
       mbar_wait(exch_full, (uint32_t)(i & 1));
       inv_phase1(P, btid, exch, lc);
       named_bar_sync(1, kThreads);
-      inv_phase2(P, btid, c, exch);
+      inv_phase2(P, btid, c, exch, wtab);
       mbar_arrive_warp(exch_empty);
       tile_advance(c, P.tiles_per_clip);
     }
@@ -552,6 +556,12 @@ static void inv_fill_ola(InvParams& P) {
   P.ola_terms = (kNfft + P.hop - 1) / P.hop;
   P.ola_dq = (2 * kThreads) / P.hop;
   P.ola_dr = (2 * kThreads) % P.hop;
+  // reference frame whose K-1 predecessors exist and whose whole hop lies inside the output
+  int f_ref = P.ola_terms - 1;
+  const int need = (P.pad + P.hop - 1) / P.hop;
+  if (f_ref < need) f_ref = need;
+  const long long s_ref = (long long)f_ref * P.hop - P.pad;
+  P.wss_ref = (f_ref <= P.n_frames - 1 && s_ref >= 0 && s_ref + P.hop <= P.out_len) ? (int)s_ref : -1;
 }
 
 static bool inv_fast_ok(const aip_stft_desc* d) {

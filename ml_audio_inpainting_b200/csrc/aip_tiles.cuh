@@ -317,6 +317,7 @@ struct InvParams {
   unsigned hop_magic;       // ceil(2^32 / hop)
   int ola_terms;            // ceil(512 / hop): frames overlapping one sample
   int ola_dq, ola_dr;       // (2 * 256) / hop and (2 * 256) % hop: per-iteration advance of a thread's pair
+  int wss_ref;              // inv_wss[wss_ref + r] = periodic value for frame offset r; < 0: no interior
 
 };
 
@@ -359,6 +360,7 @@ struct InvLoadFull {        // magnitude (+ phase) input with the dB / 10** / ex
 // nobody else touches those slots, so cp.async.wait_group is the only synchronisation needed.
 constexpr int kStageSlots = 33;
 constexpr int kStage = kStageSlots * kThreads;       // float2 elements per staging buffer
+constexpr int kMaxWtab = 1024;                       // largest hop with a shared-memory 1/wss period table
 
 // staging order of pair-job p's bins: visit(idx, k)
 template <class V>
@@ -441,7 +443,10 @@ AIP_HD void inv_phase1(const InvParams& P, int tid, float2* exch, const LaneCons
 
 // overlap-add + window-sum-square normalisation + store for one tile (256 threads): thread q, q + 256, ...
 // owns output pairs (s0 + 2q, s0 + 2q + 1); its (frame, offset) coordinates advance incrementally.
-AIP_HD void inv_phase2(const InvParams& P, int tid, const TileCursor& c, const float2* fbuf) {
+// wtab: one period of 1/window-sum-square indexed by the offset r inside a frame -- valid for every sample of
+// a tile whose 32 local frames all exist (window_sumsquare is exactly hop-periodic there, same float32
+// accumulation order); tiles at the clip edges (or wtab == null) read the global table instead.
+AIP_HD void inv_phase2(const InvParams& P, int tid, const TileCursor& c, const float2* fbuf, const float* wtab) {
   const int hop = P.hop;
   const int f_first = c.tt * P.g.FO - P.g.HL;
   const int s0 = c.tt * P.g.FO * hop;
@@ -460,7 +465,11 @@ AIP_HD void inv_phase2(const InvParams& P, int tid, const TileCursor& c, const f
     const int s = s0 + 2 * q;
     if (s >= P.out_len) break;
     float2 v = ola_pair(fbuf, h, r, hop, P.ola_terms, edge, fl_min, fl_max);
-    if (s + 1 < P.out_len) {
+    if (!edge && wtab && P.vec_ok && s + 1 < P.out_len) {
+      const float2 nw = *reinterpret_cast<const float2*>(wtab + r);
+      v.x *= nw.x; v.y *= nw.y;
+      *reinterpret_cast<float2*>(dst + s) = v;
+    } else if (s + 1 < P.out_len) {
       if (P.vec_ok) {
         const float2 nw = *reinterpret_cast<const float2*>(P.inv_wss + s);
         v.x *= nw.x; v.y *= nw.y;
