@@ -443,6 +443,47 @@ AIP_HD void inv_phase1(const InvParams& P, int tid, float2* exch, const LaneCons
 
 // overlap-add + window-sum-square normalisation + store for one tile (256 threads): thread q, q + 256, ...
 // owns output pairs (s0 + 2q, s0 + 2q + 1); its (frame, offset) coordinates advance incrementally.
+// interior tile, K terms per sample, vector stores, periodic 1/wss table: kU pairs in flight per thread
+template <int K>
+AIP_HD void inv_ola_interior(const InvParams& P, int tid, int s0, const float2* fbuf, const float* wtab, float* dst) {
+  constexpr int kU = 4;
+  const int hop = P.hop;
+  const int n_pairs = (P.g.FO * hop) >> 1;
+  const int u0 = 2 * tid + P.pad + P.g.HL * hop;
+  int h = magic_div(u0, P.hop_magic);
+  int r = u0 - h * hop;
+  for (int q = tid; q < n_pairs; q += kU * kThreads) {
+    int hh[kU], rr[kU];
+    float2 v[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      hh[u] = h; rr[u] = r;
+      h += P.ola_dq; r += P.ola_dr;
+      if (r >= hop) { r -= hop; ++h; }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int qq = q + u * kThreads;
+      // rows past the tile / output end read a valid (clamped) slot and are not stored
+      const bool ok = qq < n_pairs && s0 + 2 * qq + 1 < P.out_len;
+      v[u] = ola_pair_fixed<K>(fbuf, ok ? hh[u] : P.g.HL + K, ok ? rr[u] : 0, hop);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int qq = q + u * kThreads;
+      const int s = s0 + 2 * qq;
+      if (qq < n_pairs && s + 1 < P.out_len) {
+        const float2 nw = *reinterpret_cast<const float2*>(wtab + rr[u]);
+        *reinterpret_cast<float2*>(dst + s) = make_float2(v[u].x * nw.x, v[u].y * nw.y);
+      } else if (qq < n_pairs && s < P.out_len) {
+        dst[s] = ola_pair_fixed<K>(fbuf, hh[u], rr[u], hop).x * wtab[rr[u]];
+      }
+    }
+  }
+}
+
+// overlap-add + window-sum-square normalisation + store for one tile (256 threads): thread q, q + 256, ...
+// owns output pairs (s0 + 2q, s0 + 2q + 1); its (frame, offset) coordinates advance incrementally.
 // wtab: one period of 1/window-sum-square indexed by the offset r inside a frame -- valid for every sample of
 // a tile whose 32 local frames all exist (window_sumsquare is exactly hop-periodic there, same float32
 // accumulation order); tiles at the clip edges (or wtab == null) read the global table instead.
@@ -455,8 +496,14 @@ AIP_HD void inv_phase2(const InvParams& P, int tid, const TileCursor& c, const f
   int fl_max = P.n_frames - 1 - f_first;
   if (fl_max > kFR - 1) fl_max = kFR - 1;
   const bool edge = fl_min > 0 || fl_max < kFR - 1;
-  const int n_pairs = (P.g.FO * hop) >> 1;
   float* dst = P.out + (long long)c.b * P.out_pitch;
+  if (!edge && wtab && P.vec_ok) {
+    if (P.ola_terms == 3) return inv_ola_interior<3>(P, tid, s0, fbuf, wtab, dst);
+    if (P.ola_terms == 4) return inv_ola_interior<4>(P, tid, s0, fbuf, wtab, dst);
+    if (P.ola_terms == 2) return inv_ola_interior<2>(P, tid, s0, fbuf, wtab, dst);
+    if (P.ola_terms == 1) return inv_ola_interior<1>(P, tid, s0, fbuf, wtab, dst);
+  }
+  const int n_pairs = (P.g.FO * hop) >> 1;
   // position of pair q relative to local frame 0: u = 2q + pad + HL*hop = h*hop + r
   const int u0 = 2 * tid + P.pad + P.g.HL * hop;
   int h = magic_div(u0, P.hop_magic);
@@ -464,23 +511,9 @@ AIP_HD void inv_phase2(const InvParams& P, int tid, const TileCursor& c, const f
   for (int q = tid; q < n_pairs; q += kThreads) {
     const int s = s0 + 2 * q;
     if (s >= P.out_len) break;
-    float2 v = ola_pair(fbuf, h, r, hop, P.ola_terms, edge, fl_min, fl_max);
-    if (!edge && wtab && P.vec_ok && s + 1 < P.out_len) {
-      const float2 nw = *reinterpret_cast<const float2*>(wtab + r);
-      v.x *= nw.x; v.y *= nw.y;
-      *reinterpret_cast<float2*>(dst + s) = v;
-    } else if (s + 1 < P.out_len) {
-      if (P.vec_ok) {
-        const float2 nw = *reinterpret_cast<const float2*>(P.inv_wss + s);
-        v.x *= nw.x; v.y *= nw.y;
-        *reinterpret_cast<float2*>(dst + s) = v;
-      } else {
-        dst[s] = v.x * P.inv_wss[s];
-        dst[s + 1] = v.y * P.inv_wss[s + 1];
-      }
-    } else {
-      dst[s] = v.x * P.inv_wss[s];
-    }
+    const float2 v = ola_pair(fbuf, h, r, hop, P.ola_terms, fl_min, fl_max);
+    dst[s] = v.x * P.inv_wss[s];
+    if (s + 1 < P.out_len) dst[s + 1] = v.y * P.inv_wss[s + 1];
     h += P.ola_dq;
     r += P.ola_dr;
     if (r >= hop) { r -= hop; ++h; }
