@@ -23,8 +23,8 @@
 //
 // Shared memory per tile of 32 frames: the staged waveform (31*hop + 512 floats, every sample
 // fetched from HBM once although frames overlap 2.67x / 4x) and one exchange buffer of
-// 16*16*33 float2 (index (k2*16 + n1)*33 + frame: conflict-free for both the lane = n1 writers and
-// the lane = frame readers).
+// 16*16*33 float2 (pitch 33 per (job-pair, re/im, n1) row: conflict-free for both the lane = n1 writers
+// and the lane = frame readers; see exch_slot()).
 #pragma once
 #include <stdint.h>
 #include <math.h>
@@ -116,6 +116,64 @@ AIP_HD void fft16(float (&r)[16], float (&i)[16]) {
     radix4(r[4 * q], i[4 * q], r[4 * q + 1], i[4 * q + 1], r[4 * q + 2], i[4 * q + 2], r[4 * q + 3], i[4 * q + 3]);
 }
 
+// ---- packed FP32x2 (Blackwell FADD2 / FMUL2 / FFMA2: two fp32 lanes per issue slot) --------------------
+// The FP32 pipe does not get wider, but these kernels are issue-slot bound, and every 16-point DFT here has
+// an identical twin (the two pair-jobs of a stage-2 thread, the two frames of a stage-1 thread): .x carries
+// one, .y the other.
+#if defined(__CUDACC__)
+AIP_HD float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+AIP_HD float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }   // exact a - b
+AIP_HD float2 mul2s(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+AIP_HD float2 fma2s(float2 a, float s, float2 c) { return __ffma2_rn(a, make_float2(s, s), c); }
+#else
+AIP_HD float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+AIP_HD float2 sub2(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+AIP_HD float2 mul2s(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+AIP_HD float2 fma2s(float2 a, float s, float2 c) { return make_float2(a.x * s + c.x, a.y * s + c.y); }
+#endif
+
+AIP_HD void radix4x2(float2& ar, float2& ai, float2& br, float2& bi, float2& cr, float2& ci, float2& dr, float2& di) {
+  const float2 s0r = add2(ar, cr), s0i = add2(ai, ci), s1r = sub2(ar, cr), s1i = sub2(ai, ci);
+  const float2 s2r = add2(br, dr), s2i = add2(bi, di), s3r = sub2(br, dr), s3i = sub2(bi, di);
+  ar = add2(s0r, s2r); ai = add2(s0i, s2i);
+  cr = sub2(s0r, s2r); ci = sub2(s0i, s2i);
+  br = add2(s1r, s3i); bi = sub2(s1i, s3r);
+  dr = sub2(s1r, s3i); di = add2(s1i, s3r);
+}
+
+// x *= (wr + j wi), both lanes
+AIP_HD void cmulx2(float2& xr, float2& xi, float wr, float wi) {
+  const float2 tr = fma2s(xi, -wi, mul2s(xr, wr));
+  xi = fma2s(xi, wr, mul2s(xr, wi));
+  xr = tr;
+}
+
+// two forward 16-point complex DFTs at once (lane .x and lane .y), same slot convention as fft16()
+AIP_HD void fft16x2(float2 (&r)[16], float2 (&i)[16]) {
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+    radix4x2(r[a], i[a], r[a + 4], i[a + 4], r[a + 8], i[a + 8], r[a + 12], i[a + 12]);
+  cmulx2(r[5], i[5], kC1, -kS1);
+  cmulx2(r[9], i[9], kR2, -kR2);
+  cmulx2(r[13], i[13], kS1, -kC1);
+  cmulx2(r[6], i[6], kR2, -kR2);
+  { const float2 t = r[10]; r[10] = i[10]; i[10] = mul2s(t, -1.0f); }
+  cmulx2(r[14], i[14], -kR2, -kR2);
+  cmulx2(r[7], i[7], kS1, -kC1);
+  cmulx2(r[11], i[11], -kR2, -kR2);
+  cmulx2(r[15], i[15], -kC1, kS1);
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    radix4x2(r[4 * q], i[4 * q], r[4 * q + 1], i[4 * q + 1], r[4 * q + 2], i[4 * q + 2], r[4 * q + 3], i[4 * q + 3]);
+}
+
+// Exchange buffer (both directions): float2 slot ((p*2 + c)*16 + n1)*33 + frame holds component c (0 = re,
+// 1 = im) of the stage-1 outputs (n1, k2 = ja) in .x and (n1, k2 = jb) in .y, where (ja, jb) = (p, 16 - p) for
+// pair-job p > 0 and (0, 8) for p = 0 -- i.e. exactly the packed operand a stage-2 thread feeds to fft16x2.
+AIP_HD constexpr int exch_slot(int p, int c, int n1) { return ((p * 2 + c) * 16 + n1) * kXP; }
+AIP_HD constexpr int job_a(int p) { return p; }
+AIP_HD constexpr int job_b(int p) { return p == 0 ? 8 : 16 - p; }
+
 // Per-lane constants of the stage that runs with lane = n1 (forward stage 1, inverse stage B):
 // the 32 window taps this lane touches and the 16 inter-stage twiddles W256^(n1 k2).
 struct LaneConst {
@@ -136,25 +194,37 @@ AIP_HD void lane_const_init(LaneConst& c, const float* window, int n1, float sca
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Forward, stage 1.  One call = one (frame, n1) job: 16 strided float2 loads of the staged waveform,
-// window, 16-point DFT over n2, inter-stage twiddle, 16 float2 stores into the exchange buffer.
+// Forward, stage 1.  One call = the (n1) column of TWO frames (fa in .x, fb in .y): 2 x 16 strided float2
+// loads of the staged waveform, window, packed 16-point DFT over n2, inter-stage twiddle, 2 x 16 float2
+// stores into the exchange buffer.
 // ---------------------------------------------------------------------------------------------------
-AIP_HD void fwd_stage1(const float* tile, float2* exch, int hop, int f, int n1, const LaneConst& c) {
-  float r[16], i[16];
-  const float* src = tile + f * hop + 2 * n1;
+AIP_HD void fwd_stage1(const float* tile, float2* exch, int hop, int fa, int fb, int n1, const LaneConst& c) {
+  float2 r[16], i[16];
+  const float* sa = tile + fa * hop + 2 * n1;
+  const float* sb = tile + fb * hop + 2 * n1;
 #pragma unroll
   for (int n2 = 0; n2 < 16; ++n2) {
-    const float2 z = *reinterpret_cast<const float2*>(src + 32 * n2);
-    r[n2] = z.x * c.we[n2];
-    i[n2] = z.y * c.wo[n2];
+    const float2 za = *reinterpret_cast<const float2*>(sa + 32 * n2);
+    const float2 zb = *reinterpret_cast<const float2*>(sb + 32 * n2);
+    r[n2] = make_float2(za.x * c.we[n2], zb.x * c.we[n2]);
+    i[n2] = make_float2(za.y * c.wo[n2], zb.y * c.wo[n2]);
   }
-  fft16(r, i);
-  float2* dst = exch + n1 * kXP + f;
+  fft16x2(r, i);
+  float2* da = exch + n1 * kXP + fa;
+  float2* db = exch + n1 * kXP + fb;
 #pragma unroll
-  for (int k2 = 0; k2 < 16; ++k2) {
-    float xr = r[perm16(k2)], xi = i[perm16(k2)];
-    if (k2 > 0) cmul(xr, xi, c.twr[k2], c.twi[k2]);
-    dst[k2 * 16 * kXP] = make_float2(xr, xi);
+  for (int p = 0; p < 8; ++p) {
+    const int ka = job_a(p), kb = job_b(p);
+    // frame fa (.x lanes) and frame fb (.y lanes); the twiddled results are written as (job a, job b) pairs
+    float ar_a = r[perm16(ka)].x, ai_a = i[perm16(ka)].x, br_a = r[perm16(kb)].x, bi_a = i[perm16(kb)].x;
+    float ar_b = r[perm16(ka)].y, ai_b = i[perm16(ka)].y, br_b = r[perm16(kb)].y, bi_b = i[perm16(kb)].y;
+    if (ka > 0) { cmul(ar_a, ai_a, c.twr[ka], c.twi[ka]); cmul(ar_b, ai_b, c.twr[ka], c.twi[ka]); }
+    cmul(br_a, bi_a, c.twr[kb], c.twi[kb]);
+    cmul(br_b, bi_b, c.twr[kb], c.twi[kb]);
+    da[exch_slot(p, 0, 0)] = make_float2(ar_a, br_a);
+    da[exch_slot(p, 1, 0)] = make_float2(ai_a, bi_a);
+    db[exch_slot(p, 0, 0)] = make_float2(ar_b, br_b);
+    db[exch_slot(p, 1, 0)] = make_float2(ai_b, bi_b);
   }
 }
 
@@ -193,42 +263,37 @@ AIP_HD void fwd_pair(float zkr, float zki, float znr, float zni, float wr, float
 //   fwd_stage2_load     32 float2 of jobs (p, 16-p) or (0, 8) -> registers
 //   fwd_stage2_compute  two 16-point DFTs over n1, the split pass, 32 (p>0) / 33 (p=0) bins to the emitter
 // ---------------------------------------------------------------------------------------------------
-AIP_HD void fwd_stage2_load(const float2* exch, int f, int p, float (&ar)[16], float (&ai)[16],
-                            float (&br)[16], float (&bi)[16]) {
-  const int ja = p, jb = (p == 0) ? 8 : 16 - p;
-  const float2* sa = exch + ja * 16 * kXP + f;
-  const float2* sb = exch + jb * 16 * kXP + f;
+AIP_HD void fwd_stage2_load(const float2* exch, int f, int p, float2 (&r)[16], float2 (&i)[16]) {
+  const float2* sr = exch + exch_slot(p, 0, 0) + f;
+  const float2* si = exch + exch_slot(p, 1, 0) + f;
 #pragma unroll
   for (int n1 = 0; n1 < 16; ++n1) {
-    const float2 a = sa[n1 * kXP];
-    const float2 b = sb[n1 * kXP];
-    ar[n1] = a.x; ai[n1] = a.y; br[n1] = b.x; bi[n1] = b.y;
+    r[n1] = sr[n1 * kXP];
+    i[n1] = si[n1 * kXP];
   }
 }
 
 template <class Emit>
-AIP_HD void fwd_stage2_compute(float (&ar)[16], float (&ai)[16], float (&br)[16], float (&bi)[16],
-                               const PairTw& w, int p, Emit& emit) {
-  fft16(ar, ai);
-  fft16(br, bi);
+AIP_HD void fwd_stage2_compute(float2 (&r)[16], float2 (&i)[16], const PairTw& w, int p, Emit& emit) {
+  fft16x2(r, i);     // .x = job a, .y = job b
   if (p != 0) {
     emit.rows(p, 256 - p);
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1)
-      fwd_pair(ar[perm16(k1)], ai[perm16(k1)], br[perm16(15 - k1)], bi[perm16(15 - k1)], w.wr[k1], w.wi[k1], k1, emit);
+      fwd_pair(r[perm16(k1)].x, i[perm16(k1)].x, r[perm16(15 - k1)].y, i[perm16(15 - k1)].y, w.wr[k1], w.wi[k1], k1, emit);
   } else {
     emit.rows(0, 256);
-    const float z0r = ar[perm16(0)], z0i = ai[perm16(0)];
+    const float z0r = r[perm16(0)].x, z0i = i[perm16(0)].x;
     emit.lo(0, 2.0f * (z0r + z0i), 0.0f);
     emit.hi(0, 2.0f * (z0r - z0i), 0.0f);
 #pragma unroll
     for (int k1 = 1; k1 < 8; ++k1)
-      fwd_pair(ar[perm16(k1)], ai[perm16(k1)], ar[perm16(16 - k1)], ai[perm16(16 - k1)], w.wr[8 + k1], w.wi[8 + k1], k1, emit);
-    emit.lo(8, 2.0f * ar[perm16(8)], -2.0f * ai[perm16(8)]);
+      fwd_pair(r[perm16(k1)].x, i[perm16(k1)].x, r[perm16(16 - k1)].x, i[perm16(16 - k1)].x, w.wr[8 + k1], w.wi[8 + k1], k1, emit);
+    emit.lo(8, 2.0f * r[perm16(8)].x, -2.0f * i[perm16(8)].x);
     emit.rows(8, 248);
 #pragma unroll
     for (int k1 = 0; k1 < 8; ++k1)
-      fwd_pair(br[perm16(k1)], bi[perm16(k1)], br[perm16(15 - k1)], bi[perm16(15 - k1)], w.wr[k1], w.wi[k1], k1, emit);
+      fwd_pair(r[perm16(k1)].y, i[perm16(k1)].y, r[perm16(15 - k1)].y, i[perm16(15 - k1)].y, w.wr[k1], w.wi[k1], k1, emit);
   }
 }
 
@@ -251,8 +316,7 @@ AIP_HD void inv_pair(float akr, float aki, float bkr, float bki, float wr, float
 
 template <class Load, class BeforeStore>
 AIP_HD void inv_stageA(float2* exch, const PairTw& w, int f, int p, bool live, Load& load, BeforeStore& before_store) {
-  float ar[16], ai[16], br[16], bi[16];
-  const int ja = p, jb = (p == 0) ? 8 : 16 - p;
+  float2 r[16], i[16];          // .x = job a, .y = job b
   if (live) {
     if (p != 0) {
       load.rows(p, 256 - p);
@@ -261,66 +325,75 @@ AIP_HD void inv_stageA(float2* exch, const PairTw& w, int f, int p, bool live, L
         float xr, xi, yr, yi;
         load.lo(k1, xr, xi);
         load.hi(k1, yr, yi);
-        inv_pair(xr, xi, yr, yi, w.wr[k1], w.wi[k1], ar[k1], ai[k1], br[15 - k1], bi[15 - k1]);
+        inv_pair(xr, xi, yr, yi, w.wr[k1], w.wi[k1], r[k1].x, i[k1].x, r[15 - k1].y, i[15 - k1].y);
       }
     } else {
       float xr, xi, yr, yi;
       load.rows(0, 256);
       load.lo(0, xr, xi);
       load.hi(0, yr, yi);
-      ar[0] = xr + yr; ai[0] = xr - yr;
+      r[0].x = xr + yr; i[0].x = xr - yr;
 #pragma unroll
       for (int k1 = 1; k1 < 8; ++k1) {
         load.lo(k1, xr, xi);
         load.hi(k1, yr, yi);
-        inv_pair(xr, xi, yr, yi, w.wr[8 + k1], w.wi[8 + k1], ar[k1], ai[k1], ar[16 - k1], ai[16 - k1]);
+        inv_pair(xr, xi, yr, yi, w.wr[8 + k1], w.wi[8 + k1], r[k1].x, i[k1].x, r[16 - k1].x, i[16 - k1].x);
       }
       load.lo(8, xr, xi);
-      ar[8] = 2.0f * xr; ai[8] = -2.0f * xi;
+      r[8].x = 2.0f * xr; i[8].x = -2.0f * xi;
       load.rows(8, 248);
 #pragma unroll
       for (int k1 = 0; k1 < 8; ++k1) {
         load.lo(k1, xr, xi);
         load.hi(k1, yr, yi);
-        inv_pair(xr, xi, yr, yi, w.wr[k1], w.wi[k1], br[k1], bi[k1], br[15 - k1], bi[15 - k1]);
+        inv_pair(xr, xi, yr, yi, w.wr[k1], w.wi[k1], r[k1].y, i[k1].y, r[15 - k1].y, i[15 - k1].y);
       }
     }
-    fft16(ai, ar);      // inverse transform: swapped roles
-    fft16(bi, br);
+    fft16x2(i, r);      // inverse transform: swapped roles
   } else {
 #pragma unroll
-    for (int q = 0; q < 16; ++q) { ar[q] = ai[q] = br[q] = bi[q] = 0.0f; }
+    for (int q = 0; q < 16; ++q) { r[q] = make_float2(0.0f, 0.0f); i[q] = make_float2(0.0f, 0.0f); }
   }
   before_store();      // the exchange buffer must have been released by the previous tile's readers
-  float2* da = exch + ja * 16 * kXP + f;
-  float2* db = exch + jb * 16 * kXP + f;
+  float2* dr = exch + exch_slot(p, 0, 0) + f;
+  float2* di = exch + exch_slot(p, 1, 0) + f;
 #pragma unroll
   for (int n1 = 0; n1 < 16; ++n1) {
-    da[n1 * kXP] = make_float2(ar[perm16(n1)], ai[perm16(n1)]);
-    db[n1 * kXP] = make_float2(br[perm16(n1)], bi[perm16(n1)]);
+    dr[n1 * kXP] = r[perm16(n1)];
+    di[n1 * kXP] = i[perm16(n1)];
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Inverse, stage B.  One call = one (frame f, n1) job: conj inter-stage twiddle, inverse 16-point DFT
-// over k2, synthesis window (carrying the 1/512 of irfft), windowed samples written IN PLACE into the
-// exchange buffer, which thereby becomes the frame buffer: float2 slot (m*33 + f) = samples (2m, 2m+1)
-// of frame f, m = n1 + 16 n2.
+// Inverse, stage B.  One call = the (n1) column of TWO frames (fa in .x, fb in .y): conj inter-stage twiddle,
+// packed inverse 16-point DFT over k2, synthesis window (carrying the 1/512 of irfft), windowed samples
+// written IN PLACE into the exchange buffer, which thereby becomes the frame buffer: float2 slot
+// (m*33 + f) = samples (2m, 2m+1) of frame f, m = n1 + 16 n2 (a thread reads and writes the same 2 x 16 slots).
 // ---------------------------------------------------------------------------------------------------
-AIP_HD void inv_stageB(float2* exch, int f, int n1, const LaneConst& c) {
-  float r[16], i[16];
-  float2* p = exch + n1 * kXP + f;
+AIP_HD void inv_stageB(float2* exch, int fa, int fb, int n1, const LaneConst& c) {
+  float2 r[16], i[16];
+  float2* pa = exch + n1 * kXP + fa;
+  float2* pb = exch + n1 * kXP + fb;
 #pragma unroll
-  for (int k2 = 0; k2 < 16; ++k2) {
-    const float2 u = p[k2 * 16 * kXP];
-    float xr = u.x, xi = u.y;
-    if (k2 > 0) cmul(xr, xi, c.twr[k2], -c.twi[k2]);
-    r[k2] = xr; i[k2] = xi;
+  for (int p = 0; p < 8; ++p) {
+    const int ka = job_a(p), kb = job_b(p);
+    const float2 ra = pa[exch_slot(p, 0, 0)], ia = pa[exch_slot(p, 1, 0)];   // frame fa: (job a, job b)
+    const float2 rb = pb[exch_slot(p, 0, 0)], ib = pb[exch_slot(p, 1, 0)];   // frame fb
+    float ar_a = ra.x, ai_a = ia.x, br_a = ra.y, bi_a = ia.y;
+    float ar_b = rb.x, ai_b = ib.x, br_b = rb.y, bi_b = ib.y;
+    if (ka > 0) { cmul(ar_a, ai_a, c.twr[ka], -c.twi[ka]); cmul(ar_b, ai_b, c.twr[ka], -c.twi[ka]); }
+    cmul(br_a, bi_a, c.twr[kb], -c.twi[kb]);
+    cmul(br_b, bi_b, c.twr[kb], -c.twi[kb]);
+    r[ka] = make_float2(ar_a, ar_b); i[ka] = make_float2(ai_a, ai_b);
+    r[kb] = make_float2(br_a, br_b); i[kb] = make_float2(bi_a, bi_b);
   }
-  fft16(i, r);
+  fft16x2(i, r);
 #pragma unroll
-  for (int n2 = 0; n2 < 16; ++n2)
-    p[n2 * 16 * kXP] = make_float2(r[perm16(n2)] * c.we[n2], i[perm16(n2)] * c.wo[n2]);
+  for (int n2 = 0; n2 < 16; ++n2) {
+    const float2 zr = r[perm16(n2)], zi = i[perm16(n2)];
+    pa[n2 * 16 * kXP] = make_float2(zr.x * c.we[n2], zi.x * c.wo[n2]);
+    pb[n2 * 16 * kXP] = make_float2(zr.y * c.we[n2], zi.y * c.wo[n2]);
+  }
 }
 
 // Geometry of an inverse tile: 32 frames are computed, FO of them worth of output hops are produced;

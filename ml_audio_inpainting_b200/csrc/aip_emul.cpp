@@ -13,10 +13,6 @@
 
 using namespace aip;
 
-struct HostCopy8 {
-  void operator()(float2* dst, const float2* src) const { *dst = *src; }
-};
-
 extern "C" {
 
 int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, int center,
@@ -114,18 +110,12 @@ int emul_istft512(const float* spec, const float* mag, const float* phase, int m
     lane_const_init(lc[tid], window, tid & 15, 1.0f / 512.0f);
     pair_tw_init(pw[tid], tid >> 5);
   }
-  std::vector<float2> stage(kStage);
-  HostCopy8 copy;
   NoRelease rel;
   TileCursor c = tile_cursor(0, P.tiles_per_clip);
   for (int tix = 0; tix < P.n_tiles; ++tix) {
     for (int tid = 0; tid < kThreads; ++tid) {
-      if (spec) {
-        inv_stage_issue(P, tid, c, stage.data(), copy);          // the cp.async staging of this tile
-        inv_phase0<true>(P, tid, c, stage.data(), exch.data(), pw[tid], rel);
-      } else {
-        inv_phase0<false>(P, tid, c, stage.data(), exch.data(), pw[tid], rel);
-      }
+      if (spec) inv_phase0<INV_SPEC>(P, tid, c, exch.data(), pw[tid], rel);
+      else inv_phase0<INV_FULL>(P, tid, c, exch.data(), pw[tid], rel);
     }
     for (int tid = 0; tid < kThreads; ++tid) inv_phase1(P, tid, exch.data(), lc[tid]);
     for (int tid = 0; tid < kThreads; ++tid) inv_phase2(P, tid, c, exch.data(), wtab.empty() ? nullptr : wtab.data());

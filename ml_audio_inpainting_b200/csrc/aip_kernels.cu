@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/aip_b200.h"
 #include "aip_tiles.cuh"
@@ -173,17 +174,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
   }
 }
 
-__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-struct AsyncCopy8 {
-  __device__ __forceinline__ void operator()(float2* dst, const float2* src) const { cp_async8(dst, src); }
-};
-
 struct WaitBefore {
   uint64_t* bar;
   uint32_t parity;
@@ -192,27 +182,28 @@ struct WaitBefore {
 };
 
 // Warp-specialised, persistent, one CTA per SM (same plumbing as the forward kernel):
-//   stage-A warps (lane = frame): their bins of tile i+1 stream HBM -> private staging slots (cp.async) while
-//   they run tile i: staging -> registers, split-pass prologue, 2 x inverse 16-pt DFT -> exchange buffer
+//   stage-A warps (lane = frame): HBM -> registers, split-pass prologue, 2 x inverse 16-pt DFT -> exch[i % 3]
 //   stage-B warps (lane = n1): twiddle, inverse 16-pt DFT, synthesis window (in place: the exchange buffer
 //   becomes the frame buffer) -> named barrier -> overlap-add + 1/window-sum-square -> HBM -> release
-// Shared memory: 2 staging buffers (2 x 66 KB) + 1 exchange buffer (66 KB).
-template <bool kStaged>
+// The ring of three exchange buffers lets the stage-A warps run two tiles ahead, so their global-load
+// latency hides behind stage B and the overlap-add.
+template <int kMode>
 __global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParams P) {
   extern __shared__ __align__(128) float smem[];
-  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ __align__(8) uint64_t bars[2 * kInvBufs];
   __shared__ __align__(8) float wtab_s[kMaxWtab];
   const float* wtab = (P.wss_ref >= 0 && P.hop <= kMaxWtab) ? wtab_s : nullptr;
   if (wtab)
     for (int r = threadIdx.x; r < P.hop; r += blockDim.x) wtab_s[r] = P.inv_wss[P.wss_ref + r];
-  uint64_t* exch_full = bars;        // count 8 (stage-A warps)
-  uint64_t* exch_empty = bars + 1;   // count 8 (stage-B warps)
-  float2* exch = reinterpret_cast<float2*>(smem);
-  float2* stage0 = exch + kExch;
+  uint64_t* exch_full = bars;                // [3] count 8 (stage-A warps)
+  uint64_t* exch_empty = bars + kInvBufs;    // [3] count 8 (stage-B warps)
+  float2* exch0 = reinterpret_cast<float2*>(smem);
   const int tid = threadIdx.x;
   if (tid == 0) {
-    mbar_init(exch_full, kThreads / 32);
-    mbar_init(exch_empty, kThreads / 32);
+    for (int i = 0; i < kInvBufs; ++i) {
+      mbar_init(exch_full + i, kThreads / 32);
+      mbar_init(exch_empty + i, kThreads / 32);
+    }
   }
   __syncthreads();
   const int first = blockIdx.x * P.tiles_per_cta;
@@ -223,37 +214,30 @@ __global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParam
   if (tid < kThreads) {
     PairTw w;
     pair_tw_init(w, tid >> 5);
-    AsyncCopy8 copy;
-    TileCursor cn = c;
-    if (kStaged) {
-      inv_stage_issue(P, tid, cn, stage0, copy);
-      cp_async_commit();
-    }
+    int es = 0, use = 0;                      // ring slot and how often it has been used before
 #pragma unroll 1
     for (int i = 0; i < n; ++i) {
-      if (kStaged) {
-        tile_advance(cn, P.tiles_per_clip);
-        if (i + 1 < n) inv_stage_issue(P, tid, cn, stage0 + ((i + 1) & 1) * kStage, copy);
-        cp_async_commit();
-        cp_async_wait<1>();          // this thread's copies of tile i have landed
-      }
-      WaitBefore wb{exch_empty, (uint32_t)((i - 1) & 1), i >= 1};
-      inv_phase0<kStaged>(P, tid, c, stage0 + (i & 1) * kStage, exch, w, wb);
-      mbar_arrive_warp(exch_full);
+      WaitBefore wb{exch_empty + es, (uint32_t)((use - 1) & 1), use >= 1};
+      inv_phase0<kMode>(P, tid, c, exch0 + es * kExch, w, wb);
+      mbar_arrive_warp(exch_full + es);
       tile_advance(c, P.tiles_per_clip);
+      if (++es == kInvBufs) { es = 0; ++use; }
     }
   } else {
     const int btid = tid - kThreads;
     LaneConst lc;
     lane_const_init(lc, P.window, btid & 15, 1.0f / 512.0f);
+    int es = 0, use = 0;
 #pragma unroll 1
     for (int i = 0; i < n; ++i) {
-      mbar_wait(exch_full, (uint32_t)(i & 1));
+      float2* exch = exch0 + es * kExch;
+      mbar_wait(exch_full + es, (uint32_t)(use & 1));
       inv_phase1(P, btid, exch, lc);
       named_bar_sync(1, kThreads);
       inv_phase2(P, btid, c, exch, wtab);
-      mbar_arrive_warp(exch_empty);
+      mbar_arrive_warp(exch_empty + es);
       tile_advance(c, P.tiles_per_clip);
+      if (++es == kInvBufs) { es = 0; ++use; }
     }
   }
 }
@@ -667,13 +651,12 @@ static int run_inv(const aip_stft_desc* desc, InvParams P, long long length, voi
     P.vec_ok = ((P.out_pitch & 1) == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 7) == 0) &&
                ((reinterpret_cast<uintptr_t>(P.inv_wss) & 7) == 0);
     inv_fill_ola(P);
-    const bool staged = P.spec != nullptr;
-    const size_t smem = ((size_t)kExch + (staged ? 2 * (size_t)kStage : 0)) * sizeof(float2);
+    const size_t smem = (size_t)kInvBufs * kExch * sizeof(float2);
     int grid = di.sms;
     if (grid > P.n_tiles) grid = P.n_tiles;
     P.tiles_per_cta = (P.n_tiles + grid - 1) / grid;
     grid = (P.n_tiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
-    auto kern = staged ? istft512_kernel<true> : istft512_kernel<false>;
+    auto kern = P.spec ? istft512_kernel<INV_SPEC> : istft512_kernel<INV_FULL>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<(unsigned)grid, kFwdThreads, smem, st>>>(P);

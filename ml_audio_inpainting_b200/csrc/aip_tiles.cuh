@@ -119,14 +119,12 @@ AIP_HD void fwd_fixup(const FwdTilePlan& q, int tid, float* tile) {
   for (int i = a + tid; i < e; i += kThreads) tile[i] = 0.0f;
 }
 
-// stage 1 of the FFT for one tile: 256 threads, lane = n1 (16 lanes per frame), two frames per warp pass
+// stage 1 of the FFT for one tile: 256 threads, lane = n1 (16 lanes per frame); a thread owns column n1 of
+// frames fa and fa + 16 and runs them as the two lanes of the packed FP32x2 codelet
 AIP_HD void fwd_phase1(const FwdParams& P, int tid, const float* tile, float2* exch, const LaneConst& lc) {
   const int warp = tid >> 5, lane = tid & 31;
-#pragma unroll 1
-  for (int it = 0; it < 2; ++it) {
-    const int f = 2 * (warp + 8 * it) + (lane >> 4);
-    fwd_stage1(tile, exch, P.hop, f, lane & 15, lc);
-  }
+  const int fa = 2 * warp + (lane >> 4);
+  fwd_stage1(tile, exch, P.hop, fa, fa + 16, lane & 15, lc);
 }
 
 AIP_HD float mag_value(int mk, float xr, float xi, float eps, float power) {
@@ -272,23 +270,23 @@ AIP_HD void fwd_phase2(const FwdParams& P, int tid, const TileCursor& c, const f
   const int t0 = c.tt * kFR;
   const int n_valid = (P.T_out - t0) < kFR ? (P.T_out - t0) : kFR;
   const int fr = lane < n_valid ? lane : n_valid - 1;     // lanes past the end replay the last valid frame
-  float ar[16], ai[16], br[16], bi[16];
-  fwd_stage2_load(exch, fr, p, ar, ai, br, bi);
+  float2 zr[16], zi[16];
+  fwd_stage2_load(exch, fr, p, zr, zi);
   release();
   const long long col = (long long)c.b * kBins * P.T_out + t0 + fr;
   if (kMode == FWD_MAG_ABS || kMode == FWD_MAG_LOG10) {
     FwdEmitFast<(kMode == FWD_MAG_ABS ? (int)MAG_ABS : (int)MAG_LOG10_EPS)> emit{P.mag + col, P.T_out, P.eps, P.power, nullptr, nullptr, 0};
-    fwd_stage2_compute(ar, ai, br, bi, w, p, emit);
+    fwd_stage2_compute(zr, zi, w, p, emit);
   } else if (kMode == FWD_SPEC) {
     FwdEmitSpec emit{P.spec + col, P.T_out, nullptr, nullptr, 0};
-    fwd_stage2_compute(ar, ai, br, bi, w, p, emit);
+    fwd_stage2_compute(zr, zi, w, p, emit);
   } else if (kMode == FWD_GL) {
     FwdEmitGL emit{P.spec + col, P.gl_tprev + col, P.gl_mag + col, P.T_out, P.gl_alpha, P.gl_has_prev != 0,
                    lane < n_valid, 0, 0, 0};
-    fwd_stage2_compute(ar, ai, br, bi, w, p, emit);
+    fwd_stage2_compute(zr, zi, w, p, emit);
   } else {
     FwdEmitFull emit = fwd_make_emit_full(P, c.b, t0 + fr, kBins, lane < n_valid);
-    fwd_stage2_compute(ar, ai, br, bi, w, p, emit);
+    fwd_stage2_compute(zr, zi, w, p, emit);
   }
 }
 
@@ -355,75 +353,37 @@ struct InvLoadFull {        // magnitude (+ phase) input with the dB / 10** / ex
   }
 };
 
-// Staging of the complex input.  Each stage-A thread copies the 32 (33 for pair-job 0) bins IT will consume
-// into its private column of a staging buffer (slot idx*256 + tid) with 8-byte async copies, one tile ahead;
-// nobody else touches those slots, so cp.async.wait_group is the only synchronisation needed.
-constexpr int kStageSlots = 33;
-constexpr int kStage = kStageSlots * kThreads;       // float2 elements per staging buffer
-constexpr int kMaxWtab = 1024;                       // largest hop with a shared-memory 1/wss period table
-
-// staging order of pair-job p's bins: visit(idx, k)
-template <class V>
-AIP_HD void inv_visit_bins(int p, V& visit) {
-  if (p != 0) {
-#pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) {
-      visit(2 * k1, p + 16 * k1);
-      visit(2 * k1 + 1, 256 - p - 16 * k1);
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 9; ++j) visit(j, 16 * j);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) visit(9 + j, 256 - 16 * j);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) visit(17 + j, 8 + 16 * j);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) visit(25 + j, 248 - 16 * j);
-  }
-}
-
-template <class Copy>
-struct InvStageVisitor {
-  float2* st;               // staging buffer + tid
+struct InvLoadSpec {        // complex input straight from HBM
   const float2* col;        // spec + b*F*T + t
   int T;
-  Copy& copy;
-  AIP_HM void operator()(int idx, int k) const { copy(st + idx * kThreads, col + k * T); }
+  const float2* plo;
+  const float2* phi;
+  int s16;
+  AIP_HM void rows(int k_lo, int k_hi) { plo = col + k_lo * T; phi = col + k_hi * T; s16 = 16 * T; }
+  AIP_HM void lo(int j, float& xr, float& xi) const { const float2 v = plo[j * s16]; xr = v.x; xi = v.y; }
+  AIP_HM void hi(int j, float& xr, float& xi) const { const float2 v = phi[-(j * s16)]; xr = v.x; xi = v.y; }
 };
 
-// issue the copies of one tile for this thread (nothing for frames that do not exist)
-template <class Copy>
-AIP_HD void inv_stage_issue(const InvParams& P, int tid, const TileCursor& c, float2* stage, Copy& copy) {
-  const int warp = tid >> 5, lane = tid & 31;
-  const int t = c.tt * P.g.FO - P.g.HL + lane;
-  if (t < 0 || t >= P.n_frames) return;
-  InvStageVisitor<Copy> v{stage + tid, P.spec + ((long long)c.b * kBins * P.T + t), P.T, copy};
-  inv_visit_bins(warp, v);
-}
-
-struct InvLoadStaged {      // reads back what inv_stage_issue staged
-  const float2* st;         // staging buffer + tid
-  int blo, bhi, stride;
-  AIP_HM void rows(int k_lo, int k_hi) {
-    if (k_lo == 0 && k_hi == 256) { blo = 0; bhi = 9; stride = 1; }
-    else if (k_lo == 8 && k_hi == 248) { blo = 17; bhi = 25; stride = 1; }
-    else { blo = 0; bhi = 1; stride = 2; }
-  }
-  AIP_HM void lo(int j, float& xr, float& xi) const { const float2 v = st[(blo + j * stride) * kThreads]; xr = v.x; xi = v.y; }
-  AIP_HM void hi(int j, float& xr, float& xi) const { const float2 v = st[(bhi + j * stride) * kThreads]; xr = v.x; xi = v.y; }
+// input modes of the inverse kernel (template parameter).  (A cp.async-staged variant of the complex input,
+// one tile ahead through shared memory, measured 1.47x SLOWER than plain loads: 8-byte LDGSTS throttles the
+// LSU and adds an LDS per element; see profiles/README.md.)
+enum InvMode : int {
+  INV_FULL = 0,         // magnitude (+ phase) input with the dB / 10** / expm1 prologue
+  INV_SPEC = 1          // complex input
 };
 
-// stage A for one tile: 256 threads, lane = frame, warp = pair-job.  kStaged: complex input read from the
-// staging buffer; otherwise magnitude (+ phase) input read straight from HBM with the prologue applied.
-template <bool kStaged, class BeforeStore>
-AIP_HD void inv_phase0(const InvParams& P, int tid, const TileCursor& c, const float2* stage, float2* exch,
-                       const PairTw& w, BeforeStore& before_store) {
+constexpr int kInvBufs = 3;     // exchange-buffer ring: stage A may run two tiles ahead of stage B
+constexpr int kMaxWtab = 1024;  // largest hop with a shared-memory 1/wss period table
+
+// stage A for one tile: 256 threads, lane = frame, warp = pair-job
+template <int kMode, class BeforeStore>
+AIP_HD void inv_phase0(const InvParams& P, int tid, const TileCursor& c, float2* exch, const PairTw& w,
+                       BeforeStore& before_store) {
   const int warp = tid >> 5, lane = tid & 31;
   const int t = c.tt * P.g.FO - P.g.HL + lane;
   const bool live = (t >= 0 && t < P.n_frames);
-  if (kStaged) {
-    InvLoadStaged load{stage + tid, 0, 0, 0};
+  if (kMode == INV_SPEC) {
+    InvLoadSpec load{P.spec + ((long long)c.b * kBins * P.T + t), P.T, nullptr, nullptr, 0};
     inv_stageA(exch, w, lane, warp, live, load, before_store);
   } else {
     InvLoadFull load{P, (long long)c.b * kBins * P.T + t, P.db_flags ? (P.db_flags[c.b] != 0) : false, 0, 0, 0};
@@ -434,11 +394,8 @@ AIP_HD void inv_phase0(const InvParams& P, int tid, const TileCursor& c, const f
 // stage B for one tile: 256 threads, lane = n1
 AIP_HD void inv_phase1(const InvParams& P, int tid, float2* exch, const LaneConst& lc) {
   const int warp = tid >> 5, lane = tid & 31;
-#pragma unroll 1
-  for (int it = 0; it < 2; ++it) {
-    const int f = 2 * (warp + 8 * it) + (lane >> 4);
-    inv_stageB(exch, f, lane & 15, lc);
-  }
+  const int fa = 2 * warp + (lane >> 4);
+  inv_stageB(exch, fa, fa + 16, lane & 15, lc);
 }
 
 // overlap-add + window-sum-square normalisation + store for one tile (256 threads): thread q, q + 256, ...
