@@ -174,22 +174,31 @@ AIP_HD constexpr int exch_slot(int p, int c, int n1) { return ((p * 2 + c) * 16 
 AIP_HD constexpr int job_a(int p) { return p; }
 AIP_HD constexpr int job_b(int p) { return p == 0 ? 8 : 16 - p; }
 
-// Per-lane constants of the stage that runs with lane = n1 (forward stage 1, inverse stage B):
-// the 32 window taps this lane touches and the 16 inter-stage twiddles W256^(n1 k2).
+// Per-lane constants of the stage that runs with lane = n1 (forward stage 1, inverse stage B): the 16
+// inter-stage twiddles W256^(n1 k2) live in registers; the 32 window taps the lane touches come from a small
+// shared-memory table (row n1, pitch 36 floats: four LDS.128 quarter-warp phases, conflict-free), because
+// 64 packed data registers + 64 constants do not fit the 128-register budget of a 512-thread CTA.
 struct LaneConst {
-  float we[16], wo[16];
   float twr[16], twi[16];
 };
+constexpr int kWinPitch = 36;
+constexpr int kWinTable = 16 * kWinPitch;      // floats
 
-// window: n_fft centre-padded taps (float); scale: 0.5 forward (split pass), 1/512 inverse (irfft norm)
-AIP_HD void lane_const_init(LaneConst& c, const float* window, int n1, float scale) {
+AIP_HD void lane_const_init(LaneConst& c, int n1) {
 #pragma unroll
-  for (int n2 = 0; n2 < 16; ++n2) {
-    c.we[n2] = window[2 * (n1 + 16 * n2)] * scale;
-    c.wo[n2] = window[2 * (n1 + 16 * n2) + 1] * scale;
-    const float2 t = kTw256[(n1 * n2) & 255];   // n2 plays the role of k2 here
-    c.twr[n2] = t.x;
-    c.twi[n2] = t.y;
+  for (int k2 = 0; k2 < 16; ++k2) {
+    const float2 t = kTw256[(n1 * k2) & 255];
+    c.twr[k2] = t.x;
+    c.twi[k2] = t.y;
+  }
+}
+
+// win_s[n1*36 + 2*n2 + c] = window[2*(n1 + 16*n2) + c] * scale;  scale: 0.5 forward (split pass), 1/512
+// inverse (irfft norm).  window: n_fft centre-padded taps.
+AIP_HD void window_table_fill(float* win_s, const float* window, float scale, int tid, int nthreads) {
+  for (int idx = tid; idx < 16 * 32; idx += nthreads) {
+    const int n1 = idx >> 5, j = idx & 31;
+    win_s[n1 * kWinPitch + j] = window[2 * (n1 + 16 * (j >> 1)) + (j & 1)] * scale;
   }
 }
 
@@ -198,16 +207,23 @@ AIP_HD void lane_const_init(LaneConst& c, const float* window, int n1, float sca
 // loads of the staged waveform, window, packed 16-point DFT over n2, inter-stage twiddle, 2 x 16 float2
 // stores into the exchange buffer.
 // ---------------------------------------------------------------------------------------------------
-AIP_HD void fwd_stage1(const float* tile, float2* exch, int hop, int fa, int fb, int n1, const LaneConst& c) {
+AIP_HD void fwd_stage1(const float* tile, float2* exch, const float* win_s, int hop, int fa, int fb, int n1,
+                       const LaneConst& c) {
   float2 r[16], i[16];
   const float* sa = tile + fa * hop + 2 * n1;
   const float* sb = tile + fb * hop + 2 * n1;
+  const float4* wrow = reinterpret_cast<const float4*>(win_s + n1 * kWinPitch);
 #pragma unroll
-  for (int n2 = 0; n2 < 16; ++n2) {
-    const float2 za = *reinterpret_cast<const float2*>(sa + 32 * n2);
-    const float2 zb = *reinterpret_cast<const float2*>(sb + 32 * n2);
-    r[n2] = make_float2(za.x * c.we[n2], zb.x * c.we[n2]);
-    i[n2] = make_float2(za.y * c.wo[n2], zb.y * c.wo[n2]);
+  for (int j = 0; j < 8; ++j) {
+    const float4 w = wrow[j];        // (we, wo) of n2 = 2j and 2j + 1
+    const float2 za0 = *reinterpret_cast<const float2*>(sa + 64 * j);
+    const float2 zb0 = *reinterpret_cast<const float2*>(sb + 64 * j);
+    const float2 za1 = *reinterpret_cast<const float2*>(sa + 64 * j + 32);
+    const float2 zb1 = *reinterpret_cast<const float2*>(sb + 64 * j + 32);
+    r[2 * j] = make_float2(za0.x * w.x, zb0.x * w.x);
+    i[2 * j] = make_float2(za0.y * w.y, zb0.y * w.y);
+    r[2 * j + 1] = make_float2(za1.x * w.z, zb1.x * w.z);
+    i[2 * j + 1] = make_float2(za1.y * w.w, zb1.y * w.w);
   }
   fft16x2(r, i);
   float2* da = exch + n1 * kXP + fa;
@@ -370,7 +386,7 @@ AIP_HD void inv_stageA(float2* exch, const PairTw& w, int f, int p, bool live, L
 // written IN PLACE into the exchange buffer, which thereby becomes the frame buffer: float2 slot
 // (m*33 + f) = samples (2m, 2m+1) of frame f, m = n1 + 16 n2 (a thread reads and writes the same 2 x 16 slots).
 // ---------------------------------------------------------------------------------------------------
-AIP_HD void inv_stageB(float2* exch, int fa, int fb, int n1, const LaneConst& c) {
+AIP_HD void inv_stageB(float2* exch, const float* win_s, int fa, int fb, int n1, const LaneConst& c) {
   float2 r[16], i[16];
   float2* pa = exch + n1 * kXP + fa;
   float2* pb = exch + n1 * kXP + fb;
@@ -388,11 +404,16 @@ AIP_HD void inv_stageB(float2* exch, int fa, int fb, int n1, const LaneConst& c)
     r[kb] = make_float2(br_a, br_b); i[kb] = make_float2(bi_a, bi_b);
   }
   fft16x2(i, r);
+  const float4* wrow = reinterpret_cast<const float4*>(win_s + n1 * kWinPitch);
 #pragma unroll
-  for (int n2 = 0; n2 < 16; ++n2) {
-    const float2 zr = r[perm16(n2)], zi = i[perm16(n2)];
-    pa[n2 * 16 * kXP] = make_float2(zr.x * c.we[n2], zi.x * c.wo[n2]);
-    pb[n2 * 16 * kXP] = make_float2(zr.y * c.we[n2], zi.y * c.wo[n2]);
+  for (int j = 0; j < 8; ++j) {
+    const float4 w = wrow[j];
+    const float2 zr0 = r[perm16(2 * j)], zi0 = i[perm16(2 * j)];
+    const float2 zr1 = r[perm16(2 * j + 1)], zi1 = i[perm16(2 * j + 1)];
+    pa[(2 * j) * 16 * kXP] = make_float2(zr0.x * w.x, zi0.x * w.y);
+    pb[(2 * j) * 16 * kXP] = make_float2(zr0.y * w.x, zi0.y * w.y);
+    pa[(2 * j + 1) * 16 * kXP] = make_float2(zr1.x * w.z, zi1.x * w.w);
+    pb[(2 * j + 1) * 16 * kXP] = make_float2(zr1.y * w.z, zi1.y * w.w);
   }
 }
 

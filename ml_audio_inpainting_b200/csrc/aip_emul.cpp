@@ -41,17 +41,19 @@ int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, 
   std::vector<LaneConst> lc(kThreads);
   std::vector<PairTw> pw(kThreads);
   for (int tid = 0; tid < kThreads; ++tid) {
-    lane_const_init(lc[tid], window, tid & 15, 0.5f);
+    lane_const_init(lc[tid], tid & 15);
     pair_tw_init(pw[tid], tid >> 5);
   }
   NoRelease rel;
+  alignas(16) float win_s[kWinTable];
+  window_table_fill(win_s, window, 0.5f, 0, 1);
   const int mode = fwd_mode_of(P);
   TileCursor c = tile_cursor(0, P.tiles_per_clip);
   for (int tix = 0; tix < P.n_tiles; ++tix) {
     const FwdTilePlan q = fwd_tile_plan(P, c);
     if (q.n_bulk > 0) memcpy(tile.data() + q.v_lo, q.src + q.g0 + q.v_lo, (size_t)q.n_bulk * 4);   // the TMA bulk copy
     if (fwd_needs_fixup(q)) for (int tid = 0; tid < kThreads; ++tid) fwd_fixup(q, tid, tile.data());
-    for (int tid = 0; tid < kThreads; ++tid) fwd_phase1(P, tid, tile.data(), exch.data(), lc[tid]);
+    for (int tid = 0; tid < kThreads; ++tid) fwd_phase1(P, tid, tile.data(), exch.data(), win_s, lc[tid]);
     for (int tid = 0; tid < kThreads; ++tid) {
       switch (mode) {
         case FWD_MAG_ABS: fwd_phase2<FWD_MAG_ABS>(P, tid, c, exch.data(), pw[tid], rel); break;
@@ -107,17 +109,19 @@ int emul_istft512(const float* spec, const float* mag, const float* phase, int m
   std::vector<LaneConst> lc(kThreads);
   std::vector<PairTw> pw(kThreads);
   for (int tid = 0; tid < kThreads; ++tid) {
-    lane_const_init(lc[tid], window, tid & 15, 1.0f / 512.0f);
+    lane_const_init(lc[tid], tid & 15);
     pair_tw_init(pw[tid], tid >> 5);
   }
   NoRelease rel;
+  alignas(16) float win_s[kWinTable];
+  window_table_fill(win_s, window, 1.0f / 512.0f, 0, 1);
   TileCursor c = tile_cursor(0, P.tiles_per_clip);
   for (int tix = 0; tix < P.n_tiles; ++tix) {
     for (int tid = 0; tid < kThreads; ++tid) {
       if (spec) inv_phase0<INV_SPEC>(P, tid, c, exch.data(), pw[tid], rel);
       else inv_phase0<INV_FULL>(P, tid, c, exch.data(), pw[tid], rel);
     }
-    for (int tid = 0; tid < kThreads; ++tid) inv_phase1(P, tid, exch.data(), lc[tid]);
+    for (int tid = 0; tid < kThreads; ++tid) inv_phase1(P, tid, exch.data(), win_s, lc[tid]);
     for (int tid = 0; tid < kThreads; ++tid) inv_phase2(P, tid, c, exch.data(), wtab.empty() ? nullptr : wtab.data());
     tile_advance(c, P.tiles_per_clip);
   }

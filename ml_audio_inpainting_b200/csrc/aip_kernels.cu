@@ -102,6 +102,8 @@ template <int kMode>
 __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdParams P) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bars[8];
+  __shared__ __align__(16) float win_s[kWinTable];
+  window_table_fill(win_s, P.window, 0.5f, threadIdx.x, blockDim.x);
   uint64_t* tile_full = bars;        // [2] count 1 (+ tx bytes)
   uint64_t* tile_empty = bars + 2;   // [2] count 8 (stage-1 warps)
   uint64_t* exch_full = bars + 4;    // [2] count 8 (stage-1 warps)
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
     // ------------------------------------------------------------------ producers: stage 1
     const int ptid = tid - kThreads;
     LaneConst lc;
-    lane_const_init(lc, P.window, ptid & 15, 0.5f);
+    lane_const_init(lc, ptid & 15);
     FwdTilePlan q = fwd_tile_plan(P, c);
     if (ptid == 0) fwd_issue_tile(q, smem, tile_full);
 #pragma unroll 1
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
       }
       const int es = i & 1;
       if (i >= 2) mbar_wait(exch_empty + es, (uint32_t)(((i >> 1) - 1) & 1));
-      fwd_phase1(P, ptid, tile, exch0 + es * kExch, lc);
+      fwd_phase1(P, ptid, tile, exch0 + es * kExch, win_s, lc);
       mbar_arrive_warp(exch_full + es);
       fence_proxy_async();
       mbar_arrive_warp(tile_empty + slot);
@@ -192,6 +194,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParam
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bars[2 * kInvBufs];
   __shared__ __align__(8) float wtab_s[kMaxWtab];
+  __shared__ __align__(16) float win_s[kWinTable];
+  window_table_fill(win_s, P.window, 1.0f / 512.0f, threadIdx.x, blockDim.x);
   const float* wtab = (P.wss_ref >= 0 && P.hop <= kMaxWtab) ? wtab_s : nullptr;
   if (wtab)
     for (int r = threadIdx.x; r < P.hop; r += blockDim.x) wtab_s[r] = P.inv_wss[P.wss_ref + r];
@@ -226,13 +230,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParam
   } else {
     const int btid = tid - kThreads;
     LaneConst lc;
-    lane_const_init(lc, P.window, btid & 15, 1.0f / 512.0f);
+    lane_const_init(lc, btid & 15);
     int es = 0, use = 0;
 #pragma unroll 1
     for (int i = 0; i < n; ++i) {
       float2* exch = exch0 + es * kExch;
       mbar_wait(exch_full + es, (uint32_t)(use & 1));
-      inv_phase1(P, btid, exch, lc);
+      inv_phase1(P, btid, exch, win_s, lc);
       named_bar_sync(1, kThreads);
       inv_phase2(P, btid, c, exch, wtab);
       mbar_arrive_warp(exch_empty + es);

@@ -121,10 +121,11 @@ AIP_HD void fwd_fixup(const FwdTilePlan& q, int tid, float* tile) {
 
 // stage 1 of the FFT for one tile: 256 threads, lane = n1 (16 lanes per frame); a thread owns column n1 of
 // frames fa and fa + 16 and runs them as the two lanes of the packed FP32x2 codelet
-AIP_HD void fwd_phase1(const FwdParams& P, int tid, const float* tile, float2* exch, const LaneConst& lc) {
+AIP_HD void fwd_phase1(const FwdParams& P, int tid, const float* tile, float2* exch, const float* win_s,
+                       const LaneConst& lc) {
   const int warp = tid >> 5, lane = tid & 31;
   const int fa = 2 * warp + (lane >> 4);
-  fwd_stage1(tile, exch, P.hop, fa, fa + 16, lane & 15, lc);
+  fwd_stage1(tile, exch, win_s, P.hop, fa, fa + 16, lane & 15, lc);
 }
 
 AIP_HD float mag_value(int mk, float xr, float xi, float eps, float power) {
@@ -392,10 +393,10 @@ AIP_HD void inv_phase0(const InvParams& P, int tid, const TileCursor& c, float2*
 }
 
 // stage B for one tile: 256 threads, lane = n1
-AIP_HD void inv_phase1(const InvParams& P, int tid, float2* exch, const LaneConst& lc) {
+AIP_HD void inv_phase1(const InvParams& P, int tid, float2* exch, const float* win_s, const LaneConst& lc) {
   const int warp = tid >> 5, lane = tid & 31;
   const int fa = 2 * warp + (lane >> 4);
-  inv_stageB(exch, fa, fa + 16, lane & 15, lc);
+  inv_stageB(exch, win_s, fa, fa + 16, lane & 15, lc);
 }
 
 // overlap-add + window-sum-square normalisation + store for one tile (256 threads): thread q, q + 256, ...
