@@ -445,22 +445,6 @@ AIP_HD int magic_div(int n, unsigned m) {
 // are fl = h - m with n = r + m*hop < 512, m = 0 .. K-1, K = ceil(512 / hop); only the m = K-1 term can be
 // missing.  librosa adds frames in increasing order = decreasing m.
 
-// interior tiles (all 32 local frames exist), K known at compile time: all K loads are independent
-template <int K>
-AIP_HD float2 ola_pair_fixed(const float2* fbuf, int h, int r, int hop) {
-  const int step = (hop >> 1) * kXP - 1;            // slot(m) - slot(m-1)
-  const int n_top = r + (K - 1) * hop;
-  const float2* src = fbuf + (r >> 1) * kXP + h;     // m = 0
-  float2 v[K];
-#pragma unroll
-  for (int m = 0; m < K - 1; ++m) v[m] = src[m * step];
-  v[K - 1] = (n_top < kNfft) ? src[(K - 1) * step] : make_float2(0.0f, 0.0f);
-  float sx = 0.0f, sy = 0.0f;
-#pragma unroll
-  for (int m = K - 1; m >= 0; --m) { sx += v[m].x; sy += v[m].y; }
-  return make_float2(sx, sy);
-}
-
 // general form: any K, and clip-edge tiles where only local frames [fl_min, fl_max] exist
 AIP_HD float2 ola_pair(const float2* fbuf, int h, int r, int hop, int K, int fl_min, int fl_max) {
   const int step = (hop >> 1) * kXP - 1;

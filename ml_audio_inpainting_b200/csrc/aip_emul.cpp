@@ -93,6 +93,7 @@ int emul_istft512(const float* spec, const float* mag, const float* phase, int m
   P.tiles_per_clip = (int)((out_len + span - 1) / span);
   P.n_tiles = B * P.tiles_per_clip;
   P.hop_magic = (unsigned)((0x100000000ULL + (unsigned)hop - 1) / (unsigned)hop);
+  P.col_magic = (unsigned)((0x100000000ULL + (unsigned)(hop / 2) - 1) / (unsigned)(hop / 2));
   P.ola_terms = (kNfft + hop - 1) / hop;
   P.ola_dq = (2 * kThreads) / hop;
   P.ola_dr = (2 * kThreads) % hop;

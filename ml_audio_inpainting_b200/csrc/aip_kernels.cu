@@ -541,6 +541,7 @@ static bool fwd_fast_ok(const aip_stft_desc* d, const DevInfo& di) { return fwd_
 
 static void inv_fill_ola(InvParams& P) {
   P.hop_magic = (unsigned)((0x100000000ULL + (unsigned)P.hop - 1) / (unsigned)P.hop);
+  P.col_magic = (unsigned)((0x100000000ULL + (unsigned)(P.hop / 2) - 1) / (unsigned)(P.hop / 2));
   P.ola_terms = (kNfft + P.hop - 1) / P.hop;
   P.ola_dq = (2 * kThreads) / P.hop;
   P.ola_dr = (2 * kThreads) % P.hop;

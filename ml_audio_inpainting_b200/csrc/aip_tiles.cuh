@@ -314,6 +314,7 @@ struct InvParams {
   int tiles_per_cta;
   InvGeom g;
   unsigned hop_magic;       // ceil(2^32 / hop)
+  unsigned col_magic;       // ceil(2^32 / (hop / 2))
   int ola_terms;            // ceil(512 / hop): frames overlapping one sample
   int ola_dq, ola_dr;       // (2 * 256) / hop and (2 * 256) % hop: per-iteration advance of a thread's pair
   int wss_ref;              // inv_wss[wss_ref + r] = periodic value for frame offset r; < 0: no interior
@@ -399,43 +400,35 @@ AIP_HD void inv_phase1(const InvParams& P, int tid, float2* exch, const float* w
   inv_stageB(exch, win_s, fa, fa + 16, lane & 15, lc);
 }
 
-// overlap-add + window-sum-square normalisation + store for one tile (256 threads): thread q, q + 256, ...
-// owns output pairs (s0 + 2q, s0 + 2q + 1); its (frame, offset) coordinates advance incrementally.
-// interior tile, K terms per sample, vector stores, periodic 1/wss table: kU pairs in flight per thread
+// Interior tile (all 32 local frames exist, whole tile inside the output, vector stores legal, periodic 1/wss
+// table present), K terms per sample.  Column-wise: a thread owns the output pairs at ONE offset 2*cc inside
+// the hop and walks the hops h = g, g + G, ...  Everything that depends on the offset only -- the frame-buffer
+// base slot, the 1/wss pair, whether the m = K-1 term exists -- is loop invariant; per pair that leaves K
+// LDS.64, 2K FADD, 2 FMUL, one 8-byte store and two pointer increments.
 template <int K>
 AIP_HD void inv_ola_interior(const InvParams& P, int tid, int s0, const float2* fbuf, const float* wtab, float* dst) {
-  constexpr int kU = 4;
-  const int hop = P.hop;
-  const int n_pairs = (P.g.FO * hop) >> 1;
-  const int u0 = 2 * tid + P.pad + P.g.HL * hop;
-  int h = magic_div(u0, P.hop_magic);
-  int r = u0 - h * hop;
-  for (int q = tid; q < n_pairs; q += kU * kThreads) {
-    int hh[kU], rr[kU];
-    float2 v[kU];
+  const int hop = P.hop, C = hop >> 1;                // pair columns per hop
+  const int G = C >= kThreads ? 1 : kThreads / C;     // hop groups walking in parallel
+  const int g = C >= kThreads ? 0 : magic_div(tid, P.col_magic);
+  if (g >= G) return;
+  const int step = C * kXP - 1;                       // slot(m) - slot(m-1)
+  for (int cc = tid - g * C; cc < C; cc += kThreads) {
+    const int u = 2 * cc + P.pad;                     // offset of the pair from the start of local frame HL + h
+    const int d = magic_div(u, P.hop_magic);
+    const int r = u - d * hop;                        // offset inside frame h' = h + HL + d
+    const bool top = r + (K - 1) * hop < kNfft;
+    const float2 nw = *reinterpret_cast<const float2*>(wtab + r);
+    const float2* src = fbuf + (r >> 1) * kXP + (P.g.HL + d + g);
+    float* out = dst + s0 + g * hop + 2 * cc;
+    for (int h = g; h < P.g.FO; h += G, src += G, out += G * hop) {
+      float2 v[K];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      hh[u] = h; rr[u] = r;
-      h += P.ola_dq; r += P.ola_dr;
-      if (r >= hop) { r -= hop; ++h; }
-    }
+      for (int m = 0; m < K - 1; ++m) v[m] = src[m * step];
+      v[K - 1] = top ? src[(K - 1) * step] : make_float2(0.0f, 0.0f);
+      float sx = 0.0f, sy = 0.0f;
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int qq = q + u * kThreads;
-      // rows past the tile / output end read a valid (clamped) slot and are not stored
-      const bool ok = qq < n_pairs && s0 + 2 * qq + 1 < P.out_len;
-      v[u] = ola_pair_fixed<K>(fbuf, ok ? hh[u] : P.g.HL + K, ok ? rr[u] : 0, hop);
-    }
-#pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int qq = q + u * kThreads;
-      const int s = s0 + 2 * qq;
-      if (qq < n_pairs && s + 1 < P.out_len) {
-        const float2 nw = *reinterpret_cast<const float2*>(wtab + rr[u]);
-        *reinterpret_cast<float2*>(dst + s) = make_float2(v[u].x * nw.x, v[u].y * nw.y);
-      } else if (qq < n_pairs && s < P.out_len) {
-        dst[s] = ola_pair_fixed<K>(fbuf, hh[u], rr[u], hop).x * wtab[rr[u]];
-      }
+      for (int m = K - 1; m >= 0; --m) { sx += v[m].x; sy += v[m].y; }    // increasing frame order, like librosa
+      *reinterpret_cast<float2*>(out) = make_float2(sx * nw.x, sy * nw.y);
     }
   }
 }
@@ -455,7 +448,7 @@ AIP_HD void inv_phase2(const InvParams& P, int tid, const TileCursor& c, const f
   if (fl_max > kFR - 1) fl_max = kFR - 1;
   const bool edge = fl_min > 0 || fl_max < kFR - 1;
   float* dst = P.out + (long long)c.b * P.out_pitch;
-  if (!edge && wtab && P.vec_ok) {
+  if (!edge && wtab && P.vec_ok && s0 + P.g.FO * hop <= P.out_len) {
     if (P.ola_terms == 3) return inv_ola_interior<3>(P, tid, s0, fbuf, wtab, dst);
     if (P.ola_terms == 4) return inv_ola_interior<4>(P, tid, s0, fbuf, wtab, dst);
     if (P.ola_terms == 2) return inv_ola_interior<2>(P, tid, s0, fbuf, wtab, dst);
