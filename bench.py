@@ -198,8 +198,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=4096, help="clips per GPU (configs[1]: 4096)")
     ap.add_argument("--inv-clips", type=int, default=1024, help="clips per GPU of the iSTFT leg (configs[2]: 1024)")
-    ap.add_argument("--ref-clips", type=int, default=256, help="clips per step of the CPU arm")
-    ap.add_argument("--cpu-clips", type=int, default=512, help="clips of the cpu_baseline sample (rank 0, N=1)")
+    ap.add_argument("--ref-clips", type=int, default=1024, help="clips per step of the CPU arm")
+    ap.add_argument("--cpu-clips", type=int, default=2048, help="clips of the cpu_baseline sample (rank 0, N=1)")
+    ap.add_argument("--gl-clips", type=int, default=1024, help="clips per GPU of the Griffin-Lim leg (configs[2], 32 iterations)")
+    ap.add_argument("--no-legs", action="store_true", help="headline step only (profiling runs)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -295,15 +297,35 @@ def main():
     # ---- inverse leg (configs[2]) and round trip, reported beside the headline
     legs = {}
     Bi = min(args.inv_clips, B)
+    if args.no_legs:
+        Bi = 0
+    if Bi > 0:
+        legs = extra_legs(args, sp, plan, wave, gap_dev, Bi, T, F, L, world, peak, timed)
+
+    # ---- end to end through the host-buffer API
+    e2e = None
+    if not args.no_e2e:
+        e2e = e2e_leg(args, frontend, plan, wave, starts, g, B, L, F, T, world, dev, barrier)
+
+    if rank == 0:
+        emit_line(args, world, value, ms, B, T, roofline, cpu_baseline, e2e, clocks, legs)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extra_legs(args, sp, plan, wave, gap_dev, Bi, T, F, L, world, peak, timed):
+    import torch
+    legs = {}
+    dev = wave.device
     spec = sp.stft(wave[:Bi], plan, gap_samples=gap_dev[:Bi])["spec"]
     yout = torch.empty((Bi, plan.istft_length(T)), dtype=torch.float32, device=dev)
     ms_i, per_i = timed(lambda: sp.istft(plan, spec=spec, out=yout), args.steps, args.warmup)
     inv_bytes = Bi * (8 * F * T + 4 * yout.shape[1])
+    ach = inv_bytes / (np.mean(per_i) * 1e-3) / 1e9
     legs["istft"] = {"workload": f"configs[2]: iSTFT overlap-add of masked complex spectrograms, batch {Bi} per GPU",
                      "value": world * Bi * CLIP_S / (ms_i * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_i,
-                     "roofline": {"bound": "hbm", "achieved": inv_bytes / (np.mean(per_i) * 1e-3) / 1e9, "peak": peak,
-                                  "unit": "GB/s", "frac": inv_bytes / (np.mean(per_i) * 1e-3) / 1e9 / peak,
-                                  "traffic": recorded_traffic("istft512_kernel"),
+                     "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                  "traffic": recorded_traffic("istft512_kernel"), "kernel": "istft512_kernel<INV_SPEC>",
                                   "algorithmic_bytes_per_launch": inv_bytes}}
     sout = {"spec": spec}
 
@@ -312,54 +334,80 @@ def main():
         sp.istft(plan, spec=spec, out=yout)
 
     ms_r, _ = timed(roundtrip, args.steps, args.warmup)
-    legs["roundtrip"] = {"workload": f"STFT(complex)+gap -> iSTFT, batch {Bi} per GPU",
-                         "value": world * Bi * CLIP_S / (ms_r * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_r}
-    del spec, yout, sout
+    rt_bytes = Bi * (4 * L + 8 * F * T) + inv_bytes
+    legs["roundtrip"] = {"workload": f"STFT(complex)+gap -> iSTFT, batch {Bi} per GPU (2 launches per step)",
+                         "value": world * Bi * CLIP_S / (ms_r * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_r,
+                         "hbm_frac": rt_bytes / (ms_r * 1e-3) / 1e9 / peak}
+    # P2 (GAN parameters: win 512 / hop 128) forward, same step shape
+    plan2 = sp.get_plan(N_FFT, 128, 512, "hann", True, dev)
+    T2 = plan2.num_frames(L)
+    out2 = {"mag": torch.empty((Bi, F, T2), dtype=torch.float32, device=dev)}
+    ms_2, per_2 = timed(lambda: sp.stft(wave[:Bi], plan2, gap_samples=gap_dev[:Bi], mag_kind=sp.MAG_LOG10_EPS, eps=EPS,
+                                        want_spec=False, out=out2), args.steps, args.warmup)
+    b2 = Bi * (4 * L + 4 * F * T2)
+    legs["stft_p2"] = {"workload": f"forward log-magnitude + gap at the GAN parameters (win 512 / hop 128), batch {Bi} per GPU",
+                       "value": world * Bi * CLIP_S / (ms_2 * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_2,
+                       "hbm_frac": b2 / (np.mean(per_2) * 1e-3) / 1e9 / peak}
+    del out2, spec, sout
+    # Griffin-Lim, 32 iterations (configs[2] "+ Griffin-Lim 32 iters"): streaming bound 8 995 656 B / clip / iteration
+    Bg = min(args.gl_clips, Bi)
+    if Bg > 0:
+        mag = sp.stft(wave[:Bg], plan, mag_kind=sp.MAG_ABS, want_spec=False)["mag"]
+        gen = torch.Generator(device=dev).manual_seed(99)
+        n_iter = 32
+        ms_g, _ = timed(lambda: sp.griffinlim(plan, mag, n_iter=n_iter, generator=gen), max(2, args.steps // 5), 1)
+        gl_bytes = Bg * (n_iter * 8995656 + 2354448)
+        legs["griffinlim32"] = {"workload": f"Griffin-Lim 32 iterations (momentum 0.99, random init drawn on device), batch {Bg} per GPU, "
+                                            f"{2 * n_iter + 2} kernel launches per step",
+                                "value": world * Bg * CLIP_S / (ms_g * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_g,
+                                "streaming_bound_bytes_per_step": gl_bytes,
+                                "hbm_frac_of_streaming_bound": gl_bytes / (ms_g * 1e-3) / 1e9 / peak}
+    return legs
 
-    # ---- end to end through the host-buffer API
-    e2e = None
-    if not args.no_e2e:
-        h_wave = torch.empty((B, L), dtype=torch.float32, pin_memory=True)
-        h_wave.copy_(wave)
-        h_out = torch.empty((B, F, T), dtype=torch.float32, pin_memory=True)
-        gaps_np = np.stack([starts, starts + g], 1).astype(np.int32)
-        pipe = frontend.HostPipeline(plan, B, L, chunk=256)
 
-        def e2e_step():
-            pipe.logmag_gap(h_wave, gaps_np, h_out, eps=EPS)
+def e2e_leg(args, frontend, plan, wave, starts, g, B, L, F, T, world, dev, barrier):
+    import torch
+    import torch.distributed as dist
+    h_wave = torch.empty((B, L), dtype=torch.float32, pin_memory=True)
+    h_wave.copy_(wave)
+    h_out = torch.empty((B, F, T), dtype=torch.float32, pin_memory=True)
+    gaps_np = np.stack([starts, starts + g], 1).astype(np.int32)
+    pipe = frontend.HostPipeline(plan, B, L, chunk=256)
 
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        n_e2e = max(3, min(args.steps, 5))
-        for _ in range(n_e2e):
-            e2e_step()
-        barrier()
-        dt = (time.perf_counter() - t0) / n_e2e
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": world * B * CLIP_S / dt, "unit": "audio-s/s", "h2d_bytes_per_step": int(B * L * 4 + B * 8),
-               "d2h_bytes_per_step": int(B * F * T * 4), "ms_per_step": dt * 1e3, "steps": n_e2e,
-               "api": "ml_audio_inpainting_b200.frontend.HostPipeline.logmag_gap (pinned host in/out, 3 streams)"}
+    def e2e_step():
+        pipe.logmag_gap(h_wave, gaps_np, h_out, eps=EPS)
 
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "clips_per_gpu": B, "n_fft": N_FFT, "win_length": WIN, "hop_length": HOP,
-                       "sample_rate": SR, "clip_seconds": CLIP_S, "gap_seconds": GAP_S, "frames": T,
-                       "outputs": "log10(|S|+1e-9) f32 [B,257,T]", "sharding": f"by clip, {world} rank(s), no collective",
-                       "l2": "inputs (2.6 GB) and outputs (3.5 GB) per step exceed the 126 MB L2; no flush needed"},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": args.steps,
-            "clocks": clocks, "legs": legs,
-        }
-        print(json.dumps(line), flush=True)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(3, min(args.steps, 5))
+    for _ in range(n_e2e):
+        e2e_step()
+    barrier()
+    dt = (time.perf_counter() - t0) / n_e2e
     if world > 1:
-        dist.destroy_process_group()
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return {"value": world * B * CLIP_S / dt, "unit": "audio-s/s", "h2d_bytes_per_step": int(B * L * 4 + B * 8),
+            "d2h_bytes_per_step": int(B * F * T * 4), "ms_per_step": dt * 1e3, "steps": n_e2e,
+            "api": "ml_audio_inpainting_b200.frontend.HostPipeline.logmag_gap (pinned host in/out, 3 streams)"}
+
+
+def emit_line(args, world, value, ms, B, T, roofline, cpu_baseline, e2e, clocks, legs):
+    line = {
+        "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "clips_per_gpu": B, "n_fft": N_FFT, "win_length": WIN, "hop_length": HOP,
+                   "sample_rate": SR, "clip_seconds": CLIP_S, "gap_seconds": GAP_S, "frames": T,
+                   "outputs": "log10(|S|+1e-9) f32 [B,257,T]", "sharding": f"by clip, {world} rank(s), no collective",
+                   "l2": "inputs (2.6 GB) and outputs (3.5 GB) per step exceed the 126 MB L2; no flush needed"},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": args.steps,
+        "clocks": clocks, "legs": legs,
+    }
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

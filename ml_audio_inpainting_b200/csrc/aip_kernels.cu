@@ -187,8 +187,8 @@ struct WaitBefore {
 //   stage-A warps (lane = frame): HBM -> registers, split-pass prologue, 2 x inverse 16-pt DFT -> exch[i % 3]
 //   stage-B warps (lane = n1): twiddle, inverse 16-pt DFT, synthesis window (in place: the exchange buffer
 //   becomes the frame buffer) -> named barrier -> overlap-add + 1/window-sum-square -> HBM -> release
-// The ring of three exchange buffers lets the stage-A warps run two tiles ahead, so their global-load
-// latency hides behind stage B and the overlap-add.
+// Stage A computes tile i+1 in registers while stage B works on tile i and only then waits for the exchange
+// buffer; a ring of n_bufs buffers is supported, one measured fastest (see kInvBufsDefault).
 template <int kMode>
 __global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParams P) {
   extern __shared__ __align__(128) float smem[];
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParam
       inv_phase0<kMode>(P, tid, c, exch0 + es * kExch, w, wb);
       mbar_arrive_warp(exch_full + es);
       tile_advance(c, P.tiles_per_clip);
-      if (++es == kInvBufs) { es = 0; ++use; }
+      if (++es == P.n_bufs) { es = 0; ++use; }
     }
   } else {
     const int btid = tid - kThreads;
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParam
       inv_phase2(P, btid, c, exch, wtab);
       mbar_arrive_warp(exch_empty + es);
       tile_advance(c, P.tiles_per_clip);
-      if (++es == kInvBufs) { es = 0; ++use; }
+      if (++es == P.n_bufs) { es = 0; ++use; }
     }
   }
 }
@@ -656,7 +656,9 @@ static int run_inv(const aip_stft_desc* desc, InvParams P, long long length, voi
     P.vec_ok = ((P.out_pitch & 1) == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 7) == 0) &&
                ((reinterpret_cast<uintptr_t>(P.inv_wss) & 7) == 0);
     inv_fill_ola(P);
-    const size_t smem = (size_t)kInvBufs * kExch * sizeof(float2);
+    P.n_bufs = kInvBufsDefault;
+    if (const char* nb = getenv("AIP_INV_BUFS")) { const int v = atoi(nb); if (v >= 1 && v <= kInvBufs) P.n_bufs = v; }   // profiling switch
+    const size_t smem = (size_t)P.n_bufs * kExch * sizeof(float2);
     int grid = di.sms;
     if (grid > P.n_tiles) grid = P.n_tiles;
     P.tiles_per_cta = (P.n_tiles + grid - 1) / grid;

@@ -312,6 +312,7 @@ struct InvParams {
   int tiles_per_clip;
   int n_tiles;
   int tiles_per_cta;
+  int n_bufs;               // exchange buffers in the ring (1..kInvBufs)
   InvGeom g;
   unsigned hop_magic;       // ceil(2^32 / hop)
   unsigned col_magic;       // ceil(2^32 / (hop / 2))
@@ -374,7 +375,9 @@ enum InvMode : int {
   INV_SPEC = 1          // complex input
 };
 
-constexpr int kInvBufs = 3;     // exchange-buffer ring: stage A may run two tiles ahead of stage B
+constexpr int kInvBufs = 3;     // most exchange buffers the ring supports
+constexpr int kInvBufsDefault = 1;   // measured best (0.76 / 0.78 / 1.03 ms for 1 / 2 / 3): a deeper ring takes the
+                                     // shared-memory carve-out from L1, which the stage-A global loads rely on
 constexpr int kMaxWtab = 1024;  // largest hop with a shared-memory 1/wss period table
 
 // stage A for one tile: 256 threads, lane = frame, warp = pair-job
