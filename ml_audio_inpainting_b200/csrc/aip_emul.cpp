@@ -59,7 +59,6 @@ int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, 
         case FWD_MAG_ABS: fwd_phase2<FWD_MAG_ABS>(P, tid, c, exch.data(), pw[tid], rel); break;
         case FWD_MAG_LOG10: fwd_phase2<FWD_MAG_LOG10>(P, tid, c, exch.data(), pw[tid], rel); break;
         case FWD_SPEC: fwd_phase2<FWD_SPEC>(P, tid, c, exch.data(), pw[tid], rel); break;
-        case FWD_GL: fwd_phase2<FWD_GL>(P, tid, c, exch.data(), pw[tid], rel); break;
         default: fwd_phase2<FWD_FULL>(P, tid, c, exch.data(), pw[tid], rel); break;
       }
     }

@@ -469,6 +469,39 @@ __global__ void peak_scale_kernel(const float* in, long long in_pitch, float* ou
   }
 }
 
+// Griffin-Lim update (librosa.griffinlim loop body, utils.py:330-332), two bins per thread:
+//   angles = rebuilt - alpha * tprev ; angles /= |angles| + tiny ; angles *= S ; tprev = rebuilt
+// `spec` holds the rebuilt spectrum on entry and the new angles on exit.  Kept OUT of the forward kernel's
+// epilogue on purpose: fused there, each bin's tprev / S loads sit on a dependent chain inside a 128-register
+// thread (measured 20.6 ms per launch against 0.5 ms for the plain complex forward + 1.5 ms for this kernel).
+__global__ void __launch_bounds__(256) gl_update_kernel(float4* __restrict__ spec, float4* __restrict__ tprev,
+                                                        const float2* __restrict__ mag, long long n2, float alpha,
+                                                        int has_prev) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 rb = spec[i];
+    const float2 m = mag[i];
+    float ax = rb.x, ay = rb.y, bx = rb.z, by = rb.w;
+    if (has_prev) {
+      const float4 tp = tprev[i];
+      ax -= alpha * tp.x; ay -= alpha * tp.y; bx -= alpha * tp.z; by -= alpha * tp.w;
+    }
+    tprev[i] = rb;
+    const float sa = m.x / (sqrtf(ax * ax + ay * ay) + kFltMin);
+    const float sb = m.y / (sqrtf(bx * bx + by * by) + kFltMin);
+    spec[i] = make_float4(ax * sa, ay * sa, bx * sb, by * sb);
+  }
+}
+
+__global__ void gl_update_tail_kernel(float2* spec, float2* tprev, const float* mag, long long i, float alpha, int has_prev) {
+  const float2 rb = spec[i];
+  float ax = rb.x, ay = rb.y;
+  if (has_prev) { const float2 tp = tprev[i]; ax -= alpha * tp.x; ay -= alpha * tp.y; }
+  tprev[i] = rb;
+  const float s = mag[i] / (sqrtf(ax * ax + ay * ay) + kFltMin);
+  spec[i] = make_float2(ax * s, ay * s);
+}
+
 __global__ void scale_angles_kernel(float2* angles, const float* mag, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -577,7 +610,6 @@ static cudaError_t launch_fwd512(const FwdParams& P, const DevInfo& di, cudaStre
     case FWD_MAG_ABS: return launch_fwd512_t<FWD_MAG_ABS>(P, di, st);
     case FWD_MAG_LOG10: return launch_fwd512_t<FWD_MAG_LOG10>(P, di, st);
     case FWD_SPEC: return launch_fwd512_t<FWD_SPEC>(P, di, st);
-    case FWD_GL: return launch_fwd512_t<FWD_GL>(P, di, st);
     default: return launch_fwd512_t<FWD_FULL>(P, di, st);
   }
 }
@@ -759,6 +791,8 @@ int aip_griffinlim_f32(const aip_stft_desc* desc, const float* mag, float* angle
   if (!di.ok) return AIP_ERR_DEVICE;
   if (!desc || !mag || !angles || !tprev || !wave_out || n_iter < 0 || momentum < 0.0f) return AIP_ERR_ARG;
   if (B > 0x7fffffffLL || T > 0x7fffffffLL || B < 0 || T < 1) return AIP_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(angles) & 15) || (reinterpret_cast<uintptr_t>(tprev) & 15) ||
+      (reinterpret_cast<uintptr_t>(mag) & 7)) return AIP_ERR_ARG;     // vector access of the state arrays
   if (B == 0) return AIP_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long F = desc->n_fft / 2 + 1;
@@ -778,10 +812,21 @@ int aip_griffinlim_f32(const aip_stft_desc* desc, const float* mag, float* angle
     P.wave = wave_out; P.wave_pitch = out_pitch; P.B = (int)B; P.L = (int)out_len;
     P.mag_kind = MAG_NONE;
     P.spec = reinterpret_cast<float2*>(angles);
-    P.gl_mag = mag; P.gl_tprev = reinterpret_cast<float2*>(tprev);
-    P.gl_has_prev = it > 0; P.gl_alpha = momentum / (1.0f + momentum);
     rc = run_fwd(desc, P, T, st);
     if (rc != AIP_OK) return rc;
+    const float alpha = momentum / (1.0f + momentum);
+    const long long n2 = n / 2;
+    if (n2 > 0) {
+      long long g = (n2 + 255) / 256;
+      if (g > (long long)di.sms * 32) g = (long long)di.sms * 32;
+      gl_update_kernel<<<(unsigned)g, 256, 0, st>>>(reinterpret_cast<float4*>(angles), reinterpret_cast<float4*>(tprev),
+                                                    reinterpret_cast<const float2*>(mag), n2, alpha, it > 0);
+    }
+    if (n & 1)
+      gl_update_tail_kernel<<<1, 1, 0, st>>>(reinterpret_cast<float2*>(angles), reinterpret_cast<float2*>(tprev), mag,
+                                             n - 1, alpha, it > 0);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
   }
   return run_inv(desc, I, 0, workspace, workspace_bytes, st);
 }

@@ -46,11 +46,6 @@ struct FwdParams {
   float* mag;               // [B,257,T_out] or null
   float* phase;             // [B,257,T_out] or null
   float* mask;              // [B,257,T_out] or null
-  // Griffin-Lim update fused into the epilogue (librosa.griffinlim loop body, utils.py:330-332):
-  const float* gl_mag;      // [B,257,T_out] or null
-  float2* gl_tprev;         // [B,257,T_out] read (if gl_has_prev) then overwritten with the rebuilt spectrum
-  int gl_has_prev;
-  float gl_alpha;           // momentum / (1 + momentum)
   int tiles_per_clip;
   int n_tiles;              // B * tiles_per_clip (< 2^31)
   int tile_floats;          // floats per staged-waveform buffer (tile length rounded up to 128 B)
@@ -173,29 +168,6 @@ struct FwdEmitSpec {
   AIP_HM void hi(int j, float xr, float xi) const { phi[-(j * s16)] = make_float2(xr, xi); }
 };
 
-// Epilogue, Griffin-Lim update (librosa.griffinlim loop body, utils.py:330-332):
-//   angles = rebuilt - alpha * tprev ; angles /= |angles| + tiny ; angles *= S ; tprev = rebuilt
-struct FwdEmitGL {
-  float2* spec;             // angles out   (+ b*F*T + t)
-  float2* tprev;            // previous rebuilt spectrum, overwritten
-  const float* mag;         // target magnitudes S
-  int T;
-  float alpha;
-  bool has_prev, active;
-  int olo, ohi, s16;
-  AIP_HM void rows(int k_lo, int k_hi) { olo = k_lo * T; ohi = k_hi * T; s16 = 16 * T; }
-  AIP_HM void lo(int j, float xr, float xi) const { put(olo + j * s16, xr, xi); }
-  AIP_HM void hi(int j, float xr, float xi) const { put(ohi - j * s16, xr, xi); }
-  AIP_HM void put(int o, float xr, float xi) const {
-    if (!active) return;
-    float ar = xr, ai = xi;
-    if (has_prev) { const float2 tp = tprev[o]; ar -= alpha * tp.x; ai -= alpha * tp.y; }
-    tprev[o] = make_float2(xr, xi);
-    const float s = mag[o] / (sqrtf(ar * ar + ai * ai) + kFltMin);
-    spec[o] = make_float2(ar * s, ai * s);
-  }
-};
-
 // Epilogue, general path: any mix of complex / magnitude / phase / mask outputs and the spectrum-domain gap.
 struct FwdEmitFull {
   const FwdParams& P;
@@ -217,13 +189,6 @@ struct FwdEmitFull {
   void put(long long idx, float xr, float xi) const {
     if (!active) return;
     if (zero) { xr = 0.0f; xi = 0.0f; }
-    if (P.gl_mag) {
-      float ar = xr, ai = xi;
-      if (P.gl_has_prev) { const float2 tp = P.gl_tprev[idx]; ar -= P.gl_alpha * tp.x; ai -= P.gl_alpha * tp.y; }
-      P.gl_tprev[idx] = make_float2(xr, xi);
-      const float s = P.gl_mag[idx] / (sqrtf(ar * ar + ai * ai) + kFltMin);
-      xr = ar * s; xi = ai * s;
-    }
     if (P.spec) P.spec[idx] = make_float2(xr, xi);
     if (P.phase) P.phase[idx] = atan2f(xi, xr);
     if (P.mask) P.mask[idx] = maskv;
@@ -249,13 +214,11 @@ enum FwdMode : int {
   FWD_MAG_ABS = 0,      // |S| only
   FWD_MAG_LOG10 = 1,    // log10(|S| + eps) only
   FWD_SPEC = 2,         // complex only
-  FWD_GL = 3,           // Griffin-Lim update
-  FWD_FULL = 4          // everything else
+  FWD_FULL = 3          // everything else
 };
 
 AIP_HDX int fwd_mode_of(const FwdParams& P) {
   const bool plain = !(P.phase || P.mask || P.zero_frames);
-  if (P.gl_mag) return (plain && P.spec && P.gl_tprev && P.mag_kind == MAG_NONE) ? (int)FWD_GL : (int)FWD_FULL;
   if (plain && !P.spec && P.mag_kind == MAG_ABS) return FWD_MAG_ABS;
   if (plain && !P.spec && P.mag_kind == MAG_LOG10_EPS) return FWD_MAG_LOG10;
   if (plain && P.spec && P.mag_kind == MAG_NONE) return FWD_SPEC;
@@ -280,10 +243,6 @@ AIP_HD void fwd_phase2(const FwdParams& P, int tid, const TileCursor& c, const f
     fwd_stage2_compute(zr, zi, w, p, emit);
   } else if (kMode == FWD_SPEC) {
     FwdEmitSpec emit{P.spec + col, P.T_out, nullptr, nullptr, 0};
-    fwd_stage2_compute(zr, zi, w, p, emit);
-  } else if (kMode == FWD_GL) {
-    FwdEmitGL emit{P.spec + col, P.gl_tprev + col, P.gl_mag + col, P.T_out, P.gl_alpha, P.gl_has_prev != 0,
-                   lane < n_valid, 0, 0, 0};
     fwd_stage2_compute(zr, zi, w, p, emit);
   } else {
     FwdEmitFull emit = fwd_make_emit_full(P, c.b, t0 + fr, kBins, lane < n_valid);
