@@ -214,3 +214,27 @@ def test_full_size_properties():
     for b in range(0, B, 97):
         xz[b, int(gaps[b, 0]):int(gaps[b, 1])] = 0
         assert torch.equal(a[b], sp.stft(xz[b:b + 1], plan, mag_kind=sp.MAG_LOG10_EPS, want_spec=False)["mag"][0])
+
+
+def test_config5_end_to_end_cnnblstm_inference(golden_clips):
+    """BASELINE configs[4] shape on one GPU: GPU front-end -> random-init model -> GPU back-end (model_eval.py:146-192)."""
+    from ml_audio_inpainting_b200 import frontend, spectral as sp
+    from tests.support_cnnblstm import StandInBLSTMCNN
+    names = sorted(golden_clips)
+    x = np.stack([golden_clips[n] for n in names])                              # 9 clips x 5 s
+    xd = torch.from_numpy(x).cuda()
+    torch.manual_seed(0)
+    model = StandInBLSTMCNN().cuda().eval()
+    ev = frontend.eval_cnnlstm_batch(xd)                                         # model_eval.py:146-154
+    with torch.no_grad():
+        rec = model.reconstruct_spectrogram(ev["log_impaired_magnitude"], ev["mask"])    # :157-160
+    assert tuple(rec.shape) == (9, 257, 417)
+    # outside the gap frames the blend returns the input bit for bit
+    keep = ev["mask"] == 0
+    assert torch.equal(rec[keep], ev["log_impaired_magnitude"][keep])
+    y = frontend.backend_batch(rec, ev["original_phase"], mag_domain=sp.DOM_POW10).cpu().numpy()     # :163, :179-189 (10** fused)
+    rec_np, ph = rec.cpu().numpy(), ev["original_phase"].cpu().numpy()
+    for b in range(9):
+        ref = cp.eval_backend(10.0 ** rec_np[b], ph[b])                          # oracle: 10** then spectrogram_to_audio(phase=...)
+        assert y[b].shape == ref.shape == (79872,)
+        assert relerr(y[b], ref) < 2 * TOL
