@@ -13,7 +13,9 @@
 //     m = n1 + 16 n2,  k = k2 + 16 k1
 //     stage 1 (16 lanes per frame, lane = n1): Y[n1][k2] = sum_n2 z[n1+16 n2] W16^(n2 k2),  times W256^(n1 k2)
 //     stage 2 (lane = frame, warp = k2 pair):  Zc[k2+16 k1] = sum_n1 Y'[n1][k2] W16^(n1 k1)
-// and the real spectrum follows from the split pass
+// Every 16-point DFT is the register-resident radix-4 x radix-4 codelet fft16x2(), which runs TWO transforms
+// per thread in the two lanes of Blackwell's packed FP32x2 instructions (stage 1: two frames; stage 2: the
+// two jobs of a pair).  The real spectrum follows from the split pass
 //     X[k]     =      (E - jT),   X[256-k] = conj(E + jT),
 //     E = Zc[k] + conj Zc[256-k],  T = W512^k (Zc[k] - conj Zc[256-k])        (the 1/2 is folded into the window).
 // A stage-2 thread owns jobs (p, 16-p) (or (0, 8)), i.e. both members of every (k, 256-k) pair, so
@@ -75,45 +77,14 @@ constexpr float kC1 = 0.92387953251128674f;   // cos(pi/8)
 constexpr float kS1 = 0.38268343236508977f;   // sin(pi/8)
 constexpr float kR2 = 0.70710678118654752f;   // sqrt(1/2)
 
-// slot that holds output bin k after fft16() (4x4 index transpose)
+// slot that holds output bin k after fft16x2() (4x4 index transpose of the radix-4 x radix-4 codelet)
 AIP_HD constexpr int perm16(int k) { return ((k & 3) << 2) | (k >> 2); }
-
-AIP_HD void radix4(float& ar, float& ai, float& br, float& bi,
-                   float& cr, float& ci, float& dr, float& di) {
-  const float s0r = ar + cr, s0i = ai + ci, s1r = ar - cr, s1i = ai - ci;
-  const float s2r = br + dr, s2i = bi + di, s3r = br - dr, s3i = bi - di;
-  ar = s0r + s2r; ai = s0i + s2i;          // y0
-  cr = s0r - s2r; ci = s0i - s2i;          // y2
-  br = s1r + s3i; bi = s1i - s3r;          // y1 = s1 - j s3
-  dr = s1r - s3i; di = s1i + s3r;          // y3 = s1 + j s3
-}
 
 // x *= (wr + j wi)
 AIP_HD void cmul(float& xr, float& xi, float wr, float wi) {
   const float tr = xr * wr - xi * wi;
   xi = xr * wi + xi * wr;
   xr = tr;
-}
-
-// Forward 16-point complex DFT, in place; input natural order, output bin k in slot perm16(k).
-// The inverse (unnormalised, e^{+j}) is fft16(im, re).
-AIP_HD void fft16(float (&r)[16], float (&i)[16]) {
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-    radix4(r[a], i[a], r[a + 4], i[a + 4], r[a + 8], i[a + 8], r[a + 12], i[a + 12]);
-  // slot a + 4q now holds y_q of column a; twiddle by W16^(a q)
-  cmul(r[5], i[5], kC1, -kS1);                                   // W16^1
-  cmul(r[9], i[9], kR2, -kR2);                                   // W16^2
-  cmul(r[13], i[13], kS1, -kC1);                                 // W16^3
-  cmul(r[6], i[6], kR2, -kR2);                                   // W16^2
-  { const float t = r[10]; r[10] = i[10]; i[10] = -t; }          // W16^4 = -j
-  cmul(r[14], i[14], -kR2, -kR2);                                // W16^6
-  cmul(r[7], i[7], kS1, -kC1);                                   // W16^3
-  cmul(r[11], i[11], -kR2, -kR2);                                // W16^6
-  cmul(r[15], i[15], -kC1, kS1);                                 // W16^9
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-    radix4(r[4 * q], i[4 * q], r[4 * q + 1], i[4 * q + 1], r[4 * q + 2], i[4 * q + 2], r[4 * q + 3], i[4 * q + 3]);
 }
 
 // ---- packed FP32x2 (Blackwell FADD2 / FMUL2 / FFMA2: two fp32 lanes per issue slot) --------------------
@@ -148,7 +119,8 @@ AIP_HD void cmulx2(float2& xr, float2& xi, float wr, float wi) {
   xr = tr;
 }
 
-// two forward 16-point complex DFTs at once (lane .x and lane .y), same slot convention as fft16()
+// Two forward 16-point complex DFTs at once (lane .x and lane .y), in place; input natural order, output
+// bin k in slot perm16(k).  The inverse (unnormalised, e^{+j}) is fft16x2(im, re).
 AIP_HD void fft16x2(float2 (&r)[16], float2 (&i)[16]) {
 #pragma unroll
   for (int a = 0; a < 4; ++a)
