@@ -187,8 +187,8 @@ struct WaitBefore {
 //   stage-A warps (lane = frame): HBM -> registers, split-pass prologue, 2 x inverse 16-pt DFT -> exch[i % 3]
 //   stage-B warps (lane = n1): twiddle, inverse 16-pt DFT, synthesis window (in place: the exchange buffer
 //   becomes the frame buffer) -> named barrier -> overlap-add + 1/window-sum-square -> HBM -> release
-// Stage A computes tile i+1 in registers while stage B works on tile i and only then waits for the exchange
-// buffer; a ring of n_bufs buffers is supported, one measured fastest (see kInvBufsDefault).
+// Stage A computes tile i+1 in registers while stage B works on tile i and only then waits for an exchange
+// buffer; a ring of n_bufs buffers is supported, two measured fastest (see kInvBufsDefault).
 template <int kMode>
 __global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParams P) {
   extern __shared__ __align__(128) float smem[];

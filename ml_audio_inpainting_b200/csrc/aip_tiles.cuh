@@ -315,6 +315,12 @@ struct InvLoadFull {        // magnitude (+ phase) input with the dB / 10** / ex
   }
 };
 
+#if defined(__CUDACC__)
+AIP_HD float2 ldg_stream(const float2* p) { return __ldcg(p); }      // L2 only: the spectrum is read once
+#else
+AIP_HD float2 ldg_stream(const float2* p) { return *p; }
+#endif
+
 struct InvLoadSpec {        // complex input straight from HBM
   const float2* col;        // spec + b*F*T + t
   int T;
@@ -322,8 +328,8 @@ struct InvLoadSpec {        // complex input straight from HBM
   const float2* phi;
   int s16;
   AIP_HM void rows(int k_lo, int k_hi) { plo = col + k_lo * T; phi = col + k_hi * T; s16 = 16 * T; }
-  AIP_HM void lo(int j, float& xr, float& xi) const { const float2 v = plo[j * s16]; xr = v.x; xi = v.y; }
-  AIP_HM void hi(int j, float& xr, float& xi) const { const float2 v = phi[-(j * s16)]; xr = v.x; xi = v.y; }
+  AIP_HM void lo(int j, float& xr, float& xi) const { const float2 v = ldg_stream(plo + j * s16); xr = v.x; xi = v.y; }
+  AIP_HM void hi(int j, float& xr, float& xi) const { const float2 v = ldg_stream(phi - j * s16); xr = v.x; xi = v.y; }
 };
 
 // input modes of the inverse kernel (template parameter).  (A cp.async-staged variant of the complex input,
@@ -335,8 +341,7 @@ enum InvMode : int {
 };
 
 constexpr int kInvBufs = 3;     // most exchange buffers the ring supports
-constexpr int kInvBufsDefault = 1;   // measured best (0.76 / 0.78 / 1.03 ms for 1 / 2 / 3): a deeper ring takes the
-                                     // shared-memory carve-out from L1, which the stage-A global loads rely on
+constexpr int kInvBufsDefault = 2;   // measured 0.753 / 0.735 / 0.991 ms for 1 / 2 / 3 buffers (L2-only loads)
 constexpr int kMaxWtab = 1024;  // largest hop with a shared-memory 1/wss period table
 
 // stage A for one tile: 256 threads, lane = frame, warp = pair-job
