@@ -91,7 +91,7 @@ AIP_HD void cmul(float& xr, float& xi, float wr, float wi) {
 // The FP32 pipe does not get wider, but these kernels are issue-slot bound, and every 16-point DFT here has
 // an identical twin (the two pair-jobs of a stage-2 thread, the two frames of a stage-1 thread): .x carries
 // one, .y the other.
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) && !defined(AIP_SCALAR_FFT)
 AIP_HD float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 AIP_HD float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }   // exact a - b
 AIP_HD float2 mul2s(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
