@@ -56,9 +56,11 @@ int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, 
     for (int tid = 0; tid < kThreads; ++tid) fwd_phase1(P, tid, tile.data(), exch.data(), win_s, lc[tid]);
     for (int tid = 0; tid < kThreads; ++tid) {
       switch (mode) {
-        case FWD_MAG_ABS: fwd_phase2<FWD_MAG_ABS>(P, tid, c, exch.data(), pw[tid], rel); break;
-        case FWD_MAG_LOG10: fwd_phase2<FWD_MAG_LOG10>(P, tid, c, exch.data(), pw[tid], rel); break;
-        case FWD_SPEC: fwd_phase2<FWD_SPEC>(P, tid, c, exch.data(), pw[tid], rel); break;
+#define AIP_CASE(M) case (M): fwd_phase2<(M)>(P, tid, c, exch.data(), pw[tid], rel); break;
+        AIP_CASE(FWD_MAG_ABS) AIP_CASE(FWD_MAG_LOG10) AIP_CASE(FWD_SPEC) AIP_CASE(MAG_LOG10_EPS | FWD_MASK)
+        AIP_CASE(MAG_LOG1P_POW) AIP_CASE(MAG_LOG1P_POW | FWD_PHASE | FWD_MASK) AIP_CASE(FWD_SPEC | FWD_PHASE | FWD_MASK)
+        AIP_CASE(MAG_LOG10_EPS | FWD_ZERO) AIP_CASE(MAG_ABS | FWD_PHASE)
+#undef AIP_CASE
         default: fwd_phase2<FWD_FULL>(P, tid, c, exch.data(), pw[tid], rel); break;
       }
     }
@@ -118,8 +120,11 @@ int emul_istft512(const float* spec, const float* mag, const float* phase, int m
   TileCursor c = tile_cursor(0, P.tiles_per_clip);
   for (int tix = 0; tix < P.n_tiles; ++tix) {
     for (int tid = 0; tid < kThreads; ++tid) {
-      if (spec) inv_phase0<INV_SPEC>(P, tid, c, exch.data(), pw[tid], rel);
-      else inv_phase0<INV_FULL>(P, tid, c, exch.data(), pw[tid], rel);
+      switch (inv_mode_of(P)) {
+#define AIP_CASE(M) case (M): inv_phase0<(M)>(P, tid, c, exch.data(), pw[tid], rel); break;
+        AIP_CASE(INV_SPEC) AIP_CASE(1) AIP_CASE(2) AIP_CASE(3) AIP_CASE(4) AIP_CASE(5) AIP_CASE(6)
+#undef AIP_CASE
+      }
     }
     for (int tid = 0; tid < kThreads; ++tid) inv_phase1(P, tid, exch.data(), win_s, lc[tid]);
     for (int tid = 0; tid < kThreads; ++tid) inv_phase2(P, tid, c, exch.data(), wtab.empty() ? nullptr : wtab.data());

@@ -319,11 +319,11 @@ __global__ void __launch_bounds__(256) istft_generic_frames_kernel(const Generic
   for (int fix = blockIdx.x; fix < P.n_tiles; fix += gridDim.x) {
     const int b = (int)(fix / P.n_frames);
     const int t = (int)(fix % P.n_frames);
-    InvLoadFull load{P, (long long)b * G.F * P.T + t, P.db_flags ? (P.db_flags[b] != 0) : false, 0, 0, 0};
+    const bool db = P.db_flags ? (P.db_flags[b] != 0) : false;
+    const long long base = (long long)b * G.F * P.T + t;
     for (int k = threadIdx.x; k < G.F; k += blockDim.x) {
       float xr, xi;
-      load.rows(k, k);
-      load.lo(0, xr, xi);
+      inv_load_runtime(P, base + (long long)k * P.T, db, xr, xi);
       if (k == 0 || k == N / 2) xi = 0.0f;
       buf[__brev((unsigned)k) >> (32 - G.logN)] = make_float2(xr, xi);
       if (k != 0 && k != N / 2) buf[__brev((unsigned)(N - k)) >> (32 - G.logN)] = make_float2(xr, -xi);
@@ -610,6 +610,12 @@ static cudaError_t launch_fwd512(const FwdParams& P, const DevInfo& di, cudaStre
     case FWD_MAG_ABS: return launch_fwd512_t<FWD_MAG_ABS>(P, di, st);
     case FWD_MAG_LOG10: return launch_fwd512_t<FWD_MAG_LOG10>(P, di, st);
     case FWD_SPEC: return launch_fwd512_t<FWD_SPEC>(P, di, st);
+    case MAG_LOG10_EPS | FWD_MASK: return launch_fwd512_t<MAG_LOG10_EPS | FWD_MASK>(P, di, st);
+    case MAG_LOG1P_POW: return launch_fwd512_t<MAG_LOG1P_POW>(P, di, st);
+    case MAG_LOG1P_POW | FWD_PHASE | FWD_MASK: return launch_fwd512_t<MAG_LOG1P_POW | FWD_PHASE | FWD_MASK>(P, di, st);
+    case FWD_SPEC | FWD_PHASE | FWD_MASK: return launch_fwd512_t<FWD_SPEC | FWD_PHASE | FWD_MASK>(P, di, st);
+    case MAG_LOG10_EPS | FWD_ZERO: return launch_fwd512_t<MAG_LOG10_EPS | FWD_ZERO>(P, di, st);
+    case MAG_ABS | FWD_PHASE: return launch_fwd512_t<MAG_ABS | FWD_PHASE>(P, di, st);
     default: return launch_fwd512_t<FWD_FULL>(P, di, st);
   }
 }
@@ -695,7 +701,16 @@ static int run_inv(const aip_stft_desc* desc, InvParams P, long long length, voi
     if (grid > P.n_tiles) grid = P.n_tiles;
     P.tiles_per_cta = (P.n_tiles + grid - 1) / grid;
     grid = (P.n_tiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
-    auto kern = P.spec ? istft512_kernel<INV_SPEC> : istft512_kernel<INV_FULL>;
+    void (*kern)(const InvParams) = nullptr;
+    switch (inv_mode_of(P)) {
+      case INV_SPEC: kern = istft512_kernel<INV_SPEC>; break;
+      case inv_mag_mode(0, false): kern = istft512_kernel<inv_mag_mode(0, false)>; break;
+      case inv_mag_mode(0, true): kern = istft512_kernel<inv_mag_mode(0, true)>; break;
+      case inv_mag_mode(1, false): kern = istft512_kernel<inv_mag_mode(1, false)>; break;
+      case inv_mag_mode(1, true): kern = istft512_kernel<inv_mag_mode(1, true)>; break;
+      case inv_mag_mode(2, false): kern = istft512_kernel<inv_mag_mode(2, false)>; break;
+      default: kern = istft512_kernel<inv_mag_mode(2, true)>; break;
+    }
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<(unsigned)grid, kFwdThreads, smem, st>>>(P);

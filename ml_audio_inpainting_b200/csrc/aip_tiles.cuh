@@ -131,41 +131,39 @@ AIP_HD float mag_value(int mk, float xr, float xi, float eps, float power) {
   return (mk == MAG_LOG1P_POW) ? log1pf(mp) : mp;
 }
 
-// Epilogue, magnitude-only fast path.  A stage-2 thread writes bins k_lo + 16 j and k_hi - 16 j of ONE frame
-// (its lane): two row pointers are set per job (rows()), each store is then pointer + j * (16 T) -- and, the
-// lane being the frame index, a warp's store of one bin is 32 consecutive floats of that row.  No predicates:
-// in the last tile of a clip the lanes past T_out recompute the last valid frame and store the same values.
-template <int kMag>
-struct FwdEmitFast {
-  float* col;               // mag + b*F*T_out + t
-  int T;                    // T_out
-  float eps, power;
-  float* plo;
-  float* phi;
-  int s16;
-  AIP_HM void rows(int k_lo, int k_hi) {
-    plo = col + k_lo * T;
-    phi = col + k_hi * T;
-    s16 = 16 * T;
-  }
-  AIP_HM void lo(int j, float xr, float xi) const { plo[j * s16] = mag_value(kMag, xr, xi, eps, power); }
-  AIP_HM void hi(int j, float xr, float xi) const { phi[-(j * s16)] = mag_value(kMag, xr, xi, eps, power); }
-};
+// Forward kernel variants: a bit mask of what the epilogue produces, a template parameter of the kernel so
+// that each variant is straight-line code (no per-bin branches, no calls).
+//   bits 0..2  magnitude kind (MagKind: 0 none, 1 |S|, 2 log10(|S|+eps), 3 log1p(|S|), 4 reserved -> fallback)
+//   FWD_SPEC   complex output          FWD_PHASE  angle(S)        FWD_MASK  dense frame mask
+//   FWD_ZERO   spectrum-domain gap (frames [f0,f1) zeroed before the epilogue, models/model_eval.py:154)
+//   FWD_FULL   run-time flags, out-of-line epilogue: every other combination (|S|**p with p != 1, ...)
+enum FwdModeBits : int { FWD_SPEC = 8, FWD_PHASE = 16, FWD_MASK = 32, FWD_ZERO = 64, FWD_FULL = 128 };
+constexpr int FWD_MAG_ABS = MAG_ABS, FWD_MAG_LOG10 = MAG_LOG10_EPS;      // the two magnitude-only variants
 
-// Epilogue, complex-only fast path (utils.extract_spectrogram's own output): one float2 store per bin.
-struct FwdEmitSpec {
-  float2* col;              // spec + b*F*T_out + t
-  int T;
-  float2* plo;
-  float2* phi;
-  int s16;
-  AIP_HM void rows(int k_lo, int k_hi) {
-    plo = col + k_lo * T;
-    phi = col + k_hi * T;
-    s16 = 16 * T;
+// A stage-2 thread writes bins k_lo + 16 j and k_hi - 16 j of ONE frame (its lane): two row offsets are set
+// per job (rows()), each store is then column pointer + offset + j * (16 T) -- and, the lane being the frame
+// index, a warp's store of one bin is 32 consecutive elements of that row.  No predicates: in the last tile
+// of a clip the lanes past T_out recompute the last valid frame and store the same values.
+template <int kM>
+struct FwdEmitT {
+  float* mag;               // column pointers: array + b*F*T_out + t
+  float2* spec;
+  float* phase;
+  float* mask;
+  int T;                    // T_out
+  float eps, maskv;
+  bool zero;
+  int olo, ohi, s16;
+  AIP_HM void rows(int k_lo, int k_hi) { olo = k_lo * T; ohi = k_hi * T; s16 = 16 * T; }
+  AIP_HM void lo(int j, float xr, float xi) const { put(olo + j * s16, xr, xi); }
+  AIP_HM void hi(int j, float xr, float xi) const { put(ohi - j * s16, xr, xi); }
+  AIP_HM void put(int o, float xr, float xi) const {
+    if (kM & FWD_ZERO) { if (zero) { xr = 0.0f; xi = 0.0f; } }
+    if (kM & FWD_SPEC) spec[o] = make_float2(xr, xi);
+    if (kM & FWD_PHASE) phase[o] = atan2f(xi, xr);
+    if (kM & FWD_MASK) mask[o] = maskv;
+    if (kM & 7) mag[o] = mag_value(kM & 7, xr, xi, eps, 1.0f);
   }
-  AIP_HM void lo(int j, float xr, float xi) const { plo[j * s16] = make_float2(xr, xi); }
-  AIP_HM void hi(int j, float xr, float xi) const { phi[-(j * s16)] = make_float2(xr, xi); }
 };
 
 // Epilogue, general path: any mix of complex / magnitude / phase / mask outputs and the spectrum-domain gap.
@@ -209,20 +207,21 @@ AIP_HD FwdEmitFull fwd_make_emit_full(const FwdParams& P, int b, int t, int n_bi
 
 struct NoRelease { AIP_HM void operator()() const {} };
 
-// kernel variants (template parameter kMode of the forward kernel)
-enum FwdMode : int {
-  FWD_MAG_ABS = 0,      // |S| only
-  FWD_MAG_LOG10 = 1,    // log10(|S| + eps) only
-  FWD_SPEC = 2,         // complex only
-  FWD_FULL = 3          // everything else
-};
+// the variants that are instantiated; anything else runs FWD_FULL
+AIP_HDX bool fwd_mode_is_fast(int m) {
+  return m == FWD_MAG_ABS || m == FWD_MAG_LOG10 || m == FWD_SPEC || m == (MAG_LOG10_EPS | FWD_MASK) ||
+         m == MAG_LOG1P_POW || m == (MAG_LOG1P_POW | FWD_PHASE | FWD_MASK) || m == (FWD_SPEC | FWD_PHASE | FWD_MASK) ||
+         m == (MAG_LOG10_EPS | FWD_ZERO) || m == (MAG_ABS | FWD_PHASE);
+}
 
 AIP_HDX int fwd_mode_of(const FwdParams& P) {
-  const bool plain = !(P.phase || P.mask || P.zero_frames);
-  if (plain && !P.spec && P.mag_kind == MAG_ABS) return FWD_MAG_ABS;
-  if (plain && !P.spec && P.mag_kind == MAG_LOG10_EPS) return FWD_MAG_LOG10;
-  if (plain && P.spec && P.mag_kind == MAG_NONE) return FWD_SPEC;
-  return FWD_FULL;
+  int m = P.mag_kind;
+  if (P.mag_kind == MAG_POW || (P.mag_kind == MAG_LOG1P_POW && P.power != 1.0f)) return FWD_FULL;
+  if (P.spec) m |= FWD_SPEC;
+  if (P.phase) m |= FWD_PHASE;
+  if (P.mask) m |= FWD_MASK;
+  if (P.zero_frames) m |= FWD_ZERO;
+  return fwd_mode_is_fast(m) ? m : (int)FWD_FULL;
 }
 
 // stage 2 + split pass + epilogue for one tile: 256 threads, lane = frame, warp = pair-job.
@@ -238,14 +237,20 @@ AIP_HD void fwd_phase2(const FwdParams& P, int tid, const TileCursor& c, const f
   fwd_stage2_load(exch, fr, p, zr, zi);
   release();
   const long long col = (long long)c.b * kBins * P.T_out + t0 + fr;
-  if (kMode == FWD_MAG_ABS || kMode == FWD_MAG_LOG10) {
-    FwdEmitFast<(kMode == FWD_MAG_ABS ? (int)MAG_ABS : (int)MAG_LOG10_EPS)> emit{P.mag + col, P.T_out, P.eps, P.power, nullptr, nullptr, 0};
-    fwd_stage2_compute(zr, zi, w, p, emit);
-  } else if (kMode == FWD_SPEC) {
-    FwdEmitSpec emit{P.spec + col, P.T_out, nullptr, nullptr, 0};
+  if (kMode == FWD_FULL) {
+    FwdEmitFull emit = fwd_make_emit_full(P, c.b, t0 + fr, kBins, lane < n_valid);
     fwd_stage2_compute(zr, zi, w, p, emit);
   } else {
-    FwdEmitFull emit = fwd_make_emit_full(P, c.b, t0 + fr, kBins, lane < n_valid);
+    const int t = t0 + fr;
+    FwdEmitT<kMode> emit{(kMode & 7) ? P.mag + col : nullptr, (kMode & FWD_SPEC) ? P.spec + col : nullptr,
+                         (kMode & FWD_PHASE) ? P.phase + col : nullptr, (kMode & FWD_MASK) ? P.mask + col : nullptr,
+                         P.T_out, P.eps, 0.0f, false, 0, 0, 0};
+    if (kMode & FWD_MASK) {
+      bool in = false;
+      if (P.mask_frames) in = (t >= P.mask_frames[2 * c.b] && t < P.mask_frames[2 * c.b + 1]);
+      emit.maskv = (in == (P.mask_in_gap_is_one != 0)) ? 1.0f : 0.0f;
+    }
+    if (kMode & FWD_ZERO) emit.zero = (t >= P.zero_frames[2 * c.b] && t < P.zero_frames[2 * c.b + 1]);
     fwd_stage2_compute(zr, zi, w, p, emit);
   }
 }
@@ -283,33 +288,28 @@ struct InvParams {
 
 // Prologue loaders.  A stage-A thread reads bins k_lo + 16 j and k_hi - 16 j of ONE frame (its lane), so a
 // warp's load of one bin is 32 consecutive elements of that row of the [F, T] input.
-struct InvLoadFull {        // magnitude (+ phase) input with the dB / 10** / expm1 prologue
-  const InvParams& P;
-  long long base;           // b*F*T + t
-  bool db;
-  long long off_lo, off_hi;
-  int s16;
-  AIP_HM void rows(int k_lo, int k_hi) {
-    off_lo = base + (long long)k_lo * P.T;
-    off_hi = base + (long long)k_hi * P.T;
-    s16 = 16 * P.T;
-  }
-  AIP_HM void lo(int j, float& xr, float& xi) const { get(off_lo + j * s16, xr, xi); }
-  AIP_HM void hi(int j, float& xr, float& xi) const { get(off_hi - j * s16, xr, xi); }
-  AIP_HM void get(long long idx, float& xr, float& xi) const {
-    if (P.spec) {
-      const float2 v = P.spec[idx];
-      xr = v.x; xi = v.y;
-      return;
-    }
-    float m = P.mag[idx];
-    const int dom = db ? (int)DOM_DB : P.mag_domain;
-    if (dom == DOM_POW10) m = fast_exp2(m * kLog2of10);
-    else if (dom == DOM_DB) m = fast_exp2(m * (kLog2of10 * 0.05f));
-    else if (dom == DOM_EXPM1) m = expm1f(m);
-    if (P.phase) {
+// Magnitude (+ phase) input with the prologue fused, specialised at compile time.
+//   kDom 0: linear, or dB where the clip's auto flag says so (utils.py:313-314)   1: 2**(x*scale) (10**x or dB)
+//   kDom 2: expm1(x)
+template <int kDom, bool kPhase>
+struct InvLoadMag {
+  const float* mag;         // column pointers: array + b*F*T + t
+  const float* phase;
+  int T;
+  float scale;              // log2(10) for 10**x, log2(10)/20 for dB
+  bool db;                  // kDom == 0: this clip is in dB
+  int olo, ohi, s16;
+  AIP_HM void rows(int k_lo, int k_hi) { olo = k_lo * T; ohi = k_hi * T; s16 = 16 * T; }
+  AIP_HM void lo(int j, float& xr, float& xi) const { get(olo + j * s16, xr, xi); }
+  AIP_HM void hi(int j, float& xr, float& xi) const { get(ohi - j * s16, xr, xi); }
+  AIP_HM void get(int o, float& xr, float& xi) const {
+    float m = mag[o];
+    if (kDom == 0) m = db ? fast_exp2(m * (kLog2of10 * 0.05f)) : m;
+    else if (kDom == 1) m = fast_exp2(m * scale);
+    else m = expm1f(m);
+    if (kPhase) {
       float s, c;
-      fast_sincos(P.phase[idx], s, c);
+      fast_sincos(phase[o], s, c);
       xr = m * c; xi = m * s;
     } else { xr = m; xi = 0.0f; }
   }
@@ -332,13 +332,30 @@ struct InvLoadSpec {        // complex input straight from HBM
   AIP_HM void hi(int j, float& xr, float& xi) const { const float2 v = ldg_stream(phi - j * s16); xr = v.x; xi = v.y; }
 };
 
-// input modes of the inverse kernel (template parameter).  (A cp.async-staged variant of the complex input,
-// one tile ahead through shared memory, measured 1.47x SLOWER than plain loads: 8-byte LDGSTS throttles the
-// LSU and adds an LDS per element; see profiles/README.md.)
-enum InvMode : int {
-  INV_FULL = 0,         // magnitude (+ phase) input with the dB / 10** / expm1 prologue
-  INV_SPEC = 1          // complex input
-};
+// run-time flavoured element fetch (generic n_fft kernels only)
+AIP_HD void inv_load_runtime(const InvParams& P, long long idx, bool db, float& xr, float& xi) {
+  if (P.spec) { const float2 v = P.spec[idx]; xr = v.x; xi = v.y; return; }
+  float m = P.mag[idx];
+  const int dom = db ? (int)DOM_DB : P.mag_domain;
+  if (dom == DOM_POW10) m = fast_exp2(m * kLog2of10);
+  else if (dom == DOM_DB) m = fast_exp2(m * (kLog2of10 * 0.05f));
+  else if (dom == DOM_EXPM1) m = expm1f(m);
+  if (P.phase) { float sn, cs; fast_sincos(P.phase[idx], sn, cs); xr = m * cs; xi = m * sn; }
+  else { xr = m; xi = 0.0f; }
+}
+
+// Input modes of the inverse kernel (template parameter): INV_SPEC = complex input; otherwise
+// 1 + 2*kDom + kPhase for magnitude (+ phase) input.  (A cp.async-staged variant of the complex input, one tile
+// ahead through shared memory, measured 1.47x SLOWER than plain loads: 8-byte LDGSTS throttles the LSU and adds
+// an LDS per element; see profiles/README.md.)
+constexpr int INV_SPEC = 0;
+AIP_HDX constexpr int inv_mag_mode(int dom, bool phase) { return 1 + 2 * dom + (phase ? 1 : 0); }
+
+AIP_HDX int inv_mode_of(const InvParams& P) {
+  if (P.spec) return INV_SPEC;
+  const int dom = (P.mag_domain == DOM_LINEAR) ? 0 : (P.mag_domain == DOM_EXPM1 ? 2 : 1);
+  return inv_mag_mode(dom, P.phase != nullptr);
+}
 
 constexpr int kInvBufs = 3;     // most exchange buffers the ring supports
 constexpr int kInvBufsDefault = 2;   // measured 0.753 / 0.735 / 0.991 ms for 1 / 2 / 3 buffers (L2-only loads)
@@ -351,11 +368,16 @@ AIP_HD void inv_phase0(const InvParams& P, int tid, const TileCursor& c, float2*
   const int warp = tid >> 5, lane = tid & 31;
   const int t = c.tt * P.g.FO - P.g.HL + lane;
   const bool live = (t >= 0 && t < P.n_frames);
+  const long long col = (long long)c.b * kBins * P.T + t;
   if (kMode == INV_SPEC) {
-    InvLoadSpec load{P.spec + ((long long)c.b * kBins * P.T + t), P.T, nullptr, nullptr, 0};
+    InvLoadSpec load{P.spec + col, P.T, nullptr, nullptr, 0};
     inv_stageA(exch, w, lane, warp, live, load, before_store);
   } else {
-    InvLoadFull load{P, (long long)c.b * kBins * P.T + t, P.db_flags ? (P.db_flags[c.b] != 0) : false, 0, 0, 0};
+    constexpr int kDom = (kMode - 1) >> 1;
+    constexpr bool kPhase = ((kMode - 1) & 1) != 0;
+    InvLoadMag<kDom, kPhase> load{P.mag + col, kPhase ? P.phase + col : nullptr, P.T,
+                                  P.mag_domain == DOM_DB ? kLog2of10 * 0.05f : kLog2of10,
+                                  P.db_flags ? (P.db_flags[c.b] != 0) : false, 0, 0, 0};
     inv_stageA(exch, w, lane, warp, live, load, before_store);
   }
 }
