@@ -11,6 +11,7 @@
  *                           + time-domain gap zeroing before the transform         utils.py:141-142, :180-183, add_gaps.py:28-32
  *   aip_istft_f32           librosa.istft as called by utils.spectrogram_to_audio  utils.py:316-327
  *                           (complex input, or magnitude * exp(j*phase), dB / 10** / expm1 prologue)
+ *   aip_istft_blend_f32     mask blend + 10** + phase reuse + istft               models/CNNBLSTM/model.py:108, models/model_eval.py:160-189
  *   aip_griffinlim_f32      librosa.griffinlim (momentum 0.99)                     utils.py:328-332
  *   aip_db_heuristic_f32    "max < 0 and mean < 0 => dB" test                      utils.py:313-314
  *   aip_gap_zero_f32        zero a sample range per clip                           utils.py:180-183, add_gaps.py:28-32, pre_process_dataset.py:38
@@ -97,6 +98,15 @@ int aip_istft_f32(const aip_stft_desc* desc,
                   int64_t B, int64_t T, int64_t length, const float* inv_wss,
                   float* wave_out, int64_t out_pitch,
                   void* workspace, size_t workspace_bytes, void* stream);
+/* The model hand-off of the CNN-BLSTM path fused into the inverse prologue (reference models/CNNBLSTM/model.py:108,
+ * models/model_eval.py:160-163, :179-189):  m = model_out * blend_mask + blend_in * (1 - blend_mask);
+ * magnitude = 10 ** m (AIP_DOM_POW10) or 10 ** (m / 20) (AIP_DOM_DB);  X = magnitude * exp(j * phase);  istft(X).
+ * All four inputs are [B,F,T] float32.                                                                        */
+int aip_istft_blend_f32(const aip_stft_desc* desc, const float* model_out, const float* blend_in,
+                        const float* blend_mask, const float* phase, int32_t mag_domain,
+                        int64_t B, int64_t T, int64_t length, const float* inv_wss,
+                        float* wave_out, int64_t out_pitch,
+                        void* workspace, size_t workspace_bytes, void* stream);
 /* 0 when the (n_fft, hop, center) combination runs the fused n_fft = 512 kernel. */
 size_t aip_istft_workspace_bytes(const aip_stft_desc* desc, int64_t B, int64_t T);
 

@@ -71,9 +71,11 @@ int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, 
 
 int emul_istft512(const float* spec, const float* mag, const float* phase, int mag_domain,
                   const int* db_flags, int B, int T, int length, int hop, int center,
-                  const float* window, const float* inv_wss, float* out, long long out_pitch) {
+                  const float* window, const float* inv_wss, float* out, long long out_pitch,
+                  const float* blend_in, const float* blend_mask) {
   InvParams P;
   memset(&P, 0, sizeof(P));
+  P.blend_in = blend_in; P.blend_mask = blend_mask;
   P.spec = reinterpret_cast<const float2*>(spec); P.mag = mag; P.phase = phase; P.mag_domain = mag_domain;
   P.db_flags = db_flags; P.B = B; P.T = T;
   P.hop = hop; P.pad = center ? 256 : 0;
@@ -122,7 +124,7 @@ int emul_istft512(const float* spec, const float* mag, const float* phase, int m
     for (int tid = 0; tid < kThreads; ++tid) {
       switch (inv_mode_of(P)) {
 #define AIP_CASE(M) case (M): inv_phase0<(M)>(P, tid, c, exch.data(), pw[tid], rel); break;
-        AIP_CASE(INV_SPEC) AIP_CASE(1) AIP_CASE(2) AIP_CASE(3) AIP_CASE(4) AIP_CASE(5) AIP_CASE(6)
+        AIP_CASE(INV_SPEC) AIP_CASE(1) AIP_CASE(2) AIP_CASE(3) AIP_CASE(4) AIP_CASE(5) AIP_CASE(6) AIP_CASE(INV_BLEND)
 #undef AIP_CASE
       }
     }

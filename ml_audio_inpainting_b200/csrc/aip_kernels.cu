@@ -709,6 +709,7 @@ static int run_inv(const aip_stft_desc* desc, InvParams P, long long length, voi
       case inv_mag_mode(1, false): kern = istft512_kernel<inv_mag_mode(1, false)>; break;
       case inv_mag_mode(1, true): kern = istft512_kernel<inv_mag_mode(1, true)>; break;
       case inv_mag_mode(2, false): kern = istft512_kernel<inv_mag_mode(2, false)>; break;
+      case INV_BLEND: kern = istft512_kernel<INV_BLEND>; break;
       default: kern = istft512_kernel<inv_mag_mode(2, true)>; break;
     }
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -768,6 +769,19 @@ int aip_stft_fwd_f32(const aip_stft_desc* desc, const float* wave, int64_t B, in
   P.mag_kind = mag_kind; P.eps = eps; P.power = power;
   P.spec = reinterpret_cast<float2*>(spec_out); P.mag = mag_out; P.phase = phase_out; P.mask = mask_out;
   return run_fwd(desc, P, T_out, static_cast<cudaStream_t>(stream));
+}
+
+int aip_istft_blend_f32(const aip_stft_desc* desc, const float* model_out, const float* blend_in, const float* blend_mask,
+                        const float* phase, int32_t mag_domain, int64_t B, int64_t T, int64_t length,
+                        const float* inv_wss, float* wave_out, int64_t out_pitch, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  if (B > 0x7fffffffLL || T > 0x7fffffffLL) return AIP_ERR_ARG;
+  if (!model_out || !blend_in || !blend_mask || !phase) return AIP_ERR_ARG;
+  if (mag_domain != DOM_POW10 && mag_domain != DOM_DB) return AIP_ERR_UNSUPPORTED;
+  InvParams P{};
+  P.mag = model_out; P.blend_in = blend_in; P.blend_mask = blend_mask; P.phase = phase; P.mag_domain = mag_domain;
+  P.B = (int)B; P.T = (int)T; P.inv_wss = inv_wss; P.out = wave_out; P.out_pitch = out_pitch;
+  return run_inv(desc, P, length, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 size_t aip_istft_workspace_bytes(const aip_stft_desc* desc, int64_t B, int64_t T) {

@@ -264,6 +264,8 @@ struct InvParams {
   const float* phase;       // [B,257,T] or null (zero phase)
   int mag_domain;
   const int* db_flags;      // [B] or null: per clip, non-zero => treat mag as dB (utils.py:313-314 heuristic)
+  const float* blend_in;    // [B,257,T] or null: mag := mag * blend_mask + blend_in * (1 - blend_mask) first
+  const float* blend_mask;  // [B,257,T]        (StackedBLSTMCNN.reconstruct_spectrogram, models/CNNBLSTM/model.py:108)
   int B, T;                 // T = frames per clip in the input (row pitch)
   int n_frames;             // frames used (librosa.istft: min(T, ceil(padded_length / hop)) when length given)
   int hop, pad;
@@ -291,10 +293,12 @@ struct InvParams {
 // Magnitude (+ phase) input with the prologue fused, specialised at compile time.
 //   kDom 0: linear, or dB where the clip's auto flag says so (utils.py:313-314)   1: 2**(x*scale) (10**x or dB)
 //   kDom 2: expm1(x)
-template <int kDom, bool kPhase>
+template <int kDom, bool kPhase, bool kBlend>
 struct InvLoadMag {
   const float* mag;         // column pointers: array + b*F*T + t
   const float* phase;
+  const float* bin;         // blend input / mask (kBlend)
+  const float* bmask;
   int T;
   float scale;              // log2(10) for 10**x, log2(10)/20 for dB
   bool db;                  // kDom == 0: this clip is in dB
@@ -304,6 +308,7 @@ struct InvLoadMag {
   AIP_HM void hi(int j, float& xr, float& xi) const { get(ohi - j * s16, xr, xi); }
   AIP_HM void get(int o, float& xr, float& xi) const {
     float m = mag[o];
+    if (kBlend) { const float g = bmask[o]; m = m * g + bin[o] * (1.0f - g); }
     if (kDom == 0) m = db ? fast_exp2(m * (kLog2of10 * 0.05f)) : m;
     else if (kDom == 1) m = fast_exp2(m * scale);
     else m = expm1f(m);
@@ -336,6 +341,7 @@ struct InvLoadSpec {        // complex input straight from HBM
 AIP_HD void inv_load_runtime(const InvParams& P, long long idx, bool db, float& xr, float& xi) {
   if (P.spec) { const float2 v = P.spec[idx]; xr = v.x; xi = v.y; return; }
   float m = P.mag[idx];
+  if (P.blend_in) { const float g = P.blend_mask[idx]; m = m * g + P.blend_in[idx] * (1.0f - g); }
   const int dom = db ? (int)DOM_DB : P.mag_domain;
   if (dom == DOM_POW10) m = fast_exp2(m * kLog2of10);
   else if (dom == DOM_DB) m = fast_exp2(m * (kLog2of10 * 0.05f));
@@ -345,14 +351,17 @@ AIP_HD void inv_load_runtime(const InvParams& P, long long idx, bool db, float& 
 }
 
 // Input modes of the inverse kernel (template parameter): INV_SPEC = complex input; otherwise
-// 1 + 2*kDom + kPhase for magnitude (+ phase) input.  (A cp.async-staged variant of the complex input, one tile
+// 1 + 2*kDom + kPhase for magnitude (+ phase) input; INV_BLEND = the model hand-off: blended log10 magnitude
+// (out * mask + in * (1 - mask)) -> 10** -> times exp(j phase).  (A cp.async-staged variant of the complex input, one tile
 // ahead through shared memory, measured 1.47x SLOWER than plain loads: 8-byte LDGSTS throttles the LSU and adds
 // an LDS per element; see profiles/README.md.)
 constexpr int INV_SPEC = 0;
+constexpr int INV_BLEND = 7;
 AIP_HDX constexpr int inv_mag_mode(int dom, bool phase) { return 1 + 2 * dom + (phase ? 1 : 0); }
 
 AIP_HDX int inv_mode_of(const InvParams& P) {
   if (P.spec) return INV_SPEC;
+  if (P.blend_in) return INV_BLEND;
   const int dom = (P.mag_domain == DOM_LINEAR) ? 0 : (P.mag_domain == DOM_EXPM1 ? 2 : 1);
   return inv_mag_mode(dom, P.phase != nullptr);
 }
@@ -372,10 +381,14 @@ AIP_HD void inv_phase0(const InvParams& P, int tid, const TileCursor& c, float2*
   if (kMode == INV_SPEC) {
     InvLoadSpec load{P.spec + col, P.T, nullptr, nullptr, 0};
     inv_stageA(exch, w, lane, warp, live, load, before_store);
+  } else if (kMode == INV_BLEND) {
+    InvLoadMag<1, true, true> load{P.mag + col, P.phase + col, P.blend_in + col, P.blend_mask + col, P.T,
+                                   P.mag_domain == DOM_DB ? kLog2of10 * 0.05f : kLog2of10, false, 0, 0, 0};
+    inv_stageA(exch, w, lane, warp, live, load, before_store);
   } else {
     constexpr int kDom = (kMode - 1) >> 1;
     constexpr bool kPhase = ((kMode - 1) & 1) != 0;
-    InvLoadMag<kDom, kPhase> load{P.mag + col, kPhase ? P.phase + col : nullptr, P.T,
+    InvLoadMag<kDom, kPhase, false> load{P.mag + col, kPhase ? P.phase + col : nullptr, nullptr, nullptr, P.T,
                                   P.mag_domain == DOM_DB ? kLog2of10 * 0.05f : kLog2of10,
                                   P.db_flags ? (P.db_flags[c.b] != 0) : false, 0, 0, 0};
     inv_stageA(exch, w, lane, warp, live, load, before_store);

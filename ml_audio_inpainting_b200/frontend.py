@@ -22,7 +22,7 @@ import torch
 
 from . import gaps, spectral as sp
 
-__all__ = ["cnnblstm_batch", "gan_batch", "eval_cnnlstm_batch", "eval_gan_batch", "backend_batch",
+__all__ = ["cnnblstm_batch", "gan_batch", "eval_cnnlstm_batch", "eval_gan_batch", "backend_batch", "cnnblstm_backend_batch",
            "HostPipeline"]
 
 
@@ -129,6 +129,15 @@ def backend_batch(magnitude: torch.Tensor, phase: torch.Tensor, n_fft: int = 512
     plan = sp.get_plan(n_fft, hop_length, win_length, "hann", True, magnitude.device)
     return sp.istft(plan, mag=magnitude, phase=phase, mag_domain=mag_domain,
                     db_auto=db_auto and mag_domain == sp.DOM_LINEAR)
+
+
+def cnnblstm_backend_batch(model_out: torch.Tensor, log_spectrogram_gap: torch.Tensor, gap_mask: torch.Tensor,
+                           phase: torch.Tensor, n_fft: int = 512, hop_length: int = 192, win_length: int = 384) -> torch.Tensor:
+    """Everything between the network's raw output and the waveform in ONE kernel: reconstruct_spectrogram's blend
+    ``out * mask + in * (1 - mask)`` (models/CNNBLSTM/model.py:108), ``10 **`` (models/model_eval.py:163) and
+    ``utils.spectrogram_to_audio(mag, phase=phase)`` (:179-189)."""
+    plan = sp.get_plan(n_fft, hop_length, win_length, "hann", True, model_out.device)
+    return sp.istft_blend(plan, model_out, log_spectrogram_gap, gap_mask, phase, mag_domain=sp.DOM_POW10)
 
 
 class HostPipeline:

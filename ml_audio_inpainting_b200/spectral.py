@@ -25,7 +25,7 @@ from . import _cabi
 from ._cabi import (DOM_DB, DOM_EXPM1, DOM_LINEAR, DOM_POW10, MAG_ABS, MAG_LOG10_EPS, MAG_LOG1P_POW,
                     MAG_NONE, MAG_POW, StftDesc, check)
 
-__all__ = ["StftPlan", "get_plan", "stft", "istft", "griffinlim", "db_heuristic", "fft_window",
+__all__ = ["StftPlan", "get_plan", "stft", "istft", "istft_blend", "griffinlim", "db_heuristic", "fft_window",
            "MAG_NONE", "MAG_ABS", "MAG_LOG10_EPS", "MAG_LOG1P_POW", "MAG_POW",
            "DOM_LINEAR", "DOM_POW10", "DOM_DB", "DOM_EXPM1"]
 
@@ -256,6 +256,34 @@ def istft(plan: StftPlan, spec: Optional[torch.Tensor] = None, mag: Optional[tor
                                 _ptr(mag), _ptr(phase), int(mag_domain), _ptr(flags), B, T, int(length or 0),
                                 _ptr(inv), _ptr(out), out.stride(0), _ptr(ws), ws_bytes, _stream()),
               "aip_istft_f32")
+    return out[0] if squeeze else out
+
+
+def istft_blend(plan: StftPlan, model_out: torch.Tensor, blend_in: torch.Tensor, blend_mask: torch.Tensor,
+                phase: torch.Tensor, mag_domain: int = DOM_POW10, length: Optional[int] = None) -> torch.Tensor:
+    """istft(10 ** (model_out * mask + blend_in * (1 - mask)) * exp(j * phase)): the CNN-BLSTM hand-off
+    (reference models/CNNBLSTM/model.py:108 + models/model_eval.py:163, :179-189) in one kernel."""
+    ts = []
+    for name, t in (("model_out", model_out), ("blend_in", blend_in), ("blend_mask", blend_mask), ("phase", phase)):
+        _require_cuda(t, name)
+        t = t.to(torch.float32)
+        ts.append((t.unsqueeze(0) if t.ndim == 2 else t).contiguous())
+    squeeze = model_out.ndim == 2
+    B, F, T = ts[0].shape
+    if any(tuple(t.shape) != (B, F, T) for t in ts):
+        raise ValueError("model_out, blend_in, blend_mask and phase must have the same [B, F, T] shape")
+    if F != plan.n_bins:
+        raise ValueError(f"expected {plan.n_bins} frequency bins for n_fft={plan.n_fft}, got {F}")
+    dev = ts[0].device
+    lib = _cabi.load()
+    out = torch.empty((B, plan.istft_length(T, length)), dtype=torch.float32, device=dev)
+    inv = plan.inv_wss(T, length)
+    ws_bytes = int(lib.aip_istft_workspace_bytes(C.byref(plan.desc), B, T))
+    ws = torch.empty(max(ws_bytes, 4) // 4, dtype=torch.float32, device=dev) if ws_bytes else None
+    with torch.cuda.device(dev):
+        check(lib.aip_istft_blend_f32(C.byref(plan.desc), _ptr(ts[0]), _ptr(ts[1]), _ptr(ts[2]), _ptr(ts[3]),
+                                      int(mag_domain), B, T, int(length or 0), _ptr(inv), _ptr(out), out.stride(0),
+                                      _ptr(ws), ws_bytes, _stream()), "aip_istft_blend_f32")
     return out[0] if squeeze else out
 
 

@@ -163,6 +163,24 @@ def test_inverse_mag_phase_and_domains():
     assert relerr(emul.istft(192, win(384), iw, spec=S2[None])[0], lr.istft(S, hop_length=192, win_length=384, n_fft=512)) < TOL
 
 
+def test_inverse_blend_prologue():
+    """model.py:108 blend + 10** + phase reuse fused into the inverse prologue."""
+    x = noise(1, 8000, seed=12)
+    S = lr.stft(x[0], n_fft=512, hop_length=192, win_length=384)
+    T = S.shape[1]
+    rng = np.random.default_rng(0)
+    log_in = np.log10(np.abs(S) + 1e-9).astype(np.float32)
+    model_out = (log_in + 0.3 * rng.standard_normal(log_in.shape)).astype(np.float32)
+    mask = np.zeros_like(log_in)
+    mask[:, 10:17] = 1
+    blended = model_out * mask + log_in * (1 - mask)
+    ref = lr.istft(((10.0 ** blended) * np.exp(1j * np.angle(S))).astype(np.complex64), hop_length=192, win_length=384, n_fft=512)
+    iw = inv_wss("hann", 384, 192, T, len(ref))
+    y = emul.istft(192, win(384), iw, mag=model_out[None], phase=np.angle(S)[None], mag_domain=1,
+                   blend_in=log_in[None], blend_mask=mask[None])
+    assert relerr(y[0], ref) < 2 * TOL
+
+
 def test_round_trip_snr(golden_clips):
     name = sorted(golden_clips)[0]
     x = golden_clips[name][:32000]

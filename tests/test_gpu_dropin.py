@@ -234,7 +234,12 @@ def test_config5_end_to_end_cnnblstm_inference(golden_clips):
     assert torch.equal(rec[keep], ev["log_impaired_magnitude"][keep])
     y = frontend.backend_batch(rec, ev["original_phase"], mag_domain=sp.DOM_POW10).cpu().numpy()     # :163, :179-189 (10** fused)
     rec_np, ph = rec.cpu().numpy(), ev["original_phase"].cpu().numpy()
+    # the same hand-off with the blend fused too (raw network output in, waveform out: one kernel)
+    with torch.no_grad():
+        raw = model(ev["log_impaired_magnitude"].unsqueeze(1))
+    yf = frontend.cnnblstm_backend_batch(raw, ev["log_impaired_magnitude"], ev["mask"], ev["original_phase"]).cpu().numpy()
     for b in range(9):
         ref = cp.eval_backend(10.0 ** rec_np[b], ph[b])                          # oracle: 10** then spectrogram_to_audio(phase=...)
         assert y[b].shape == ref.shape == (79872,)
         assert relerr(y[b], ref) < 2 * TOL
+        assert relerr(yf[b], ref) < 2 * TOL
