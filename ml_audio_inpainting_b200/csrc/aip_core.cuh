@@ -96,12 +96,20 @@ AIP_HD float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 AIP_HD float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }   // exact a - b
 AIP_HD float2 mul2s(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
 AIP_HD float2 fma2s(float2 a, float s, float2 c) { return __ffma2_rn(a, make_float2(s, s), c); }
+AIP_HD float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+AIP_HD float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 #else
 AIP_HD float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 AIP_HD float2 sub2(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 AIP_HD float2 mul2s(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 AIP_HD float2 fma2s(float2 a, float s, float2 c) { return make_float2(a.x * s + c.x, a.y * s + c.y); }
+AIP_HD float2 mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+AIP_HD float2 fma2(float2 a, float2 b, float2 c) { return make_float2(a.x * b.x + c.x, a.y * b.y + c.y); }
 #endif
+// half swap / full negate of a packed pair: ptxas folds both into the F32x2 operand modifiers of the consumer
+// (R.F32x2.LO_HI, -R.F32x2.HI_LO), so they cost no instruction
+AIP_HD float2 swap2(float2 a) { return make_float2(a.y, a.x); }
+AIP_HD float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 
 AIP_HD void radix4x2(float2& ar, float2& ai, float2& br, float2& bi, float2& cr, float2& ci, float2& dr, float2& di) {
   const float2 s0r = add2(ar, cr), s0i = add2(ai, ci), s1r = sub2(ar, cr), s1i = sub2(ai, ci);
@@ -156,10 +164,23 @@ struct LaneConst {
 constexpr int kWinPitch = 36;
 constexpr int kWinTable = 16 * kWinPitch;      // floats
 
-AIP_HD void lane_const_init(LaneConst& c, int n1) {
+// tw_s[n1*17 + k2] = W256^(n1 k2): the per-lane twiddle rows, staged in shared memory once per CTA.  The lanes
+// read their row from THERE, not from the __constant__ table: an indexed constant load serialises over the 16
+// distinct lane addresses, and ptxas re-materialises constant loads inside the tile loop whenever the stage runs
+// out of registers (measured: 9 such LDCs per tile cost 25 % of the forward kernel).
+constexpr int kTwPitch = 17;                   // float2 per row (odd: conflict-free LDS.64 over n1)
+constexpr int kTwTable = 16 * kTwPitch;        // float2
+AIP_HD void twiddle_table_fill(float2* tw_s, int tid, int nthreads) {
+  for (int idx = tid; idx < 256; idx += nthreads) {
+    const int n1 = idx >> 4, k2 = idx & 15;
+    tw_s[n1 * kTwPitch + k2] = kTw256[(n1 * k2) & 255];
+  }
+}
+
+AIP_HD void lane_const_init(LaneConst& c, const float2* tw_s, int n1) {
 #pragma unroll
   for (int k2 = 0; k2 < 16; ++k2) {
-    const float2 t = kTw256[(n1 * k2) & 255];
+    const float2 t = tw_s[n1 * kTwPitch + k2];
     c.twr[k2] = t.x;
     c.twi[k2] = t.y;
   }
@@ -217,32 +238,62 @@ AIP_HD void fwd_stage1(const float* tile, float2* exch, const float* win_s, int 
 }
 
 // Split-pass twiddles of one pair-job, register resident (a stage-2 / stage-A warp keeps its job p for
-// the whole kernel).  p > 0: w[k1] = W512^(p + 16 k1).  p = 0: w[k1] = W512^(8 + 16 k1) for k1 < 8 (job 8)
-// and w[8 + k1] = W512^(16 k1), k1 = 1..7 (job 0).
+// the whole kernel), stored the way the PACKED split pass consumes them.
+//   p > 0:  (wr2[j], wi2[j]) = ( (Re W^k, Re W^k'), (Im W^k, -Im W^k') ),  W = W512, k = p + 16 j, k' = p + 16 (15 - j)
+//   p = 0:  .x = W512^(8 + 16 j) (job 8),  .y = W512^(16 j) (job 0, j = 1..7)
 struct PairTw {
-  float wr[16], wi[16];
+  float2 wr2[8], wi2[8];
 };
 
 AIP_HD void pair_tw_init(PairTw& w, int p) {
 #pragma unroll
-  for (int k1 = 0; k1 < 16; ++k1) {
-    const int k = (p != 0) ? p + 16 * k1 : (k1 < 8 ? 8 + 16 * k1 : 16 * (k1 - 8));
-    const float2 t = kTw512[k];
-    w.wr[k1] = t.x;
-    w.wi[k1] = t.y;
+  for (int j = 0; j < 8; ++j) {
+    if (p != 0) {
+      const float2 a = kTw512[p + 16 * j], b = kTw512[p + 16 * (15 - j)];
+      w.wr2[j] = make_float2(a.x, b.x);
+      w.wi2[j] = make_float2(a.y, -b.y);
+    } else {
+      const float2 a = kTw512[8 + 16 * j], b = kTw512[16 * j];
+      w.wr2[j] = make_float2(a.x, b.x);
+      w.wi2[j] = make_float2(a.y, b.y);
+    }
   }
 }
+// scalar view for p > 0: W512^(p + 16 k1), k1 = 0..15
+AIP_HD float pair_tw_r(const PairTw& w, int k1) { return k1 < 8 ? w.wr2[k1].x : w.wr2[15 - k1].y; }
+AIP_HD float pair_tw_i(const PairTw& w, int k1) { return k1 < 8 ? w.wi2[k1].x : -w.wi2[15 - k1].y; }
 
-// split pass for one (k, 256-k) pair: Zk = Zc[k], Zn = Zc[256-k], (wr, wi) = W512^k.
-// Output rows are addressed through the emitter's two cursors: lo(j) = bin k_lo + 16 j, hi(j) = bin k_hi - 16 j.
+// Split pass for one (k, 256-k) pair, scalar: Zk = Zc[k], Zn = Zc[256-k], (wr, wi) = W512^k.  Both results go to
+// the emitter as one packed pair (.x = bin k at offset o_lo, .y = bin 256-k at offset o_hi) so that the magnitude
+// epilogue runs on FP32x2.
 template <class Emit>
-AIP_HD void fwd_pair(float zkr, float zki, float znr, float zni, float wr, float wi, int j, Emit& emit) {
+AIP_HD void fwd_pair(float zkr, float zki, float znr, float zni, float wr, float wi, typename Emit::off_t o_lo,
+                     typename Emit::off_t o_hi, Emit& emit) {
   const float er = zkr + znr, ei = zki - zni;
   const float orr = zkr - znr, oi = zki + zni;
   const float tr = orr * wr - oi * wi;
   const float ti = orr * wi + oi * wr;
-  emit.lo(j, er + ti, ei - tr);
-  emit.hi(j, er - ti, -(ei + tr));
+  emit.template put2<1, -1>(o_lo, o_hi, make_float2(er + ti, er - ti), make_float2(ei - tr, ei + tr));
+}
+
+// Split pass for TWO pairs at once, packed.  After fft16x2 a stage-2 thread of pair-job p > 0 holds, in slot j,
+// U = (Za[j], Zb[j]) with Za[j] = Zc[p + 16 j] and Zb[j] = Zc[(16 - p) + 16 j].  For k = p + 16 j and
+// k' = p + 16 (15 - j) the partners are Zc[256 - k] = Zb[15 - j] and Zc[256 - k'] = Zb[j], i.e.
+//     U = slot j      = (Zk , Zn')          V = slot 15 - j = (Zk', Zn)
+// so (U, swap(V)) are the (Zk, Zn) operands of pair k in lane .x and, with the roles of Z and its partner
+// exchanged, of pair k' in lane .y.  Exchanged roles flip the sign of Re O and Im E in lane .y; with the lane-.y
+// twiddle conjugated (PairTw) every product comes out right up to the sign of the IMAGINARY outputs of lane .y,
+// which the emitter fixes only when it actually stores imaginary parts or phases.
+template <class Emit>
+AIP_HD void fwd_pair2(float2 ur, float2 ui, float2 vr, float2 vi, float2 wr2, float2 wi2, typename Emit::off_t lo_x,
+                      typename Emit::off_t lo_y, typename Emit::off_t hi_x, typename Emit::off_t hi_y, Emit& emit) {
+  const float2 vsr = swap2(vr), vsi = swap2(vi);
+  const float2 er = add2(ur, vsr), oi = add2(ui, vsi);       // (Re E, Re E'), (Im O, Im O')
+  const float2 dr = sub2(ur, vsr), di = sub2(ui, vsi);       // (Re O, -Re O'), (Im E, -Im E')
+  const float2 tr = fma2(neg2(oi), wi2, mul2(dr, wr2));      // (Re T, -Re T'),  T = W O
+  const float2 ti = fma2(dr, wi2, mul2(oi, wr2));            // (Im T,  Im T')
+  emit.template put2<1, -1>(lo_x, lo_y, add2(er, ti), sub2(di, tr));     // X[k], X[k']:   (er + ti, ei - tr)
+  emit.template put2<-1, 1>(hi_x, hi_y, sub2(er, ti), add2(di, tr));     // X[256-k], X[256-k']: (er - ti, -(ei + tr))
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -266,22 +317,32 @@ AIP_HD void fwd_stage2_compute(float2 (&r)[16], float2 (&i)[16], const PairTw& w
   fft16x2(r, i);     // .x = job a, .y = job b
   if (p != 0) {
     emit.rows(p, 256 - p);
+#if defined(AIP_SPLIT_SCALAR)
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1)
-      fwd_pair(r[perm16(k1)].x, i[perm16(k1)].x, r[perm16(15 - k1)].y, i[perm16(15 - k1)].y, w.wr[k1], w.wi[k1], k1, emit);
+      fwd_pair(r[perm16(k1)].x, i[perm16(k1)].x, r[perm16(15 - k1)].y, i[perm16(15 - k1)].y, pair_tw_r(w, k1),
+               pair_tw_i(w, k1), emit.lo(k1), emit.hi(k1), emit);
+#else
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      fwd_pair2(r[perm16(j)], i[perm16(j)], r[perm16(15 - j)], i[perm16(15 - j)], w.wr2[j], w.wi2[j],
+                emit.lo(j), emit.lo(15 - j), emit.hi(j), emit.hi(15 - j), emit);
+#endif
   } else {
     emit.rows(0, 256);
     const float z0r = r[perm16(0)].x, z0i = i[perm16(0)].x;
-    emit.lo(0, 2.0f * (z0r + z0i), 0.0f);
-    emit.hi(0, 2.0f * (z0r - z0i), 0.0f);
+    emit.template put2<1, 1>(emit.lo(0), emit.hi(0), make_float2(2.0f * (z0r + z0i), 2.0f * (z0r - z0i)),
+                             make_float2(0.0f, 0.0f));
 #pragma unroll
     for (int k1 = 1; k1 < 8; ++k1)
-      fwd_pair(r[perm16(k1)].x, i[perm16(k1)].x, r[perm16(16 - k1)].x, i[perm16(16 - k1)].x, w.wr[8 + k1], w.wi[8 + k1], k1, emit);
-    emit.lo(8, 2.0f * r[perm16(8)].x, -2.0f * i[perm16(8)].x);
+      fwd_pair(r[perm16(k1)].x, i[perm16(k1)].x, r[perm16(16 - k1)].x, i[perm16(16 - k1)].x, w.wr2[k1].y, w.wi2[k1].y,
+               emit.lo(k1), emit.hi(k1), emit);
+    emit.put1(emit.lo(8), 2.0f * r[perm16(8)].x, -2.0f * i[perm16(8)].x);
     emit.rows(8, 248);
 #pragma unroll
     for (int k1 = 0; k1 < 8; ++k1)
-      fwd_pair(r[perm16(k1)].y, i[perm16(k1)].y, r[perm16(15 - k1)].y, i[perm16(15 - k1)].y, w.wr[k1], w.wi[k1], k1, emit);
+      fwd_pair(r[perm16(k1)].y, i[perm16(k1)].y, r[perm16(15 - k1)].y, i[perm16(15 - k1)].y, w.wr2[k1].x, w.wi2[k1].x,
+               emit.lo(k1), emit.hi(k1), emit);
   }
 }
 
@@ -313,7 +374,7 @@ AIP_HD void inv_stageA(float2* exch, const PairTw& w, int f, int p, bool live, L
         float xr, xi, yr, yi;
         load.lo(k1, xr, xi);
         load.hi(k1, yr, yi);
-        inv_pair(xr, xi, yr, yi, w.wr[k1], w.wi[k1], r[k1].x, i[k1].x, r[15 - k1].y, i[15 - k1].y);
+        inv_pair(xr, xi, yr, yi, pair_tw_r(w, k1), pair_tw_i(w, k1), r[k1].x, i[k1].x, r[15 - k1].y, i[15 - k1].y);
       }
     } else {
       float xr, xi, yr, yi;
@@ -325,7 +386,7 @@ AIP_HD void inv_stageA(float2* exch, const PairTw& w, int f, int p, bool live, L
       for (int k1 = 1; k1 < 8; ++k1) {
         load.lo(k1, xr, xi);
         load.hi(k1, yr, yi);
-        inv_pair(xr, xi, yr, yi, w.wr[8 + k1], w.wi[8 + k1], r[k1].x, i[k1].x, r[16 - k1].x, i[16 - k1].x);
+        inv_pair(xr, xi, yr, yi, w.wr2[k1].y, w.wi2[k1].y, r[k1].x, i[k1].x, r[16 - k1].x, i[16 - k1].x);
       }
       load.lo(8, xr, xi);
       r[8].x = 2.0f * xr; i[8].x = -2.0f * xi;
@@ -334,7 +395,7 @@ AIP_HD void inv_stageA(float2* exch, const PairTw& w, int f, int p, bool live, L
       for (int k1 = 0; k1 < 8; ++k1) {
         load.lo(k1, xr, xi);
         load.hi(k1, yr, yi);
-        inv_pair(xr, xi, yr, yi, w.wr[k1], w.wi[k1], r[k1].y, i[k1].y, r[15 - k1].y, i[15 - k1].y);
+        inv_pair(xr, xi, yr, yi, w.wr2[k1].x, w.wi2[k1].x, r[k1].y, i[k1].y, r[15 - k1].y, i[15 - k1].y);
       }
     }
     fft16x2(i, r);      // inverse transform: swapped roles

@@ -40,8 +40,10 @@ int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, 
   std::vector<float2> exch(kExch);
   std::vector<LaneConst> lc(kThreads);
   std::vector<PairTw> pw(kThreads);
+  std::vector<float2> tw_s(kTwTable);
+  twiddle_table_fill(tw_s.data(), 0, 1);
   for (int tid = 0; tid < kThreads; ++tid) {
-    lane_const_init(lc[tid], tid & 15);
+    lane_const_init(lc[tid], tw_s.data(), tid & 15);
     pair_tw_init(pw[tid], tid >> 5);
   }
   NoRelease rel;
@@ -112,8 +114,10 @@ int emul_istft512(const float* spec, const float* mag, const float* phase, int m
   std::vector<float2> exch(kExch);
   std::vector<LaneConst> lc(kThreads);
   std::vector<PairTw> pw(kThreads);
+  std::vector<float2> tw_s(kTwTable);
+  twiddle_table_fill(tw_s.data(), 0, 1);
   for (int tid = 0; tid < kThreads; ++tid) {
-    lane_const_init(lc[tid], tid & 15);
+    lane_const_init(lc[tid], tw_s.data(), tid & 15);
     pair_tw_init(pw[tid], tid >> 5);
   }
   NoRelease rel;

@@ -103,7 +103,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bars[8];
   __shared__ __align__(16) float win_s[kWinTable];
+  __shared__ __align__(8) float2 tw_s[kTwTable];
   window_table_fill(win_s, P.window, 0.5f, threadIdx.x, blockDim.x);
+  twiddle_table_fill(tw_s, threadIdx.x, blockDim.x);
   uint64_t* tile_full = bars;        // [2] count 1 (+ tx bytes)
   uint64_t* tile_empty = bars + 2;   // [2] count 8 (stage-1 warps)
   uint64_t* exch_full = bars + 4;    // [2] count 8 (stage-1 warps)
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
     // ------------------------------------------------------------------ producers: stage 1
     const int ptid = tid - kThreads;
     LaneConst lc;
-    lane_const_init(lc, ptid & 15);
+    lane_const_init(lc, tw_s, ptid & 15);
     FwdTilePlan q = fwd_tile_plan(P, c);
     if (ptid == 0) fwd_issue_tile(q, smem, tile_full);
 #pragma unroll 1
@@ -195,7 +197,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParam
   __shared__ __align__(8) uint64_t bars[2 * kInvBufs];
   __shared__ __align__(8) float wtab_s[kMaxWtab];
   __shared__ __align__(16) float win_s[kWinTable];
+  __shared__ __align__(8) float2 tw_s[kTwTable];
   window_table_fill(win_s, P.window, 1.0f / 512.0f, threadIdx.x, blockDim.x);
+  twiddle_table_fill(tw_s, threadIdx.x, blockDim.x);
   const float* wtab = (P.wss_ref >= 0 && P.hop <= kMaxWtab) ? wtab_s : nullptr;
   if (wtab)
     for (int r = threadIdx.x; r < P.hop; r += blockDim.x) wtab_s[r] = P.inv_wss[P.wss_ref + r];
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParam
   } else {
     const int btid = tid - kThreads;
     LaneConst lc;
-    lane_const_init(lc, btid & 15);
+    lane_const_init(lc, tw_s, btid & 15);
     int es = 0, use = 0;
 #pragma unroll 1
     for (int i = 0; i < n; ++i) {
@@ -299,7 +303,7 @@ __global__ void __launch_bounds__(256) stft_generic_fwd_kernel(const GenericFwdP
     for (int k = threadIdx.x; k < G.F; k += blockDim.x) {
       const float2 x = buf[k];
       emit.rows(k, k);
-      emit.lo(0, x.x, (k == 0 || k == N / 2) ? 0.0f : x.y);
+      emit.put1(emit.lo(0), x.x, (k == 0 || k == N / 2) ? 0.0f : x.y);
     }
     __syncthreads();
   }

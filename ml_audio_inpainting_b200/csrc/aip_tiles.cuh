@@ -131,6 +131,18 @@ AIP_HD float mag_value(int mk, float xr, float xi, float eps, float power) {
   return (mk == MAG_LOG1P_POW) ? log1pf(mp) : mp;
 }
 
+// two bins at once on FP32x2 (power == 1); the MUFU ops stay scalar
+AIP_HD float2 mag_value2(int mk, float2 xr, float2 xi, float eps) {
+  const float2 pw = fma2(xi, xi, mul2(xr, xr));
+  const float2 m = make_float2(fast_sqrt(pw.x), fast_sqrt(pw.y));
+  if (mk == MAG_ABS) return m;
+  if (mk == MAG_LOG10_EPS) {
+    const float2 l = add2(m, make_float2(eps, eps));
+    return mul2s(make_float2(fast_log2(l.x), fast_log2(l.y)), kLog10of2);
+  }
+  return (mk == MAG_LOG1P_POW) ? make_float2(log1pf(m.x), log1pf(m.y)) : m;
+}
+
 // Forward kernel variants: a bit mask of what the epilogue produces, a template parameter of the kernel so
 // that each variant is straight-line code (no per-bin branches, no calls).
 //   bits 0..2  magnitude kind (MagKind: 0 none, 1 |S|, 2 log10(|S|+eps), 3 log1p(|S|), 4 reserved -> fallback)
@@ -141,11 +153,14 @@ enum FwdModeBits : int { FWD_SPEC = 8, FWD_PHASE = 16, FWD_MASK = 32, FWD_ZERO =
 constexpr int FWD_MAG_ABS = MAG_ABS, FWD_MAG_LOG10 = MAG_LOG10_EPS;      // the two magnitude-only variants
 
 // A stage-2 thread writes bins k_lo + 16 j and k_hi - 16 j of ONE frame (its lane): two row offsets are set
-// per job (rows()), each store is then column pointer + offset + j * (16 T) -- and, the lane being the frame
-// index, a warp's store of one bin is 32 consecutive elements of that row.  No predicates: in the last tile
-// of a clip the lanes past T_out recompute the last valid frame and store the same values.
+// per job (rows()), lo(j) / hi(j) give the element offset of a bin from the column pointer -- and, the lane being
+// the frame index, a warp's store of one bin is 32 consecutive elements of that row.  No predicates: in the last
+// tile of a clip the lanes past T_out recompute the last valid frame and store the same values.
+// put2<SX, SY> takes two bins as a packed pair whose imaginary parts still carry the signs (SX, SY) (see
+// fwd_pair2); magnitudes ignore them, complex / phase outputs apply them.
 template <int kM>
 struct FwdEmitT {
+  typedef int off_t;
   float* mag;               // column pointers: array + b*F*T_out + t
   float2* spec;
   float* phase;
@@ -155,19 +170,40 @@ struct FwdEmitT {
   bool zero;
   int olo, ohi, s16;
   AIP_HM void rows(int k_lo, int k_hi) { olo = k_lo * T; ohi = k_hi * T; s16 = 16 * T; }
-  AIP_HM void lo(int j, float xr, float xi) const { put(olo + j * s16, xr, xi); }
-  AIP_HM void hi(int j, float xr, float xi) const { put(ohi - j * s16, xr, xi); }
-  AIP_HM void put(int o, float xr, float xi) const {
+  AIP_HM int lo(int j) const { return olo + j * s16; }
+  AIP_HM int hi(int j) const { return ohi - j * s16; }
+  AIP_HM void put1(int o, float xr, float xi) const {
     if (kM & FWD_ZERO) { if (zero) { xr = 0.0f; xi = 0.0f; } }
     if (kM & FWD_SPEC) spec[o] = make_float2(xr, xi);
     if (kM & FWD_PHASE) phase[o] = atan2f(xi, xr);
     if (kM & FWD_MASK) mask[o] = maskv;
     if (kM & 7) mag[o] = mag_value(kM & 7, xr, xi, eps, 1.0f);
   }
+  template <int SX, int SY>
+  AIP_HM void put2(int ox, int oy, float2 xr, float2 xi) const {
+    if (kM & FWD_ZERO) { if (zero) { xr = make_float2(0.0f, 0.0f); xi = make_float2(0.0f, 0.0f); } }
+    if (kM & (FWD_SPEC | FWD_PHASE)) {
+      const float ix = SX < 0 ? -xi.x : xi.x, iy = SY < 0 ? -xi.y : xi.y;
+      if (kM & FWD_SPEC) { spec[ox] = make_float2(xr.x, ix); spec[oy] = make_float2(xr.y, iy); }
+      if (kM & FWD_PHASE) { phase[ox] = atan2f(ix, xr.x); phase[oy] = atan2f(iy, xr.y); }
+    }
+    if (kM & FWD_MASK) { mask[ox] = maskv; mask[oy] = maskv; }
+    if (kM & 7) {
+#if defined(AIP_MAG_SCALAR)
+      mag[ox] = mag_value(kM & 7, xr.x, xi.x, eps, 1.0f);
+      mag[oy] = mag_value(kM & 7, xr.y, xi.y, eps, 1.0f);
+#else
+      const float2 m = mag_value2(kM & 7, xr, xi, eps);
+      mag[ox] = m.x;
+      mag[oy] = m.y;
+#endif
+    }
+  }
 };
 
 // Epilogue, general path: any mix of complex / magnitude / phase / mask outputs and the spectrum-domain gap.
 struct FwdEmitFull {
+  typedef long long off_t;
   const FwdParams& P;
   long long base;           // b*F*T_out + t
   bool active, zero;
@@ -179,12 +215,17 @@ struct FwdEmitFull {
     off_hi = base + (long long)k_hi * P.T_out;
     s16 = 16 * P.T_out;
   }
-  AIP_HM void lo(int j, float xr, float xi) const { put(off_lo + j * s16, xr, xi); }
-  AIP_HM void hi(int j, float xr, float xi) const { put(off_hi - j * s16, xr, xi); }
+  AIP_HM long long lo(int j) const { return off_lo + j * s16; }
+  AIP_HM long long hi(int j) const { return off_hi - j * s16; }
+  template <int SX, int SY>
+  AIP_HM void put2(long long ox, long long oy, float2 xr, float2 xi) const {
+    put1(ox, xr.x, SX < 0 ? -xi.x : xi.x);
+    put1(oy, xr.y, SY < 0 ? -xi.y : xi.y);
+  }
 #if defined(__CUDACC__)
   __device__ __noinline__      // called 65 times per job: keep the kernel inside the instruction cache
 #endif
-  void put(long long idx, float xr, float xi) const {
+  void put1(long long idx, float xr, float xi) const {
     if (!active) return;
     if (zero) { xr = 0.0f; xi = 0.0f; }
     if (P.spec) P.spec[idx] = make_float2(xr, xi);
