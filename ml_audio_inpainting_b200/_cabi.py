@@ -17,7 +17,7 @@ DOM_LINEAR, DOM_POW10, DOM_DB, DOM_EXPM1 = 0, 1, 2, 3
 class StftDesc(C.Structure):
     """struct aip_stft_desc"""
     _fields_ = [("n_fft", C.c_int32), ("hop", C.c_int32), ("center", C.c_int32),
-                ("reserved", C.c_int32), ("window", C.c_void_p)]
+                ("win_length", C.c_int32), ("window", C.c_void_p)]
 
 
 class AipError(RuntimeError):

@@ -127,12 +127,25 @@ AIP_HD void cmulx2(float2& xr, float2& xi, float wr, float wi) {
   xr = tr;
 }
 
-// Two forward 16-point complex DFTs at once (lane .x and lane .y), in place; input natural order, output
-// bin k in slot perm16(k).  The inverse (unnormalised, e^{+j}) is fft16x2(im, re).
-AIP_HD void fft16x2(float2 (&r)[16], float2 (&i)[16]) {
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-    radix4x2(r[a], i[a], r[a + 4], i[a + 4], r[a + 8], i[a + 8], r[a + 12], i[a + 12]);
+// radix-4 butterflies with one input known to be zero (pruned window taps, see fwd_stage1<ZP>): 12 instead of 16 ops
+AIP_HD void radix4x2_a0(float2& ar, float2& ai, float2& br, float2& bi, float2& cr, float2& ci, float2& dr, float2& di) {
+  const float2 s2r = add2(br, dr), s2i = add2(bi, di), s3r = sub2(br, dr), s3i = sub2(bi, di);
+  ar = add2(cr, s2r); ai = add2(ci, s2i);                       // s0 = c, s1 = -c
+  br = sub2(s3i, cr); bi = sub2(neg2(ci), s3r);
+  dr = sub2(neg2(cr), s3i); di = sub2(s3r, ci);
+  cr = sub2(cr, s2r); ci = sub2(ci, s2i);
+}
+AIP_HD void radix4x2_d0(float2& ar, float2& ai, float2& br, float2& bi, float2& cr, float2& ci, float2& dr, float2& di) {
+  const float2 s0r = add2(ar, cr), s0i = add2(ai, ci), s1r = sub2(ar, cr), s1i = sub2(ai, ci);
+  ar = add2(s0r, br); ai = add2(s0i, bi);                       // s2 = s3 = b
+  cr = sub2(s0r, br); ci = sub2(s0i, bi);
+  dr = sub2(s1r, bi); di = add2(s1i, br);
+  const float2 tr = add2(s1r, bi);
+  bi = sub2(s1i, br); br = tr;
+}
+
+// second half of the 16-point codelet: W16 twiddles + the radix-4 pass over the slot groups
+AIP_HD void fft16x2_tail(float2 (&r)[16], float2 (&i)[16]) {
   cmulx2(r[5], i[5], kC1, -kS1);
   cmulx2(r[9], i[9], kR2, -kR2);
   cmulx2(r[13], i[13], kS1, -kC1);
@@ -145,6 +158,24 @@ AIP_HD void fft16x2(float2 (&r)[16], float2 (&i)[16]) {
 #pragma unroll
   for (int q = 0; q < 4; ++q)
     radix4x2(r[4 * q], i[4 * q], r[4 * q + 1], i[4 * q + 1], r[4 * q + 2], i[4 * q + 2], r[4 * q + 3], i[4 * q + 3]);
+}
+
+// Two forward 16-point complex DFTs at once (lane .x and lane .y), in place; input natural order, output
+// bin k in slot perm16(k).  The inverse (unnormalised, e^{+j}) is fft16x2(im, re).
+AIP_HD void fft16x2(float2 (&r)[16], float2 (&i)[16]) {
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+    radix4x2(r[a], i[a], r[a + 4], i[a + 4], r[a + 8], i[a + 8], r[a + 12], i[a + 12]);
+  fft16x2_tail(r, i);
+}
+
+// Same transform when inputs 0, 1, 14 and 15 are zero (never read: the slots may hold anything)
+AIP_HD void fft16x2_in_z2(float2 (&r)[16], float2 (&i)[16]) {
+  radix4x2_a0(r[0], i[0], r[4], i[4], r[8], i[8], r[12], i[12]);
+  radix4x2_a0(r[1], i[1], r[5], i[5], r[9], i[9], r[13], i[13]);
+  radix4x2_d0(r[2], i[2], r[6], i[6], r[10], i[10], r[14], i[14]);
+  radix4x2_d0(r[3], i[3], r[7], i[7], r[11], i[11], r[15], i[15]);
+  fft16x2_tail(r, i);
 }
 
 // Exchange buffer (both directions): float2 slot ((p*2 + c)*16 + n1)*33 + frame holds component c (0 = re,
@@ -200,6 +231,10 @@ AIP_HD void window_table_fill(float* win_s, const float* window, float scale, in
 // loads of the staged waveform, window, packed 16-point DFT over n2, inter-stage twiddle, 2 x 16 float2
 // stores into the exchange buffer.
 // ---------------------------------------------------------------------------------------------------
+// ZP = number of leading AND trailing n2 groups (32 samples each) whose window taps are all zero -- librosa's
+// pad_center of a win_length < n_fft window (config.py: win 384 in n_fft 512 => 64 zero taps each side => ZP = 2):
+// those samples are neither loaded nor multiplied, and the first radix-4 pass runs its pruned form.
+template <int ZP>
 AIP_HD void fwd_stage1(const float* tile, float2* exch, const float* win_s, int hop, int fa, int fb, int n1,
                        const LaneConst& c) {
   float2 r[16], i[16];
@@ -207,7 +242,7 @@ AIP_HD void fwd_stage1(const float* tile, float2* exch, const float* win_s, int 
   const float* sb = tile + fb * hop + 2 * n1;
   const float4* wrow = reinterpret_cast<const float4*>(win_s + n1 * kWinPitch);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = ZP / 2; j < 8 - ZP / 2; ++j) {
     const float4 w = wrow[j];        // (we, wo) of n2 = 2j and 2j + 1
     const float2 za0 = *reinterpret_cast<const float2*>(sa + 64 * j);
     const float2 zb0 = *reinterpret_cast<const float2*>(sb + 64 * j);
@@ -218,7 +253,8 @@ AIP_HD void fwd_stage1(const float* tile, float2* exch, const float* win_s, int 
     r[2 * j + 1] = make_float2(za1.x * w.z, zb1.x * w.z);
     i[2 * j + 1] = make_float2(za1.y * w.w, zb1.y * w.w);
   }
-  fft16x2(r, i);
+  if (ZP == 2) fft16x2_in_z2(r, i);
+  else fft16x2(r, i);
   float2* da = exch + n1 * kXP + fa;
   float2* db = exch + n1 * kXP + fb;
 #pragma unroll
@@ -240,7 +276,7 @@ AIP_HD void fwd_stage1(const float* tile, float2* exch, const float* win_s, int 
 // Split-pass twiddles of one pair-job, register resident (a stage-2 / stage-A warp keeps its job p for
 // the whole kernel), stored the way the PACKED split pass consumes them.
 //   p > 0:  (wr2[j], wi2[j]) = ( (Re W^k, Re W^k'), (Im W^k, -Im W^k') ),  W = W512, k = p + 16 j, k' = p + 16 (15 - j)
-//   p = 0:  .x = W512^(8 + 16 j) (job 8),  .y = W512^(16 j) (job 0, j = 1..7)
+//   p = 0:  .x = W512^(16 (j + 1)) (job 0, pair j + 1 <-> 15 - j, j = 0..6),  .y = W512^(8 + 16 j) (job 8, pair j <-> 15 - j)
 struct PairTw {
   float2 wr2[8], wi2[8];
 };
@@ -253,7 +289,7 @@ AIP_HD void pair_tw_init(PairTw& w, int p) {
       w.wr2[j] = make_float2(a.x, b.x);
       w.wi2[j] = make_float2(a.y, -b.y);
     } else {
-      const float2 a = kTw512[8 + 16 * j], b = kTw512[16 * j];
+      const float2 a = kTw512[16 * (j + 1)], b = kTw512[8 + 16 * j];
       w.wr2[j] = make_float2(a.x, b.x);
       w.wi2[j] = make_float2(a.y, b.y);
     }
@@ -312,6 +348,18 @@ AIP_HD void fwd_stage2_load(const float2* exch, int f, int p, float2 (&r)[16], f
   }
 }
 
+// Two pairs at once with the SAME roles in both lanes (pair-job 0): lane .x is a pair of job 0, lane .y one of job 8.
+template <class Emit>
+AIP_HD void fwd_pair2s(float2 zkr, float2 zki, float2 znr, float2 zni, float2 wr2, float2 wi2, typename Emit::off_t lo_x,
+                       typename Emit::off_t lo_y, typename Emit::off_t hi_x, typename Emit::off_t hi_y, Emit& emit) {
+  const float2 er = add2(zkr, znr), ei = sub2(zki, zni);
+  const float2 orr = sub2(zkr, znr), oi = add2(zki, zni);
+  const float2 tr = fma2(neg2(oi), wi2, mul2(orr, wr2));
+  const float2 ti = fma2(orr, wi2, mul2(oi, wr2));
+  emit.template put2<1, 1>(lo_x, lo_y, add2(er, ti), sub2(ei, tr));
+  emit.template put2<-1, -1>(hi_x, hi_y, sub2(er, ti), add2(ei, tr));
+}
+
 template <class Emit>
 AIP_HD void fwd_stage2_compute(float2 (&r)[16], float2 (&i)[16], const PairTw& w, int p, Emit& emit) {
   fft16x2(r, i);     // .x = job a, .y = job b
@@ -329,20 +377,22 @@ AIP_HD void fwd_stage2_compute(float2 (&r)[16], float2 (&i)[16], const PairTw& w
                 emit.lo(j), emit.lo(15 - j), emit.hi(j), emit.hi(15 - j), emit);
 #endif
   } else {
-    emit.rows(0, 256);
+    // Job 0 (.x: bins 16 k1, pairs k1 <-> 16 - k1) and job 8 (.y: bins 8 + 16 k1, pairs k1 <-> 15 - k1).  Pair j + 1 of
+    // job 0 and pair j of job 8 share their partner slot 15 - j; their own operands sit in slots j + 1 (.x) and j (.y),
+    // so one register move per component lines them up for the packed split pass.
     const float z0r = r[perm16(0)].x, z0i = i[perm16(0)].x;
-    emit.template put2<1, 1>(emit.lo(0), emit.hi(0), make_float2(2.0f * (z0r + z0i), 2.0f * (z0r - z0i)),
+    emit.template put2<1, 1>(emit.bin(0), emit.bin(256), make_float2(2.0f * (z0r + z0i), 2.0f * (z0r - z0i)),
                              make_float2(0.0f, 0.0f));
+    emit.put1(emit.bin(128), 2.0f * r[perm16(8)].x, -2.0f * i[perm16(8)].x);
 #pragma unroll
-    for (int k1 = 1; k1 < 8; ++k1)
-      fwd_pair(r[perm16(k1)].x, i[perm16(k1)].x, r[perm16(16 - k1)].x, i[perm16(16 - k1)].x, w.wr2[k1].y, w.wi2[k1].y,
-               emit.lo(k1), emit.hi(k1), emit);
-    emit.put1(emit.lo(8), 2.0f * r[perm16(8)].x, -2.0f * i[perm16(8)].x);
-    emit.rows(8, 248);
-#pragma unroll
-    for (int k1 = 0; k1 < 8; ++k1)
-      fwd_pair(r[perm16(k1)].y, i[perm16(k1)].y, r[perm16(15 - k1)].y, i[perm16(15 - k1)].y, w.wr2[k1].x, w.wi2[k1].x,
-               emit.lo(k1), emit.hi(k1), emit);
+    for (int j = 0; j < 7; ++j) {
+      const float2 zkr = make_float2(r[perm16(j + 1)].x, r[perm16(j)].y);
+      const float2 zki = make_float2(i[perm16(j + 1)].x, i[perm16(j)].y);
+      fwd_pair2s(zkr, zki, r[perm16(15 - j)], i[perm16(15 - j)], w.wr2[j], w.wi2[j], emit.bin(16 * (j + 1)),
+                 emit.bin(8 + 16 * j), emit.bin(256 - 16 * (j + 1)), emit.bin(248 - 16 * j), emit);
+    }
+    fwd_pair(r[perm16(7)].y, i[perm16(7)].y, r[perm16(8)].y, i[perm16(8)].y, w.wr2[7].y, w.wi2[7].y, emit.bin(120),
+             emit.bin(136), emit);
   }
 }
 
@@ -386,7 +436,7 @@ AIP_HD void inv_stageA(float2* exch, const PairTw& w, int f, int p, bool live, L
       for (int k1 = 1; k1 < 8; ++k1) {
         load.lo(k1, xr, xi);
         load.hi(k1, yr, yi);
-        inv_pair(xr, xi, yr, yi, w.wr2[k1].y, w.wi2[k1].y, r[k1].x, i[k1].x, r[16 - k1].x, i[16 - k1].x);
+        inv_pair(xr, xi, yr, yi, w.wr2[k1 - 1].x, w.wi2[k1 - 1].x, r[k1].x, i[k1].x, r[16 - k1].x, i[16 - k1].x);
       }
       load.lo(8, xr, xi);
       r[8].x = 2.0f * xr; i[8].x = -2.0f * xi;
@@ -395,7 +445,7 @@ AIP_HD void inv_stageA(float2* exch, const PairTw& w, int f, int p, bool live, L
       for (int k1 = 0; k1 < 8; ++k1) {
         load.lo(k1, xr, xi);
         load.hi(k1, yr, yi);
-        inv_pair(xr, xi, yr, yi, w.wr2[k1].x, w.wi2[k1].x, r[k1].y, i[k1].y, r[15 - k1].y, i[15 - k1].y);
+        inv_pair(xr, xi, yr, yi, w.wr2[k1].y, w.wi2[k1].y, r[k1].y, i[k1].y, r[15 - k1].y, i[15 - k1].y);
       }
     }
     fft16x2(i, r);      // inverse transform: swapped roles

@@ -15,7 +15,7 @@ using namespace aip;
 
 extern "C" {
 
-int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, int center,
+int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, int center, int win_length,
                      const float* window, const int* gap_samples, const int* zero_frames,
                      const int* mask_frames, int mask_in_gap_is_one, int mag_kind, float eps, float power,
                      int T_out, float* spec, float* mag, float* phase, float* mask, int vec_ok) {
@@ -35,6 +35,7 @@ int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, 
   P.n_tiles = B * P.tiles_per_clip;
   P.tile_floats = (fwd_tile_len(hop) + 31) & ~31;
   P.n_tile_bufs = 1;
+  P.zero_groups = win_zero_groups(win_length);
   P.vec_ok = vec_ok && ((hop & 3) == 0) && ((pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(wave) & 15) == 0);
   std::vector<float> tile(P.tile_floats);
   std::vector<float2> exch(kExch);
@@ -55,7 +56,10 @@ int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, 
     const FwdTilePlan q = fwd_tile_plan(P, c);
     if (q.n_bulk > 0) memcpy(tile.data() + q.v_lo, q.src + q.g0 + q.v_lo, (size_t)q.n_bulk * 4);   // the TMA bulk copy
     if (fwd_needs_fixup(q)) for (int tid = 0; tid < kThreads; ++tid) fwd_fixup(q, tid, tile.data());
-    for (int tid = 0; tid < kThreads; ++tid) fwd_phase1(P, tid, tile.data(), exch.data(), win_s, lc[tid]);
+    for (int tid = 0; tid < kThreads; ++tid) {
+      if (P.zero_groups == 2) fwd_phase1<2>(P, tid, tile.data(), exch.data(), win_s, lc[tid]);
+      else fwd_phase1<0>(P, tid, tile.data(), exch.data(), win_s, lc[tid]);
+    }
     for (int tid = 0; tid < kThreads; ++tid) {
       switch (mode) {
 #define AIP_CASE(M) case (M): fwd_phase2<(M)>(P, tid, c, exch.data(), pw[tid], rel); break;

@@ -98,7 +98,7 @@ constexpr int kFwdThreads = 2 * kThreads;   // 8 stage-2 (consumer) warps + 8 st
 // with mbarrier hand-offs (tile_full / tile_empty / exch_full / exch_empty), so the copy of tile i+1,
 // stage 1 of tile i+1 and stage 2 of tile i overlap, and each role keeps ITS constants in registers
 // (stage 1: 32 window taps + 16 W256 twiddles per lane; stage 2: 16 W512 twiddles per warp).
-template <int kMode>
+template <int kMode, int kZP>
 __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdParams P) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bars[8];
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
       }
       const int es = i & 1;
       if (i >= 2) mbar_wait(exch_empty + es, (uint32_t)(((i >> 1) - 1) & 1));
-      fwd_phase1(P, ptid, tile, exch0 + es * kExch, win_s, lc);
+      fwd_phase1<kZP>(P, ptid, tile, exch0 + es * kExch, win_s, lc);
       mbar_arrive_warp(exch_full + es);
       fence_proxy_async();
       mbar_arrive_warp(tile_empty + slot);
@@ -597,7 +597,7 @@ static bool inv_fast_ok(const aip_stft_desc* d) {
 
 template <int kMode>
 static cudaError_t launch_fwd512_t(FwdParams P, const DevInfo& di, cudaStream_t st) {
-  auto kern = stft512_fwd_kernel<kMode>;
+  auto kern = P.zero_groups == 2 ? stft512_fwd_kernel<kMode, 2> : stft512_fwd_kernel<kMode, 0>;
   const size_t smem = fwd_smem_bytes(P.hop, P.n_tile_bufs);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -663,6 +663,7 @@ static int run_fwd(const aip_stft_desc* desc, FwdParams P, long long T_out, cuda
     P.n_tiles = (int)((long long)P.B * P.tiles_per_clip);
     P.tile_floats = (fwd_tile_len(P.hop) + 31) & ~31;
     P.n_tile_bufs = fwd_tile_bufs(desc, di);
+    P.zero_groups = win_zero_groups(desc->win_length);
     P.vec_ok = ((P.hop & 3) == 0) && ((P.pad & 3) == 0) && ((P.wave_pitch & 3) == 0) &&
                ((reinterpret_cast<uintptr_t>(P.wave) & 15) == 0);
     e = launch_fwd512(P, di, st);

@@ -52,6 +52,7 @@ struct FwdParams {
   int n_tile_bufs;          // 2: the next tile's copy overlaps stage 1; 1: large hops
   int tiles_per_cta;        // contiguous run of tiles per CTA
   int vec_ok;               // 16-byte bulk copies of the waveform are legal (alignment)
+  int zero_groups;          // win_zero_groups(win_length): the first / last 32 * zero_groups window taps are zero
 };
 
 AIP_HDX int fwd_tile_len(int hop) { return (kFR - 1) * hop + kNfft; }
@@ -116,11 +117,17 @@ AIP_HD void fwd_fixup(const FwdTilePlan& q, int tid, float* tile) {
 
 // stage 1 of the FFT for one tile: 256 threads, lane = n1 (16 lanes per frame); a thread owns column n1 of
 // frames fa and fa + 16 and runs them as the two lanes of the packed FP32x2 codelet
+template <int ZP>
 AIP_HD void fwd_phase1(const FwdParams& P, int tid, const float* tile, float2* exch, const float* win_s,
                        const LaneConst& lc) {
   const int warp = tid >> 5, lane = tid & 31;
   const int fa = 2 * warp + (lane >> 4);
-  fwd_stage1(tile, exch, win_s, P.hop, fa, fa + 16, lane & 15, lc);
+  fwd_stage1<ZP>(tile, exch, win_s, P.hop, fa, fa + 16, lane & 15, lc);
+}
+
+// zero n2 groups (32 taps) at each end of the centre-padded window that the kernels exploit: 2 or 0
+AIP_HDX int win_zero_groups(int win_length) {
+  return (win_length > 0 && win_length <= kNfft - 128) ? 2 : 0;
 }
 
 AIP_HD float mag_value(int mk, float xr, float xi, float eps, float power) {
@@ -172,6 +179,7 @@ struct FwdEmitT {
   AIP_HM void rows(int k_lo, int k_hi) { olo = k_lo * T; ohi = k_hi * T; s16 = 16 * T; }
   AIP_HM int lo(int j) const { return olo + j * s16; }
   AIP_HM int hi(int j) const { return ohi - j * s16; }
+  AIP_HM int bin(int k) const { return k * T; }
   AIP_HM void put1(int o, float xr, float xi) const {
     if (kM & FWD_ZERO) { if (zero) { xr = 0.0f; xi = 0.0f; } }
     if (kM & FWD_SPEC) spec[o] = make_float2(xr, xi);
@@ -217,6 +225,7 @@ struct FwdEmitFull {
   }
   AIP_HM long long lo(int j) const { return off_lo + j * s16; }
   AIP_HM long long hi(int j) const { return off_hi - j * s16; }
+  AIP_HM long long bin(int k) const { return base + (long long)k * P.T_out; }
   template <int SX, int SY>
   AIP_HM void put2(long long ox, long long oy, float2 xr, float2 xi) const {
     put1(ox, xr.x, SX < 0 ? -xi.x : xi.x);

@@ -144,7 +144,7 @@ def get_plan(n_fft: int, hop_length: Optional[int] = None, win_length: Optional[
                                    "the kernels are built for sm_100a only and there is no fallback")
         w = fft_window(window, win_length, n_fft).astype(np.float32)
         wd = torch.from_numpy(w).to(device)
-        desc = StftDesc(n_fft, hop_length, int(bool(center)), 0, wd.data_ptr())
+        desc = StftDesc(n_fft, hop_length, int(bool(center)), win_length, wd.data_ptr())
         plan = StftPlan(n_fft, hop_length, win_length, window, bool(center), device, wd, desc)
         _plans[key] = plan
     return plan

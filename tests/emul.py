@@ -27,7 +27,8 @@ def _i(a):
 
 def stft(wave, hop, window, center=True, gap_samples=None, zero_frames=None, mask_frames=None,
          mask_in_gap_is_one=True, mag_kind=0, eps=1e-9, power=1.0, t_out=None, want_spec=True,
-         want_phase=False, want_mask=False, vec_ok=True):
+         want_phase=False, want_mask=False, vec_ok=True, win_length=0):
+    """win_length > 0 promises that `window` is a win_length window centre-padded with zeros (zero-tap pruning)."""
     wave = np.ascontiguousarray(wave, dtype=np.float32)
     B, L = wave.shape
     pad = 256 if center else 0
@@ -40,7 +41,7 @@ def stft(wave, hop, window, center=True, gap_samples=None, zero_frames=None, mas
     mask = np.full((B, 257, t_out), -1, np.float32) if want_mask else None
     conv = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.int32)
     g, z, m = conv(gap_samples), conv(zero_frames), conv(mask_frames)
-    rc = lib().emul_stft512_fwd(_f(wave), B, L, C.c_longlong(L), hop, int(center), _f(window), _i(g), _i(z), _i(m),
+    rc = lib().emul_stft512_fwd(_f(wave), B, L, C.c_longlong(L), hop, int(center), int(win_length), _f(window), _i(g), _i(z), _i(m),
                                 int(mask_in_gap_is_one), mag_kind, C.c_float(eps), C.c_float(power), t_out,
                                 _f(spec), _f(mag), _f(phase), _f(mask), int(vec_ok))
     assert rc == 0, rc

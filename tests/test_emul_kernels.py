@@ -38,18 +38,28 @@ def inv_wss(window_name, win_length, hop, T, out_len, center=True):
 @pytest.mark.parametrize("L", [512, 777, 6001, 16000])
 def test_forward_complex(hop, wl, L):
     x = noise(2, L, seed=hop + L)
-    S = emul.stft(x, hop, win(wl))["spec"]
+    S = emul.stft(x, hop, win(wl), win_length=wl)["spec"]
     for b in range(2):
         ref = lr.stft(x[b], n_fft=512, hop_length=hop, win_length=wl)
         assert S[b].shape == ref.shape
         assert relerr(S[b], ref) < TOL
 
 
+@pytest.mark.parametrize("wl", [384, 256, 300])
+def test_forward_zero_tap_pruning_matches_full_transform(wl):
+    """win_length <= 384 lets stage 1 skip the 2 x 64 zero taps of the centre-padded window: same spectrum."""
+    x = noise(2, 9000, seed=wl)
+    full = emul.stft(x, 192, win(wl))["spec"]
+    pruned = emul.stft(x, 192, win(wl), win_length=wl)["spec"]
+    assert relerr(pruned, full) < 2e-6
+    assert relerr(pruned[0], lr.stft(x[0], n_fft=512, hop_length=192, win_length=wl)) < TOL
+
+
 @pytest.mark.parametrize("center", [True, False])
 @pytest.mark.parametrize("vec_ok", [True, False])
 def test_forward_center_and_scalar_path(center, vec_ok):
     x = noise(1, 5003, seed=3)
-    S = emul.stft(x, 192, win(384), center=center, vec_ok=vec_ok)["spec"]
+    S = emul.stft(x, 192, win(384), center=center, vec_ok=vec_ok, win_length=384)["spec"]
     ref = lr.stft(x[0], n_fft=512, hop_length=192, win_length=384, center=center)
     assert S[0].shape == ref.shape and relerr(S[0], ref) < TOL
 
@@ -67,7 +77,7 @@ def test_forward_gap_logmag_mask_crop():
     x = noise(B, L, seed=1)
     gaps = np.array([[0, 1600], [7000, 10200], [L - 1600, L], [5000, 5000]])
     frames = np.array([[0, 9], [36, 54], [75, 84], [10, 10]])
-    out = emul.stft(x, 192, win(384), gap_samples=gaps, mask_frames=frames, mag_kind=2, want_spec=False,
+    out = emul.stft(x, 192, win(384), win_length=384, gap_samples=gaps, mask_frames=frames, mag_kind=2, want_spec=False,
                     want_mask=True, t_out=80)
     for b in range(B):
         xg = x[b].copy()
@@ -98,7 +108,7 @@ def test_forward_gan_epilogue_and_spec_gap():
     assert relerr(np.expm1(imp["mag"][0].astype(np.float64)), np.expm1(ref["impaired_magnitude"].astype(np.float64))) < TOL
     # model_eval.py:154 spectrum-domain gap
     ev = cp.eval_frontend_cnnlstm(x[0], t0=0.3, t1=0.38)
-    z = emul.stft(x, 192, win(384), zero_frames=np.array([ev["gap_frames"]]), mag_kind=2, want_spec=False)
+    z = emul.stft(x, 192, win(384), win_length=384, zero_frames=np.array([ev["gap_frames"]]), mag_kind=2, want_spec=False)
     assert relerr(10.0 ** z["mag"][0].astype(np.float64), 10.0 ** ev["log_impaired_magnitude"].astype(np.float64)) < TOL
     assert np.all(z["mag"][0][:, ev["gap_frames"][0]:ev["gap_frames"][1]] == np.float32(-9.0))
 
@@ -184,7 +194,7 @@ def test_inverse_blend_prologue():
 def test_round_trip_snr(golden_clips):
     name = sorted(golden_clips)[0]
     x = golden_clips[name][:32000]
-    S = emul.stft(x[None], 192, win(384))["spec"]
+    S = emul.stft(x[None], 192, win(384), win_length=384)["spec"]
     T = S.shape[2]
     y = emul.istft(192, win(384), inv_wss("hann", 384, 192, T, 192 * (T - 1)), spec=S)[0]
     n = len(y)

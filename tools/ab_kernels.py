@@ -15,6 +15,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from ml_audio_inpainting_b200 import _cabi  # noqa: E402  (signatures only)
 
 SR, N_FFT = 16000, 512
+NO_PRUNE = "--no-prune" in sys.argv
 
 
 def load(path):
@@ -71,9 +72,10 @@ def main():
         out_len = hop * (T - 1)
         wav_out = torch.empty(Bi, out_len, device=dev)
         inv_wss = torch.empty(out_len, device=dev)
-        for path in sys.argv[1:]:
+        for path in [a for a in sys.argv[1:] if not a.startswith("--")]:
             lib = load(path)
-            desc = _cabi.StftDesc(N_FFT, hop, 1, 0, window.data_ptr())
+            # win_length in the descriptor enables the zero-tap pruning of newer builds (older builds ignore the field)
+            desc = _cabi.StftDesc(N_FFT, hop, 1, 0 if NO_PRUNE else win, window.data_ptr())
             d = C.byref(desc)
 
             def fwd():
