@@ -169,6 +169,44 @@ AIP_HD void fft16x2(float2 (&r)[16], float2 (&i)[16]) {
   fft16x2_tail(r, i);
 }
 
+// radix-4 butterflies that skip one OUTPUT (its slot is left untouched): inverse stage B drops the samples whose
+// synthesis-window tap is zero
+AIP_HD void radix4x2_noA(float2& ar, float2& ai, float2& br, float2& bi, float2& cr, float2& ci, float2& dr, float2& di) {
+  const float2 s0r = add2(ar, cr), s0i = add2(ai, ci), s1r = sub2(ar, cr), s1i = sub2(ai, ci);
+  const float2 s2r = add2(br, dr), s2i = add2(bi, di), s3r = sub2(br, dr), s3i = sub2(bi, di);
+  cr = sub2(s0r, s2r); ci = sub2(s0i, s2i);
+  br = add2(s1r, s3i); bi = sub2(s1i, s3r);
+  dr = sub2(s1r, s3i); di = add2(s1i, s3r);
+}
+AIP_HD void radix4x2_noD(float2& ar, float2& ai, float2& br, float2& bi, float2& cr, float2& ci, float2& dr, float2& di) {
+  const float2 s0r = add2(ar, cr), s0i = add2(ai, ci), s1r = sub2(ar, cr), s1i = sub2(ai, ci);
+  const float2 s2r = add2(br, dr), s2i = add2(bi, di), s3r = sub2(br, dr), s3i = sub2(bi, di);
+  ar = add2(s0r, s2r); ai = add2(s0i, s2i);
+  cr = sub2(s0r, s2r); ci = sub2(s0i, s2i);
+  br = add2(s1r, s3i); bi = sub2(s1i, s3r);
+}
+
+// fft16x2 whose outputs 0, 1, 14 and 15 (slots perm16(k)) are not needed and not computed
+AIP_HD void fft16x2_out_z2(float2 (&r)[16], float2 (&i)[16]) {
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+    radix4x2(r[a], i[a], r[a + 4], i[a + 4], r[a + 8], i[a + 8], r[a + 12], i[a + 12]);
+  cmulx2(r[5], i[5], kC1, -kS1);
+  cmulx2(r[9], i[9], kR2, -kR2);
+  cmulx2(r[13], i[13], kS1, -kC1);
+  cmulx2(r[6], i[6], kR2, -kR2);
+  { const float2 t = r[10]; r[10] = i[10]; i[10] = mul2s(t, -1.0f); }
+  cmulx2(r[14], i[14], -kR2, -kR2);
+  cmulx2(r[7], i[7], kS1, -kC1);
+  cmulx2(r[11], i[11], -kR2, -kR2);
+  cmulx2(r[15], i[15], -kC1, kS1);
+  // slot group q holds bins q, q + 4, q + 8, q + 12 in positions A, B, C, D
+  radix4x2_noA(r[0], i[0], r[1], i[1], r[2], i[2], r[3], i[3]);          // bin 0 dropped
+  radix4x2_noA(r[4], i[4], r[5], i[5], r[6], i[6], r[7], i[7]);          // bin 1 dropped
+  radix4x2_noD(r[8], i[8], r[9], i[9], r[10], i[10], r[11], i[11]);      // bin 14 dropped
+  radix4x2_noD(r[12], i[12], r[13], i[13], r[14], i[14], r[15], i[15]);  // bin 15 dropped
+}
+
 // Same transform when inputs 0, 1, 14 and 15 are zero (never read: the slots may hold anything)
 AIP_HD void fft16x2_in_z2(float2 (&r)[16], float2 (&i)[16]) {
   radix4x2_a0(r[0], i[0], r[4], i[4], r[8], i[8], r[12], i[12]);
@@ -469,6 +507,10 @@ AIP_HD void inv_stageA(float2* exch, const PairTw& w, int f, int p, bool live, L
 // written IN PLACE into the exchange buffer, which thereby becomes the frame buffer: float2 slot
 // (m*33 + f) = samples (2m, 2m+1) of frame f, m = n1 + 16 n2 (a thread reads and writes the same 2 x 16 slots).
 // ---------------------------------------------------------------------------------------------------
+// ZP = 2: the first / last 64 synthesis-window taps are zero (win 384 in n_fft 512): those samples are neither computed
+// nor stored -- their frame-buffer slots keep stale data, so only an overlap-add that skips them may follow
+// (inv_ola_fast<192, 0, 1>).
+template <int ZP>
 AIP_HD void inv_stageB(float2* exch, const float* win_s, int fa, int fb, int n1, const LaneConst& c) {
   float2 r[16], i[16];
   float2* pa = exch + n1 * kXP + fa;
@@ -486,10 +528,11 @@ AIP_HD void inv_stageB(float2* exch, const float* win_s, int fa, int fb, int n1,
     r[ka] = make_float2(ar_a, ar_b); i[ka] = make_float2(ai_a, ai_b);
     r[kb] = make_float2(br_a, br_b); i[kb] = make_float2(bi_a, bi_b);
   }
-  fft16x2(i, r);
+  if (ZP == 2) fft16x2_out_z2(i, r);
+  else fft16x2(i, r);
   const float4* wrow = reinterpret_cast<const float4*>(win_s + n1 * kWinPitch);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = ZP / 2; j < 8 - ZP / 2; ++j) {
     const float4 w = wrow[j];
     const float2 zr0 = r[perm16(2 * j)], zi0 = i[perm16(2 * j)];
     const float2 zr1 = r[perm16(2 * j + 1)], zi1 = i[perm16(2 * j + 1)];
@@ -498,6 +541,16 @@ AIP_HD void inv_stageB(float2* exch, const float* win_s, int fa, int fb, int n1,
     pa[(2 * j + 1) * 16 * kXP] = make_float2(zr1.x * w.z, zi1.x * w.w);
     pb[(2 * j + 1) * 16 * kXP] = make_float2(zr1.y * w.z, zi1.y * w.w);
   }
+}
+
+// clip-edge tiles after inv_stageB<2>: the general overlap-add reads every tap, so the skipped ones must read as zero
+AIP_HD void inv_stageB_zero_pruned(float2* exch, int fa, int fb, int n1) {
+  float2* pa = exch + n1 * kXP + fa;
+  float2* pb = exch + n1 * kXP + fb;
+  const float2 z = make_float2(0.0f, 0.0f);
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2)
+    if (n2 < 2 || n2 >= 14) { pa[n2 * 16 * kXP] = z; pb[n2 * 16 * kXP] = z; }
 }
 
 // Geometry of an inverse tile: 32 frames are computed, FO of them worth of output hops are produced;

@@ -76,7 +76,7 @@ int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, 
 }
 
 int emul_istft512(const float* spec, const float* mag, const float* phase, int mag_domain,
-                  const int* db_flags, int B, int T, int length, int hop, int center,
+                  const int* db_flags, int B, int T, int length, int hop, int center, int win_length,
                   const float* window, const float* inv_wss, float* out, long long out_pitch,
                   const float* blend_in, const float* blend_mask) {
   InvParams P;
@@ -113,6 +113,7 @@ int emul_istft512(const float* spec, const float* mag, const float* phase, int m
     const long long s_ref = (long long)f_ref * hop - P.pad;
     P.wss_ref = (f_ref <= P.n_frames - 1 && s_ref >= 0 && s_ref + hop <= out_len) ? (int)s_ref : -1;
   }
+  P.ola_fast = inv_ola_fast_kind(hop, P.pad, win_length);
   std::vector<float> wtab;
   if (P.wss_ref >= 0 && hop <= kMaxWtab) wtab.assign(inv_wss + P.wss_ref, inv_wss + P.wss_ref + hop);
   std::vector<float2> exch(kExch);
@@ -136,8 +137,17 @@ int emul_istft512(const float* spec, const float* mag, const float* phase, int m
 #undef AIP_CASE
       }
     }
-    for (int tid = 0; tid < kThreads; ++tid) inv_phase1(P, tid, exch.data(), win_s, lc[tid]);
-    for (int tid = 0; tid < kThreads; ++tid) inv_phase2(P, tid, c, exch.data(), wtab.empty() ? nullptr : wtab.data());
+    const float* wt = wtab.empty() ? nullptr : wtab.data();
+    for (int tid = 0; tid < kThreads; ++tid) {
+      if (P.ola_fast == 1) inv_phase1<1>(P, tid, c, exch.data(), win_s, lc[tid]);
+      else if (P.ola_fast == 2) inv_phase1<2>(P, tid, c, exch.data(), win_s, lc[tid]);
+      else inv_phase1<0>(P, tid, c, exch.data(), win_s, lc[tid]);
+    }
+    for (int tid = 0; tid < kThreads; ++tid) {
+      if (P.ola_fast == 1) inv_phase2<1>(P, tid, c, exch.data(), wt);
+      else if (P.ola_fast == 2) inv_phase2<2>(P, tid, c, exch.data(), wt);
+      else inv_phase2<0>(P, tid, c, exch.data(), wt);
+    }
     tile_advance(c, P.tiles_per_clip);
   }
   return 0;

@@ -11,6 +11,7 @@
 //                        per CTA, shared-memory radix-2.  Correct, not tuned: the reference's
 //                        models only ever use n_fft = 512 (config.py:28, GAN/config.yaml:12).
 //   small elementwise / reduction kernels for the gap, mask, dB-heuristic and peak-normalise rows.
+#include <cuda.h>            // CUtensorMap types only: the encoder is fetched through cudaGetDriverEntryPoint
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -54,6 +55,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// global -> shared TMA tensor tile (SASS: UTMALDG), 4-D coordinates, completion on the mbarrier; elements outside the
+// tensor are zero-filled and still counted in the transaction bytes
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -191,7 +199,7 @@ struct WaitBefore {
 //   becomes the frame buffer) -> named barrier -> overlap-add + 1/window-sum-square -> HBM -> release
 // Stage A computes tile i+1 in registers while stage B works on tile i and only then waits for an exchange
 // buffer; a ring of n_bufs buffers is supported, two measured fastest (see kInvBufsDefault).
-template <int kMode>
+template <int kMode, int kFast>
 __global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParams P) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bars[2 * kInvBufs];
@@ -240,9 +248,151 @@ __global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParam
     for (int i = 0; i < n; ++i) {
       float2* exch = exch0 + es * kExch;
       mbar_wait(exch_full + es, (uint32_t)(use & 1));
-      inv_phase1(P, btid, exch, win_s, lc);
+      inv_phase1<kFast>(P, btid, c, exch, win_s, lc);
       named_bar_sync(1, kThreads);
-      inv_phase2(P, btid, c, exch, wtab);
+      inv_phase2<kFast>(P, btid, c, exch, wtab);
+      mbar_arrive_warp(exch_empty + es);
+      tile_advance(c, P.tiles_per_clip);
+      if (++es == P.n_bufs) { es = 0; ++use; }
+    }
+  }
+}
+
+// ---- complex input staged by TMA tensor tiles ---------------------------------------------------------
+// The direct-load kernel above keeps at most a few spectrum loads per thread in flight (the 64 data registers of the
+// packed codelet leave no room for more), which bounds it by HBM latency.  Here every stage-A warp owns a private,
+// double-buffered staging area that TMA fills one tile ahead: the spectrogram is described to the TMA unit as the
+// 4-D tensor (2t, p, j, b) with bin k = 16 j + p, so the 16 rows p + 16 j a pair-job reads are ONE box of
+// 68 floats x 1 x 16 x 1, the 16 partner rows 256 - p - 16 j a second one, and frames outside [0, n_frames) arrive
+// as zeros.  Needs an even T (row pitch 8 T bytes must be a multiple of 16) and a 16-byte aligned base.
+// The TMA unit needs the innermost start coordinate 16-byte aligned (an odd first frame raises an illegal-instruction
+// fault, tools/microbench/tma3d_probe.cu), so a box starts at the even frame below t0 and is 34 frames wide.
+constexpr int kStageFr = kFR + 2;                       // frames per staged row
+constexpr int kStageB = 592;                            // float2 offset of region B (128-byte aligned: 4736 B)
+constexpr int kStageSlot = 1136;                        // float2 per slot (9088 B): A = rows 0..16 (17 x 34), B = 16 rows
+constexpr int kStageBytesWarp = 2 * kStageSlot * 8;     // two slots
+
+struct InvLoadStaged {      // stage-A loader out of the warp's staging slot (lane = frame)
+  const float2* slot;       // + lane + (t0 & 1)
+  const float2* plo;
+  const float2* phi;
+  __device__ __forceinline__ void rows(int k_lo, int k_hi) {
+    if (k_hi == 256) { plo = slot; phi = slot + 16 * kStageFr; }                               // job 0: rows j and 16 - j of region A
+    else if (k_lo == 8) { plo = slot + kStageB; phi = slot + kStageB + 15 * kStageFr; }       // job 8: region B
+    else { plo = slot; phi = slot + kStageB + 15 * kStageFr; }                                 // p > 0: A = p + 16 j, B = (16-p) + 16 j'
+  }
+  __device__ __forceinline__ void lo(int j, float& xr, float& xi) const { const float2 v = plo[j * kStageFr]; xr = v.x; xi = v.y; }
+  __device__ __forceinline__ void hi(int j, float& xr, float& xi) const { const float2 v = phi[-j * kStageFr]; xr = v.x; xi = v.y; }
+};
+
+// one elected lane: the two (p > 0) or three (p = 0) boxes of a tile into a staging slot
+__device__ __forceinline__ void inv_issue_stage(const InvParams& P, const CUtensorMap* map16, const CUtensorMap* map1,
+                                                const TileCursor& c, int p, float2* slot, uint64_t* bar) {
+  const int t0e = (c.tt * P.g.FO - P.g.HL) & ~1;
+  if (p != 0) {
+    mbar_expect_tx(bar, 2u * 16u * kStageFr * 8u);
+    tma_load_4d(slot, map16, 2 * t0e, p, 0, c.b, bar);
+    tma_load_4d(slot + kStageB, map16, 2 * t0e, 16 - p, 0, c.b, bar);
+  } else {
+    mbar_expect_tx(bar, 33u * kStageFr * 8u);
+    tma_load_4d(slot, map16, 2 * t0e, 0, 0, c.b, bar);
+    tma_load_4d(slot + 16 * kStageFr, map1, 2 * t0e, 0, 16, c.b, bar);
+    tma_load_4d(slot + kStageB, map16, 2 * t0e, 8, 0, c.b, bar);
+  }
+}
+
+struct StagedBefore {       // runs once the slot has been read into registers: refill it, then wait for the exchange buffer
+  const InvParams& P;
+  const CUtensorMap* map16;
+  const CUtensorMap* map1;
+  const TileCursor& next2;
+  int p;
+  float2* slot;
+  uint64_t* full;
+  bool refill;
+  uint64_t* exch_bar;
+  uint32_t exch_parity;
+  bool exch_wait;
+  __device__ __forceinline__ void operator()() const {
+    __syncwarp();
+    if (refill && (threadIdx.x & 31) == 0) {
+      fence_proxy_async();
+      inv_issue_stage(P, map16, map1, next2, p, slot, full);
+    }
+    if (exch_wait) mbar_wait(exch_bar, exch_parity);
+  }
+};
+
+template <int kFast>
+__global__ void __launch_bounds__(kFwdThreads, 1) istft512_tma_kernel(const InvParams P, const __grid_constant__ CUtensorMap map16,
+                                                                       const __grid_constant__ CUtensorMap map1) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bars[2 * kInvBufs + 16];
+  __shared__ __align__(8) float wtab_s[kMaxWtab];
+  __shared__ __align__(16) float win_s[kWinTable];
+  __shared__ __align__(8) float2 tw_s[kTwTable];
+  window_table_fill(win_s, P.window, 1.0f / 512.0f, threadIdx.x, blockDim.x);
+  twiddle_table_fill(tw_s, threadIdx.x, blockDim.x);
+  const float* wtab = (P.wss_ref >= 0 && P.hop <= kMaxWtab) ? wtab_s : nullptr;
+  if (wtab)
+    for (int r = threadIdx.x; r < P.hop; r += blockDim.x) wtab_s[r] = P.inv_wss[P.wss_ref + r];
+  uint64_t* exch_full = bars;
+  uint64_t* exch_empty = bars + kInvBufs;
+  uint64_t* stage_full = bars + 2 * kInvBufs;      // [warp][slot], count 1 (+ tx bytes)
+  float2* stage0 = reinterpret_cast<float2*>(smem);                         // 8 warps x 2 slots
+  float2* exch0 = stage0 + 8 * 2 * kStageSlot;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int i = 0; i < kInvBufs; ++i) {
+      mbar_init(exch_full + i, kThreads / 32);
+      mbar_init(exch_empty + i, kThreads / 32);
+    }
+    for (int i = 0; i < 16; ++i) mbar_init(stage_full + i, 1);
+  }
+  __syncthreads();
+  const int first = blockIdx.x * P.tiles_per_cta;
+  int n = P.n_tiles - first;
+  if (n > P.tiles_per_cta) n = P.tiles_per_cta;
+  if (n <= 0) return;
+  TileCursor c = tile_cursor(first, P.tiles_per_clip);
+  if (tid < kThreads) {
+    const int warp = tid >> 5, lane = tid & 31;
+    PairTw w;
+    pair_tw_init(w, warp);
+    float2* my_stage = stage0 + warp * 2 * kStageSlot;
+    uint64_t* my_full = stage_full + 2 * warp;
+    TileCursor c2 = c;                                  // cursor of the tile two ahead (the next refill)
+    if (lane == 0) inv_issue_stage(P, &map16, &map1, c2, warp, my_stage, my_full);
+    tile_advance(c2, P.tiles_per_clip);
+    if (lane == 0 && n > 1) inv_issue_stage(P, &map16, &map1, c2, warp, my_stage + kStageSlot, my_full + 1);
+    tile_advance(c2, P.tiles_per_clip);
+    int es = 0, use = 0;
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+      const int s = i & 1;
+      float2* slot = my_stage + s * kStageSlot;
+      mbar_wait(my_full + s, (uint32_t)((i >> 1) & 1));
+      InvLoadStaged load{slot + lane + ((c.tt * P.g.FO - P.g.HL) & 1), nullptr, nullptr};
+      StagedBefore sb{P, &map16, &map1, c2, warp, slot, my_full + s, i + 2 < n,
+                      exch_empty + es, (uint32_t)((use - 1) & 1), use >= 1};
+      inv_stageA(exch0 + es * kExch, w, lane, warp, true, load, sb);
+      mbar_arrive_warp(exch_full + es);
+      tile_advance(c, P.tiles_per_clip);
+      tile_advance(c2, P.tiles_per_clip);
+      if (++es == P.n_bufs) { es = 0; ++use; }
+    }
+  } else {
+    const int btid = tid - kThreads;
+    LaneConst lc;
+    lane_const_init(lc, tw_s, btid & 15);
+    int es = 0, use = 0;
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+      float2* exch = exch0 + es * kExch;
+      mbar_wait(exch_full + es, (uint32_t)(use & 1));
+      inv_phase1<kFast>(P, btid, c, exch, win_s, lc);
+      named_bar_sync(1, kThreads);
+      inv_phase2<kFast>(P, btid, c, exch, wtab);
       mbar_arrive_warp(exch_empty + es);
       tile_advance(c, P.tiles_per_clip);
       if (++es == P.n_bufs) { es = 0; ++use; }
@@ -576,6 +726,43 @@ static int fwd_tile_bufs(const aip_stft_desc* d, const DevInfo& di) {
 
 static bool fwd_fast_ok(const aip_stft_desc* d, const DevInfo& di) { return fwd_tile_bufs(d, di) > 0; }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// complex spectrogram [B, 257, T] as the float32 tensor (2t, p, j, b), bin = 16 j + p; box = 64 floats x 1 x rows_j x 1
+static bool inv_make_map(CUtensorMap* map, const float2* spec, int B, int T, int n_frames, int rows_j) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[4] = {2ull * (cuuint64_t)n_frames, 16ull, 17ull, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {8ull * T, 128ull * T, 8ull * kBins * T};          // bytes, dims 1..3
+  const cuuint32_t box[4] = {2u * kStageFr, 1u, (cuuint32_t)rows_j, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float2*>(spec), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool inv_tma_ok(const InvParams& P) {
+  if (!P.spec || (P.T & 1) || (reinterpret_cast<uintptr_t>(P.spec) & 15)) return false;
+  // Off unless AIP_INV_TMA=1: measured 0.568 ms against 0.535 ms for the direct-load kernel (1024 x 10 s, hop 192) -- the
+  // staging slots leave room for ONE exchange buffer only, and stage A is not the slower role (profiles/README.md).
+  const char* e = getenv("AIP_INV_TMA");
+  return e && atoi(e) != 0;
+}
+
 static void inv_fill_ola(InvParams& P) {
   P.hop_magic = (unsigned)((0x100000000ULL + (unsigned)P.hop - 1) / (unsigned)P.hop);
   P.col_magic = (unsigned)((0x100000000ULL + (unsigned)(P.hop / 2) - 1) / (unsigned)(P.hop / 2));
@@ -699,24 +886,43 @@ static int run_inv(const aip_stft_desc* desc, InvParams P, long long length, voi
     P.vec_ok = ((P.out_pitch & 1) == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 7) == 0) &&
                ((reinterpret_cast<uintptr_t>(P.inv_wss) & 7) == 0);
     inv_fill_ola(P);
+    P.ola_fast = inv_ola_fast_kind(P.hop, P.pad, desc->win_length);
+    if (const char* of = getenv("AIP_OLA_FAST")) { if (!((atoi(of) >> (P.ola_fast - 1)) & 1)) P.ola_fast = 0; }   // profiling switch (bit mask of kinds)
     P.n_bufs = kInvBufsDefault;
     if (const char* nb = getenv("AIP_INV_BUFS")) { const int v = atoi(nb); if (v >= 1 && v <= kInvBufs) P.n_bufs = v; }   // profiling switch
-    const size_t smem = (size_t)P.n_bufs * kExch * sizeof(float2);
     int grid = di.sms;
     if (grid > P.n_tiles) grid = P.n_tiles;
     P.tiles_per_cta = (P.n_tiles + grid - 1) / grid;
     grid = (P.n_tiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
-    void (*kern)(const InvParams) = nullptr;
-    switch (inv_mode_of(P)) {
-      case INV_SPEC: kern = istft512_kernel<INV_SPEC>; break;
-      case inv_mag_mode(0, false): kern = istft512_kernel<inv_mag_mode(0, false)>; break;
-      case inv_mag_mode(0, true): kern = istft512_kernel<inv_mag_mode(0, true)>; break;
-      case inv_mag_mode(1, false): kern = istft512_kernel<inv_mag_mode(1, false)>; break;
-      case inv_mag_mode(1, true): kern = istft512_kernel<inv_mag_mode(1, true)>; break;
-      case inv_mag_mode(2, false): kern = istft512_kernel<inv_mag_mode(2, false)>; break;
-      case INV_BLEND: kern = istft512_kernel<INV_BLEND>; break;
-      default: kern = istft512_kernel<inv_mag_mode(2, true)>; break;
+    if (inv_tma_ok(P)) {
+      CUtensorMap map16, map1;
+      if (inv_make_map(&map16, P.spec, P.B, P.T, P.n_frames, 16) && inv_make_map(&map1, P.spec, P.B, P.T, P.n_frames, 1)) {
+        P.n_bufs = 1;      // 8 x 2 staging slots (142 KB) + one exchange buffer (66 KB)
+        const size_t smem_tma = (size_t)8 * kStageBytesWarp + (size_t)kExch * sizeof(float2);
+        auto tk = P.ola_fast == 1 ? istft512_tma_kernel<1> : (P.ola_fast == 2 ? istft512_tma_kernel<2> : istft512_tma_kernel<0>);
+        e = cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
+        if (e != cudaSuccess) return (int)e;
+        tk<<<(unsigned)grid, kFwdThreads, smem_tma, st>>>(P, map16, map1);
+        return (int)cudaGetLastError();
+      }
     }
+    const size_t smem = (size_t)P.n_bufs * kExch * sizeof(float2);
+    void (*kern)(const InvParams) = nullptr;
+#define AIP_INV_CASE(M) \
+    case (M): kern = P.ola_fast == 1 ? istft512_kernel<(M), 1> : (P.ola_fast == 2 ? istft512_kernel<(M), 2> : istft512_kernel<(M), 0>); break;
+    switch (inv_mode_of(P)) {
+      AIP_INV_CASE(INV_SPEC)
+      AIP_INV_CASE(inv_mag_mode(0, false))
+      AIP_INV_CASE(inv_mag_mode(0, true))
+      AIP_INV_CASE(inv_mag_mode(1, false))
+      AIP_INV_CASE(inv_mag_mode(1, true))
+      AIP_INV_CASE(inv_mag_mode(2, false))
+      AIP_INV_CASE(INV_BLEND)
+      default: kern = P.ola_fast == 1 ? istft512_kernel<inv_mag_mode(2, true), 1>
+                                      : (P.ola_fast == 2 ? istft512_kernel<inv_mag_mode(2, true), 2> : istft512_kernel<inv_mag_mode(2, true), 0>);
+               break;
+    }
+#undef AIP_INV_CASE
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<(unsigned)grid, kFwdThreads, smem, st>>>(P);

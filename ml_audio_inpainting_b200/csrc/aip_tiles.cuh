@@ -335,6 +335,8 @@ struct InvParams {
   int ola_terms;            // ceil(512 / hop): frames overlapping one sample
   int ola_dq, ola_dr;       // (2 * 256) / hop and (2 * 256) % hop: per-iteration advance of a thread's pair
   int wss_ref;              // inv_wss[wss_ref + r] = periodic value for frame offset r; < 0: no interior
+  int ola_fast;             // compile-time specialised overlap-add of interior tiles: 0 none, 1 = hop 192 with the 2 x 64 zero
+                            // taps of a win <= 384 window (2 terms), 2 = hop 128, full window (4 terms); centre padding only
 
 };
 
@@ -445,11 +447,70 @@ AIP_HD void inv_phase0(const InvParams& P, int tid, const TileCursor& c, float2*
   }
 }
 
-// stage B for one tile: 256 threads, lane = n1
-AIP_HD void inv_phase1(const InvParams& P, int tid, float2* exch, const float* win_s, const LaneConst& lc) {
+// which specialised overlap-add (if any) the launch may use: decided once on the host
+AIP_HDX int inv_ola_fast_kind(int hop, int pad, int win_length) {
+  if (pad != kNfft / 2) return 0;
+  if (hop == 192 && win_zero_groups(win_length) == 2) return 1;
+  if (hop == 128) return 2;
+  return 0;
+}
+
+// Interior tile: all 32 local frames exist, the whole tile lies inside the output, vector stores are legal and the
+// periodic 1/window-sum-square table is present.  Only such tiles run the specialised phases.
+AIP_HD bool inv_tile_interior(const InvParams& P, const TileCursor& c) {
+  const int f_first = c.tt * P.g.FO - P.g.HL;
+  const bool edge = f_first < 0 || P.n_frames - 1 - f_first < kFR - 1;
+  const bool has_wtab = P.wss_ref >= 0 && P.hop <= 1024;
+  return !edge && has_wtab && P.vec_ok && (c.tt + 1) * P.g.FO * P.hop <= P.out_len;
+}
+
+// stage B for one tile: 256 threads, lane = n1.  kFast (template parameter of the kernel) = InvParams::ola_fast.
+template <int kFast>
+AIP_HD void inv_phase1(const InvParams& P, int tid, const TileCursor& c, float2* exch, const float* win_s, const LaneConst& lc) {
   const int warp = tid >> 5, lane = tid & 31;
   const int fa = 2 * warp + (lane >> 4);
-  inv_stageB(exch, win_s, fa, fa + 16, lane & 15, lc);
+  if (kFast == 1) {
+    inv_stageB<2>(exch, win_s, fa, fa + 16, lane & 15, lc);
+    if (!inv_tile_interior(P, c)) inv_stageB_zero_pruned(exch, fa, fa + 16, lane & 15);
+  } else {
+    inv_stageB<0>(exch, win_s, fa, fa + 16, lane & 15, lc);
+  }
+}
+
+// Overlap-add of an interior tile with everything but the thread's column known at compile time (centre padding).
+// The output pair at offset u = 2 cc + 256 of local frame F0 = HL + h is the sum over e = EMIN..EMAX of frame F0 + e at
+// offset u - e HOP; for (HOP 192, window 384) that is e in {0, 1} for every column (the third covering frame only
+// contributes zero taps), for (HOP 128, window 512) e in {-1, 0, 1, 2}.  A thread owns pair columns pc and pc + C/2
+// (conflict-free LDS.64 over consecutive pc) and walks the hops h = g, g + G, ... fully unrolled: per pair
+// (EMAX - EMIN + 1) LDS.64, (EMAX - EMIN) FADD2, one FMUL2 and one 8-byte store, no integer work.
+template <int HOP, int EMIN, int EMAX>
+AIP_HD void inv_ola_fast(const InvParams& P, int tid, int s0, const float2* fbuf, const float* wtab, float* dst) {
+  constexpr int C = HOP / 2, TC = C / 2;               // pair columns per hop, thread columns
+  constexpr int G = kThreads / TC;                     // hop groups walking in parallel
+  constexpr int HL = (kNfft - 1 - kNfft / 2) / HOP, HH = (kNfft / 2 - 1) / HOP, FO = kFR - 1 - HL - HH;
+  constexpr int NIT = (FO + G - 1) / G;
+  constexpr int STEP = C * kXP - 1;                    // slot(frame F, offset n) - slot(frame F + 1, offset n - HOP)
+  const int g = tid / TC, pc = tid - g * TC;
+  if (g >= G) return;
+  const int u1 = 2 * pc + kNfft / 2, u2 = u1 + 2 * TC;
+  const float2 nw1 = *reinterpret_cast<const float2*>(wtab + (u1 % HOP));
+  const float2 nw2 = *reinterpret_cast<const float2*>(wtab + (u2 % HOP));
+  const float2* src1 = fbuf + (u1 >> 1) * kXP + HL + g;
+  const float2* src2 = src1 + TC * kXP;
+  float* out = dst + s0 + g * HOP + 2 * pc;
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    if (it * G + G <= FO || g + it * G < FO) {
+      float2 a1 = src1[it * G - EMIN * STEP], a2 = src2[it * G - EMIN * STEP];     // increasing frame order, like librosa
+#pragma unroll
+      for (int e = EMIN + 1; e <= EMAX; ++e) {
+        a1 = add2(a1, src1[it * G - e * STEP]);
+        a2 = add2(a2, src2[it * G - e * STEP]);
+      }
+      *reinterpret_cast<float2*>(out + it * G * HOP) = mul2(a1, nw1);
+      *reinterpret_cast<float2*>(out + it * G * HOP + 2 * TC) = mul2(a2, nw2);
+    }
+  }
 }
 
 // Interior tile (all 32 local frames exist, whole tile inside the output, vector stores legal, periodic 1/wss
@@ -490,6 +551,7 @@ AIP_HD void inv_ola_interior(const InvParams& P, int tid, int s0, const float2* 
 // wtab: one period of 1/window-sum-square indexed by the offset r inside a frame -- valid for every sample of
 // a tile whose 32 local frames all exist (window_sumsquare is exactly hop-periodic there, same float32
 // accumulation order); tiles at the clip edges (or wtab == null) read the global table instead.
+template <int kFast>
 AIP_HD void inv_phase2(const InvParams& P, int tid, const TileCursor& c, const float2* fbuf, const float* wtab) {
   const int hop = P.hop;
   const int f_first = c.tt * P.g.FO - P.g.HL;
@@ -501,6 +563,8 @@ AIP_HD void inv_phase2(const InvParams& P, int tid, const TileCursor& c, const f
   const bool edge = fl_min > 0 || fl_max < kFR - 1;
   float* dst = P.out + (long long)c.b * P.out_pitch;
   if (!edge && wtab && P.vec_ok && s0 + P.g.FO * hop <= P.out_len) {
+    if (kFast == 1) return inv_ola_fast<192, 0, 1>(P, tid, s0, fbuf, wtab, dst);
+    if (kFast == 2) return inv_ola_fast<128, -1, 2>(P, tid, s0, fbuf, wtab, dst);
     if (P.ola_terms == 3) return inv_ola_interior<3>(P, tid, s0, fbuf, wtab, dst);
     if (P.ola_terms == 4) return inv_ola_interior<4>(P, tid, s0, fbuf, wtab, dst);
     if (P.ola_terms == 2) return inv_ola_interior<2>(P, tid, s0, fbuf, wtab, dst);

@@ -120,12 +120,28 @@ def test_inverse_complex(hop, wl, L):
     S = np.stack([lr.stft(x[b], n_fft=512, hop_length=hop, win_length=wl) for b in range(2)])
     T = S.shape[2]
     ref = np.stack([lr.istft(S[b], hop_length=hop, win_length=wl, n_fft=512) for b in range(2)])
-    y = emul.istft(hop, win(wl), inv_wss("hann", wl, hop, T, ref.shape[1]), spec=S)
+    y = emul.istft(hop, win(wl), inv_wss("hann", wl, hop, T, ref.shape[1]), spec=S, win_length=wl)
     good = np.ones(ref.shape[1], bool)
     if hop == wl:   # window-sum-square has (near-)zeros: compare where it is well conditioned
         good = inv_wss("hann", wl, hop, T, ref.shape[1]) < 100.0
     for b in range(2):
         assert relerr(y[b][good], ref[b][good]) < TOL
+
+
+@pytest.mark.parametrize("hop,wl", [(192, 384), (192, 256), (128, 512), (128, 384)])
+def test_inverse_specialised_overlap_add_matches_generic(hop, wl):
+    """Interior tiles of hop 192 / 128 run the compile-time overlap-add (and, for win <= 384 at hop 192, the
+    output-pruned stage B); win_length = 0 keeps the generic phases: same waveform, many tiles, ragged tail."""
+    x = noise(2, 48000 + 77, seed=hop + wl)
+    S = np.stack([lr.stft(x[b], n_fft=512, hop_length=hop, win_length=wl) for b in range(2)])
+    T = S.shape[2]
+    iw = inv_wss("hann", wl, hop, T, hop * (T - 1))
+    fast = emul.istft(hop, win(wl), iw, spec=S, win_length=wl)
+    generic = emul.istft(hop, win(wl), iw, spec=S, win_length=0) if hop == 192 else None
+    ref = np.stack([lr.istft(S[b], hop_length=hop, win_length=wl, n_fft=512) for b in range(2)])
+    assert relerr(fast, ref) < TOL
+    if generic is not None:
+        assert relerr(fast, generic) < 2e-6
 
 
 @pytest.mark.parametrize("length", [3000, 15872, 16000, 20000])
@@ -136,7 +152,7 @@ def test_inverse_length_argument(length):
     T = S.shape[1]
     n_frames = min(T, int(np.ceil((length + 512) / 192)))
     iw = inv_wss("hann", 384, 192, n_frames, length)
-    y = emul.istft(192, win(384), iw, spec=S[None], length=length)
+    y = emul.istft(192, win(384), iw, spec=S[None], length=length, win_length=384)
     assert y.shape[1] == len(ref) == length
     good = iw < 100.0        # past the last frame's centre the window sum decays to ~0: ill-conditioned in the reference too
     assert good.sum() >= min(length, 15936) - 8 and relerr(y[0][good], ref[good]) < TOL
@@ -159,7 +175,7 @@ def test_inverse_mag_phase_and_domains():
     ref = lr.istft((np.abs(S) * np.exp(1j * np.angle(S))).astype(np.complex64), hop_length=192, win_length=384, n_fft=512)
     iw = inv_wss("hann", 384, 192, T, len(ref))
     mag, ph = np.abs(S)[None], np.angle(S)[None]
-    assert relerr(emul.istft(192, win(384), iw, mag=mag, phase=ph)[0], ref) < TOL
+    assert relerr(emul.istft(192, win(384), iw, mag=mag, phase=ph, win_length=384)[0], ref) < TOL
     assert relerr(emul.istft(192, win(384), iw, mag=np.log10(mag + 1e-12), phase=ph, mag_domain=1)[0], ref) < 2 * TOL
     db = 20 * np.log10(mag / mag.max() * 0.5 + 1e-12)
     ref_db = lr.istft((lr.db_to_amplitude(db[0]) * np.exp(1j * ph[0])).astype(np.complex64), hop_length=192, win_length=384, n_fft=512)
@@ -196,7 +212,7 @@ def test_round_trip_snr(golden_clips):
     x = golden_clips[name][:32000]
     S = emul.stft(x[None], 192, win(384), win_length=384)["spec"]
     T = S.shape[2]
-    y = emul.istft(192, win(384), inv_wss("hann", 384, 192, T, 192 * (T - 1)), spec=S)[0]
+    y = emul.istft(192, win(384), inv_wss("hann", 384, 192, T, 192 * (T - 1)), spec=S, win_length=384)[0]
     n = len(y)
     err = (x[512:n - 512] - y[512:n - 512]).astype(np.float64)
     snr = 10 * np.log10((x[512:n - 512].astype(np.float64) ** 2).sum() / (err ** 2).sum())
