@@ -39,6 +39,7 @@ CLIP_S = 10.0
 GAP_S = 0.2
 EPS = 1e-9
 METRIC = "audio-seconds/sec (STFT->mask->iSTFT)"
+_RESULT_OUT = sys.stdout
 
 
 # ----------------------------------------------------------------------------------------------- CPU
@@ -183,7 +184,7 @@ def reference_arm(args, rank: int):
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 WORKLOAD = ("configs[1]: batched STFT log-magnitude + gap masking, 4096 synthetic 16 kHz 10 s clips per GPU "
@@ -205,6 +206,14 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout
+    # when NCCL_DEBUG=VERSION is set in the environment): keep a private handle on the real stdout for the result line
+    # and send everything else to stderr.
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -416,7 +425,7 @@ def emit_line(args, world, value, ms, B, T, roofline, cpu_baseline, e2e, clocks,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": args.steps,
         "clocks": clocks, "legs": legs,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 if __name__ == "__main__":

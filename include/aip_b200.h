@@ -137,6 +137,17 @@ int aip_gap_mask_f32(float* mask, int64_t pitch, int64_t B, int64_t L, const int
 /* mask[b, f, t] = 1/0 by frame range (see aip_stft_fwd_f32). */
 int aip_frame_mask_f32(float* mask, int64_t B, int64_t F, int64_t T, const int32_t* mask_frames,
                        int32_t mask_in_gap_is_one, void* stream);
+/* aip_istft_f32 followed by librosa.util.normalize (norm = inf) of every clip -- what the reference's callers do with
+ * spectrogram_to_audio's result before writing it (utils.save_audio, utils.py:84; models/CNNBLSTM/train.py:184-186,
+ * models/model_eval.py:130,179).  The per-clip peak max|y| is taken inside the overlap-add of the inverse kernel (one
+ * atomic per warp and tile), so the waveform is read back only once, by the in-place scaling pass.
+ * peaks: device [B] float, out (the peak of each clip BEFORE scaling); clips whose peak is < FLT_MIN stay unscaled.   */
+int aip_istft_normalized_f32(const aip_stft_desc* desc,
+                             const float* spec, const float* mag, const float* phase, int32_t mag_domain,
+                             const int32_t* db_flags,
+                             int64_t B, int64_t T, int64_t length, const float* inv_wss,
+                             float* wave_out, int64_t out_pitch, float* peaks,
+                             void* workspace, size_t workspace_bytes, void* stream);
 /* y_b / max|y_b| unless max|y_b| < FLT_MIN; peaks: [B] float scratch/out (the per-clip max|y|). */
 int aip_peak_normalize_f32(const float* in, int64_t in_pitch, float* out, int64_t out_pitch,
                            int64_t B, int64_t L, float* peaks, void* stream);

@@ -36,6 +36,7 @@ SIGNATURES = {
     "aip_stft_fwd_f32": (C.c_int, [_D, _P, _I64, _I64, _I64, _P, _P, _P, _I32, _I32, _F, _F, _I64,
                                    _P, _P, _P, _P, _P]),
     "aip_istft_f32": (C.c_int, [_D, _P, _P, _P, _I32, _P, _I64, _I64, _I64, _P, _P, _I64, _P, _SZ, _P]),
+    "aip_istft_normalized_f32": (C.c_int, [_D, _P, _P, _P, _I32, _P, _I64, _I64, _I64, _P, _P, _I64, _P, _P, _SZ, _P]),
     "aip_istft_blend_f32": (C.c_int, [_D, _P, _P, _P, _P, _I32, _I64, _I64, _I64, _P, _P, _I64, _P, _SZ, _P]),
     "aip_istft_workspace_bytes": (_SZ, [_D, _I64, _I64]),
     "aip_inv_window_sumsquare_f32": (C.c_int, [_D, _I64, _I64, _P, _I64, _P]),

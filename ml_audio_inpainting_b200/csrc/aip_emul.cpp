@@ -78,10 +78,10 @@ int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, 
 int emul_istft512(const float* spec, const float* mag, const float* phase, int mag_domain,
                   const int* db_flags, int B, int T, int length, int hop, int center, int win_length,
                   const float* window, const float* inv_wss, float* out, long long out_pitch,
-                  const float* blend_in, const float* blend_mask) {
+                  const float* blend_in, const float* blend_mask, float* peaks) {
   InvParams P;
   memset(&P, 0, sizeof(P));
-  P.blend_in = blend_in; P.blend_mask = blend_mask;
+  P.blend_in = blend_in; P.blend_mask = blend_mask; P.peaks = peaks;
   P.spec = reinterpret_cast<const float2*>(spec); P.mag = mag; P.phase = phase; P.mag_domain = mag_domain;
   P.db_flags = db_flags; P.B = B; P.T = T;
   P.hop = hop; P.pad = center ? 256 : 0;

@@ -100,6 +100,26 @@ struct ArriveRelease {
 
 constexpr int kFwdThreads = 2 * kThreads;   // 8 stage-2 (consumer) warps + 8 stage-1 (producer) warps
 
+// Which warps play which role.  A warp runs on scheduler (warp & 3); bit q of the map says whether the warp in slot
+// q = warp >> 2 of every scheduler is a consumer (stage 2 forward / stage A inverse), so each scheduler always hosts
+// two warps of each role.  0b0011 = warps 0..7 consume, 8..15 produce (the arbiter favours the producers then).
+#ifndef AIP_ROLE_MAP
+#define AIP_ROLE_MAP 0x3
+#endif
+struct WarpRole {
+  bool consumer;
+  int rtid;      // thread index 0..255 inside the role
+};
+__device__ __forceinline__ WarpRole warp_role(int tid) {
+  const int w = tid >> 5, q = w >> 2, s = w & 3;
+  const bool cons = (AIP_ROLE_MAP >> q) & 1;
+  const int below = cons ? __popc(AIP_ROLE_MAP & ((1 << q) - 1)) : __popc(~AIP_ROLE_MAP & ((1 << q) - 1));
+  WarpRole r;
+  r.consumer = cons;
+  r.rtid = ((below * 4 + s) << 5) | (tid & 31);
+  return r;
+}
+
 // Warp-specialised, persistent, one CTA per SM.  Tiles blockIdx.x, +gridDim.x, ... flow through
 //   TMA bulk copy -> tile[slot] -> stage-1 warps (lane = n1; window, 16-pt DFT, twiddle) -> exch[es]
 //   -> stage-2 warps (lane = frame; 2 x 16-pt DFT, split pass, |.|/log epilogue) -> HBM
@@ -135,9 +155,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
   if (n > P.tiles_per_cta) n = P.tiles_per_cta;      // this CTA's run: tiles [first, first + n)
   if (n <= 0) return;
   TileCursor c = tile_cursor(first, P.tiles_per_clip);
-  if (tid >= kThreads) {
+  const WarpRole role = warp_role(tid);
+  if (!role.consumer) {
     // ------------------------------------------------------------------ producers: stage 1
-    const int ptid = tid - kThreads;
+    const int ptid = role.rtid;
     LaneConst lc;
     lane_const_init(lc, tw_s, ptid & 15);
     FwdTilePlan q = fwd_tile_plan(P, c);
@@ -173,14 +194,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
     }
   } else {
     // ------------------------------------------------------------------ consumers: stage 2 + epilogue
+    const int ctid = role.rtid;
     PairTw w;
-    pair_tw_init(w, tid >> 5);
+    pair_tw_init(w, ctid >> 5);
 #pragma unroll 1
     for (int i = 0; i < n; ++i) {
       const int es = i & 1;
       mbar_wait(exch_full + es, (uint32_t)((i >> 1) & 1));
       ArriveRelease rel{exch_empty + es};
-      fwd_phase2<kMode>(P, tid, c, exch0 + es * kExch, w, rel);
+      fwd_phase2<kMode>(P, ctid, c, exch0 + es * kExch, w, rel);
       tile_advance(c, P.tiles_per_clip);
     }
   }
@@ -1009,6 +1031,38 @@ int aip_istft_f32(const aip_stft_desc* desc, const float* spec, const float* mag
   P.spec = reinterpret_cast<const float2*>(spec); P.mag = mag; P.phase = phase; P.mag_domain = mag_domain;
   P.db_flags = db_flags; P.B = (int)B; P.T = (int)T; P.inv_wss = inv_wss; P.out = wave_out; P.out_pitch = out_pitch;
   return run_inv(desc, P, length, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int aip_istft_normalized_f32(const aip_stft_desc* desc, const float* spec, const float* mag, const float* phase,
+                             int32_t mag_domain, const int32_t* db_flags, int64_t B, int64_t T, int64_t length,
+                             const float* inv_wss, float* wave_out, int64_t out_pitch, float* peaks, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  if (B > 0x7fffffffLL || T > 0x7fffffffLL || B < 0 || !peaks || !desc) return AIP_ERR_ARG;
+  if (B == 0) return AIP_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const DevInfo di = dev_info();
+  if (!di.ok) return AIP_ERR_DEVICE;
+  cudaError_t e = cudaMemsetAsync(peaks, 0, (size_t)B * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  const bool fused = inv_fast_ok(desc);
+  InvParams P{};
+  P.spec = reinterpret_cast<const float2*>(spec); P.mag = mag; P.phase = phase; P.mag_domain = mag_domain;
+  P.db_flags = db_flags; P.B = (int)B; P.T = (int)T; P.inv_wss = inv_wss; P.out = wave_out; P.out_pitch = out_pitch;
+  P.peaks = fused ? peaks : nullptr;
+  const int rc = run_inv(desc, P, length, workspace, workspace_bytes, st);
+  if (rc != AIP_OK) return rc;
+  const long long out_len = istft_length(T, desc->n_fft, desc->hop, desc->center, length);
+  if (out_len <= 0) return AIP_OK;
+  if (!fused) {      // generic n_fft path: separate peak pass
+    if (B > 65535) return AIP_ERR_UNSUPPORTED;
+    long long gx = (out_len + 256 * 8 - 1) / (256 * 8);
+    if (gx > 64) gx = 64;
+    peak_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, st>>>(wave_out, out_pitch, out_len, peaks);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  peak_scale_kernel<<<ew_grid(B * out_len, di.sms), 256, 0, st>>>(wave_out, out_pitch, wave_out, out_pitch, B, out_len, peaks);
+  return (int)cudaGetLastError();
 }
 
 int aip_inv_window_sumsquare_f32(const aip_stft_desc* desc, int64_t T, int64_t length, float* inv_wss,

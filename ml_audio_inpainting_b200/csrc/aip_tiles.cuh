@@ -323,6 +323,7 @@ struct InvParams {
   const float* inv_wss;     // [out_len]: 1/window_sumsquare where > tiny else 1 (librosa.istft normalisation)
   int out_len;
   float* out;               // [B, out_len], row pitch out_pitch
+  float* peaks;             // [B] or null: running max |sample| per clip (zeroed by the caller; fused peak normalisation)
   long long out_pitch;
   int vec_ok;               // float2 loads of inv_wss / stores of the output are legal
   int tiles_per_clip;
@@ -483,21 +484,23 @@ AIP_HD void inv_phase1(const InvParams& P, int tid, const TileCursor& c, float2*
 // contributes zero taps), for (HOP 128, window 512) e in {-1, 0, 1, 2}.  A thread owns pair columns pc and pc + C/2
 // (conflict-free LDS.64 over consecutive pc) and walks the hops h = g, g + G, ... fully unrolled: per pair
 // (EMAX - EMIN + 1) LDS.64, (EMAX - EMIN) FADD2, one FMUL2 and one 8-byte store, no integer work.
+// Returns max |sample| over what this thread stored (peak tracking of the fused normalisation, utils.py:84).
 template <int HOP, int EMIN, int EMAX>
-AIP_HD void inv_ola_fast(const InvParams& P, int tid, int s0, const float2* fbuf, const float* wtab, float* dst) {
+AIP_HD float inv_ola_fast(const InvParams& P, int tid, int s0, const float2* fbuf, const float* wtab, float* dst) {
   constexpr int C = HOP / 2, TC = C / 2;               // pair columns per hop, thread columns
   constexpr int G = kThreads / TC;                     // hop groups walking in parallel
   constexpr int HL = (kNfft - 1 - kNfft / 2) / HOP, HH = (kNfft / 2 - 1) / HOP, FO = kFR - 1 - HL - HH;
   constexpr int NIT = (FO + G - 1) / G;
   constexpr int STEP = C * kXP - 1;                    // slot(frame F, offset n) - slot(frame F + 1, offset n - HOP)
   const int g = tid / TC, pc = tid - g * TC;
-  if (g >= G) return;
+  if (g >= G) return 0.0f;
   const int u1 = 2 * pc + kNfft / 2, u2 = u1 + 2 * TC;
   const float2 nw1 = *reinterpret_cast<const float2*>(wtab + (u1 % HOP));
   const float2 nw2 = *reinterpret_cast<const float2*>(wtab + (u2 % HOP));
   const float2* src1 = fbuf + (u1 >> 1) * kXP + HL + g;
   const float2* src2 = src1 + TC * kXP;
   float* out = dst + s0 + g * HOP + 2 * pc;
+  float pk = 0.0f;
 #pragma unroll
   for (int it = 0; it < NIT; ++it) {
     if (it * G + G <= FO || g + it * G < FO) {
@@ -507,10 +510,14 @@ AIP_HD void inv_ola_fast(const InvParams& P, int tid, int s0, const float2* fbuf
         a1 = add2(a1, src1[it * G - e * STEP]);
         a2 = add2(a2, src2[it * G - e * STEP]);
       }
-      *reinterpret_cast<float2*>(out + it * G * HOP) = mul2(a1, nw1);
-      *reinterpret_cast<float2*>(out + it * G * HOP + 2 * TC) = mul2(a2, nw2);
+      a1 = mul2(a1, nw1);
+      a2 = mul2(a2, nw2);
+      *reinterpret_cast<float2*>(out + it * G * HOP) = a1;
+      *reinterpret_cast<float2*>(out + it * G * HOP + 2 * TC) = a2;
+      if (P.peaks) pk = fmaxf(fmaxf(pk, fmaxf(fabsf(a1.x), fabsf(a1.y))), fmaxf(fabsf(a2.x), fabsf(a2.y)));
     }
   }
+  return pk;
 }
 
 // Interior tile (all 32 local frames exist, whole tile inside the output, vector stores legal, periodic 1/wss
@@ -519,11 +526,12 @@ AIP_HD void inv_ola_fast(const InvParams& P, int tid, int s0, const float2* fbuf
 // base slot, the 1/wss pair, whether the m = K-1 term exists -- is loop invariant; per pair that leaves K
 // LDS.64, 2K FADD, 2 FMUL, one 8-byte store and two pointer increments.
 template <int K>
-AIP_HD void inv_ola_interior(const InvParams& P, int tid, int s0, const float2* fbuf, const float* wtab, float* dst) {
+AIP_HD float inv_ola_interior(const InvParams& P, int tid, int s0, const float2* fbuf, const float* wtab, float* dst) {
   const int hop = P.hop, C = hop >> 1;                // pair columns per hop
   const int G = C >= kThreads ? 1 : kThreads / C;     // hop groups walking in parallel
   const int g = C >= kThreads ? 0 : magic_div(tid, P.col_magic);
-  if (g >= G) return;
+  if (g >= G) return 0.0f;
+  float pk = 0.0f;
   const int step = C * kXP - 1;                       // slot(m) - slot(m-1)
   for (int cc = tid - g * C; cc < C; cc += kThreads) {
     const int u = 2 * cc + P.pad;                     // offset of the pair from the start of local frame HL + h
@@ -541,9 +549,22 @@ AIP_HD void inv_ola_interior(const InvParams& P, int tid, int s0, const float2* 
       float sx = 0.0f, sy = 0.0f;
 #pragma unroll
       for (int m = K - 1; m >= 0; --m) { sx += v[m].x; sy += v[m].y; }    // increasing frame order, like librosa
-      *reinterpret_cast<float2*>(out) = make_float2(sx * nw.x, sy * nw.y);
+      sx *= nw.x; sy *= nw.y;
+      *reinterpret_cast<float2*>(out) = make_float2(sx, sy);
+      pk = fmaxf(pk, fmaxf(fabsf(sx), fabsf(sy)));
     }
   }
+  return pk;
+}
+
+// per-clip peak of the fused normalisation: non-negative floats order like their bit patterns
+AIP_HD void inv_peak_commit(float* peak, float pk) {
+#if defined(__CUDACC__)
+  const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(pk));
+  if ((threadIdx.x & 31) == 0 && m != 0u) atomicMax(reinterpret_cast<unsigned*>(peak), m);
+#else
+  if (pk > *peak) *peak = pk;
+#endif
 }
 
 // overlap-add + window-sum-square normalisation + store for one tile (256 threads): thread q, q + 256, ...
@@ -562,13 +583,21 @@ AIP_HD void inv_phase2(const InvParams& P, int tid, const TileCursor& c, const f
   if (fl_max > kFR - 1) fl_max = kFR - 1;
   const bool edge = fl_min > 0 || fl_max < kFR - 1;
   float* dst = P.out + (long long)c.b * P.out_pitch;
+  float pk = 0.0f;
+  bool done = false;
   if (!edge && wtab && P.vec_ok && s0 + P.g.FO * hop <= P.out_len) {
-    if (kFast == 1) return inv_ola_fast<192, 0, 1>(P, tid, s0, fbuf, wtab, dst);
-    if (kFast == 2) return inv_ola_fast<128, -1, 2>(P, tid, s0, fbuf, wtab, dst);
-    if (P.ola_terms == 3) return inv_ola_interior<3>(P, tid, s0, fbuf, wtab, dst);
-    if (P.ola_terms == 4) return inv_ola_interior<4>(P, tid, s0, fbuf, wtab, dst);
-    if (P.ola_terms == 2) return inv_ola_interior<2>(P, tid, s0, fbuf, wtab, dst);
-    if (P.ola_terms == 1) return inv_ola_interior<1>(P, tid, s0, fbuf, wtab, dst);
+    done = true;
+    if (kFast == 1) pk = inv_ola_fast<192, 0, 1>(P, tid, s0, fbuf, wtab, dst);
+    else if (kFast == 2) pk = inv_ola_fast<128, -1, 2>(P, tid, s0, fbuf, wtab, dst);
+    else if (P.ola_terms == 3) pk = inv_ola_interior<3>(P, tid, s0, fbuf, wtab, dst);
+    else if (P.ola_terms == 4) pk = inv_ola_interior<4>(P, tid, s0, fbuf, wtab, dst);
+    else if (P.ola_terms == 2) pk = inv_ola_interior<2>(P, tid, s0, fbuf, wtab, dst);
+    else if (P.ola_terms == 1) pk = inv_ola_interior<1>(P, tid, s0, fbuf, wtab, dst);
+    else done = false;
+  }
+  if (done) {
+    if (P.peaks) inv_peak_commit(P.peaks + c.b, pk);
+    return;
   }
   const int n_pairs = (P.g.FO * hop) >> 1;
   // position of pair q relative to local frame 0: u = 2q + pad + HL*hop = h*hop + r
@@ -579,12 +608,19 @@ AIP_HD void inv_phase2(const InvParams& P, int tid, const TileCursor& c, const f
     const int s = s0 + 2 * q;
     if (s >= P.out_len) break;
     const float2 v = ola_pair(fbuf, h, r, hop, P.ola_terms, fl_min, fl_max);
-    dst[s] = v.x * P.inv_wss[s];
-    if (s + 1 < P.out_len) dst[s + 1] = v.y * P.inv_wss[s + 1];
+    const float y0 = v.x * P.inv_wss[s];
+    dst[s] = y0;
+    pk = fmaxf(pk, fabsf(y0));
+    if (s + 1 < P.out_len) {
+      const float y1 = v.y * P.inv_wss[s + 1];
+      dst[s + 1] = y1;
+      pk = fmaxf(pk, fabsf(y1));
+    }
     h += P.ola_dq;
     r += P.ola_dr;
     if (r >= hop) { r -= hop; ++h; }
   }
+  if (P.peaks) inv_peak_commit(P.peaks + c.b, pk);
 }
 
 }  // namespace aip

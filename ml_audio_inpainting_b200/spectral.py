@@ -216,10 +216,14 @@ def db_heuristic(x: torch.Tensor) -> torch.Tensor:
 
 def istft(plan: StftPlan, spec: Optional[torch.Tensor] = None, mag: Optional[torch.Tensor] = None,
           phase: Optional[torch.Tensor] = None, mag_domain: int = DOM_LINEAR, db_auto: bool = False,
-          length: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+          length: Optional[int] = None, out: Optional[torch.Tensor] = None, normalize: bool = False,
+          peaks_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Inverse transform: complex ``spec`` or ``mag`` (+ ``phase``) -> waveform [B, out_len] float32.
 
-    ``db_auto`` applies the reference's per-clip dB test to ``mag`` on the device (no host sync)."""
+    ``db_auto`` applies the reference's per-clip dB test to ``mag`` on the device (no host sync).
+    ``normalize`` additionally peak-normalises every clip like ``librosa.util.normalize`` in the reference's
+    ``save_audio`` (utils.py:84), with the per-clip peak taken inside the inverse kernel's overlap-add
+    (``aip_istft_normalized_f32``); ``peaks_out`` [B] float32 receives the peaks before scaling."""
     src = spec if spec is not None else mag
     if src is None:
         raise ValueError("istft needs spec or mag")
@@ -252,10 +256,22 @@ def istft(plan: StftPlan, spec: Optional[torch.Tensor] = None, mag: Optional[tor
     ws_bytes = int(lib.aip_istft_workspace_bytes(C.byref(plan.desc), B, T))
     ws = torch.empty(max(ws_bytes, 4) // 4, dtype=torch.float32, device=dev) if ws_bytes else None
     with torch.cuda.device(dev):
-        check(lib.aip_istft_f32(C.byref(plan.desc), _ptr(spec.view(torch.float32) if spec is not None else None),
-                                _ptr(mag), _ptr(phase), int(mag_domain), _ptr(flags), B, T, int(length or 0),
-                                _ptr(inv), _ptr(out), out.stride(0), _ptr(ws), ws_bytes, _stream()),
-              "aip_istft_f32")
+        if normalize:
+            if peaks_out is None:
+                peaks_out = torch.empty(B, dtype=torch.float32, device=dev)
+            elif tuple(peaks_out.shape) != (B,) or peaks_out.dtype != torch.float32 or not peaks_out.is_contiguous():
+                raise ValueError("peaks_out must be a contiguous float32 [B] tensor")
+            check(lib.aip_istft_normalized_f32(C.byref(plan.desc),
+                                               _ptr(spec.view(torch.float32) if spec is not None else None),
+                                               _ptr(mag), _ptr(phase), int(mag_domain), _ptr(flags), B, T,
+                                               int(length or 0), _ptr(inv), _ptr(out), out.stride(0), _ptr(peaks_out),
+                                               _ptr(ws), ws_bytes, _stream()),
+                  "aip_istft_normalized_f32")
+        else:
+            check(lib.aip_istft_f32(C.byref(plan.desc), _ptr(spec.view(torch.float32) if spec is not None else None),
+                                    _ptr(mag), _ptr(phase), int(mag_domain), _ptr(flags), B, T, int(length or 0),
+                                    _ptr(inv), _ptr(out), out.stride(0), _ptr(ws), ws_bytes, _stream()),
+                  "aip_istft_f32")
     return out[0] if squeeze else out
 
 

@@ -58,7 +58,7 @@ def stft(wave, hop, window, center=True, gap_samples=None, zero_frames=None, mas
 
 
 def istft(hop, window, inv_wss, spec=None, mag=None, phase=None, mag_domain=0, db_flags=None, center=True, length=0,
-          blend_in=None, blend_mask=None, win_length=0):
+          blend_in=None, blend_mask=None, win_length=0, peaks=None):
     window = np.ascontiguousarray(window, dtype=np.float32)
     inv_wss = np.ascontiguousarray(inv_wss, dtype=np.float32)
     if spec is not None:
@@ -76,6 +76,7 @@ def istft(hop, window, inv_wss, spec=None, mag=None, phase=None, mag_domain=0, d
     rc = lib().emul_istft512(_f(sp), _f(mg), _f(ph), mag_domain, _i(fl), B, T, int(length), hop, int(center), int(win_length),
                              _f(window), _f(inv_wss), _f(out), C.c_longlong(out_len),
                              _f(None if blend_in is None else np.ascontiguousarray(blend_in, dtype=np.float32)),
-                             _f(None if blend_mask is None else np.ascontiguousarray(blend_mask, dtype=np.float32)))
+                             _f(None if blend_mask is None else np.ascontiguousarray(blend_mask, dtype=np.float32)),
+                             _f(peaks))
     assert rc == 0, rc
     return out

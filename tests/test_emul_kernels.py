@@ -217,3 +217,15 @@ def test_round_trip_snr(golden_clips):
     err = (x[512:n - 512] - y[512:n - 512]).astype(np.float64)
     snr = 10 * np.log10((x[512:n - 512].astype(np.float64) ** 2).sum() / (err ** 2).sum())
     assert snr >= 100.0, snr
+
+
+@pytest.mark.parametrize("hop,wl", [(192, 384), (128, 512), (64, 256)])
+def test_inverse_peak_tracking(hop, wl):
+    """The overlap-add records max |y| per clip (fused peak normalisation, utils.py:84): equals the peak of the output."""
+    x = noise(3, 20000 + 33, seed=hop)
+    x[1] *= 3.0
+    S = np.stack([lr.stft(x[b], n_fft=512, hop_length=hop, win_length=wl) for b in range(3)])
+    T = S.shape[2]
+    peaks = np.zeros(3, np.float32)
+    y = emul.istft(hop, win(wl), inv_wss("hann", wl, hop, T, hop * (T - 1)), spec=S, win_length=wl, peaks=peaks)
+    assert np.array_equal(peaks, np.abs(y).max(axis=1))

@@ -67,6 +67,27 @@ def test_istft_matches_oracle_and_round_trip(sp, par):
         assert snr_db(x[b, 512:n - 512], y[b, 512:n - 512]) >= 100.0
 
 
+@pytest.mark.parametrize("par,L", [(P1, 80000), (P2, 80000), (P1, 3000), (dict(n_fft=1024, hop=256, win=1024), 20000)],
+                         ids=["P1", "P2", "P1-short", "generic-1024"])
+def test_istft_fused_peak_normalisation(sp, par, L):
+    """spectrogram_to_audio -> save_audio's librosa.util.normalize (utils.py:84, :316-327) in one call: the peak is taken
+    inside the inverse kernel; result = oracle istft / max|.|, a silent clip stays untouched."""
+    x = _noise(3, L, seed=11)
+    x[1] *= 0.01
+    x[2] = 0.0
+    plan = sp.get_plan(par["n_fft"], par["hop"], par["win"], "hann", True, "cuda:0")
+    S = sp.stft(torch.from_numpy(x).cuda(), plan)["spec"]
+    peaks = torch.empty(3, device="cuda:0")
+    y = sp.istft(plan, spec=S, normalize=True, peaks_out=peaks).cpu().numpy()
+    raw = sp.istft(plan, spec=S).cpu().numpy()
+    assert np.array_equal(peaks.cpu().numpy(), np.abs(raw).max(axis=1))           # the fused peak IS the peak of the output
+    for b in range(3):
+        ref_S = lr.stft(x[b], n_fft=par["n_fft"], hop_length=par["hop"], win_length=par["win"])
+        ref = up.peak_normalize(lr.istft(ref_S, hop_length=par["hop"], win_length=par["win"], n_fft=par["n_fft"]))
+        assert relerr(y[b], ref) < TOL if b < 2 else np.all(y[b] == 0.0)
+    assert abs(np.abs(y[0]).max() - 1.0) < 1e-6 and abs(np.abs(y[1]).max() - 1.0) < 1e-6
+
+
 def test_logmag_gap_epilogue(sp):
     L, B = 80000, 4
     x = _noise(B, L, seed=11)
