@@ -99,6 +99,7 @@ struct ArriveRelease {
 };
 
 constexpr int kFwdThreads = 2 * kThreads;   // 8 stage-2 (consumer) warps + 8 stage-1 (producer) warps
+constexpr int kFwdTileBufs = 3;             // deepest ring of staged-waveform buffers
 
 // Which warps play which role.  A warp runs on scheduler (warp & 3); bit q of the map says whether the warp in slot
 // q = warp >> 2 of every scheduler is a consumer (stage 2 forward / stage A inverse), so each scheduler always hosts
@@ -129,22 +130,24 @@ __device__ __forceinline__ WarpRole warp_role(int tid) {
 template <int kMode, int kZP>
 __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdParams P) {
   extern __shared__ __align__(128) float smem[];
-  __shared__ __align__(8) uint64_t bars[8];
+  __shared__ __align__(8) uint64_t bars[2 * kFwdTileBufs + 4];
   __shared__ __align__(16) float win_s[kWinTable];
   __shared__ __align__(8) float2 tw_s[kTwTable];
   window_table_fill(win_s, P.window, 0.5f, threadIdx.x, blockDim.x);
   twiddle_table_fill(tw_s, threadIdx.x, blockDim.x);
-  uint64_t* tile_full = bars;        // [2] count 1 (+ tx bytes)
-  uint64_t* tile_empty = bars + 2;   // [2] count 8 (stage-1 warps)
-  uint64_t* exch_full = bars + 4;    // [2] count 8 (stage-1 warps)
-  uint64_t* exch_empty = bars + 6;   // [2] count 8 (stage-2 warps)
+  uint64_t* tile_full = bars;                          // [3] count 1 (+ tx bytes)
+  uint64_t* tile_empty = bars + kFwdTileBufs;          // [3] count 8 (stage-1 warps)
+  uint64_t* exch_full = bars + 2 * kFwdTileBufs;       // [2] count 8 (stage-1 warps)
+  uint64_t* exch_empty = bars + 2 * kFwdTileBufs + 2;  // [2] count 8 (stage-2 warps)
   const int ntb = P.n_tile_bufs;
   float2* exch0 = reinterpret_cast<float2*>(smem + ntb * P.tile_floats);
   const int tid = threadIdx.x;
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kFwdTileBufs; ++i) {
       mbar_init(tile_full + i, 1);
       mbar_init(tile_empty + i, kThreads / 32);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(exch_full + i, kThreads / 32);
       mbar_init(exch_empty + i, kThreads / 32);
     }
@@ -158,22 +161,31 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
   const WarpRole role = warp_role(tid);
   if (!role.consumer) {
     // ------------------------------------------------------------------ producers: stage 1
+    // The staged waveform sits in a ring of ntb buffers; ntb - 1 bulk copies are in flight while a tile is being
+    // transformed.  (With two buffers the stage-1 warps spent 11 % of their time waiting for the ONE copy in flight:
+    // under this kernel's write-heavy traffic a 26 KB read takes about as long as a tile, see profiles/README.md.)
     const int ptid = role.rtid;
     LaneConst lc;
     lane_const_init(lc, tw_s, ptid & 15);
-    FwdTilePlan q = fwd_tile_plan(P, c);
-    if (ptid == 0) fwd_issue_tile(q, smem, tile_full);
+    TileCursor cn = c;                   // next tile to request (thread ptid == 0 only)
+    if (ptid == 0) {
+      for (int k = 0; k < ntb - 1 && k < n; ++k) {
+        fwd_issue_tile(fwd_tile_plan(P, cn), smem + k * P.tile_floats, tile_full + k);
+        tile_advance(cn, P.tiles_per_clip);
+      }
+      if (ntb == 1) { fwd_issue_tile(fwd_tile_plan(P, cn), smem, tile_full); tile_advance(cn, P.tiles_per_clip); }
+    }
+    int slot = 0, use = 0;               // ring slot of tile i and how often it has been used before
 #pragma unroll 1
     for (int i = 0; i < n; ++i) {
-      const int slot = (ntb == 2) ? (i & 1) : 0;
-      const int use = (ntb == 2) ? (i >> 1) : i;
       float* tile = smem + slot * P.tile_floats;
-      tile_advance(c, P.tiles_per_clip);
-      const FwdTilePlan qn = fwd_tile_plan(P, c);      // next tile (unused when i + 1 == n)
-      if (ntb == 2 && ptid == 0 && i + 1 < n) {
-        // the other slot was last read by tile i-1
-        if (i >= 1) mbar_wait(tile_empty + (slot ^ 1), (uint32_t)(((i - 1) >> 1) & 1));
-        fwd_issue_tile(qn, smem + (slot ^ 1) * P.tile_floats, tile_full + (slot ^ 1));
+      const FwdTilePlan q = fwd_tile_plan(P, c);
+      if (ntb > 1 && ptid == 0 && i + ntb - 1 < n) {
+        // tile i + ntb - 1 goes into the slot that tile i - 1 has just left
+        const int ns = slot == 0 ? ntb - 1 : slot - 1;
+        if (i >= 1) mbar_wait(tile_empty + ns, (uint32_t)((slot == 0 ? use - 1 : use) & 1));
+        fwd_issue_tile(fwd_tile_plan(P, cn), smem + ns * P.tile_floats, tile_full + ns);
+        tile_advance(cn, P.tiles_per_clip);
       }
       mbar_wait(tile_full + slot, (uint32_t)(use & 1));
       if (fwd_needs_fixup(q)) {
@@ -188,9 +200,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
       mbar_arrive_warp(tile_empty + slot);
       if (ntb == 1 && ptid == 0 && i + 1 < n) {
         mbar_wait(tile_empty, (uint32_t)(i & 1));
-        fwd_issue_tile(qn, smem, tile_full);
+        fwd_issue_tile(fwd_tile_plan(P, cn), smem, tile_full);
+        tile_advance(cn, P.tiles_per_clip);
       }
-      q = qn;
+      tile_advance(c, P.tiles_per_clip);
+      if (++slot == ntb) { slot = 0; ++use; }
     }
   } else {
     // ------------------------------------------------------------------ consumers: stage 2 + epilogue
@@ -741,8 +755,10 @@ static size_t fwd_smem_bytes(int hop, int n_tile_bufs) {
 
 static int fwd_tile_bufs(const aip_stft_desc* d, const DevInfo& di) {
   if (d->n_fft != 512 || (d->hop & 1)) return 0;
-  if (fwd_smem_bytes(d->hop, 2) + 1024 <= (size_t)di.max_smem) return 2;
-  if (fwd_smem_bytes(d->hop, 1) + 1024 <= (size_t)di.max_smem) return 1;
+  int most = kFwdTileBufs;
+  if (const char* e = getenv("AIP_FWD_TILE_BUFS")) { const int v = atoi(e); if (v >= 1 && v <= kFwdTileBufs) most = v; }   // profiling switch
+  for (int nb = most; nb >= 1; --nb)
+    if (fwd_smem_bytes(d->hop, nb) + 6 * 1024 <= (size_t)di.max_smem) return nb;       // + static tables and barriers
   return 0;
 }
 
@@ -872,6 +888,9 @@ static int run_fwd(const aip_stft_desc* desc, FwdParams P, long long T_out, cuda
     P.n_tiles = (int)((long long)P.B * P.tiles_per_clip);
     P.tile_floats = (fwd_tile_len(P.hop) + 31) & ~31;
     P.n_tile_bufs = fwd_tile_bufs(desc, di);
+    // measured (4096 / 1024 clips x 10 s, hop 192): magnitude-only output 1.649 -> 1.592 ms with three buffers, complex output
+    // 0.532 -> 0.572 ms: with 8 bytes written per bin the extra read in flight only competes with the stores
+    if (P.spec && P.n_tile_bufs > 2 && !getenv("AIP_FWD_TILE_BUFS")) P.n_tile_bufs = 2;
     P.zero_groups = win_zero_groups(desc->win_length);
     P.vec_ok = ((P.hop & 3) == 0) && ((P.pad & 3) == 0) && ((P.wave_pitch & 3) == 0) &&
                ((reinterpret_cast<uintptr_t>(P.wave) & 15) == 0);
