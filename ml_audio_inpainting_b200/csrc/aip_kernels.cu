@@ -84,7 +84,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // one elected thread: start the bulk copy of a tile's in-range samples (or just complete the phase)
 __device__ __forceinline__ void fwd_issue_tile(const FwdTilePlan& q, float* tile, uint64_t* bar) {
+#if defined(AIP_ABLATE_LOADS)      // timing experiment only: no waveform traffic, stage 1 runs on whatever the buffer holds
+  if (false) {
+#else
   if (q.n_bulk > 0) {
+#endif
     const uint32_t bytes = (uint32_t)q.n_bulk * 4u;
     mbar_expect_tx(bar, bytes);
     tma_load_1d(tile + q.v_lo, q.src + q.g0 + q.v_lo, bytes, bar);

@@ -202,8 +202,13 @@ struct FwdEmitT {
       mag[oy] = mag_value(kM & 7, xr.y, xi.y, eps, 1.0f);
 #else
       const float2 m = mag_value2(kM & 7, xr, xi, eps);
+#if defined(AIP_ABLATE_STORES)     // timing experiment only: everything is computed, (almost) nothing is written
+      if (m.x == 123.456f) mag[ox] = m.x;
+      if (m.y == 123.456f) mag[oy] = m.y;
+#else
       mag[ox] = m.x;
       mag[oy] = m.y;
+#endif
 #endif
     }
   }
@@ -382,12 +387,23 @@ AIP_HD float2 ldg_stream(const float2* p) { return *p; }
 struct InvLoadSpec {        // complex input straight from HBM
   const float2* col;        // spec + b*F*T + t
   int T;
-  const float2* plo;
-  const float2* phi;
-  int s16;
-  AIP_HM void rows(int k_lo, int k_hi) { plo = col + k_lo * T; phi = col + k_hi * T; s16 = 16 * T; }
-  AIP_HM void lo(int j, float& xr, float& xi) const { const float2 v = ldg_stream(plo + j * s16); xr = v.x; xi = v.y; }
-  AIP_HM void hi(int j, float& xr, float& xi) const { const float2 v = ldg_stream(phi - j * s16); xr = v.x; xi = v.y; }
+  const char* plo;
+  const char* phi;
+  unsigned s16b;            // bytes between rows k and k + 16 (T < 2^22)
+  AIP_HM void rows(int k_lo, int k_hi) {
+    plo = reinterpret_cast<const char*>(col + k_lo * T);
+    phi = reinterpret_cast<const char*>(col + k_hi * T);
+    s16b = 128u * (unsigned)T;
+  }
+  // row address = base +- j * s16b as ONE 32 x 32 + 64 bit multiply-add (IMAD.WIDE) instead of a shift / add-with-carry chain
+  AIP_HM void lo(int j, float& xr, float& xi) const {
+    const float2 v = ldg_stream(reinterpret_cast<const float2*>(plo + (unsigned long long)s16b * (unsigned)j));
+    xr = v.x; xi = v.y;
+  }
+  AIP_HM void hi(int j, float& xr, float& xi) const {
+    const float2 v = ldg_stream(reinterpret_cast<const float2*>(phi + (long long)(int)s16b * (long long)(-j)));
+    xr = v.x; xi = v.y;
+  }
 };
 
 // run-time flavoured element fetch (generic n_fft kernels only)
@@ -432,7 +448,7 @@ AIP_HD void inv_phase0(const InvParams& P, int tid, const TileCursor& c, float2*
   const bool live = (t >= 0 && t < P.n_frames);
   const long long col = (long long)c.b * kBins * P.T + t;
   if (kMode == INV_SPEC) {
-    InvLoadSpec load{P.spec + col, P.T, nullptr, nullptr, 0};
+    InvLoadSpec load{P.spec + col, P.T, nullptr, nullptr, 0u};
     inv_stageA(exch, w, lane, warp, live, load, before_store);
   } else if (kMode == INV_BLEND) {
     InvLoadMag<1, true, true> load{P.mag + col, P.phase + col, P.blend_in + col, P.blend_mask + col, P.T,
