@@ -40,6 +40,25 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 // blocks until the phase with the given parity has completed (try_wait parks the warp for a hardware-
 // defined time per attempt; a longer suspend-time hint measured SLOWER: later wake-ups)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if defined(AIP_MBAR_HINT_NS)
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra LAB_DONE;\n"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(AIP_MBAR_HINT_NS) : "memory");
+#elif defined(AIP_MBAR_SLEEP_NS)
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (!ok) __nanosleep(AIP_MBAR_SLEEP_NS);
+  } while (!ok);
+#else
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -49,6 +68,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra LAB_WAIT;\n"
       "LAB_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
 }
 
 // global -> shared bulk copy, completion signalled on the mbarrier (SASS: UBLKCP)
