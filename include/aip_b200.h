@@ -120,7 +120,9 @@ int aip_inv_window_sumsquare_f32(const aip_stft_desc* desc, int64_t T, int64_t l
 /* Griffin-Lim: n_iter x (istft, stft, phase update) and a final istft.
  *   mag     [B,F,T] linear magnitudes (8-byte aligned);
  *   angles  [B,F,T,2] in: initial unit phasors (caller-drawn); used as the iteration state (16-byte aligned);
- *   tprev   [B,F,T,2] scratch (16-byte aligned);  wave_out [B, out_len] doubles as the iteration buffer. */
+ *   tprev   [B,F,T,2] scratch (16-byte aligned);  wave_out [B, out_len] doubles as the iteration buffer;
+ *   workspace: aip_istft_workspace_bytes(...) rounded up to 16, optionally followed by B*F*T*8 more bytes -- with that
+ *   extra array the rebuilt spectra of consecutive iterations ping-pong and no `tprev = rebuilt` copy is made.       */
 int aip_griffinlim_f32(const aip_stft_desc* desc, const float* mag, float* angles, float* tprev,
                        int64_t B, int64_t T, int32_t n_iter, float momentum, const float* inv_wss,
                        float* wave_out, int64_t out_pitch,

@@ -707,6 +707,35 @@ __global__ void __launch_bounds__(256) gl_update_kernel(float4* __restrict__ spe
   }
 }
 
+// Same update when the rebuilt spectra of consecutive iterations ping-pong between two buffers: tprev IS the previous
+// iteration's output, so nothing is copied (7 instead of 9 array passes per iteration).
+__global__ void __launch_bounds__(256) gl_update_pp_kernel(const float4* __restrict__ rebuilt, const float4* __restrict__ tprev,
+                                                           const float2* __restrict__ mag, float4* __restrict__ angles,
+                                                           long long n2, float alpha, int has_prev) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 rb = __ldcs(rebuilt + i);
+    const float2 m = mag[i];
+    float ax = rb.x, ay = rb.y, bx = rb.z, by = rb.w;
+    if (has_prev) {
+      const float4 tp = __ldcs(tprev + i);
+      ax -= alpha * tp.x; ay -= alpha * tp.y; bx -= alpha * tp.z; by -= alpha * tp.w;
+    }
+    const float sa = m.x / (sqrtf(ax * ax + ay * ay) + kFltMin);
+    const float sb = m.y / (sqrtf(bx * bx + by * by) + kFltMin);
+    angles[i] = make_float4(ax * sa, ay * sa, bx * sb, by * sb);
+  }
+}
+
+__global__ void gl_update_pp_tail_kernel(const float2* rebuilt, const float2* tprev, const float* mag, float2* angles,
+                                         long long i, float alpha, int has_prev) {
+  const float2 rb = rebuilt[i];
+  float ax = rb.x, ay = rb.y;
+  if (has_prev) { const float2 tp = tprev[i]; ax -= alpha * tp.x; ay -= alpha * tp.y; }
+  const float s = mag[i] / (sqrtf(ax * ax + ay * ay) + kFltMin);
+  angles[i] = make_float2(ax * s, ay * s);
+}
+
 __global__ void gl_update_tail_kernel(float2* spec, float2* tprev, const float* mag, long long i, float alpha, int has_prev) {
   const float2 rb = spec[i];
   float ax = rb.x, ay = rb.y;
@@ -1142,26 +1171,45 @@ int aip_griffinlim_f32(const aip_stft_desc* desc, const float* mag, float* angle
   InvParams I{};
   I.spec = reinterpret_cast<const float2*>(angles); I.B = (int)B; I.T = (int)T; I.inv_wss = inv_wss;
   I.out = wave_out; I.out_pitch = out_pitch;
+  // With room for one more [B,F,T] complex array behind the istft workspace the rebuilt spectra ping-pong between
+  // `tprev` and that array and the update reads the previous one in place of a copy.
+  const size_t ws_istft = (aip_istft_workspace_bytes(desc, B, T) + 15) & ~(size_t)15;
+  const size_t ws_pp = (size_t)n * sizeof(float2);
+  char* ws_base = static_cast<char*>(workspace);
+  float2* rb[2] = {reinterpret_cast<float2*>(tprev), nullptr};
+  if (workspace && workspace_bytes >= ws_istft + ws_pp && ((reinterpret_cast<uintptr_t>(ws_base + ws_istft) & 15) == 0))
+    rb[1] = reinterpret_cast<float2*>(ws_base + ws_istft);
+  const bool pingpong = rb[1] != nullptr;
+  const float alpha = momentum / (1.0f + momentum);
+  const long long n2 = n / 2;
+  long long g = (n2 + 255) / 256;
+  if (g > (long long)di.sms * 32) g = (long long)di.sms * 32;
   for (int it = 0; it < n_iter; ++it) {
     int rc = run_inv(desc, I, 0, workspace, workspace_bytes, st);
     if (rc != AIP_OK) return rc;
+    float2* rebuilt = pingpong ? rb[it & 1] : reinterpret_cast<float2*>(angles);
     FwdParams P{};
     P.wave = wave_out; P.wave_pitch = out_pitch; P.B = (int)B; P.L = (int)out_len;
     P.mag_kind = MAG_NONE;
-    P.spec = reinterpret_cast<float2*>(angles);
+    P.spec = rebuilt;
     rc = run_fwd(desc, P, T, st);
     if (rc != AIP_OK) return rc;
-    const float alpha = momentum / (1.0f + momentum);
-    const long long n2 = n / 2;
-    if (n2 > 0) {
-      long long g = (n2 + 255) / 256;
-      if (g > (long long)di.sms * 32) g = (long long)di.sms * 32;
-      gl_update_kernel<<<(unsigned)g, 256, 0, st>>>(reinterpret_cast<float4*>(angles), reinterpret_cast<float4*>(tprev),
-                                                    reinterpret_cast<const float2*>(mag), n2, alpha, it > 0);
+    if (pingpong) {
+      const float2* prev = rb[(it + 1) & 1];
+      if (n2 > 0)
+        gl_update_pp_kernel<<<(unsigned)g, 256, 0, st>>>(reinterpret_cast<const float4*>(rebuilt), reinterpret_cast<const float4*>(prev),
+                                                         reinterpret_cast<const float2*>(mag), reinterpret_cast<float4*>(angles), n2,
+                                                         alpha, it > 0);
+      if (n & 1)
+        gl_update_pp_tail_kernel<<<1, 1, 0, st>>>(rebuilt, prev, mag, reinterpret_cast<float2*>(angles), n - 1, alpha, it > 0);
+    } else {
+      if (n2 > 0)
+        gl_update_kernel<<<(unsigned)g, 256, 0, st>>>(reinterpret_cast<float4*>(angles), reinterpret_cast<float4*>(tprev),
+                                                      reinterpret_cast<const float2*>(mag), n2, alpha, it > 0);
+      if (n & 1)
+        gl_update_tail_kernel<<<1, 1, 0, st>>>(reinterpret_cast<float2*>(angles), reinterpret_cast<float2*>(tprev), mag,
+                                               n - 1, alpha, it > 0);
     }
-    if (n & 1)
-      gl_update_tail_kernel<<<1, 1, 0, st>>>(reinterpret_cast<float2*>(angles), reinterpret_cast<float2*>(tprev), mag,
-                                             n - 1, alpha, it > 0);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }

@@ -333,8 +333,9 @@ def griffinlim(plan: StftPlan, mag: torch.Tensor, n_iter: int = 32, momentum: fl
     out = torch.empty((B, out_len), dtype=torch.float32, device=dev)
     inv = plan.inv_wss(T)
     lib = _cabi.load()
-    ws_bytes = int(lib.aip_istft_workspace_bytes(C.byref(plan.desc), B, T))
-    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
+    # istft workspace (generic n_fft only) + one more complex [B,F,T] array: rebuilt spectra ping-pong, no tprev copy
+    ws_bytes = ((int(lib.aip_istft_workspace_bytes(C.byref(plan.desc), B, T)) + 15) // 16) * 16 + B * F * T * 8
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         check(lib.aip_griffinlim_f32(C.byref(plan.desc), _ptr(mag), _ptr(ang.view(torch.float32)),
                                      _ptr(tprev.view(torch.float32)), B, T, int(n_iter), float(momentum),
