@@ -194,21 +194,27 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
     TileCursor cn = c;                   // next tile to request (thread ptid == 0 only)
     if (ptid == 0) {
       for (int k = 0; k < ntb - 1 && k < n; ++k) {
-        fwd_issue_tile(fwd_tile_plan(P, cn), smem + k * P.tile_floats, tile_full + k);
+        fwd_issue_tile(fwd_tile_plan_gap(P, cn, 0, 0), smem + k * P.tile_floats, tile_full + k);
         tile_advance(cn, P.tiles_per_clip);
       }
-      if (ntb == 1) { fwd_issue_tile(fwd_tile_plan(P, cn), smem, tile_full); tile_advance(cn, P.tiles_per_clip); }
+      if (ntb == 1) { fwd_issue_tile(fwd_tile_plan_gap(P, cn, 0, 0), smem, tile_full); tile_advance(cn, P.tiles_per_clip); }
     }
     int slot = 0, use = 0;               // ring slot of tile i and how often it has been used before
+    int gs = 0, ge = 0, gap_clip = -1;   // gap range of the clip the cursor is in
 #pragma unroll 1
     for (int i = 0; i < n; ++i) {
       float* tile = smem + slot * P.tile_floats;
-      const FwdTilePlan q = fwd_tile_plan(P, c);
+      if (P.gap_samples && c.b != gap_clip) {
+        gs = P.gap_samples[2 * c.b];
+        ge = P.gap_samples[2 * c.b + 1];
+        gap_clip = c.b;
+      }
+      const FwdTilePlan q = fwd_tile_plan_gap(P, c, gs, ge);
       if (ntb > 1 && ptid == 0 && i + ntb - 1 < n) {
         // tile i + ntb - 1 goes into the slot that tile i - 1 has just left
         const int ns = slot == 0 ? ntb - 1 : slot - 1;
         if (i >= 1) mbar_wait(tile_empty + ns, (uint32_t)((slot == 0 ? use - 1 : use) & 1));
-        fwd_issue_tile(fwd_tile_plan(P, cn), smem + ns * P.tile_floats, tile_full + ns);
+        fwd_issue_tile(fwd_tile_plan_gap(P, cn, 0, 0), smem + ns * P.tile_floats, tile_full + ns);
         tile_advance(cn, P.tiles_per_clip);
       }
       mbar_wait(tile_full + slot, (uint32_t)(use & 1));
@@ -224,7 +230,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
       mbar_arrive_warp(tile_empty + slot);
       if (ntb == 1 && ptid == 0 && i + 1 < n) {
         mbar_wait(tile_empty, (uint32_t)(i & 1));
-        fwd_issue_tile(fwd_tile_plan(P, cn), smem, tile_full);
+        fwd_issue_tile(fwd_tile_plan_gap(P, cn, 0, 0), smem, tile_full);
         tile_advance(cn, P.tiles_per_clip);
       }
       tile_advance(c, P.tiles_per_clip);

@@ -99,6 +99,22 @@ AIP_HD FwdTilePlan fwd_tile_plan(const FwdParams& P, const TileCursor& c) {
   return q;
 }
 
+// The same plan with the clip's gap range supplied by the caller: the persistent kernel fetches it from global memory
+// once per CLIP, not once per tile (the load's latency sat in front of every tile's fix-up test).
+AIP_HD FwdTilePlan fwd_tile_plan_gap(const FwdParams& P, const TileCursor& c, int gs, int ge) {
+  FwdTilePlan q;
+  q.len = fwd_tile_len(P.hop);
+  q.g0 = c.tt * kFR * P.hop - P.pad;
+  q.src = P.wave + (long long)c.b * P.wave_pitch;
+  q.v_lo = q.g0 < 0 ? -q.g0 : 0;
+  const int hi = P.L - q.g0;
+  q.v_hi = hi < q.len ? (hi > 0 ? hi : 0) : q.len;
+  if (q.v_lo > q.v_hi) q.v_lo = q.v_hi;
+  q.n_bulk = P.vec_ok ? ((q.v_hi - q.v_lo) & ~3) : 0;
+  q.gs = gs; q.ge = ge;
+  return q;
+}
+
 AIP_HD bool fwd_needs_fixup(const FwdTilePlan& q) {
   return q.v_lo > 0 || q.v_lo + q.n_bulk < q.len || (q.ge > q.g0 && q.gs < q.g0 + q.len && q.ge > q.gs);
 }
