@@ -16,6 +16,7 @@ from ml_audio_inpainting_b200 import _cabi  # noqa: E402  (signatures only)
 
 SR, N_FFT = 16000, 512
 NO_PRUNE = "--no-prune" in sys.argv
+CLIP_L = next((int(a.split("=")[1]) for a in sys.argv if a.startswith("--L=")), 160000)   # samples per clip
 
 
 def load(path):
@@ -58,7 +59,7 @@ def main():
     g = torch.Generator(device=dev).manual_seed(1234)
     res = {}
     for win, hop, B, tag in ((384, 192, 4096, "p1"), (512, 128, 1024, "p2")):
-        L = 160000
+        L = CLIP_L
         wave = (0.1 * torch.randn(B, L, device=dev, generator=g)).clamp_(-1, 1)
         window = torch.from_numpy(hann_padded(win)).to(dev)
         T = 1 + L // hop
