@@ -2,11 +2,14 @@
 //
 // Kernels
 //   stft512_fwd_kernel   persistent; tile = 32 frames of one clip; waveform staged once in shared
-//                        memory, register 16x16 FFT, split pass, fused |S| / log / phase / mask /
-//                        Griffin-Lim epilogue, coalesced [F,T] stores (see aip_core.cuh).
+//                        memory by TMA bulk copies, register 16x16 FFT (zero window taps pruned), packed
+//                        split pass, fused |S| / log / phase / mask epilogues, coalesced [F,T] stores.
 //   istft512_kernel      persistent; tile = 32 frames -> FO hops of output; split-pass prologue,
 //                        register inverse FFT, synthesis window, overlap-add and window-sum-square
-//                        normalisation out of shared memory (no global atomics, halo frames recomputed).
+//                        normalisation out of shared memory (no global atomics, halo frames recomputed),
+//                        optional per-clip peak for the fused normalisation.
+//   istft512_tma_kernel  the same with stage A's rows staged by 4-D TMA tensor boxes (switch AIP_INV_TMA=1).
+//   gl_update*_kernel    the Griffin-Lim phase update between the two transforms.
 //   stft_generic_* / istft_generic_*   any power-of-two n_fft in [32, 4096] (or odd hop): one frame
 //                        per CTA, shared-memory radix-2.  Correct, not tuned: the reference's
 //                        models only ever use n_fft = 512 (config.py:28, GAN/config.yaml:12).
@@ -127,7 +130,8 @@ constexpr int kFwdTileBufs = 3;             // deepest ring of staged-waveform b
 
 // Which warps play which role.  A warp runs on scheduler (warp & 3); bit q of the map says whether the warp in slot
 // q = warp >> 2 of every scheduler is a consumer (stage 2 forward / stage A inverse), so each scheduler always hosts
-// two warps of each role.  0b0011 = warps 0..7 consume, 8..15 produce (the arbiter favours the producers then).
+// two warps of each role.  0b0011 = warps 0..7 consume, 8..15 produce.  (Five layouts measured 1.642-1.646 ms: the
+// mapping does not matter; the switch stays for experiments.)
 #ifndef AIP_ROLE_MAP
 #define AIP_ROLE_MAP 0x3
 #endif
@@ -145,12 +149,12 @@ __device__ __forceinline__ WarpRole warp_role(int tid) {
   return r;
 }
 
-// Warp-specialised, persistent, one CTA per SM.  Tiles blockIdx.x, +gridDim.x, ... flow through
-//   TMA bulk copy -> tile[slot] -> stage-1 warps (lane = n1; window, 16-pt DFT, twiddle) -> exch[es]
-//   -> stage-2 warps (lane = frame; 2 x 16-pt DFT, split pass, |.|/log epilogue) -> HBM
-// with mbarrier hand-offs (tile_full / tile_empty / exch_full / exch_empty), so the copy of tile i+1,
+// Warp-specialised, persistent, one CTA per SM, a contiguous run of tiles per CTA.  Tiles flow through
+//   TMA bulk copy -> tile[slot] (ring of up to 3) -> stage-1 warps (lane = n1; window, 16-pt DFT, twiddle) -> exch[es]
+//   -> stage-2 warps (lane = frame; 2 x 16-pt DFT, packed split pass, |.|/log epilogue) -> HBM
+// with mbarrier hand-offs (tile_full / tile_empty / exch_full / exch_empty), so the copies of tiles i+1 and i+2,
 // stage 1 of tile i+1 and stage 2 of tile i overlap, and each role keeps ITS constants in registers
-// (stage 1: 32 window taps + 16 W256 twiddles per lane; stage 2: 16 W512 twiddles per warp).
+// (stage 1: 16 W256 twiddles per lane, read once from a shared-memory table; stage 2: 16 W512 twiddles per warp).
 template <int kMode, int kZP>
 __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdParams P) {
   extern __shared__ __align__(128) float smem[];
