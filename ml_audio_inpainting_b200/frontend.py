@@ -146,7 +146,7 @@ class HostPipeline:
     The batch is cut into chunks; chunk i's H2D copy, kernel and D2H copy run on stream i % 3 with
     per-stream device buffers, so copies of neighbouring chunks overlap the kernel (PCIe is the bound)."""
 
-    def __init__(self, plan: sp.StftPlan, batch: int, n_samples: int, chunk: int = 256, n_streams: int = 3,
+    def __init__(self, plan: sp.StftPlan, batch: int, n_samples: int, chunk: int = 64, n_streams: int = 4,
                  t_out: Optional[int] = None):
         self.plan, self.B, self.L = plan, int(batch), int(n_samples)
         self.chunk = max(1, min(int(chunk), self.B))
