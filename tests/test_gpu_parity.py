@@ -129,6 +129,31 @@ def test_randomised_geometry_sweep(sp):
         assert relerr(y[1][good], ref_y[good]) < TOL, (case, hop, wl, L, length)
 
 
+def test_randomised_gap_positions(sp):
+    """Time-domain gaps (utils.py:141-142, :180-183) at the clip start, the clip end, across tile borders and of every
+    length from one sample to almost the whole clip: log10(|stft(x with the gap zeroed)| + 1e-9) against the oracle."""
+    rng = np.random.default_rng(20260103)
+    L = 30000
+    x = _noise(16, L, seed=77)
+    plan = sp.get_plan(512, 192, 384, "hann", True, "cuda:0")
+    glen = rng.integers(1, L - 1, size=16)
+    glen[:4] = [1, 2, 191, 6144]
+    g0 = np.array([int(rng.integers(0, L - g)) for g in glen])
+    g0[4], g0[5] = 0, L - glen[5]                      # at the very start / the very end
+    g0[6] = 32 * 192 - 256 - glen[6] // 2 if glen[6] < 5000 else 0     # straddles the first tile border
+    g0 = np.clip(g0, 0, L - glen)
+    gaps_ = np.stack([g0, g0 + glen], 1)
+    mag = sp.stft(torch.from_numpy(x).cuda(), plan, gap_samples=gaps_, mag_kind=sp.MAG_LOG10_EPS, eps=1e-9,
+                  want_spec=False)["mag"].cpu().numpy()
+    for b in range(16):
+        xg = x[b].copy()
+        xg[gaps_[b, 0]:gaps_[b, 1]] = 0
+        ref = np.abs(lr.stft(xg, n_fft=512, hop_length=192, win_length=384))
+        assert relerr(10.0 ** mag[b].astype(np.float64), ref + 1e-9) < TOL, (b, gaps_[b])
+        silent = ref == 0.0                              # frames entirely inside the gap: exactly log10(1e-9)
+        assert np.all(mag[b][silent] == np.float32(-9.0))
+
+
 def test_logmag_gap_epilogue(sp):
     L, B = 80000, 4
     x = _noise(B, L, seed=11)
