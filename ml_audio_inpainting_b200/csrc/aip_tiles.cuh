@@ -120,14 +120,19 @@ AIP_HD bool fwd_needs_fixup(const FwdTilePlan& q) {
 }
 
 // everything of the tile that the bulk copy does not deliver
+// Every element is written by at most ONE thread here: the scalar copy applies the gap itself (a separate zeroing
+// pass by other threads would race with it -- seen on hardware with unaligned waveforms), the zeroing pass below only
+// touches what the bulk copy delivered.
 AIP_HD void fwd_fixup(const FwdTilePlan& q, int tid, float* tile) {
-  for (int i = tid; i < q.v_lo; i += kThreads) tile[i] = 0.0f;
-  for (int i = q.v_lo + q.n_bulk + tid; i < q.v_hi; i += kThreads) tile[i] = q.src[q.g0 + i];
-  for (int i = q.v_hi + tid; i < q.len; i += kThreads) tile[i] = 0.0f;
-  // gap zeroing (utils.py:141-142, :180-183) on the staged samples
-  int a = q.gs - q.g0, e = q.ge - q.g0;
+  int a = q.gs - q.g0, e = q.ge - q.g0;        // gap range (utils.py:141-142, :180-183) in tile elements
   if (a < 0) a = 0;
   if (e > q.len) e = q.len;
+  for (int i = tid; i < q.v_lo; i += kThreads) tile[i] = 0.0f;
+  const int bulk_end = q.v_lo + q.n_bulk;
+  for (int i = bulk_end + tid; i < q.v_hi; i += kThreads) tile[i] = (i >= a && i < e) ? 0.0f : q.src[q.g0 + i];
+  for (int i = q.v_hi + tid; i < q.len; i += kThreads) tile[i] = 0.0f;
+  if (a < q.v_lo) a = q.v_lo;
+  if (e > bulk_end) e = bulk_end;
   for (int i = a + tid; i < e; i += kThreads) tile[i] = 0.0f;
 }
 

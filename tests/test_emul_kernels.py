@@ -249,3 +249,27 @@ def test_randomised_geometry_forward_and_inverse():
         y = emul.istft(hop, win(wl), iw, spec=ref_S[None], length=length, win_length=wl)
         good = iw < 100.0                      # window-sum-square (near) zero at a truncated tail: ill conditioned in the reference too
         assert relerr(y[0][good], ref_y[good]) < TOL, (case, hop, wl, L, length)
+
+
+@pytest.mark.parametrize("L,hop,wl", [(6001, 192, 384), (16000, 192, 384), (9000, 128, 512), (20011, 250, 500)])
+def test_forward_multi_clip_gaps_masks_and_unaligned_rows(L, hop, wl):
+    """Several clips with per-clip gaps and frame masks; odd L makes the row pitch unaligned, so the waveform is staged
+    by the threads instead of TMA -- the gap must still be exact (a separate zeroing pass used to race with that copy)."""
+    B = 5
+    x = noise(B, L, seed=L)
+    rng = np.random.default_rng(L)
+    g0 = rng.integers(0, L - 700, size=B)
+    g0[1] = 0
+    gaps_ = np.stack([g0, g0 + rng.integers(1, 700, size=B)], 1)
+    gaps_[2] = [L - 3, L]                                 # the ragged tail of a clip
+    T = 1 + L // hop
+    frames = np.stack([rng.integers(0, T // 2, size=B), rng.integers(T // 2, T, size=B)], 1)
+    a = emul.stft(x, hop, win(wl), gap_samples=gaps_, mask_frames=frames, mag_kind=2, want_spec=True, want_mask=True,
+                  win_length=wl)
+    for i in range(B):
+        xg = x[i].copy()
+        xg[gaps_[i, 0]:gaps_[i, 1]] = 0
+        assert relerr(a["spec"][i], lr.stft(xg, n_fft=512, hop_length=hop, win_length=wl)) < TOL, (i, gaps_[i])
+        m = np.zeros(T, np.float32)
+        m[frames[i, 0]:frames[i, 1]] = 1
+        assert np.array_equal(a["mask"][i], np.broadcast_to(m, (257, T)))

@@ -154,6 +154,27 @@ def test_randomised_gap_positions(sp):
         assert np.all(mag[b][silent] == np.float32(-9.0))
 
 
+@pytest.mark.parametrize("L", [6001, 16003, 9998])
+def test_gaps_on_unaligned_waveforms(sp, L):
+    """Row pitch not a multiple of 4 samples: the waveform is staged by the threads, not by TMA, and the gap must still
+    be exact (a separate zeroing pass used to race with that copy), also on the last samples of a clip; several clips per
+    tile stream so that packed tiles cross clip borders."""
+    B = 6
+    x = _noise(B, L, seed=L)
+    rng = np.random.default_rng(L)
+    g0 = rng.integers(0, L - 900, size=B)
+    glen = rng.integers(1, 900, size=B)
+    g0[0], glen[0] = L - 5, 5                              # the ragged tail of the clip
+    g0[1] = 0
+    gaps_ = np.stack([g0, g0 + glen], 1)
+    plan = sp.get_plan(512, 192, 384, "hann", True, "cuda:0")
+    S = sp.stft(torch.from_numpy(x).cuda(), plan, gap_samples=gaps_)["spec"].cpu().numpy()
+    for b in range(B):
+        xg = x[b].copy()
+        xg[gaps_[b, 0]:gaps_[b, 1]] = 0
+        assert relerr(S[b], lr.stft(xg, n_fft=512, hop_length=192, win_length=384)) < TOL, (b, gaps_[b])
+
+
 def test_logmag_gap_epilogue(sp):
     L, B = 80000, 4
     x = _noise(B, L, seed=11)
