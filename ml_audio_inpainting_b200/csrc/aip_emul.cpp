@@ -65,7 +65,7 @@ int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, 
 #define AIP_CASE(M) case (M): fwd_phase2<(M)>(P, tid, c, exch.data(), pw[tid], rel); break;
         AIP_CASE(FWD_MAG_ABS) AIP_CASE(FWD_MAG_LOG10) AIP_CASE(FWD_SPEC) AIP_CASE(MAG_LOG10_EPS | FWD_MASK)
         AIP_CASE(MAG_LOG1P_POW) AIP_CASE(MAG_LOG1P_POW | FWD_PHASE | FWD_MASK) AIP_CASE(FWD_SPEC | FWD_PHASE | FWD_MASK)
-        AIP_CASE(MAG_LOG10_EPS | FWD_ZERO) AIP_CASE(MAG_ABS | FWD_PHASE)
+        AIP_CASE(MAG_LOG10_EPS | FWD_ZERO) AIP_CASE(MAG_ABS | FWD_PHASE) AIP_CASE(MAG_LOG1P_POW | FWD_PHASE) AIP_CASE(FWD_SPEC | FWD_PHASE)
 #undef AIP_CASE
         default: fwd_phase2<FWD_FULL>(P, tid, c, exch.data(), pw[tid], rel); break;
       }
@@ -73,6 +73,14 @@ int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, 
     tile_advance(c, P.tiles_per_clip);
   }
   return 0;
+}
+
+// the epilogue's scalar helpers, for the accuracy tests
+void emul_fast_math(int n, const float* y, const float* x, float* out_atan2, float* out_log1p) {
+  for (int i = 0; i < n; ++i) {
+    out_atan2[i] = fast_atan2(y[i], x[i]);
+    out_log1p[i] = fast_log1p(fabsf(x[i]));
+  }
 }
 
 int emul_istft512(const float* spec, const float* mag, const float* phase, int mag_domain,

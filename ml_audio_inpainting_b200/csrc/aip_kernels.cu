@@ -653,13 +653,27 @@ __global__ void gap_mask_kernel(float* mask, long long pitch, long long B, long 
   }
 }
 
-__global__ void frame_mask_kernel(float* mask, long long B, long long F, long long T, const int* fr, int one_in_gap) {
-  const long long total = B * F * T;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long b = i / (F * T), t = i % T;
-    const bool in = fr && t >= fr[2 * b] && t < fr[2 * b + 1];
-    mask[i] = (in == (one_in_gap != 0)) ? 1.0f : 0.0f;
+// one (clip, bin) row per WARP and loop trip: no per-element division, 16-byte stores where the row allows
+__global__ void __launch_bounds__(256) frame_mask_kernel(float* mask, long long B, long long F, long long T, const int* fr,
+                                                         int one_in_gap) {
+  const long long rows = B * F;
+  const float in_v = one_in_gap ? 1.0f : 0.0f, out_v = 1.0f - in_v;
+  const int lane = threadIdx.x & 31;
+  for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * 8) {
+    const long long b = row / F;
+    const int f0 = fr ? fr[2 * b] : 0, f1 = fr ? fr[2 * b + 1] : 0;
+    float* dst = mask + row * T;
+    const int head = (int)((4 - ((reinterpret_cast<uintptr_t>(dst) >> 2) & 3)) & 3);       // elements before 16-byte alignment
+    const int n4 = T > head ? (int)((T - head) >> 2) : 0;
+    if (lane < head && lane < T) dst[lane] = (lane >= f0 && lane < f1) ? in_v : out_v;
+    float4* d4 = reinterpret_cast<float4*>(dst + head);
+    for (int q = lane; q < n4; q += 32) {
+      const int t = head + 4 * q;
+      d4[q] = make_float4((t >= f0 && t < f1) ? in_v : out_v, (t + 1 >= f0 && t + 1 < f1) ? in_v : out_v,
+                          (t + 2 >= f0 && t + 2 < f1) ? in_v : out_v, (t + 3 >= f0 && t + 3 < f1) ? in_v : out_v);
+    }
+    const int t = head + 4 * n4 + lane;
+    if (t < T) dst[t] = (t >= f0 && t < f1) ? in_v : out_v;
   }
 }
 
@@ -908,6 +922,8 @@ static cudaError_t launch_fwd512(const FwdParams& P, const DevInfo& di, cudaStre
     case FWD_SPEC | FWD_PHASE | FWD_MASK: return launch_fwd512_t<FWD_SPEC | FWD_PHASE | FWD_MASK>(P, di, st);
     case MAG_LOG10_EPS | FWD_ZERO: return launch_fwd512_t<MAG_LOG10_EPS | FWD_ZERO>(P, di, st);
     case MAG_ABS | FWD_PHASE: return launch_fwd512_t<MAG_ABS | FWD_PHASE>(P, di, st);
+    case MAG_LOG1P_POW | FWD_PHASE: return launch_fwd512_t<MAG_LOG1P_POW | FWD_PHASE>(P, di, st);
+    case FWD_SPEC | FWD_PHASE: return launch_fwd512_t<FWD_SPEC | FWD_PHASE>(P, di, st);
     default: return launch_fwd512_t<FWD_FULL>(P, di, st);
   }
 }
@@ -1261,8 +1277,9 @@ int aip_frame_mask_f32(float* mask, int64_t B, int64_t F, int64_t T, const int32
   if (!di.ok) return AIP_ERR_DEVICE;
   if (!mask || B < 0 || F < 0 || T < 0) return AIP_ERR_ARG;
   if (B * F * T == 0) return AIP_OK;
-  frame_mask_kernel<<<ew_grid(B * F * T, di.sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      mask, B, F, T, mask_frames, mask_in_gap_is_one);
+  long long grid = (B * F + 7) / 8;
+  if (grid > (long long)di.sms * 16) grid = (long long)di.sms * 16;
+  frame_mask_kernel<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, B, F, T, mask_frames, mask_in_gap_is_one);
   return (int)cudaGetLastError();
 }
 

@@ -24,6 +24,40 @@ AIP_HD float fast_log2(float x) { return log2f(x); }
 AIP_HD float fast_exp2(float x) { return exp2f(x); }
 AIP_HD void fast_sincos(float a, float& s, float& c) { s = sinf(a); c = cosf(a); }
 #endif
+#if defined(__CUDACC__)
+AIP_HD float fast_div(float a, float b) { return __fdividef(a, b); }
+#else
+AIP_HD float fast_div(float a, float b) { return a / b; }
+#endif
+
+// np.angle / atan2 for the phase outputs (models/GAN/dataset.py:123, models/model_eval.py:86): one division, a degree-7
+// polynomial in a^2 on [0, 1] (fitted for this file; max error 1.3e-7 rad in fp32, i.e. half an ulp of pi) and three
+// sign / quadrant selects -- about a third of atan2f's instructions in an epilogue that runs once per bin.
+AIP_HD float fast_atan2(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float a = mx > 0.0f ? fast_div(mn, mx) : 0.0f;
+  const float s = a * a;
+  float p = -0.004054083023220301f;
+  p = p * s + 0.021861141547560692f;
+  p = p * s - 0.05590960383415222f;
+  p = p * s + 0.09641990065574646f;
+  p = p * s - 0.13908545672893524f;
+  p = p * s + 0.19946548342704773f;
+  p = p * s - 0.33329859375953674f;
+  p = p * s + 0.9999993443489075f;
+  float r = p * a;
+  if (ay > ax) r = 1.57079632679489662f - r;
+  if (copysignf(1.0f, x) < 0.0f) r = 3.14159265358979324f - r;      // sign bit, so that atan2(+0, -0) = pi like IEEE / numpy
+  return copysignf(r, y);
+}
+
+// log1p(m), m >= 0 (models/GAN/dataset.py:122,135): log(u) * m / (u - 1) with u = fl(1 + m) cancels the rounding of u
+AIP_HD float fast_log1p(float m) {
+  const float u = 1.0f + m, d = u - 1.0f;
+  const float r = fast_log2(u) * 0.693147180559945309f;
+  return d == 0.0f ? m : r * fast_div(m, d);
+}
 
 // ===================================================================================================
 // Forward
@@ -156,7 +190,7 @@ AIP_HD float mag_value(int mk, float xr, float xi, float eps, float power) {
   if (mk == MAG_ABS) return m;
   if (mk == MAG_LOG10_EPS) return fast_log2(m + eps) * kLog10of2;
   const float mp = (power == 1.0f) ? m : powf(m, power);
-  return (mk == MAG_LOG1P_POW) ? log1pf(mp) : mp;
+  return (mk == MAG_LOG1P_POW) ? fast_log1p(mp) : mp;
 }
 
 // two bins at once on FP32x2 (power == 1); the MUFU ops stay scalar
@@ -168,7 +202,7 @@ AIP_HD float2 mag_value2(int mk, float2 xr, float2 xi, float eps) {
     const float2 l = add2(m, make_float2(eps, eps));
     return mul2s(make_float2(fast_log2(l.x), fast_log2(l.y)), kLog10of2);
   }
-  return (mk == MAG_LOG1P_POW) ? make_float2(log1pf(m.x), log1pf(m.y)) : m;
+  return (mk == MAG_LOG1P_POW) ? make_float2(fast_log1p(m.x), fast_log1p(m.y)) : m;
 }
 
 // Forward kernel variants: a bit mask of what the epilogue produces, a template parameter of the kernel so
@@ -204,7 +238,7 @@ struct FwdEmitT {
   AIP_HM void put1(int o, float xr, float xi) const {
     if (kM & FWD_ZERO) { if (zero) { xr = 0.0f; xi = 0.0f; } }
     if (kM & FWD_SPEC) spec[o] = make_float2(xr, xi);
-    if (kM & FWD_PHASE) phase[o] = atan2f(xi, xr);
+    if (kM & FWD_PHASE) phase[o] = fast_atan2(xi, xr);
     if (kM & FWD_MASK) mask[o] = maskv;
     if (kM & 7) mag[o] = mag_value(kM & 7, xr, xi, eps, 1.0f);
   }
@@ -214,7 +248,7 @@ struct FwdEmitT {
     if (kM & (FWD_SPEC | FWD_PHASE)) {
       const float ix = SX < 0 ? -xi.x : xi.x, iy = SY < 0 ? -xi.y : xi.y;
       if (kM & FWD_SPEC) { spec[ox] = make_float2(xr.x, ix); spec[oy] = make_float2(xr.y, iy); }
-      if (kM & FWD_PHASE) { phase[ox] = atan2f(ix, xr.x); phase[oy] = atan2f(iy, xr.y); }
+      if (kM & FWD_PHASE) { phase[ox] = fast_atan2(ix, xr.x); phase[oy] = fast_atan2(iy, xr.y); }
     }
     if (kM & FWD_MASK) { mask[ox] = maskv; mask[oy] = maskv; }
     if (kM & 7) {
@@ -264,7 +298,7 @@ struct FwdEmitFull {
     if (!active) return;
     if (zero) { xr = 0.0f; xi = 0.0f; }
     if (P.spec) P.spec[idx] = make_float2(xr, xi);
-    if (P.phase) P.phase[idx] = atan2f(xi, xr);
+    if (P.phase) P.phase[idx] = fast_atan2(xi, xr);
     if (P.mask) P.mask[idx] = maskv;
     if (P.mag_kind != MAG_NONE) P.mag[idx] = mag_value(P.mag_kind, xr, xi, P.eps, P.power);
   }
@@ -287,7 +321,8 @@ struct NoRelease { AIP_HM void operator()() const {} };
 AIP_HDX bool fwd_mode_is_fast(int m) {
   return m == FWD_MAG_ABS || m == FWD_MAG_LOG10 || m == FWD_SPEC || m == (MAG_LOG10_EPS | FWD_MASK) ||
          m == MAG_LOG1P_POW || m == (MAG_LOG1P_POW | FWD_PHASE | FWD_MASK) || m == (FWD_SPEC | FWD_PHASE | FWD_MASK) ||
-         m == (MAG_LOG10_EPS | FWD_ZERO) || m == (MAG_ABS | FWD_PHASE);
+         m == (MAG_LOG10_EPS | FWD_ZERO) || m == (MAG_ABS | FWD_PHASE) || m == (MAG_LOG1P_POW | FWD_PHASE) ||
+         m == (FWD_SPEC | FWD_PHASE);
 }
 
 AIP_HDX int fwd_mode_of(const FwdParams& P) {

@@ -273,3 +273,25 @@ def test_forward_multi_clip_gaps_masks_and_unaligned_rows(L, hop, wl):
         m = np.zeros(T, np.float32)
         m[frames[i, 0]:frames[i, 1]] = 1
         assert np.array_equal(a["mask"][i], np.broadcast_to(m, (257, T)))
+
+
+def test_epilogue_atan2_and_log1p_accuracy():
+    """fast_atan2 / fast_log1p (phase and log1p outputs of the GAN front-end) against numpy on a dense sweep and on the
+    special points: all four quadrants, the axes, signed zeros, tiny and huge arguments."""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    n = 200000
+    y = (rng.standard_normal(n) * 10.0 ** rng.uniform(-6, 3, n)).astype(np.float32)
+    x = (rng.standard_normal(n) * 10.0 ** rng.uniform(-6, 3, n)).astype(np.float32)
+    special = np.array([0.0, -0.0, 1.0, -1.0, 1e-30, -1e-30, 3e30, -3e30], np.float32)
+    y[:64] = np.repeat(special, 8)
+    x[:64] = np.tile(special, 8)
+    a = np.empty(n, np.float32)
+    l = np.empty(n, np.float32)
+    FP = C.POINTER(C.c_float)
+    emul.lib().emul_fast_math(n, y.ctypes.data_as(FP), x.ctypes.data_as(FP), a.ctypes.data_as(FP), l.ctypes.data_as(FP))
+    ref_a = np.arctan2(y.astype(np.float64), x.astype(np.float64))
+    assert np.abs(a - ref_a).max() < 5e-7                                   # ~1 ulp of pi
+    assert np.array_equal(np.signbit(a[:64]), np.signbit(ref_a[:64].astype(np.float32)))
+    ref_l = np.log1p(np.abs(x).astype(np.float64))
+    assert (np.abs(l - ref_l) / np.maximum(ref_l, 1e-30)).max() < 1e-6

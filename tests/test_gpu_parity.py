@@ -326,6 +326,38 @@ def test_small_kernels(sp):
     assert flags.cpu().tolist() == [1, 0]
 
 
+@pytest.mark.parametrize("one_in_gap", [1, 0])
+def test_frame_mask_kernel_and_fused_mask_output_agree(sp, one_in_gap):
+    """The dense frame mask (models/CNNBLSTM/dataset.py:115-118, models/GAN/dataset.py:150-152) two ways through the C ABI:
+    the streaming aip_frame_mask_f32 (what the Python API uses) and mask_out of aip_stft_fwd_f32 -- bit-identical, and equal
+    to the reference's definition; odd T so that rows start unaligned."""
+    import ctypes as C
+    from ml_audio_inpainting_b200 import _cabi
+    lib = _cabi.load()
+    B, L = 7, 80000
+    x = torch.from_numpy(_noise(B, L, seed=3)).cuda()
+    plan = sp.get_plan(512, 192, 384, "hann", True, "cuda:0")
+    T = plan.num_frames(L)                                   # 417
+    fr = np.array([[0, 5], [166, 173], [410, 417], [200, 200], [0, 417], [416, 417], [30, 31]], dtype=np.int32)
+    frd = torch.from_numpy(fr).cuda()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    m1 = torch.empty((B, 257, T), device="cuda")
+    _cabi.check(lib.aip_frame_mask_f32(m1.data_ptr(), B, 257, T, frd.data_ptr(), one_in_gap, st), "frame_mask")
+    m2 = torch.full((B, 257, T), -1.0, device="cuda")
+    mag = torch.empty((B, 257, T), device="cuda")
+    _cabi.check(lib.aip_stft_fwd_f32(C.byref(plan.desc), x.data_ptr(), B, L, L, None, None, frd.data_ptr(), one_in_gap,
+                                     sp.MAG_LOG10_EPS, 1e-9, 1.0, T, None, mag.data_ptr(), None, m2.data_ptr(), st), "fwd")
+    assert torch.equal(m1, m2)
+    for b in range(B):
+        row = np.full(T, 0.0 if one_in_gap else 1.0, np.float32)
+        row[fr[b, 0]:fr[b, 1]] = 1.0 if one_in_gap else 0.0
+        assert np.array_equal(m1[b].cpu().numpy(), np.broadcast_to(row, (257, T)))
+    # and through the Python API
+    res = sp.stft(x, plan, mask_frames=fr, mask_in_gap_is_one=bool(one_in_gap), mag_kind=sp.MAG_LOG10_EPS, want_spec=False,
+                  want_mask=True)
+    assert torch.equal(res["mask"], m1) and torch.equal(res["mag"], mag)
+
+
 def test_config1_reference_clips_round_trip(sp, golden_clips):
     """BASELINE.json configs[0]: STFT -> add gap -> iSTFT on the 9 test_samples clips (model_eval.py shape)."""
     import json
