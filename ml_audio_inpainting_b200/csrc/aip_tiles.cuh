@@ -84,7 +84,9 @@ struct FwdParams {
   int n_tiles;              // B * tiles_per_clip (< 2^31)
   int tile_floats;          // floats per staged-waveform buffer (tile length rounded up to 128 B)
   int n_tile_bufs;          // 2: the next tile's copy overlaps stage 1; 1: large hops
-  int tiles_per_cta;        // contiguous run of tiles per CTA
+  int tiles_per_cta;        // (unused by the forward kernel since tiles are handed out dynamically)
+  int chunk;                // tiles per draw from the dynamic schedule
+  unsigned* tile_counter;   // device counter of the dynamic schedule, zero at launch
   int vec_ok;               // 16-byte bulk copies of the waveform are legal (alignment)
   int zero_groups;          // win_zero_groups(win_length): the first / last 32 * zero_groups window taps are zero
 };
