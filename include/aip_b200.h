@@ -26,8 +26,9 @@
  *   - spectrogram layout is the reference's: [B, F = n_fft/2 + 1, T] with T contiguous
  *     (complex as interleaved float pairs); waveforms are [B, L] rows with an explicit pitch;
  *   - return value: 0 = ok, < 0 = argument / support error (AIP_ERR_*), > 0 = cudaError_t;
- *   - re-entrant and thread-safe: there is no mutable global state (twiddle tables are constants
- *     in the image; windows are caller-supplied);
+ *   - re-entrant and thread-safe: the only mutable global state is a ring of 64 four-byte tile counters in device
+ *     memory (the forward kernel's dynamic tile schedule); every launch takes the next one and zeroes it on its own
+ *     stream, so launches are independent unless more than 64 of them are in flight at once;
  *   - there is NO CPU fallback: on a device that is not compute capability 10.x every entry point
  *     returns AIP_ERR_DEVICE.
  */
