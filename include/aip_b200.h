@@ -18,6 +18,7 @@
  *   aip_gap_mask_f32        dense sample-domain 1/0 mask                           utils.py:141-142
  *   aip_frame_mask_f32      dense [F,T] frame mask                                 models/CNNBLSTM/dataset.py:115-118, models/GAN/dataset.py:150-152
  *   aip_peak_normalize_f32  librosa.util.normalize (norm=inf)                      utils.py:84
+ *   aip_stft_gap_variants_f32  the gaps_per_audio loop of one dataset item        models/CNNBLSTM/dataset.py:93-111
  *
  * Conventions
  *   - every pointer is a DEVICE pointer on the current CUDA device unless stated otherwise;
@@ -151,6 +152,20 @@ int aip_istft_normalized_f32(const aip_stft_desc* desc,
                              int64_t B, int64_t T, int64_t length, const float* inv_wss,
                              float* wave_out, int64_t out_pitch, float* peaks,
                              void* workspace, size_t workspace_bytes, void* stream);
+/* Gap variants of one file: models/CNNBLSTM/dataset.py:93-111 loads a file gaps_per_audio times, zeroes a
+ * different random range each time (utils.add_random_gap, utils.py:179-183) and runs a full STFT per gap; a gap only changes
+ * the frames whose n_fft-sample span meets it.  Variant v = i * G + j is gap j of wave row i:
+ *   mag_out[v] := clean_mag[i] everywhere, then the <= ceil((gap_len_max + n_fft) / hop) + 1 frames around gap_samples[v]
+ *   are re-transformed from wave row i with samples [gap_samples[v][0], gap_samples[v][1]) zeroed (same kernel, same
+ *   arithmetic as aip_stft_fwd_f32 with gap_samples: the result is bit-identical to G full transforms).
+ * clean_mag [N, F, T_out] is the caller's aip_stft_fwd_f32(..., mag_kind, eps, T_out) of the un-gapped rows.
+ * gap_len_max: the caller's bound on gap_samples[v][1] - gap_samples[v][0] (a longer gap is NOT detected).
+ * mag_kind: AIP_MAG_ABS | AIP_MAG_LOG10_EPS | AIP_MAG_LOG1P_POW (power 1); n_fft 512 only (else AIP_ERR_UNSUPPORTED). */
+int aip_stft_gap_variants_f32(const aip_stft_desc* desc, const float* wave, int64_t N, int64_t L, int64_t wave_pitch,
+                              int64_t G, const int32_t* gap_samples /* [N*G, 2] */, int32_t gap_len_max,
+                              int32_t mag_kind, float eps, int64_t T_out, const float* clean_mag /* [N, F, T_out] */,
+                              float* mag_out /* [N*G, F, T_out] */, void* stream);
+
 /* y_b / max|y_b| unless max|y_b| < FLT_MIN; peaks: [B] float scratch/out (the per-clip max|y|). */
 int aip_peak_normalize_f32(const float* in, int64_t in_pitch, float* out, int64_t out_pitch,
                            int64_t B, int64_t L, float* peaks, void* stream);

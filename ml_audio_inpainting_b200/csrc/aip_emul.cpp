@@ -75,6 +75,65 @@ int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, 
   return 0;
 }
 
+// aip_stft_gap_variants_f32: the copy pass (plain loops) and the variant tiles, replayed thread by thread
+int emul_stft512_variants(const float* wave, int N, int L, long long pitch, int hop, int center, int win_length,
+                          const float* window, int G, const int* gap_samples, int gap_len_max, int mag_kind, float eps,
+                          int T_out, const float* clean_mag, float* mag, int vec_ok) {
+  FwdParams P;
+  memset(&P, 0, sizeof(P));
+  P.wave = wave; P.wave_pitch = pitch; P.B = N * G; P.L = L;
+  P.hop = hop; P.pad = center ? 256 : 0;
+  P.T = 1 + (L + 2 * P.pad - 512) / hop;
+  if (T_out > P.T || (hop & 1)) return -1;
+  P.T_out = T_out;
+  P.window = window;
+  P.gap_samples = gap_samples;
+  P.mag_kind = mag_kind; P.eps = eps; P.power = 1.0f; P.mag = mag;
+  P.var_div = G;
+  P.tiles_per_clip = var_tiles(gap_len_max, hop, T_out);
+  P.n_tiles = P.B * P.tiles_per_clip;
+  P.tile_floats = (fwd_tile_len(hop) + 31) & ~31;
+  P.n_tile_bufs = 1;
+  P.zero_groups = win_zero_groups(win_length);
+  P.vec_ok = vec_ok && ((hop & 3) == 0) && ((pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(wave) & 15) == 0);
+  const long long FT = (long long)kBins * T_out;
+  for (int v = 0; v < P.B; ++v) memcpy(mag + v * FT, clean_mag + (v / G) * FT, (size_t)FT * sizeof(float));
+  std::vector<float> tile(P.tile_floats);
+  std::vector<float2> exch(kExch);
+  std::vector<LaneConst> lc(kThreads);
+  std::vector<PairTw> pw(kThreads);
+  std::vector<float2> tw_s(kTwTable);
+  twiddle_table_fill(tw_s.data(), 0, 1);
+  for (int tid = 0; tid < kThreads; ++tid) {
+    lane_const_init(lc[tid], tw_s.data(), tid & 15);
+    pair_tw_init(pw[tid], tid >> 5);
+  }
+  NoRelease rel;
+  alignas(16) float win_s[kWinTable];
+  window_table_fill(win_s, window, 0.5f, 0, 1);
+  TileCursor c = tile_cursor(0, P.tiles_per_clip);
+  for (int tix = 0; tix < P.n_tiles; ++tix) {
+    const int gs = gap_samples[2 * c.b], ge = gap_samples[2 * c.b + 1];
+    const FwdTilePlan q = fwd_tile_plan_var(P, c, gs, ge, var_frame_base(P, gs));
+    if (q.n_bulk > 0) memcpy(tile.data() + q.v_lo, q.src + q.g0 + q.v_lo, (size_t)q.n_bulk * 4);   // the TMA bulk copy
+    if (fwd_needs_fixup(q)) for (int tid = 0; tid < kThreads; ++tid) fwd_fixup(q, tid, tile.data());
+    for (int tid = 0; tid < kThreads; ++tid) {
+      if (P.zero_groups == 2) fwd_phase1<2>(P, tid, tile.data(), exch.data(), win_s, lc[tid]);
+      else fwd_phase1<0>(P, tid, tile.data(), exch.data(), win_s, lc[tid]);
+    }
+    for (int tid = 0; tid < kThreads; ++tid) {
+      switch (mag_kind) {
+        case MAG_ABS: fwd_phase2<FWD_MAG_ABS | FWD_VARIANT>(P, tid, c, exch.data(), pw[tid], rel); break;
+        case MAG_LOG10_EPS: fwd_phase2<FWD_MAG_LOG10 | FWD_VARIANT>(P, tid, c, exch.data(), pw[tid], rel); break;
+        case MAG_LOG1P_POW: fwd_phase2<MAG_LOG1P_POW | FWD_VARIANT>(P, tid, c, exch.data(), pw[tid], rel); break;
+        default: return -2;
+      }
+    }
+    tile_advance(c, P.tiles_per_clip);
+  }
+  return 0;
+}
+
 // the epilogue's scalar helpers, for the accuracy tests
 void emul_fast_math(int n, const float* y, const float* x, float* out_atan2, float* out_log1p) {
   for (int i = 0; i < n; ++i) {

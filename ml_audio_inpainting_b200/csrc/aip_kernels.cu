@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
     lane_const_init(lc, tw_s, ptid & 15);
     TileFeed fn{0, 0, TileCursor{0, 0}};     // request cursor (thread ptid == 0 only): draws the chunks
     bool more = true;                        // the request cursor has not hit the end of the batch yet
+    int req_clip = -1, req_fb = 0;           // FWD_VARIANT: frame base of the variant the request cursor is in
     auto request = [&](float* buf, uint64_t* bar) {      // ptid == 0: start the copy of the next tile, if there is one
       if (fn.left == 0) {
         const int s = (int)atomicAdd(P.tile_counter, (unsigned)P.chunk);
@@ -232,7 +233,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
         fn.c = tile_cursor(s, P.tiles_per_clip);
         fn.left = cnt;
       }
-      fwd_issue_tile(fwd_tile_plan_gap(P, fn.c, 0, 0), buf, bar);
+      if (kMode & FWD_VARIANT) {
+        if (fn.c.b != req_clip) { req_fb = var_frame_base(P, P.gap_samples[2 * fn.c.b]); req_clip = fn.c.b; }
+        fwd_issue_tile(fwd_tile_plan_var(P, fn.c, 0, 0, req_fb), buf, bar);
+      } else {
+        fwd_issue_tile(fwd_tile_plan_gap(P, fn.c, 0, 0), buf, bar);
+      }
       tile_advance(fn.c, P.tiles_per_clip);
       --fn.left;
     };
@@ -242,6 +248,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
     TileFeed f{0, 0, TileCursor{0, 0}};
     int slot = 0, use = 0;               // ring slot of tile i and how often it has been used before
     int gs = 0, ge = 0, gap_clip = -1;   // gap range of the clip the cursor is in
+    int fb = 0;                          // FWD_VARIANT: first recomputed frame of that variant
 #pragma unroll 1
     for (int i = 0;; ++i) {
       if (f.left == 0 && !feed_next(P, f, sched_start, sched_bar)) break;
@@ -251,8 +258,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
         gs = P.gap_samples[2 * c.b];
         ge = P.gap_samples[2 * c.b + 1];
         gap_clip = c.b;
+        if (kMode & FWD_VARIANT) fb = var_frame_base(P, gs);
       }
-      const FwdTilePlan q = fwd_tile_plan_gap(P, c, gs, ge);
+      const FwdTilePlan q = (kMode & FWD_VARIANT) ? fwd_tile_plan_var(P, c, gs, ge, fb) : fwd_tile_plan_gap(P, c, gs, ge);
       if (ntb > 1 && ptid == 0 && more) {
         // the next request goes into the slot that tile i - 1 has just left
         const int ns = slot == 0 ? ntb - 1 : slot - 1;
@@ -718,6 +726,35 @@ __global__ void __launch_bounds__(256) frame_mask_kernel(float* mask, long long 
   }
 }
 
+// Gap variants, copy pass: row (variant v, bin k) of `out` := row (v / G, k) of the clean spectrogram, one row per WARP and
+// loop trip.  Source and destination rows start at different 16-byte phases in general (T = 417, 834 are odd), so the loads are
+// 4-byte (they hit L2 / L1: every clean row is read G times) and the stores 16-byte.  Vectors that lie completely inside the
+// frame range the transform kernel rewrites afterwards ([fb, fb + nt * kFR), see var_frame_base) are skipped.
+__global__ void __launch_bounds__(256) variant_fill_kernel(const float* __restrict__ clean, float* __restrict__ out, long long NG,
+                                                           int G, int F, int T, const int* __restrict__ gaps, FwdParams P) {
+  const long long rows = NG * F;
+  const int lane = threadIdx.x & 31;
+  for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * 8) {
+    const long long v = row / F;
+    const int k = (int)(row - v * F);
+    const int s0 = var_frame_base(P, gaps[2 * v]), s1 = s0 + P.tiles_per_clip * kFR;
+    const float* src = clean + ((v / G) * F + k) * T;
+    float* dst = out + row * T;
+    const int head = (int)((4 - ((reinterpret_cast<uintptr_t>(dst) >> 2) & 3)) & 3);
+    const int n4 = T > head ? ((T - head) >> 2) : 0;
+    if (lane < head && lane < T) dst[lane] = src[lane];
+    float4* d4 = reinterpret_cast<float4*>(dst + head);
+#pragma unroll 4
+    for (int q = lane; q < n4; q += 32) {
+      const int t = head + 4 * q;
+      if (t >= s0 && t + 3 < s1) continue;
+      d4[q] = make_float4(src[t], src[t + 1], src[t + 2], src[t + 3]);
+    }
+    const int t = head + 4 * n4 + lane;
+    if (t < T) dst[t] = src[t];
+  }
+}
+
 __global__ void __launch_bounds__(256) peak_kernel(const float* in, long long pitch, long long L, float* peaks) {
   __shared__ float sm[8];
   const long long b = blockIdx.y;
@@ -967,7 +1004,6 @@ static cudaError_t launch_fwd512_t(FwdParams P, const DevInfo& di, cudaStream_t 
   if (const char* c = getenv("AIP_FWD_CHUNK")) { const int cv = atoi(c); if (cv >= 1 && cv <= 4096) P.chunk = cv; }    // profiling switch
   const int n_chunks = (P.n_tiles + P.chunk - 1) / P.chunk;
   if (grid > n_chunks) grid = n_chunks;
-  P.tiles_per_cta = 0;
   P.tile_counter = next_tile_counter(st, &e);
   if (e != cudaSuccess) return e;
   kern<<<(unsigned)grid, kFwdThreads, smem, st>>>(P);
@@ -975,6 +1011,14 @@ static cudaError_t launch_fwd512_t(FwdParams P, const DevInfo& di, cudaStream_t 
 }
 
 static cudaError_t launch_fwd512(const FwdParams& P, const DevInfo& di, cudaStream_t st) {
+  if (P.var_div > 0) {      // gap variants: magnitude-only epilogues
+    switch (fwd_mode_of(P)) {
+      case FWD_MAG_ABS: return launch_fwd512_t<FWD_MAG_ABS | FWD_VARIANT>(P, di, st);
+      case FWD_MAG_LOG10: return launch_fwd512_t<FWD_MAG_LOG10 | FWD_VARIANT>(P, di, st);
+      case MAG_LOG1P_POW: return launch_fwd512_t<MAG_LOG1P_POW | FWD_VARIANT>(P, di, st);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (fwd_mode_of(P)) {
     case FWD_MAG_ABS: return launch_fwd512_t<FWD_MAG_ABS>(P, di, st);
     case FWD_MAG_LOG10: return launch_fwd512_t<FWD_MAG_LOG10>(P, di, st);
@@ -1344,6 +1388,42 @@ int aip_frame_mask_f32(float* mask, int64_t B, int64_t F, int64_t T, const int32
   if (grid > (long long)di.sms * 16) grid = (long long)di.sms * 16;
   frame_mask_kernel<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, B, F, T, mask_frames, mask_in_gap_is_one);
   return (int)cudaGetLastError();
+}
+
+int aip_stft_gap_variants_f32(const aip_stft_desc* desc, const float* wave, int64_t N, int64_t L, int64_t wave_pitch,
+                              int64_t G, const int32_t* gap_samples, int32_t gap_len_max, int32_t mag_kind, float eps,
+                              int64_t T_out, const float* clean_mag, float* mag_out, void* stream) {
+  const DevInfo di = dev_info();
+  if (!di.ok) return AIP_ERR_DEVICE;
+  if (!desc || !desc->window || !wave || !gap_samples || !clean_mag || !mag_out) return AIP_ERR_ARG;
+  if (N < 0 || G < 1 || L < 0 || wave_pitch < L || gap_len_max < 0 || N * G > 0x7fffffffLL || L > 0x7fffffffLL) return AIP_ERR_ARG;
+  if (mag_kind != MAG_ABS && mag_kind != MAG_LOG10_EPS && mag_kind != MAG_LOG1P_POW) return AIP_ERR_UNSUPPORTED;
+  if (!fwd_fast_ok(desc, di)) return AIP_ERR_UNSUPPORTED;       // n_fft 512 register-FFT path only
+  const long long T = num_frames(L, desc->n_fft, desc->hop, desc->center);
+  if (T < 1 || T_out < 0 || T_out > T || T_out > (1 << 22)) return AIP_ERR_ARG;
+  if (N == 0 || T_out == 0) return AIP_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  FwdParams P{};
+  P.wave = wave; P.wave_pitch = wave_pitch; P.B = (int)(N * G); P.L = (int)L;
+  P.gap_samples = gap_samples; P.mag_kind = mag_kind; P.eps = eps; P.power = 1.0f; P.mag = mag_out;
+  P.hop = desc->hop; P.pad = desc->center ? desc->n_fft / 2 : 0;
+  P.T = (int)T; P.T_out = (int)T_out; P.window = desc->window;
+  P.var_div = (int)G;
+  P.tiles_per_clip = var_tiles(gap_len_max, P.hop, P.T_out);
+  if ((long long)P.B * P.tiles_per_clip > 0x3fffffffLL) return AIP_ERR_UNSUPPORTED;
+  P.n_tiles = P.B * P.tiles_per_clip;
+  P.tile_floats = (fwd_tile_len(P.hop) + 31) & ~31;
+  P.n_tile_bufs = fwd_tile_bufs(desc, di);
+  P.zero_groups = win_zero_groups(desc->win_length);
+  P.vec_ok = ((P.hop & 3) == 0) && ((P.pad & 3) == 0) && ((P.wave_pitch & 3) == 0) &&
+             ((reinterpret_cast<uintptr_t>(P.wave) & 15) == 0);
+  const int F = desc->n_fft / 2 + 1;
+  long long grid = ((long long)P.B * F + 7) / 8;
+  if (grid > (long long)di.sms * 16) grid = (long long)di.sms * 16;
+  variant_fill_kernel<<<(unsigned)grid, 256, 0, st>>>(clean_mag, mag_out, (long long)P.B, (int)G, F, P.T_out, gap_samples, P);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  return (int)launch_fwd512(P, di, st);
 }
 
 int aip_peak_normalize_f32(const float* in, int64_t in_pitch, float* out, int64_t out_pitch, int64_t B,

@@ -84,7 +84,9 @@ struct FwdParams {
   int n_tiles;              // B * tiles_per_clip (< 2^31)
   int tile_floats;          // floats per staged-waveform buffer (tile length rounded up to 128 B)
   int n_tile_bufs;          // 2: the next tile's copy overlaps stage 1; 1: large hops
-  int tiles_per_cta;        // (unused by the forward kernel since tiles are handed out dynamically)
+  int var_div;              // gap-variant mode (FWD_VARIANT, aip_stft_gap_variants_f32), else 0: "clip" b is variant b of
+                            // wave row b / var_div (gaps_per_audio, models/CNNBLSTM/dataset.py:93) and only the tiles_per_clip
+                            // tiles starting at frame var_frame_base(P, gap start of b) are transformed
   int chunk;                // tiles per draw from the dynamic schedule
   unsigned* tile_counter;   // device counter of the dynamic schedule, zero at launch
   int vec_ok;               // 16-byte bulk copies of the waveform are legal (alignment)
@@ -146,6 +148,42 @@ AIP_HD FwdTilePlan fwd_tile_plan_gap(const FwdParams& P, const TileCursor& c, in
   const int hi = P.L - q.g0;
   q.v_hi = hi < q.len ? (hi > 0 ? hi : 0) : q.len;
   if (q.v_lo > q.v_hi) q.v_lo = q.v_hi;
+  q.n_bulk = P.vec_ok ? ((q.v_hi - q.v_lo) & ~3) : 0;
+  q.gs = gs; q.ge = ge;
+  return q;
+}
+
+// ---- gap variants (models/CNNBLSTM/dataset.py:93-111 computes gaps_per_audio full STFTs per file) ----
+// A gap [gs, ge) changes only the frames whose 512-sample span [t hop - pad, t hop - pad + 512) meets it:
+//   t in [ floor((gs + pad - 512) / hop) + 1 , ceil((ge + pad) / hop) ).
+// A variant recomputes tiles_per_clip tiles of kFR frames starting at the frame below; every other frame is a copy of
+// the clean spectrogram.  The base is pulled back so that the run ends at T_out (all tiles full) where it would overshoot.
+AIP_HDX int var_first_frame(int gs, int pad, int hop) {
+  const int a = gs + pad - kNfft;                 // floor(a / hop) + 1, a may be negative
+  return a < 0 ? 0 : a / hop + 1;
+}
+AIP_HDX int var_tiles(int gap_len_max, int hop, int T_out) {
+  // frames met by a gap of <= gap_len_max samples: at most ceil((gap_len_max + 512) / hop) + 1
+  const int n_aff = (gap_len_max + kNfft + hop - 1) / hop + 1;
+  const int need = (n_aff + kFR - 1) / kFR, all = (T_out + kFR - 1) / kFR;
+  return need < all ? need : all;
+}
+AIP_HD int var_frame_base(const FwdParams& P, int gs) {
+  int fb = var_first_frame(gs, P.pad, P.hop);
+  const int last = P.T_out - P.tiles_per_clip * kFR;
+  if (fb > last) fb = last;
+  return fb < 0 ? 0 : fb;
+}
+AIP_HD FwdTilePlan fwd_tile_plan_var(const FwdParams& P, const TileCursor& c, int gs, int ge, int fb) {
+  FwdTilePlan q;
+  q.len = fwd_tile_len(P.hop);
+  q.g0 = (fb + c.tt * kFR) * P.hop - P.pad;
+  q.src = P.wave + (long long)(c.b / P.var_div) * P.wave_pitch;
+  q.v_lo = q.g0 < 0 ? -q.g0 : 0;
+  const int hi = P.L - q.g0;
+  q.v_hi = hi < q.len ? (hi > 0 ? hi : 0) : q.len;
+  if (q.v_lo > q.v_hi) q.v_lo = q.v_hi;
+  // the bulk copy needs a 16-byte aligned source: g0 + v_lo is a multiple of 4 when hop, pad are (vec_ok) and fb is any int
   q.n_bulk = P.vec_ok ? ((q.v_hi - q.v_lo) & ~3) : 0;
   q.gs = gs; q.ge = ge;
   return q;
@@ -213,7 +251,7 @@ AIP_HD float2 mag_value2(int mk, float2 xr, float2 xi, float eps) {
 //   FWD_SPEC   complex output          FWD_PHASE  angle(S)        FWD_MASK  dense frame mask
 //   FWD_ZERO   spectrum-domain gap (frames [f0,f1) zeroed before the epilogue, models/model_eval.py:154)
 //   FWD_FULL   run-time flags, out-of-line epilogue: every other combination (|S|**p with p != 1, ...)
-enum FwdModeBits : int { FWD_SPEC = 8, FWD_PHASE = 16, FWD_MASK = 32, FWD_ZERO = 64, FWD_FULL = 128 };
+enum FwdModeBits : int { FWD_SPEC = 8, FWD_PHASE = 16, FWD_MASK = 32, FWD_ZERO = 64, FWD_FULL = 128, FWD_VARIANT = 256 };
 constexpr int FWD_MAG_ABS = MAG_ABS, FWD_MAG_LOG10 = MAG_LOG10_EPS;      // the two magnitude-only variants
 
 // A stage-2 thread writes bins k_lo + 16 j and k_hi - 16 j of ONE frame (its lane): two row offsets are set
@@ -343,7 +381,8 @@ template <int kMode, class Release>
 AIP_HD void fwd_phase2(const FwdParams& P, int tid, const TileCursor& c, const float2* exch, const PairTw& w,
                        Release& release) {
   const int p = tid >> 5, lane = tid & 31;
-  const int t0 = c.tt * kFR;
+  int t0 = c.tt * kFR;
+  if (kMode & FWD_VARIANT) t0 += var_frame_base(P, P.gap_samples[2 * c.b]);
   const int n_valid = (P.T_out - t0) < kFR ? (P.T_out - t0) : kFR;
   const int fr = lane < n_valid ? lane : n_valid - 1;     // lanes past the end replay the last valid frame
   float2 zr[16], zi[16];

@@ -2,6 +2,8 @@
 into the transform kernels and run for a whole batch of clips per launch.
 
   cnnblstm_batch      models/CNNBLSTM/dataset.py:89-119  (log10(|S_gap|+1e-9), complex target, frame mask)
+  cnnblstm_dataset_batch  models/CNNBLSTM/dataset.py:74-121  (a whole __getitem__: gaps_per_audio gaps per file from ONE clean
+                      transform; only the frames a gap touches are re-transformed)
   gan_batch           models/GAN/dataset.py:104-166      (log1p magnitudes, phase, 0-in-gap mask)
   eval_cnnlstm_batch  models/model_eval.py:146-154       (spectrum-domain gap)
   eval_gan_batch      models/model_eval.py:61-111
@@ -22,7 +24,7 @@ import torch
 
 from . import gaps, spectral as sp
 
-__all__ = ["cnnblstm_batch", "gan_batch", "eval_cnnlstm_batch", "eval_gan_batch", "backend_batch", "cnnblstm_backend_batch",
+__all__ = ["cnnblstm_batch", "cnnblstm_dataset_batch", "gan_batch", "eval_cnnlstm_batch", "eval_gan_batch", "backend_batch", "cnnblstm_backend_batch",
            "HostPipeline"]
 
 
@@ -63,6 +65,58 @@ def cnnblstm_batch(wave: torch.Tensor, gap_len_s: float = 0.2, sample_rate: int 
         out["gap_mask"] = res["mask"]
     if want_target:
         out["spectrogram_target_phase"] = sp.stft(wave, plan, t_out=t_crop)["spec"]        # dataset.py:102,110
+    return out
+
+
+def cnnblstm_dataset_batch(wave: torch.Tensor, gaps_per_audio: int = 25, gap_len_s: float = 0.2, sample_rate: int = 16000,
+                           max_len_s: float = 5.0, n_fft: int = 512, hop_len: int = 192, win_len: int = 384,
+                           starts: Optional[np.ndarray] = None, want_mask: bool = True) -> dict:
+    """``LibriSpeechDataset.__getitem__`` (models/CNNBLSTM/dataset.py:74-121) for a batch of files: row ``i`` of ``wave``
+    [N, L] is one decoded file (``utils.load_audio`` output), and the item holds ``gaps_per_audio`` random gaps of it.
+
+    The reference decodes the file twice and runs two full STFTs per gap (dataset.py:93-103).  Here the clean transform
+    runs ONCE per file (complex target + clean log-magnitude); a gap changes only the ~(gap + n_fft) / hop frames whose
+    span meets it, so each variant is a streaming copy of the clean log-magnitude plus a re-transform of those frames
+    (``spectral.stft_gap_variants``).  Draw order: one ``np.random.randint(0, L - g)`` per (file, gap) in the reference's
+    order -- file-major, gap-minor (utils.py:179).
+
+    Returns ``spectrogram_gaps`` f32 [N, G, F, Tc], ``gap_ints`` f32 [N, G, 2] (host), ``gap_masks`` f32 [N, G, F, Tc],
+    ``spectrogram_target_phases`` c64 [N, G, F, Tc] (an expanded VIEW of the one clean spectrogram per file: the reference
+    stores G identical copies, dataset.py:110), plus ``gap_samples`` / ``gap_frames`` int64 [N, G, 2]."""
+    wave = _as_batch(wave)
+    N, L = wave.shape
+    G = int(gaps_per_audio)
+    g = gaps.gap_len_samples(gap_len_s, sample_rate)
+    if g >= L:
+        raise ValueError(f"Gap length ({g}s) exceeds audio length ({L / sample_rate}s)")   # utils.py:175-176
+    if starts is None:
+        starts = gaps.draw_starts_exclusive(L, g, N * G)                                     # utils.py:179
+    starts = np.asarray(starts, dtype=np.int64).reshape(N * G)
+    t0, t1 = gaps.seconds_interval(starts, g, sample_rate)                                  # utils.py:186
+    f0 = np.atleast_1d(gaps.time_to_frames(t0, sample_rate, hop_len))                       # dataset.py:116
+    f1 = np.atleast_1d(gaps.time_to_frames(t1, sample_rate, hop_len))                       # dataset.py:117
+    plan = sp.get_plan(n_fft, hop_len, win_len, "hann", True, wave.device)
+    t_crop = min(gaps.cnnblstm_crop_frames(sample_rate, max_len_s, hop_len), plan.num_frames(L))   # dataset.py:89
+    sam = np.stack([starts, starts + g], 1)
+    frm = np.stack([f0, f1], 1)
+    F = plan.n_bins
+    target = sp.stft(wave, plan, t_out=t_crop)["spec"]                                      # dataset.py:102,110 (once per file)
+    if n_fft == 512:
+        mag = sp.stft_gap_variants(wave, plan, sam, G, mag_kind=sp.MAG_LOG10_EPS, eps=1e-9, t_out=t_crop)["mag"]
+    else:       # the generic kernels have no variant mode: G full transforms
+        mag = sp.stft(wave.repeat_interleave(G, 0), plan, gap_samples=sam, mag_kind=sp.MAG_LOG10_EPS, eps=1e-9,
+                      t_out=t_crop, want_spec=False)["mag"]
+    out = {"spectrogram_gaps": mag.view(N, G, F, t_crop),
+           "gap_ints": np.stack([t0, t1], 1).astype(np.float32).reshape(N, G, 2),            # dataset.py:112
+           "spectrogram_target_phases": target.unsqueeze(1).expand(N, G, F, t_crop),
+           "gap_samples": sam.reshape(N, G, 2), "gap_frames": frm.reshape(N, G, 2)}
+    if want_mask:
+        mask = torch.empty((N * G, F, t_crop), dtype=torch.float32, device=wave.device)
+        lib = sp._cabi.load()
+        with torch.cuda.device(wave.device):
+            sp.check(lib.aip_frame_mask_f32(sp._ptr(mask), N * G, F, t_crop, sp._ptr(sp._pairs(frm, N * G, wave.device)), 1,
+                                            sp._stream()), "aip_frame_mask_f32")            # dataset.py:115-119
+        out["gap_masks"] = mask.view(N, G, F, t_crop)
     return out
 
 

@@ -25,7 +25,7 @@ from . import _cabi
 from ._cabi import (DOM_DB, DOM_EXPM1, DOM_LINEAR, DOM_POW10, MAG_ABS, MAG_LOG10_EPS, MAG_LOG1P_POW,
                     MAG_NONE, MAG_POW, StftDesc, check)
 
-__all__ = ["StftPlan", "get_plan", "stft", "istft", "istft_blend", "griffinlim", "db_heuristic", "fft_window",
+__all__ = ["StftPlan", "get_plan", "stft", "stft_gap_variants", "istft", "istft_blend", "griffinlim", "db_heuristic", "fft_window",
            "MAG_NONE", "MAG_ABS", "MAG_LOG10_EPS", "MAG_LOG1P_POW", "MAG_POW",
            "DOM_LINEAR", "DOM_POW10", "DOM_DB", "DOM_EXPM1"]
 
@@ -207,6 +207,55 @@ def stft(wave: torch.Tensor, plan: StftPlan, *, gap_samples=None, zero_frames=No
         if t is not None:
             res[name] = t[0] if squeeze else t
     return res
+
+
+def stft_gap_variants(wave: torch.Tensor, plan: StftPlan, gap_samples, variants_per_row: int, *,
+                      mag_kind: int = MAG_LOG10_EPS, eps: float = 1e-9, t_out: Optional[int] = None,
+                      clean_mag: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> dict:
+    """``variants_per_row`` gapped magnitude spectrograms per row of ``wave`` [N, L] (the gaps_per_audio loop of
+    models/CNNBLSTM/dataset.py:93-111) without ``variants_per_row`` full transforms: one clean transform per row, a
+    streaming copy, and a re-transform of the few frames each gap touches (``aip_stft_gap_variants_f32``).
+
+    ``gap_samples``: int [N * variants_per_row, 2] sample ranges (host array or CUDA int32 tensor), variant
+    ``i * variants_per_row + j`` belongs to row ``i``.  Returns ``mag`` f32 [N * variants_per_row, F, t_out] and
+    ``clean_mag`` f32 [N, F, t_out].  Bit-identical to ``stft(wave.repeat_interleave(G, 0), gap_samples=...)``."""
+    _require_cuda(wave, "wave")
+    if plan.n_fft != 512:
+        raise NotImplementedError("gap variants run on the n_fft = 512 register-FFT kernels only")
+    if wave.dtype != torch.float32:
+        wave = wave.to(torch.float32)
+    if wave.ndim == 1:
+        wave = wave.unsqueeze(0)
+    if wave.stride(1) != 1:
+        wave = wave.contiguous()
+    N, L = wave.shape
+    G = int(variants_per_row)
+    if G < 1:
+        raise ValueError("variants_per_row must be >= 1")
+    T = plan.num_frames(L)
+    t_out = T if t_out is None else min(int(t_out), T)
+    F = plan.n_bins
+    dev = wave.device
+    if isinstance(gap_samples, torch.Tensor):
+        gmax = int((gap_samples[:, 1] - gap_samples[:, 0]).max().item()) if gap_samples.numel() else 0
+    else:
+        g_np = np.asarray(gap_samples, dtype=np.int64).reshape(-1, 2)
+        gmax = int((g_np[:, 1] - g_np[:, 0]).max()) if g_np.size else 0
+    gaps = _pairs(gap_samples, N * G, dev)
+    if clean_mag is None:
+        clean_mag = stft(wave, plan, mag_kind=mag_kind, eps=eps, t_out=t_out, want_spec=False)["mag"]
+    elif tuple(clean_mag.shape) != (N, F, t_out) or clean_mag.dtype != torch.float32 or not clean_mag.is_contiguous():
+        raise ValueError("clean_mag has the wrong shape/dtype/layout")
+    if out is None:
+        out = torch.empty((N * G, F, t_out), dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != (N * G, F, t_out) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out has the wrong shape/dtype/layout")
+    lib = _cabi.load()
+    with torch.cuda.device(dev):
+        check(lib.aip_stft_gap_variants_f32(
+            C.byref(plan.desc), _ptr(wave), N, L, wave.stride(0), G, _ptr(gaps), max(gmax, 0), int(mag_kind), float(eps),
+            t_out, _ptr(clean_mag), _ptr(out), _stream()), "aip_stft_gap_variants_f32")
+    return {"mag": out, "clean_mag": clean_mag}
 
 
 def db_heuristic(x: torch.Tensor) -> torch.Tensor:

@@ -3,6 +3,7 @@
 TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py`` (parity unpinned; see there).
 
   cnnblstm_item     <- models/CNNBLSTM/dataset.py:89-119  (one of the gaps_per_audio iterations)
+  cnnblstm_getitem  <- models/CNNBLSTM/dataset.py:74-121  (the whole item: gaps_per_audio iterations stacked)
   gan_item          <- models/GAN/dataset.py:104-166
   eval_frontend_*   <- models/model_eval.py:61-111, :146-154
   eval_backend      <- models/model_eval.py:130-143, :179-192 (spectrogram_to_audio with phase reuse)
@@ -40,6 +41,20 @@ def cnnblstm_item(audio_data, sample_rate=16000, max_len_s=5.0, gap_len_s=0.2,
     mask[:, f0:f1] = 1                                                        # dataset.py:118
     return dict(spectrogram_gap=spec_gap, gap_int_s=gap_int, gap_mask=mask,
                 spectrogram_target_phase=target, gap_frames=(f0, f1), gap_int_s64=gap_int_s)
+
+
+def cnnblstm_getitem(audio_data, gaps_per_audio=25, sample_rate=16000, max_len_s=5.0, gap_len_s=0.2,
+                     n_fft=512, hop_len=192, win_len=384):
+    """LibriSpeechDataset.__getitem__ (dataset.py:74-121) for one decoded file: ``gaps_per_audio`` iterations of the
+    loop body above stacked into the four pre-allocated arrays (dataset.py:88-91).  Consumes ``gaps_per_audio`` draws
+    of the global np.random stream, in order."""
+    items = [cnnblstm_item(audio_data, sample_rate, max_len_s, gap_len_s, n_fft, hop_len, win_len)
+             for _ in range(gaps_per_audio)]                                               # dataset.py:93
+    return dict(spectrogram_gaps=np.stack([it["spectrogram_gap"] for it in items]),       # dataset.py:111
+                gap_ints=np.stack([it["gap_int_s"] for it in items]),                     # dataset.py:112
+                gap_masks=np.stack([it["gap_mask"] for it in items]),                     # dataset.py:119
+                spectrogram_target_phases=np.stack([it["spectrogram_target_phase"] for it in items]),   # dataset.py:110
+                gap_frames=np.array([it["gap_frames"] for it in items]))
 
 
 def gan_frame_mask_range(gap_start_sample, gap_end_sample, hop_length, num_frames):

@@ -57,6 +57,27 @@ def stft(wave, hop, window, center=True, gap_samples=None, zero_frames=None, mas
     return out
 
 
+def stft_variants(wave, hop, window, G, gap_samples, mag_kind=2, eps=1e-9, center=True, t_out=None, vec_ok=True,
+                  win_length=0, gap_len_max=None):
+    """aip_stft_gap_variants_f32 replayed: the clean magnitudes come from the plain replay (``stft``)."""
+    wave = np.ascontiguousarray(wave, dtype=np.float32)
+    N, L = wave.shape
+    pad = 256 if center else 0
+    T = 1 + (L + 2 * pad - 512) // hop
+    t_out = T if t_out is None else t_out
+    window = np.ascontiguousarray(window, dtype=np.float32)
+    g = np.ascontiguousarray(gap_samples, dtype=np.int32).reshape(N * G, 2)
+    if gap_len_max is None:
+        gap_len_max = int((g[:, 1] - g[:, 0]).max())
+    clean = stft(wave, hop, window, center=center, mag_kind=mag_kind, eps=eps, t_out=t_out, want_spec=False,
+                 vec_ok=vec_ok, win_length=win_length)["mag"]
+    mag = np.full((N * G, 257, t_out), np.nan, np.float32)
+    rc = lib().emul_stft512_variants(_f(wave), N, L, C.c_longlong(L), hop, int(center), int(win_length), _f(window), G, _i(g),
+                                     int(gap_len_max), mag_kind, C.c_float(eps), t_out, _f(clean), _f(mag), int(vec_ok))
+    assert rc == 0, rc
+    return {"mag": mag, "clean_mag": clean}
+
+
 def istft(hop, window, inv_wss, spec=None, mag=None, phase=None, mag_domain=0, db_flags=None, center=True, length=0,
           blend_in=None, blend_mask=None, win_length=0, peaks=None):
     window = np.ascontiguousarray(window, dtype=np.float32)

@@ -295,3 +295,57 @@ def test_epilogue_atan2_and_log1p_accuracy():
     assert np.array_equal(np.signbit(a[:64]), np.signbit(ref_a[:64].astype(np.float32)))
     ref_l = np.log1p(np.abs(x).astype(np.float64))
     assert (np.abs(l - ref_l) / np.maximum(ref_l, 1e-30)).max() < 1e-6
+
+
+# ---- gap variants (aip_stft_gap_variants_f32; SURVEY 8f rank 3, models/CNNBLSTM/dataset.py:93-111) ----------------------
+@pytest.mark.parametrize("hop,wl,L,g,t_out", [(192, 384, 16000, 3200, None), (192, 384, 6001, 700, None),
+                                              (192, 384, 16000, 3200, 80), (128, 512, 9000, 1280, None),
+                                              (64, 256, 6000, 500, 70), (250, 500, 20011, 1600, None),
+                                              (192, 384, 16000, 9000, None)])
+@pytest.mark.parametrize("vec_ok", [True, False])
+def test_gap_variants_bit_identical_to_full_transforms(hop, wl, L, g, t_out, vec_ok):
+    """Every variant = copy of the clean log-magnitude + re-transform of the frames the gap touches; that must equal the
+    full transform of the gapped clip BIT FOR BIT (a missed frame would keep its clean value), for gaps at the clip start,
+    the clip end, every phase against the tile grid, and of zero length."""
+    N = 2
+    x = noise(N, L, seed=hop + L)
+    starts = np.unique(np.concatenate([np.arange(0, L - g, 211), [L - g - 1, L - g, 0, 1]]))
+    G = len(starts)
+    gaps = np.stack([starts, starts + g], 1)
+    gaps[3] = [starts[3], starts[3]]          # a zero-length gap: the variant is the clean spectrogram
+    gaps = np.concatenate([gaps, gaps[::-1]])  # row 1 takes them in the other order
+    w = win(wl)
+    var = emul.stft_variants(x, hop, w, G, gaps, mag_kind=2, t_out=t_out, vec_ok=vec_ok, win_length=wl, gap_len_max=g)
+    full = emul.stft(np.repeat(x, G, 0), hop, w, gap_samples=gaps, mag_kind=2, t_out=t_out, want_spec=False,
+                     vec_ok=vec_ok, win_length=wl)["mag"]
+    assert not np.isnan(var["mag"]).any()
+    assert np.array_equal(var["mag"], full)
+    assert np.array_equal(var["mag"][3], var["clean_mag"][0])
+    # and against the oracle for a few of them
+    for v in (0, G // 2, G - 1, G + 1):
+        xg = x[v // G].copy()
+        xg[gaps[v, 0]:gaps[v, 1]] = 0
+        ref = np.abs(lr.stft(xg, n_fft=512, hop_length=hop, win_length=wl))[:, :var["mag"].shape[2]]
+        assert relerr(10.0 ** var["mag"][v].astype(np.float64), ref + 1e-9) < TOL
+
+
+def test_gap_variants_other_magnitudes_and_getitem_shape():
+    """|S| and log1p variants, and the dataset item against the oracle's restatement of __getitem__ (same np.random draws)."""
+    L, G = 16000, 5
+    x = noise(1, L, seed=9)
+    w = win(384)
+    np.random.seed(3)
+    ref = cp.cnnblstm_getitem(x[0], gaps_per_audio=G, max_len_s=1.0)
+    np.random.seed(3)
+    starts = np.array([np.random.randint(0, L - 3200) for _ in range(G)])
+    gaps = np.stack([starts, starts + 3200], 1)
+    n_t = ref["spectrogram_gaps"].shape[2]
+    for kind, fn in ((2, None), (1, lambda m: m), (3, np.log1p)):
+        var = emul.stft_variants(x, 192, w, G, gaps, mag_kind=kind, t_out=n_t, win_length=384)["mag"]
+        full = emul.stft(np.repeat(x, G, 0), 192, w, gap_samples=gaps, mag_kind=kind, t_out=n_t, want_spec=False,
+                         win_length=384)["mag"]
+        assert np.array_equal(var, full)
+    var = emul.stft_variants(x, 192, w, G, gaps, mag_kind=2, t_out=n_t, win_length=384)["mag"]
+    assert var.shape == ref["spectrogram_gaps"].shape
+    lin_ref = 10.0 ** ref["spectrogram_gaps"].astype(np.float64)
+    assert relerr(10.0 ** var.astype(np.float64), lin_ref) < TOL

@@ -433,3 +433,67 @@ def test_no_out_of_bounds_writes(sp, L, hop, win):
         sp.istft(plan, spec=S, length=length, out=y)
         torch.cuda.synchronize()
         assert intact(flat) and not bool(y.eq(SENT).any()), length
+
+
+# ---- gap variants (aip_stft_gap_variants_f32 / frontend.cnnblstm_dataset_batch) -------------------------
+@pytest.mark.parametrize("par,L,g,G,t_out", [(P1, 80000, 3200, 25, 417), (P1, 80001, 3200, 7, None), (P2, 80000, 3200, 9, None),
+                                             (P1, 16000, 9000, 5, 80), (P1, 6001, 700, 29, None)],
+                         ids=["P1-dataset", "P1-unaligned", "P2", "P1-long-gap-crop", "P1-short-clip"])
+def test_gap_variants_bit_identical_to_full_transforms(sp, par, L, g, G, t_out):
+    """copy + re-transform of the touched frames == G full transforms of the gapped clips, bit for bit; gaps at the clip
+    start / end / every phase against the 32-frame tile grid; then the oracle on a few variants."""
+    N = 3
+    x = _noise(N, L, seed=L + G)
+    rng = np.random.default_rng(G)
+    starts = rng.integers(0, L - g + 1, size=(N, G))
+    starts[:, 0] = 0
+    starts[:, 1] = L - g
+    starts[0, 2:] = np.linspace(0, L - g, G - 2).astype(np.int64)
+    gaps = np.stack([starts, starts + g], -1).reshape(N * G, 2)
+    gaps[3] = [gaps[3, 0], gaps[3, 0]]                      # zero-length gap
+    plan = sp.get_plan(par["n_fft"], par["hop"], par["win"], "hann", True, "cuda:0")
+    xd = torch.from_numpy(x).cuda()
+    var = sp.stft_gap_variants(xd, plan, gaps, G, mag_kind=sp.MAG_LOG10_EPS, t_out=t_out)
+    full = sp.stft(xd.repeat_interleave(G, 0), plan, gap_samples=gaps, mag_kind=sp.MAG_LOG10_EPS, t_out=t_out,
+                   want_spec=False)["mag"]
+    assert torch.equal(var["mag"], full)
+    assert torch.equal(var["mag"][3], var["clean_mag"][0])
+    out = var["mag"].cpu().numpy()
+    for v in (0, 1, G + 2, N * G - 1):
+        xg = x[v // G].copy()
+        xg[gaps[v, 0]:gaps[v, 1]] = 0
+        ref = np.abs(lr.stft(xg, n_fft=par["n_fft"], hop_length=par["hop"], win_length=par["win"]))[:, :out.shape[2]]
+        assert relerr(10.0 ** out[v].astype(np.float64), ref + 1e-9) < TOL
+    for kind in (sp.MAG_ABS, sp.MAG_LOG1P_POW):
+        a = sp.stft_gap_variants(xd, plan, gaps, G, mag_kind=kind, t_out=t_out)["mag"]
+        b = sp.stft(xd.repeat_interleave(G, 0), plan, gap_samples=gaps, mag_kind=kind, t_out=t_out, want_spec=False)["mag"]
+        assert torch.equal(a, b)
+
+
+def test_cnnblstm_dataset_batch_matches_reference_getitem(golden_clips):
+    """frontend.cnnblstm_dataset_batch against the oracle's restatement of LibriSpeechDataset.__getitem__
+    (models/CNNBLSTM/dataset.py:74-121): same np.random draws in the same order, intervals and masks bit-exact,
+    log-magnitudes and the complex target within 1e-4."""
+    from ml_audio_inpainting_b200 import frontend
+    G = 4
+    clips = [np.asarray(c, dtype=np.float32)[:80000] for c in list(golden_clips.values())[:2]]
+    np.random.seed(11)
+    refs = [cp.cnnblstm_getitem(c, gaps_per_audio=G) for c in clips]
+    np.random.seed(11)
+    out = frontend.cnnblstm_dataset_batch(torch.from_numpy(np.stack(clips)).cuda(), gaps_per_audio=G)
+    for i, ref in enumerate(refs):
+        assert np.array_equal(out["gap_ints"][i], ref["gap_ints"])
+        assert np.array_equal(out["gap_frames"][i], ref["gap_frames"])
+        assert np.array_equal(out["gap_masks"][i].cpu().numpy(), ref["gap_masks"])
+        got = out["spectrogram_gaps"][i].cpu().numpy()
+        assert got.shape == ref["spectrogram_gaps"].shape == (G, 257, 417)
+        assert relerr(10.0 ** got.astype(np.float64), 10.0 ** ref["spectrogram_gaps"].astype(np.float64)) < TOL
+        tgt = out["spectrogram_target_phases"][i].cpu().numpy()
+        assert tgt.shape == ref["spectrogram_target_phases"].shape
+        assert relerr(tgt, ref["spectrogram_target_phases"]) < TOL
+    # the global stream has advanced by exactly N * G draws
+    a = np.random.randint(0, 1 << 30)
+    np.random.seed(11)
+    for _ in range(2 * G):
+        np.random.randint(0, 80000 - 3200)
+    assert a == np.random.randint(0, 1 << 30)
