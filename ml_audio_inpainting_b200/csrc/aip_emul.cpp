@@ -116,16 +116,27 @@ int emul_stft512_variants(const float* wave, int N, int L, long long pitch, int 
     const int gs = gap_samples[2 * c.b], ge = gap_samples[2 * c.b + 1];
     const FwdTilePlan q = fwd_tile_plan_var(P, c, gs, ge, var_frame_base(P, gs));
     if (q.n_bulk > 0) memcpy(tile.data() + q.v_lo, q.src + q.g0 + q.v_lo, (size_t)q.n_bulk * 4);   // the TMA bulk copy
-    if (fwd_needs_fixup(q)) for (int tid = 0; tid < kThreads; ++tid) fwd_fixup(q, tid, tile.data());
-    for (int tid = 0; tid < kThreads; ++tid) {
-      if (P.zero_groups == 2) fwd_phase1<2>(P, tid, tile.data(), exch.data(), win_s, lc[tid]);
-      else fwd_phase1<0>(P, tid, tile.data(), exch.data(), win_s, lc[tid]);
+    const bool own = !fwd_needs_edge_fixup(q);      // barrier-free path: each warp zeroes the gap for its own frames only
+    if (!own && fwd_needs_fixup(q)) for (int tid = 0; tid < kThreads; ++tid) fwd_fixup(q, tid, tile.data());
+    std::vector<float> mine;
+    for (int w = 0; w < kThreads / 32; ++w) {
+      // replayed warp by warp on a PRIVATE copy of the staged tile: a warp must not depend on another warp's zeroing
+      float* t = tile.data();
+      if (own) {
+        mine = tile;
+        t = mine.data();
+        for (int tid = 32 * w; tid < 32 * w + 32; ++tid) fwd_gap_zero_own(q, P.hop, tid, t);
+      }
+      for (int tid = 32 * w; tid < 32 * w + 32; ++tid) {
+        if (P.zero_groups == 2) fwd_phase1<2>(P, tid, t, exch.data(), win_s, lc[tid]);
+        else fwd_phase1<0>(P, tid, t, exch.data(), win_s, lc[tid]);
+      }
     }
     for (int tid = 0; tid < kThreads; ++tid) {
       switch (mag_kind) {
-        case MAG_ABS: fwd_phase2<FWD_MAG_ABS | FWD_VARIANT>(P, tid, c, exch.data(), pw[tid], rel); break;
-        case MAG_LOG10_EPS: fwd_phase2<FWD_MAG_LOG10 | FWD_VARIANT>(P, tid, c, exch.data(), pw[tid], rel); break;
-        case MAG_LOG1P_POW: fwd_phase2<MAG_LOG1P_POW | FWD_VARIANT>(P, tid, c, exch.data(), pw[tid], rel); break;
+        case MAG_ABS: fwd_phase2<FWD_MAG_ABS | FWD_VARIANT>(P, tid, c, exch.data(), pw[tid], rel, var_frame_base(P, gs)); break;
+        case MAG_LOG10_EPS: fwd_phase2<FWD_MAG_LOG10 | FWD_VARIANT>(P, tid, c, exch.data(), pw[tid], rel, var_frame_base(P, gs)); break;
+        case MAG_LOG1P_POW: fwd_phase2<MAG_LOG1P_POW | FWD_VARIANT>(P, tid, c, exch.data(), pw[tid], rel, var_frame_base(P, gs)); break;
         default: return -2;
       }
     }

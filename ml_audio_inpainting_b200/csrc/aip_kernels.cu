@@ -88,6 +88,14 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, i
                ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
 }
 
+// shared -> global bulk copy (SASS: UBLKCP), tracked by the issuing thread's bulk async-group; 16-byte aligned on both sides
+__device__ __forceinline__ void tma_store_1d(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -221,6 +229,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
     TileFeed fn{0, 0, TileCursor{0, 0}};     // request cursor (thread ptid == 0 only): draws the chunks
     bool more = true;                        // the request cursor has not hit the end of the batch yet
     int req_clip = -1, req_fb = 0;           // FWD_VARIANT: frame base of the variant the request cursor is in
+    int req_nxt_clip = -1, req_nxt_gs = 0;   // FWD_VARIANT: gap start of the request cursor's next variant
     auto request = [&](float* buf, uint64_t* bar) {      // ptid == 0: start the copy of the next tile, if there is one
       if (fn.left == 0) {
         const int s = (int)atomicAdd(P.tile_counter, (unsigned)P.chunk);
@@ -234,13 +243,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
         fn.left = cnt;
       }
       if (kMode & FWD_VARIANT) {
-        if (fn.c.b != req_clip) { req_fb = var_frame_base(P, P.gap_samples[2 * fn.c.b]); req_clip = fn.c.b; }
+        if (fn.c.b != req_clip) {
+          req_fb = var_frame_base(P, fn.c.b == req_nxt_clip ? req_nxt_gs : P.gap_samples[2 * fn.c.b]);
+          req_clip = fn.c.b;
+        }
         fwd_issue_tile(fwd_tile_plan_var(P, fn.c, 0, 0, req_fb), buf, bar);
       } else {
         fwd_issue_tile(fwd_tile_plan_gap(P, fn.c, 0, 0), buf, bar);
       }
       tile_advance(fn.c, P.tiles_per_clip);
       --fn.left;
+      if (kMode & FWD_VARIANT) {      // the next request's gap start, fetched a tile ahead (this thread also runs stage 1)
+        if (fn.left > 0 && fn.c.b != req_clip) { req_nxt_gs = P.gap_samples[2 * fn.c.b]; req_nxt_clip = fn.c.b; }
+      }
     };
     if (ptid == 0) {
       for (int k = 0; k < (ntb > 1 ? ntb - 1 : 1) && more; ++k) request(smem + k * P.tile_floats, tile_full + k);
@@ -249,16 +264,28 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
     int slot = 0, use = 0;               // ring slot of tile i and how often it has been used before
     int gs = 0, ge = 0, gap_clip = -1;   // gap range of the clip the cursor is in
     int fb = 0;                          // FWD_VARIANT: first recomputed frame of that variant
+    int nxt_clip = -1, nxt_gs = 0, nxt_ge = 0;   // FWD_VARIANT: gap range of the next tile's variant, fetched ahead
 #pragma unroll 1
     for (int i = 0;; ++i) {
       if (f.left == 0 && !feed_next(P, f, sched_start, sched_bar)) break;
       const TileCursor c = f.c;
       float* tile = smem + slot * P.tile_floats;
-      if (P.gap_samples && c.b != gap_clip) {
+      if (kMode & FWD_VARIANT) {
+        // a variant is one or two tiles: its gap range is fetched one tile ahead (the load's latency would sit in front of
+        // EVERY tile's plan otherwise)
+        if (c.b != gap_clip) {
+          if (c.b == nxt_clip) { gs = nxt_gs; ge = nxt_ge; }
+          else { gs = P.gap_samples[2 * c.b]; ge = P.gap_samples[2 * c.b + 1]; }
+          gap_clip = c.b;
+          fb = var_frame_base(P, gs);
+        }
+        TileCursor n = c;
+        tile_advance(n, P.tiles_per_clip);
+        if (n.b != c.b && n.b < P.B) { nxt_gs = P.gap_samples[2 * n.b]; nxt_ge = P.gap_samples[2 * n.b + 1]; nxt_clip = n.b; }
+      } else if (P.gap_samples && c.b != gap_clip) {
         gs = P.gap_samples[2 * c.b];
         ge = P.gap_samples[2 * c.b + 1];
         gap_clip = c.b;
-        if (kMode & FWD_VARIANT) fb = var_frame_base(P, gs);
       }
       const FwdTilePlan q = (kMode & FWD_VARIANT) ? fwd_tile_plan_var(P, c, gs, ge, fb) : fwd_tile_plan_gap(P, c, gs, ge);
       if (ntb > 1 && ptid == 0 && more) {
@@ -268,7 +295,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
         request(smem + ns * P.tile_floats, tile_full + ns);
       }
       mbar_wait(tile_full + slot, (uint32_t)(use & 1));
-      if (fwd_needs_fixup(q)) {
+      if ((kMode & FWD_VARIANT) && !fwd_needs_edge_fixup(q)) {
+        fwd_gap_zero_own(q, P.hop, ptid, tile);        // every variant tile holds a gap: no CTA-wide barrier for it
+        __syncwarp();
+      } else if (fwd_needs_fixup(q)) {
         fwd_fixup(q, ptid, tile);
         named_bar_sync(1, kThreads);
       }
@@ -292,13 +322,25 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
     PairTw w;
     pair_tw_init(w, ctid >> 5);
     TileFeed f{0, 0, TileCursor{0, 0}};
+    int var_clip = -1, fb_cur = 0, nxt_clip = -1, nxt_gs = 0;     // FWD_VARIANT: frame base of this / gap start of the next variant
 #pragma unroll 1
     for (int i = 0;; ++i) {
       if (f.left == 0 && !feed_next(P, f, sched_start, sched_bar)) break;
       const int es = i & 1;
+      int fb = 0;
+      if (kMode & FWD_VARIANT) {
+        if (f.c.b != var_clip) {
+          fb_cur = var_frame_base(P, f.c.b == nxt_clip ? nxt_gs : P.gap_samples[2 * f.c.b]);
+          var_clip = f.c.b;
+        }
+        fb = fb_cur;
+        TileCursor n = f.c;
+        tile_advance(n, P.tiles_per_clip);
+        if (n.b != f.c.b && n.b < P.B) { nxt_gs = P.gap_samples[2 * n.b]; nxt_clip = n.b; }     // lands while this tile runs
+      }
       mbar_wait(exch_full + es, (uint32_t)((i >> 1) & 1));
       ArriveRelease rel{exch_empty + es};
-      fwd_phase2<kMode>(P, ctid, f.c, exch0 + es * kExch, w, rel);
+      fwd_phase2<kMode>(P, ctid, f.c, exch0 + es * kExch, w, rel, fb);
       tile_advance(f.c, P.tiles_per_clip);
       --f.left;
     }
@@ -726,33 +768,94 @@ __global__ void __launch_bounds__(256) frame_mask_kernel(float* mask, long long 
   }
 }
 
-// Gap variants, copy pass: row (variant v, bin k) of `out` := row (v / G, k) of the clean spectrogram, one row per WARP and
-// loop trip.  Source and destination rows start at different 16-byte phases in general (T = 417, 834 are odd), so the loads are
-// 4-byte (they hit L2 / L1: every clean row is read G times) and the stores 16-byte.  Vectors that lie completely inside the
-// frame range the transform kernel rewrites afterwards ([fb, fb + nt * kFR), see var_frame_base) are skipped.
-__global__ void __launch_bounds__(256) variant_fill_kernel(const float* __restrict__ clean, float* __restrict__ out, long long NG,
+// Gap variants, copy pass: one (file i, bin k) row of the clean spectrogram per WARP and loop trip.  The row is read ONCE
+// into registers (lanes along the frame axis, 16 x 32 frames per pass) and stored G times, into row k of each of the file's G
+// variants -- a pure store stream like frame_mask_kernel.  Plain coalesced 4-byte accesses: source and destination rows sit at
+// different 16-byte phases in general (T = 417, 834 are odd).  Frames [fb, fb + nt * kFR) of a variant are left to the
+// transform kernel that runs next on the stream (var_frame_base); lane j of the warp holds fb of variant j.
+// (Measured, 256 files x 25 gaps x 5 s: a row-per-variant copy that re-read the clean row for every variant ran at 2.9 TB/s,
+// its dependent gap-start and L2 loads in front of every 1.7 KB row; 16-byte stores fed by 16-byte-strided scalar loads at 2.0.)
+__global__ void __launch_bounds__(256) variant_fill_kernel(const float* __restrict__ clean, float* __restrict__ out, long long N,
                                                            int G, int F, int T, const int* __restrict__ gaps, FwdParams P) {
-  const long long rows = NG * F;
+  const long long rows = N * F;
   const int lane = threadIdx.x & 31;
+  const int span = P.tiles_per_clip * kFR;
   for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * 8) {
-    const long long v = row / F;
-    const int k = (int)(row - v * F);
-    const int s0 = var_frame_base(P, gaps[2 * v]), s1 = s0 + P.tiles_per_clip * kFR;
-    const float* src = clean + ((v / G) * F + k) * T;
-    float* dst = out + row * T;
-    const int head = (int)((4 - ((reinterpret_cast<uintptr_t>(dst) >> 2) & 3)) & 3);
-    const int n4 = T > head ? ((T - head) >> 2) : 0;
-    if (lane < head && lane < T) dst[lane] = src[lane];
-    float4* d4 = reinterpret_cast<float4*>(dst + head);
-#pragma unroll 4
-    for (int q = lane; q < n4; q += 32) {
-      const int t = head + 4 * q;
-      if (t >= s0 && t + 3 < s1) continue;
-      d4[q] = make_float4(src[t], src[t + 1], src[t + 2], src[t + 3]);
+    const long long i = row / F;
+    const int k = (int)(row - i * F);
+    const float* src = clean + row * T;
+    for (int t0 = lane; t0 < T; t0 += 512) {
+      float x[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) x[j] = (t0 + 32 * j < T) ? __ldg(src + t0 + 32 * j) : 0.0f;
+      for (int j0 = 0; j0 < G; j0 += 32) {
+        const int mine = (j0 + lane < G) ? var_frame_base(P, gaps[2 * (i * G + j0 + lane)]) : 0;
+        const int cnt = (G - j0) < 32 ? (G - j0) : 32;
+        for (int jj = 0; jj < cnt; ++jj) {
+          const int s0 = __shfl_sync(0xffffffffu, mine, jj), s1 = s0 + span;
+          float* dst = out + (((i * G + j0 + jj) * F + k) * (long long)T);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int t = t0 + 32 * j;
+            if (t < T && (t < s0 || t >= s1)) dst[t] = x[j];
+          }
+        }
+      }
     }
-    const int t = head + 4 * n4 + lane;
-    if (t < T) dst[t] = src[t];
   }
+}
+
+// Gap variants, copy pass through the TMA.  A variant's [F, T] block is one contiguous range, a copy of the file's clean block,
+// so the copy is flat: a CTA stages a chunk of the clean block in shared memory and thread j sends it to variant j with ONE
+// bulk copy shared -> global (UBLKCP).  Bulk copies need 16-byte aligned addresses on both sides, and the G destinations sit
+// at up to four different 16-byte phases (F T = 257 * 417 is odd), so the chunk is staged FOUR times, copy h shifted by h
+// elements (cph[m] = chunk[m + h]): the copy whose phase matches the destination feeds its aligned middle, the <= 3 + 3
+// elements around it go by scalar stores.  No per-element store instructions (the scalar-store kernel above is limited by
+// the LSU queue: ncu lg_throttle 16.7 stall cycles per issued instruction at 3.7 TB/s; a row-wise version of this kernel with
+// one 1.6 KB bulk copy per row and variant reached 4.2 TB/s).  The frames the transform kernel rewrites afterwards are
+// copied too.
+constexpr int kFillChunk = 4096;        // floats per staged chunk: 4 x 16 KB of shared memory per CTA
+constexpr int kFillThreads = 128;
+__global__ void __launch_bounds__(kFillThreads) variant_fill_tma_kernel(const float* __restrict__ clean, float* __restrict__ out,
+                                                                       long long N, int G, long long FT, int chunks_per_file) {
+  extern __shared__ __align__(128) float vsm[];        // [4][kFillChunk]
+  const int tid = threadIdx.x;
+  const long long units = N * chunks_per_file;
+  for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+    const long long i = u / chunks_per_file;
+    const long long off = (u - i * chunks_per_file) * kFillChunk;
+    const int len = (FT - off) < kFillChunk ? (int)(FT - off) : kFillChunk;
+    const float* src = clean + i * FT + off;
+    bulk_wait_read0();            // this thread's bulk copies of the previous chunk have read their source
+    __syncthreads();
+    for (int t0 = tid; t0 < len; t0 += 8 * kFillThreads) {
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = (t0 + kFillThreads * j < len) ? __ldg(src + t0 + kFillThreads * j) : 0.0f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int t = t0 + kFillThreads * j;
+        if (t < len) {
+#pragma unroll
+          for (int h = 0; h < 4; ++h)
+            if (t >= h) vsm[h * kFillChunk + t - h] = x[j];
+        }
+      }
+    }
+    fence_proxy_async();          // the staged copies become visible to the async proxy
+    __syncthreads();
+    for (int j = tid; j < G; j += kFillThreads) {
+      float* d = out + (i * G + j) * FT + off;
+      int h = (int)((4 - ((reinterpret_cast<uintptr_t>(d) >> 2) & 3)) & 3);
+      if (h > len) h = len;
+      const int n4 = (len - h) >> 2;
+      if (n4 > 0) tma_store_1d(d + h, vsm + h * kFillChunk, (uint32_t)n4 * 16u);
+      bulk_commit();
+      for (int e = 0; e < h; ++e) d[e] = vsm[e];
+      for (int e = h + 4 * n4; e < len; ++e) d[e] = vsm[e];
+    }
+  }
+  bulk_wait0();
 }
 
 __global__ void __launch_bounds__(256) peak_kernel(const float* in, long long pitch, long long L, float* peaks) {
@@ -1001,6 +1104,7 @@ static cudaError_t launch_fwd512_t(FwdParams P, const DevInfo& di, cudaStream_t 
   // (8 bytes per bin) is fastest at 2 (0.468 ms against 0.529 ms static, 0.507 ms at 8).
   const int out_bytes = (P.mag ? 4 : 0) + (P.phase ? 4 : 0) + (P.mask ? 4 : 0) + (P.spec ? 8 : 0);
   P.chunk = out_bytes <= 4 ? 12 : (P.spec ? 2 : 4);
+  if (kMode & FWD_VARIANT) P.chunk = 4;      // few tiles per CTA (one or two per variant): balance matters more than locality
   if (const char* c = getenv("AIP_FWD_CHUNK")) { const int cv = atoi(c); if (cv >= 1 && cv <= 4096) P.chunk = cv; }    // profiling switch
   const int n_chunks = (P.n_tiles + P.chunk - 1) / P.chunk;
   if (grid > n_chunks) grid = n_chunks;
@@ -1418,10 +1522,25 @@ int aip_stft_gap_variants_f32(const aip_stft_desc* desc, const float* wave, int6
   P.vec_ok = ((P.hop & 3) == 0) && ((P.pad & 3) == 0) && ((P.wave_pitch & 3) == 0) &&
              ((reinterpret_cast<uintptr_t>(P.wave) & 15) == 0);
   const int F = desc->n_fft / 2 + 1;
-  long long grid = ((long long)P.B * F + 7) / 8;
-  if (grid > (long long)di.sms * 16) grid = (long long)di.sms * 16;
-  variant_fill_kernel<<<(unsigned)grid, 256, 0, st>>>(clean_mag, mag_out, (long long)P.B, (int)G, F, P.T_out, gap_samples, P);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+  const size_t fill_smem = (size_t)4 * kFillChunk * sizeof(float);
+  const char* fill_env = getenv("AIP_VAR_FILL");                       // profiling switch: "scalar" = the store-instruction kernel
+  const bool aligned4 = ((reinterpret_cast<uintptr_t>(mag_out) | reinterpret_cast<uintptr_t>(clean_mag)) & 3) == 0;
+  if (aligned4 && !(fill_env && fill_env[0] == 's')) {
+    e = cudaFuncSetAttribute(variant_fill_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem);
+    if (e != cudaSuccess) return (int)e;
+    const long long FT = (long long)F * P.T_out;
+    const long long cpf = (FT + kFillChunk - 1) / kFillChunk;
+    if (cpf > 0x7fffffffLL) return AIP_ERR_UNSUPPORTED;
+    long long grid = (long long)N * cpf;
+    if (grid > (long long)di.sms * 3) grid = (long long)di.sms * 3;            // 3 x 64 KB of staging per SM
+    variant_fill_tma_kernel<<<(unsigned)grid, kFillThreads, fill_smem, st>>>(clean_mag, mag_out, (long long)N, (int)G, FT, (int)cpf);
+  } else {
+    long long grid = ((long long)N * F + 7) / 8;
+    if (grid > (long long)di.sms * 8) grid = (long long)di.sms * 8;
+    variant_fill_kernel<<<(unsigned)grid, 256, 0, st>>>(clean_mag, mag_out, (long long)N, (int)G, F, P.T_out, gap_samples, P);
+  }
+  e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   return (int)launch_fwd512(P, di, st);
 }

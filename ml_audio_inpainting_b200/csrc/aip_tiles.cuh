@@ -210,6 +210,26 @@ AIP_HD void fwd_fixup(const FwdTilePlan& q, int tid, float* tile) {
   for (int i = a + tid; i < e; i += kThreads) tile[i] = 0.0f;
 }
 
+// Gap zeroing WITHOUT a CTA-wide barrier (gap-variant mode, where every tile holds a gap): a stage-1 warp reads the frames
+// {2w, 2w + 1, 2w + 16, 2w + 17} of the tile (fwd_phase1), so it zeroes the gap inside the sample spans of exactly those
+// frames itself and needs a __syncwarp() only.  Frames of different warps overlap: such elements are zeroed by every warp
+// that reads them (identical values), and a warp never reads a gap element it has not zeroed.  With one barrier per tile the
+// stage-1 warps ran in lockstep with the elected thread's request path (ncu: 18 % of the samples on that barrier).
+AIP_HDX bool fwd_needs_edge_fixup(const FwdTilePlan& q) { return q.v_lo > 0 || q.v_lo + q.n_bulk < q.len; }
+AIP_HD void fwd_gap_zero_own(const FwdTilePlan& q, int hop, int tid, float* tile) {
+  int a = q.gs - q.g0, e = q.ge - q.g0;
+  if (a < 0) a = 0;
+  if (e > q.len) e = q.len;
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int half = 0; half < 2; ++half) {
+    const int f = 2 * warp + 16 * half;
+    int lo = f * hop, hi = (f + 1) * hop + kNfft;
+    if (lo < a) lo = a;
+    if (hi > e) hi = e;
+    for (int i = lo + lane; i < hi; i += 32) tile[i] = 0.0f;
+  }
+}
+
 // stage 1 of the FFT for one tile: 256 threads, lane = n1 (16 lanes per frame); a thread owns column n1 of
 // frames fa and fa + 16 and runs them as the two lanes of the packed FP32x2 codelet
 template <int ZP>
@@ -379,10 +399,10 @@ AIP_HDX int fwd_mode_of(const FwdParams& P) {
 // `release` runs once the exchange buffer has been read into registers.
 template <int kMode, class Release>
 AIP_HD void fwd_phase2(const FwdParams& P, int tid, const TileCursor& c, const float2* exch, const PairTw& w,
-                       Release& release) {
+                       Release& release, int var_fb = 0) {
   const int p = tid >> 5, lane = tid & 31;
   int t0 = c.tt * kFR;
-  if (kMode & FWD_VARIANT) t0 += var_frame_base(P, P.gap_samples[2 * c.b]);
+  if (kMode & FWD_VARIANT) t0 += var_fb;      // var_frame_base(P, gap start of variant c.b), fetched by the caller
   const int n_valid = (P.T_out - t0) < kFR ? (P.T_out - t0) : kFR;
   const int fr = lane < n_valid ? lane : n_valid - 1;     // lanes past the end replay the last valid frame
   float2 zr[16], zi[16];

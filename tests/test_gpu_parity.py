@@ -437,11 +437,16 @@ def test_no_out_of_bounds_writes(sp, L, hop, win):
 
 # ---- gap variants (aip_stft_gap_variants_f32 / frontend.cnnblstm_dataset_batch) -------------------------
 @pytest.mark.parametrize("par,L,g,G,t_out", [(P1, 80000, 3200, 25, 417), (P1, 80001, 3200, 7, None), (P2, 80000, 3200, 9, None),
-                                             (P1, 16000, 9000, 5, 80), (P1, 6001, 700, 29, None)],
-                         ids=["P1-dataset", "P1-unaligned", "P2", "P1-long-gap-crop", "P1-short-clip"])
-def test_gap_variants_bit_identical_to_full_transforms(sp, par, L, g, G, t_out):
+                                             (P1, 16000, 9000, 5, 80), (P1, 6001, 700, 29, None), (P1, 700, 100, 40, None),
+                                             (P1, 600, 100, 4, 3)],
+                         ids=["P1-dataset", "P1-unaligned", "P2", "P1-long-gap-crop", "P1-short-clip", "P1-4-frames-40-gaps",
+                              "P1-3-frames"])
+@pytest.mark.parametrize("fill", ["tma", "scalar"])
+def test_gap_variants_bit_identical_to_full_transforms(sp, par, L, g, G, t_out, fill, monkeypatch):
     """copy + re-transform of the touched frames == G full transforms of the gapped clips, bit for bit; gaps at the clip
     start / end / every phase against the 32-frame tile grid; then the oracle on a few variants."""
+    if fill == "scalar":
+        monkeypatch.setenv("AIP_VAR_FILL", "scalar")      # the store-instruction copy pass (used for very long rows)
     N = 3
     x = _noise(N, L, seed=L + G)
     rng = np.random.default_rng(G)

@@ -46,3 +46,14 @@ t_naive = timeit(lambda: frontend.cnnblstm_batch(x.repeat_interleave(G, 0), star
 print(f"frontend.cnnblstm_dataset_batch (item: mags, masks, target view)   {t_item:8.3f} ms")
 print(f"frontend.cnnblstm_batch on G repeated rows (mags, masks, G targets) {t_naive:8.3f} ms   x{t_naive / t_item:.2f}")
 print(f"files/s: {N / t_item * 1e3:,.0f}   (reference CPU loop: 2 decodes + 2 STFTs per gap)")
+# per-kernel times of one item call (CUPTI through torch.profiler; shares only, the numbers above are the clean timings)
+try:
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(3):
+            frontend.cnnblstm_dataset_batch(x, gaps_per_audio=G, starts=starts)
+        torch.cuda.synchronize()
+    for ev in sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:8]:
+        print(f"  {ev.key[:90]:90s} {ev.device_time_total / ev.count / 1e3:8.3f} ms x{ev.count}")
+except Exception as exc:      # profiling is optional
+    print("profiler unavailable:", exc)
