@@ -184,7 +184,7 @@ __device__ __forceinline__ bool feed_next(const FwdParams& P, TileFeed& f, const
 // with mbarrier hand-offs (tile_full / tile_empty / exch_full / exch_empty), so the copies of tiles i+1 and i+2,
 // stage 1 of tile i+1 and stage 2 of tile i overlap, and each role keeps ITS constants in registers
 // (stage 1: 16 W256 twiddles per lane, read once from a shared-memory table; stage 2: 16 W512 twiddles per warp).
-template <int kMode, int kZP>
+template <int kMode, int kZP, int kT = 0>
 __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdParams P) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bars[2 * kFwdTileBufs + 4];
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
       }
       mbar_wait(exch_full + es, (uint32_t)((i >> 1) & 1));
       ArriveRelease rel{exch_empty + es};
-      fwd_phase2<kMode>(P, ctid, f.c, exch0 + es * kExch, w, rel, fb);
+      fwd_phase2<kMode, ArriveRelease, kT>(P, ctid, f.c, exch0 + es * kExch, w, rel, fb);
       tile_advance(f.c, P.tiles_per_clip);
       --f.left;
     }
@@ -1094,6 +1094,12 @@ static unsigned* next_tile_counter(cudaStream_t st, cudaError_t* err) {
 template <int kMode>
 static cudaError_t launch_fwd512_t(FwdParams P, const DevInfo& di, cudaStream_t st) {
   auto kern = P.zero_groups == 2 ? stft512_fwd_kernel<kMode, 2> : stft512_fwd_kernel<kMode, 0>;
+  // shape-specialised builds of the log-magnitude variant for the reference's fixed shapes (config.py: n_fft 512 / win 384 /
+  // hop 192; 5 s clips -> 417 frames, models/CNNBLSTM/dataset.py:89; 10 s -> 834): store offsets become immediates
+  if (kMode == FWD_MAG_LOG10 && P.zero_groups == 2 && !getenv("AIP_FWD_NO_SHAPE")) {
+    if (P.T_out == 834) kern = stft512_fwd_kernel<FWD_MAG_LOG10, 2, 834>;
+    else if (P.T_out == 417) kern = stft512_fwd_kernel<FWD_MAG_LOG10, 2, 417>;
+  }
   const size_t smem = fwd_smem_bytes(P.hop, P.n_tile_bufs);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
