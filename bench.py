@@ -367,6 +367,32 @@ def extra_legs(args, sp, plan, wave, gap_dev, Bi, T, F, L, world, peak, timed):
                        "value": world * Bi * CLIP_S / (ms_2 * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_2,
                        "hbm_frac": b2 / (np.mean(per_2) * 1e-3) / 1e9 / peak}
     del out2, spec, sout
+    # dataset-shaped collate (models/CNNBLSTM/dataset.py:74-121): 256 files x 25 gaps x 5 s, log-magnitudes of
+    # all variants from ONE clean transform per file (aip_stft_gap_variants_f32) against 25 full gapped transforms
+    Nf, G, L5 = min(256, Bi), 25, 80000
+    T5 = plan.num_frames(L5)
+    w5 = wave[:Nf, :L5].contiguous()
+    g5 = int(0.2 * SR)
+    rs = np.random.RandomState(7)
+    st5 = rs.randint(0, L5 - g5, size=Nf * G)
+    gaps5 = torch.as_tensor(np.stack([st5, st5 + g5], 1).astype(np.int32), device=dev)
+    vout = torch.empty((Nf * G, F, T5), dtype=torch.float32, device=dev)
+    ms_v, _ = timed(lambda: sp.stft_gap_variants(w5, plan, gaps5, G, mag_kind=sp.MAG_LOG10_EPS, eps=EPS, t_out=T5, out=vout),
+                    args.steps, args.warmup)
+    w5r = w5.repeat_interleave(G, 0)
+    fout = {"mag": torch.empty((Nf * G, F, T5), dtype=torch.float32, device=dev)}
+    ms_f, _ = timed(lambda: sp.stft(w5r, plan, gap_samples=gaps5, mag_kind=sp.MAG_LOG10_EPS, eps=EPS, t_out=T5, want_spec=False,
+                                    out=fout), args.steps, args.warmup)
+    same = bool(torch.equal(vout, fout["mag"]))
+    vb = Nf * (4 * L5 + 4 * F * T5 * G)          # compulsory: every file read once, every variant written once
+    legs["dataset_variants"] = {"workload": f"CNNBLSTM dataset item shape: {Nf} files x {G} gaps x 5 s per GPU, log10 magnitudes of every "
+                                            "variant (clean transform + TMA copy pass + re-transform of the frames each gap touches: "
+                                            "3 launches per step)",
+                                "value": world * Nf * G * 5.0 / (ms_v * 1e-3), "unit": "gapped audio-s/s", "ms_per_step": ms_v,
+                                "hbm_frac": vb / (ms_v * 1e-3) / 1e9 / peak, "compulsory_bytes_per_step": vb,
+                                "ms_per_step_full_transforms": ms_f, "speedup_vs_full_transforms": ms_f / ms_v,
+                                "bit_identical_to_full_transforms": same}
+    del vout, fout, w5r, w5
     # Griffin-Lim, 32 iterations (configs[2] "+ Griffin-Lim 32 iters"): streaming bound 8 995 656 B / clip / iteration
     Bg = min(args.gl_clips, Bi)
     if Bg > 0:

@@ -1,4 +1,4 @@
-"""Measured cost of the DFT-as-GEMM formulation of the headline step (DESIGN.md 4.5), as a LIBRARY GEMM upper bound:
+"""Measured cost of the DFT-as-GEMM formulation of the headline step (DESIGN.md 4.6), as a LIBRARY GEMM upper bound:
 frames [N, 384] (N = 4096 clips x 834 frames; the 128 zero window taps dropped) times the windowed real-DFT matrix
 [384, 514] (257 cos + 257 sin columns).  Framing, the |.| / log epilogue and the [F, T] transposition are NOT included, so
 the GEMM formulation cannot be faster than these numbers.  Experiment only -- not a product path."""
