@@ -377,7 +377,7 @@ def extra_legs(args, sp, plan, wave, gap_dev, Bi, T, F, L, world, peak, timed):
     st5 = rs.randint(0, L5 - g5, size=Nf * G)
     gaps5 = torch.as_tensor(np.stack([st5, st5 + g5], 1).astype(np.int32), device=dev)
     vout = torch.empty((Nf * G, F, T5), dtype=torch.float32, device=dev)
-    ms_v, _ = timed(lambda: sp.stft_gap_variants(w5, plan, gaps5, G, mag_kind=sp.MAG_LOG10_EPS, eps=EPS, t_out=T5, out=vout),
+    ms_v, _ = timed(lambda: sp.stft_gap_variants(w5, plan, gaps5, G, mag_kind=sp.MAG_LOG10_EPS, eps=EPS, t_out=T5, out=vout, gap_len_max=g5),
                     args.steps, args.warmup)
     w5r = w5.repeat_interleave(G, 0)
     fout = {"mag": torch.empty((Nf * G, F, T5), dtype=torch.float32, device=dev)}

@@ -160,11 +160,13 @@ int aip_istft_normalized_f32(const aip_stft_desc* desc,
  *   arithmetic as aip_stft_fwd_f32 with gap_samples: the result is bit-identical to G full transforms).
  * clean_mag [N, F, T_out] is the caller's aip_stft_fwd_f32(..., mag_kind, eps, T_out) of the un-gapped rows.
  * gap_len_max: the caller's bound on gap_samples[v][1] - gap_samples[v][0] (a longer gap is NOT detected).
- * mag_kind: AIP_MAG_ABS | AIP_MAG_LOG10_EPS | AIP_MAG_LOG1P_POW (power 1); n_fft 512 only (else AIP_ERR_UNSUPPORTED). */
+ * mag_kind: AIP_MAG_ABS | AIP_MAG_LOG10_EPS | AIP_MAG_LOG1P_POW (power 1); n_fft 512 only (else AIP_ERR_UNSUPPORTED).
+ * workspace: 16-byte aligned device scratch of aip_stft_gap_variants_workspace_bytes(N, G) bytes (per-variant tile metadata). */
+size_t aip_stft_gap_variants_workspace_bytes(int64_t N, int64_t G);
 int aip_stft_gap_variants_f32(const aip_stft_desc* desc, const float* wave, int64_t N, int64_t L, int64_t wave_pitch,
                               int64_t G, const int32_t* gap_samples /* [N*G, 2] */, int32_t gap_len_max,
                               int32_t mag_kind, float eps, int64_t T_out, const float* clean_mag /* [N, F, T_out] */,
-                              float* mag_out /* [N*G, F, T_out] */, void* stream);
+                              float* mag_out /* [N*G, F, T_out] */, void* workspace, size_t workspace_bytes, void* stream);
 
 /* y_b / max|y_b| unless max|y_b| < FLT_MIN; peaks: [B] float scratch/out (the per-clip max|y|). */
 int aip_peak_normalize_f32(const float* in, int64_t in_pitch, float* out, int64_t out_pitch,

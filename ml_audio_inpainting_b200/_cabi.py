@@ -45,7 +45,8 @@ SIGNATURES = {
     "aip_gap_zero_f32": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, _P, _P]),
     "aip_gap_mask_f32": (C.c_int, [_P, _I64, _I64, _I64, _P, _P]),
     "aip_frame_mask_f32": (C.c_int, [_P, _I64, _I64, _I64, _P, _I32, _P]),
-    "aip_stft_gap_variants_f32": (C.c_int, [_D, _P, _I64, _I64, _I64, _I64, _P, _I32, _I32, _F, _I64, _P, _P, _P]),
+    "aip_stft_gap_variants_workspace_bytes": (_SZ, [_I64, _I64]),
+    "aip_stft_gap_variants_f32": (C.c_int, [_D, _P, _I64, _I64, _I64, _I64, _P, _I32, _I32, _F, _I64, _P, _P, _P, _SZ, _P]),
     "aip_peak_normalize_f32": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, _P, _P]),
     "aip_status_string": (C.c_char_p, [C.c_int]),
     "aip_version": (C.c_char_p, []),

@@ -114,7 +114,7 @@ int emul_stft512_variants(const float* wave, int N, int L, long long pitch, int 
   TileCursor c = tile_cursor(0, P.tiles_per_clip);
   for (int tix = 0; tix < P.n_tiles; ++tix) {
     const int gs = gap_samples[2 * c.b], ge = gap_samples[2 * c.b + 1];
-    const FwdTilePlan q = fwd_tile_plan_var(P, c, gs, ge, var_frame_base(P, gs));
+    const FwdTilePlan q = fwd_tile_plan_var(P, c, gs, ge, var_frame_base(P, gs), c.b / G);      // = variant_meta_kernel
     if (q.n_bulk > 0) memcpy(tile.data() + q.v_lo, q.src + q.g0 + q.v_lo, (size_t)q.n_bulk * 4);   // the TMA bulk copy
     const bool own = !fwd_needs_edge_fixup(q);      // barrier-free path: each warp zeroes the gap for its own frames only
     if (!own && fwd_needs_fixup(q)) for (int tid = 0; tid < kThreads; ++tid) fwd_fixup(q, tid, tile.data());

@@ -228,8 +228,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
     lane_const_init(lc, tw_s, ptid & 15);
     TileFeed fn{0, 0, TileCursor{0, 0}};     // request cursor (thread ptid == 0 only): draws the chunks
     bool more = true;                        // the request cursor has not hit the end of the batch yet
-    int req_clip = -1, req_fb = 0;           // FWD_VARIANT: frame base of the variant the request cursor is in
-    int req_nxt_clip = -1, req_nxt_gs = 0;   // FWD_VARIANT: gap start of the request cursor's next variant
     auto request = [&](float* buf, uint64_t* bar) {      // ptid == 0: start the copy of the next tile, if there is one
       if (fn.left == 0) {
         const int s = (int)atomicAdd(P.tile_counter, (unsigned)P.chunk);
@@ -243,19 +241,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
         fn.left = cnt;
       }
       if (kMode & FWD_VARIANT) {
-        if (fn.c.b != req_clip) {
-          req_fb = var_frame_base(P, fn.c.b == req_nxt_clip ? req_nxt_gs : P.gap_samples[2 * fn.c.b]);
-          req_clip = fn.c.b;
-        }
-        fwd_issue_tile(fwd_tile_plan_var(P, fn.c, 0, 0, req_fb), buf, bar);
+        const int2 m = *reinterpret_cast<const int2*>(P.var_meta + 4 * fn.c.b + 2);      // {frame base, wave row}
+        fwd_issue_tile(fwd_tile_plan_var(P, fn.c, 0, 0, m.x, m.y), buf, bar);
       } else {
         fwd_issue_tile(fwd_tile_plan_gap(P, fn.c, 0, 0), buf, bar);
       }
       tile_advance(fn.c, P.tiles_per_clip);
       --fn.left;
-      if (kMode & FWD_VARIANT) {      // the next request's gap start, fetched a tile ahead (this thread also runs stage 1)
-        if (fn.left > 0 && fn.c.b != req_clip) { req_nxt_gs = P.gap_samples[2 * fn.c.b]; req_nxt_clip = fn.c.b; }
-      }
     };
     if (ptid == 0) {
       for (int k = 0; k < (ntb > 1 ? ntb - 1 : 1) && more; ++k) request(smem + k * P.tile_floats, tile_full + k);
@@ -263,31 +255,24 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
     TileFeed f{0, 0, TileCursor{0, 0}};
     int slot = 0, use = 0;               // ring slot of tile i and how often it has been used before
     int gs = 0, ge = 0, gap_clip = -1;   // gap range of the clip the cursor is in
-    int fb = 0;                          // FWD_VARIANT: first recomputed frame of that variant
-    int nxt_clip = -1, nxt_gs = 0, nxt_ge = 0;   // FWD_VARIANT: gap range of the next tile's variant, fetched ahead
+    int fb = 0, vrow = 0;                // FWD_VARIANT: first recomputed frame and wave row of that variant
 #pragma unroll 1
     for (int i = 0;; ++i) {
       if (f.left == 0 && !feed_next(P, f, sched_start, sched_bar)) break;
       const TileCursor c = f.c;
       float* tile = smem + slot * P.tile_floats;
       if (kMode & FWD_VARIANT) {
-        // a variant is one or two tiles: its gap range is fetched one tile ahead (the load's latency would sit in front of
-        // EVERY tile's plan otherwise)
-        if (c.b != gap_clip) {
-          if (c.b == nxt_clip) { gs = nxt_gs; ge = nxt_ge; }
-          else { gs = P.gap_samples[2 * c.b]; ge = P.gap_samples[2 * c.b + 1]; }
+        if (c.b != gap_clip) {      // one 16-byte load per variant: {gap start, gap end, frame base, wave row}
+          const int4 m = *reinterpret_cast<const int4*>(P.var_meta + 4 * c.b);
+          gs = m.x; ge = m.y; fb = m.z; vrow = m.w;
           gap_clip = c.b;
-          fb = var_frame_base(P, gs);
         }
-        TileCursor n = c;
-        tile_advance(n, P.tiles_per_clip);
-        if (n.b != c.b && n.b < P.B) { nxt_gs = P.gap_samples[2 * n.b]; nxt_ge = P.gap_samples[2 * n.b + 1]; nxt_clip = n.b; }
       } else if (P.gap_samples && c.b != gap_clip) {
         gs = P.gap_samples[2 * c.b];
         ge = P.gap_samples[2 * c.b + 1];
         gap_clip = c.b;
       }
-      const FwdTilePlan q = (kMode & FWD_VARIANT) ? fwd_tile_plan_var(P, c, gs, ge, fb) : fwd_tile_plan_gap(P, c, gs, ge);
+      const FwdTilePlan q = (kMode & FWD_VARIANT) ? fwd_tile_plan_var(P, c, gs, ge, fb, vrow) : fwd_tile_plan_gap(P, c, gs, ge);
       if (ntb > 1 && ptid == 0 && more) {
         // the next request goes into the slot that tile i - 1 has just left
         const int ns = slot == 0 ? ntb - 1 : slot - 1;
@@ -322,21 +307,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
     PairTw w;
     pair_tw_init(w, ctid >> 5);
     TileFeed f{0, 0, TileCursor{0, 0}};
-    int var_clip = -1, fb_cur = 0, nxt_clip = -1, nxt_gs = 0;     // FWD_VARIANT: frame base of this / gap start of the next variant
+    int var_clip = -1, fb_cur = 0;     // FWD_VARIANT: frame base of the variant the cursor is in
 #pragma unroll 1
     for (int i = 0;; ++i) {
       if (f.left == 0 && !feed_next(P, f, sched_start, sched_bar)) break;
       const int es = i & 1;
       int fb = 0;
-      if (kMode & FWD_VARIANT) {
-        if (f.c.b != var_clip) {
-          fb_cur = var_frame_base(P, f.c.b == nxt_clip ? nxt_gs : P.gap_samples[2 * f.c.b]);
-          var_clip = f.c.b;
-        }
+      if (kMode & FWD_VARIANT) {      // issued before the wait for stage 1, used after it
+        if (f.c.b != var_clip) { fb_cur = P.var_meta[4 * f.c.b + 2]; var_clip = f.c.b; }
         fb = fb_cur;
-        TileCursor n = f.c;
-        tile_advance(n, P.tiles_per_clip);
-        if (n.b != f.c.b && n.b < P.B) { nxt_gs = P.gap_samples[2 * n.b]; nxt_clip = n.b; }     // lands while this tile runs
       }
       mbar_wait(exch_full + es, (uint32_t)((i >> 1) & 1));
       ArriveRelease rel{exch_empty + es};
@@ -766,6 +745,14 @@ __global__ void __launch_bounds__(256) frame_mask_kernel(float* mask, long long 
     const int t = head + 4 * n4 + lane;
     if (t < T) dst[t] = (t >= f0 && t < f1) ? in_v : out_v;
   }
+}
+
+// Gap variants: per-variant metadata for the transform kernel, {gap start, gap end, first re-transformed frame, wave row}
+__global__ void variant_meta_kernel(const int* __restrict__ gaps, int4* __restrict__ meta, int B, int G, FwdParams P) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= B) return;
+  const int gs = gaps[2 * v], ge = gaps[2 * v + 1];
+  meta[v] = make_int4(gs, ge, var_frame_base(P, gs), v / G);
 }
 
 // Gap variants, copy pass: one (file i, bin k) row of the clean spectrogram per WARP and loop trip.  The row is read ONCE
@@ -1500,9 +1487,14 @@ int aip_frame_mask_f32(float* mask, int64_t B, int64_t F, int64_t T, const int32
   return (int)cudaGetLastError();
 }
 
+size_t aip_stft_gap_variants_workspace_bytes(int64_t N, int64_t G) {
+  return (N > 0 && G > 0) ? (size_t)N * (size_t)G * 16u : 0;
+}
+
 int aip_stft_gap_variants_f32(const aip_stft_desc* desc, const float* wave, int64_t N, int64_t L, int64_t wave_pitch,
                               int64_t G, const int32_t* gap_samples, int32_t gap_len_max, int32_t mag_kind, float eps,
-                              int64_t T_out, const float* clean_mag, float* mag_out, void* stream) {
+                              int64_t T_out, const float* clean_mag, float* mag_out, void* workspace, size_t workspace_bytes,
+                              void* stream) {
   const DevInfo di = dev_info();
   if (!di.ok) return AIP_ERR_DEVICE;
   if (!desc || !desc->window || !wave || !gap_samples || !clean_mag || !mag_out) return AIP_ERR_ARG;
@@ -1512,6 +1504,8 @@ int aip_stft_gap_variants_f32(const aip_stft_desc* desc, const float* wave, int6
   const long long T = num_frames(L, desc->n_fft, desc->hop, desc->center);
   if (T < 1 || T_out < 0 || T_out > T || T_out > (1 << 22)) return AIP_ERR_ARG;
   if (N == 0 || T_out == 0) return AIP_OK;
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 15)) return AIP_ERR_ARG;
+  if (workspace_bytes < aip_stft_gap_variants_workspace_bytes(N, G)) return AIP_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   FwdParams P{};
   P.wave = wave; P.wave_pitch = wave_pitch; P.B = (int)(N * G); P.L = (int)L;
@@ -1529,10 +1523,16 @@ int aip_stft_gap_variants_f32(const aip_stft_desc* desc, const float* wave, int6
              ((reinterpret_cast<uintptr_t>(P.wave) & 15) == 0);
   const int F = desc->n_fft / 2 + 1;
   cudaError_t e;
+  P.var_meta = static_cast<const int*>(workspace);
+  variant_meta_kernel<<<(unsigned)((P.B + 255) / 256), 256, 0, st>>>(gap_samples, static_cast<int4*>(workspace), P.B, (int)G, P);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
   const size_t fill_smem = (size_t)4 * kFillChunk * sizeof(float);
   const char* fill_env = getenv("AIP_VAR_FILL");                       // profiling switch: "scalar" = the store-instruction kernel
   const bool aligned4 = ((reinterpret_cast<uintptr_t>(mag_out) | reinterpret_cast<uintptr_t>(clean_mag)) & 3) == 0;
-  if (aligned4 && !(fill_env && fill_env[0] == 's')) {
+  if (getenv("AIP_VAR_NO_FILL")) {
+    // profiling switch: transform kernel only (tools/variant_probe.py)
+  } else if (aligned4 && !(fill_env && fill_env[0] == 's')) {
     e = cudaFuncSetAttribute(variant_fill_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem);
     if (e != cudaSuccess) return (int)e;
     const long long FT = (long long)F * P.T_out;

@@ -91,6 +91,8 @@ struct FwdParams {
   unsigned* tile_counter;   // device counter of the dynamic schedule, zero at launch
   int vec_ok;               // 16-byte bulk copies of the waveform are legal (alignment)
   int zero_groups;          // win_zero_groups(win_length): the first / last 32 * zero_groups window taps are zero
+  const int* var_meta;      // gap-variant mode: [B, 4] = {gap start, gap end, var_frame_base, wave row} per variant, written by
+                            // variant_meta_kernel (no divisions or dependent index loads inside the tile loops)
 };
 
 AIP_HDX int fwd_tile_len(int hop) { return (kFR - 1) * hop + kNfft; }
@@ -174,11 +176,11 @@ AIP_HD int var_frame_base(const FwdParams& P, int gs) {
   if (fb > last) fb = last;
   return fb < 0 ? 0 : fb;
 }
-AIP_HD FwdTilePlan fwd_tile_plan_var(const FwdParams& P, const TileCursor& c, int gs, int ge, int fb) {
+AIP_HD FwdTilePlan fwd_tile_plan_var(const FwdParams& P, const TileCursor& c, int gs, int ge, int fb, int row) {
   FwdTilePlan q;
   q.len = fwd_tile_len(P.hop);
   q.g0 = (fb + c.tt * kFR) * P.hop - P.pad;
-  q.src = P.wave + (long long)(c.b / P.var_div) * P.wave_pitch;
+  q.src = P.wave + (long long)row * P.wave_pitch;
   q.v_lo = q.g0 < 0 ? -q.g0 : 0;
   const int hi = P.L - q.g0;
   q.v_hi = hi < q.len ? (hi > 0 ? hi : 0) : q.len;

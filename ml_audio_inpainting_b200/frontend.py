@@ -101,9 +101,11 @@ def cnnblstm_dataset_batch(wave: torch.Tensor, gaps_per_audio: int = 25, gap_len
     frm = np.stack([f0, f1], 1)
     F = plan.n_bins
     target = sp.stft(wave, plan, t_out=t_crop)["spec"]                                      # dataset.py:102,110 (once per file)
-    if n_fft == 512:
-        mag = sp.stft_gap_variants(wave, plan, sam, G, mag_kind=sp.MAG_LOG10_EPS, eps=1e-9, t_out=t_crop)["mag"]
-    else:       # the generic kernels have no variant mode: G full transforms
+    # measured per variant (5 s clips): 0.195 us for a full gapped transform against 0.116 us + 0.32 us / G for copy + re-transform
+    # + the file's clean transform => the variant path pays off from 5 gaps per file (both are bit-identical)
+    if n_fft == 512 and G >= 5:
+        mag = sp.stft_gap_variants(wave, plan, sam, G, mag_kind=sp.MAG_LOG10_EPS, eps=1e-9, t_out=t_crop, gap_len_max=g)["mag"]
+    else:       # few gaps per file, or the generic kernels (no variant mode): G full transforms
         mag = sp.stft(wave.repeat_interleave(G, 0), plan, gap_samples=sam, mag_kind=sp.MAG_LOG10_EPS, eps=1e-9,
                       t_out=t_crop, want_spec=False)["mag"]
     out = {"spectrogram_gaps": mag.view(N, G, F, t_crop),

@@ -211,14 +211,17 @@ def stft(wave: torch.Tensor, plan: StftPlan, *, gap_samples=None, zero_frames=No
 
 def stft_gap_variants(wave: torch.Tensor, plan: StftPlan, gap_samples, variants_per_row: int, *,
                       mag_kind: int = MAG_LOG10_EPS, eps: float = 1e-9, t_out: Optional[int] = None,
-                      clean_mag: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> dict:
+                      clean_mag: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                      gap_len_max: Optional[int] = None) -> dict:
     """``variants_per_row`` gapped magnitude spectrograms per row of ``wave`` [N, L] (the gaps_per_audio loop of
     models/CNNBLSTM/dataset.py:93-111) without ``variants_per_row`` full transforms: one clean transform per row, a
     streaming copy, and a re-transform of the few frames each gap touches (``aip_stft_gap_variants_f32``).
 
     ``gap_samples``: int [N * variants_per_row, 2] sample ranges (host array or CUDA int32 tensor), variant
-    ``i * variants_per_row + j`` belongs to row ``i``.  Returns ``mag`` f32 [N * variants_per_row, F, t_out] and
-    ``clean_mag`` f32 [N, F, t_out].  Bit-identical to ``stft(wave.repeat_interleave(G, 0), gap_samples=...)``."""
+    ``i * variants_per_row + j`` belongs to row ``i``.  ``gap_len_max``: an upper bound of the gap lengths (computed from
+    ``gap_samples`` when omitted -- for a CUDA tensor that costs a device synchronisation).  Returns ``mag`` f32
+    [N * variants_per_row, F, t_out] and ``clean_mag`` f32 [N, F, t_out].  Bit-identical to
+    ``stft(wave.repeat_interleave(G, 0), gap_samples=...)``."""
     _require_cuda(wave, "wave")
     if plan.n_fft != 512:
         raise NotImplementedError("gap variants run on the n_fft = 512 register-FFT kernels only")
@@ -236,7 +239,9 @@ def stft_gap_variants(wave: torch.Tensor, plan: StftPlan, gap_samples, variants_
     t_out = T if t_out is None else min(int(t_out), T)
     F = plan.n_bins
     dev = wave.device
-    if isinstance(gap_samples, torch.Tensor):
+    if gap_len_max is not None:
+        gmax = int(gap_len_max)
+    elif isinstance(gap_samples, torch.Tensor):
         gmax = int((gap_samples[:, 1] - gap_samples[:, 0]).max().item()) if gap_samples.numel() else 0
     else:
         g_np = np.asarray(gap_samples, dtype=np.int64).reshape(-1, 2)
@@ -251,10 +256,12 @@ def stft_gap_variants(wave: torch.Tensor, plan: StftPlan, gap_samples, variants_
     elif tuple(out.shape) != (N * G, F, t_out) or out.dtype != torch.float32 or not out.is_contiguous():
         raise ValueError("out has the wrong shape/dtype/layout")
     lib = _cabi.load()
+    ws_bytes = int(lib.aip_stft_gap_variants_workspace_bytes(N, G))
+    ws = torch.empty((max(ws_bytes, 16) + 3) // 4, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         check(lib.aip_stft_gap_variants_f32(
             C.byref(plan.desc), _ptr(wave), N, L, wave.stride(0), G, _ptr(gaps), max(gmax, 0), int(mag_kind), float(eps),
-            t_out, _ptr(clean_mag), _ptr(out), _stream()), "aip_stft_gap_variants_f32")
+            t_out, _ptr(clean_mag), _ptr(out), _ptr(ws), ws_bytes, _stream()), "aip_stft_gap_variants_f32")
     return {"mag": out, "clean_mag": clean_mag}
 
 

@@ -475,12 +475,12 @@ def test_gap_variants_bit_identical_to_full_transforms(sp, par, L, g, G, t_out, 
         assert torch.equal(a, b)
 
 
-def test_cnnblstm_dataset_batch_matches_reference_getitem(golden_clips):
+@pytest.mark.parametrize("G", [6, 3], ids=["variant-path", "few-gaps-full-transforms"])
+def test_cnnblstm_dataset_batch_matches_reference_getitem(golden_clips, G):
     """frontend.cnnblstm_dataset_batch against the oracle's restatement of LibriSpeechDataset.__getitem__
     (models/CNNBLSTM/dataset.py:74-121): same np.random draws in the same order, intervals and masks bit-exact,
     log-magnitudes and the complex target within 1e-4."""
     from ml_audio_inpainting_b200 import frontend
-    G = 4
     clips = [np.asarray(c, dtype=np.float32)[:80000] for c in list(golden_clips.values())[:2]]
     np.random.seed(11)
     refs = [cp.cnnblstm_getitem(c, gaps_per_audio=G) for c in clips]

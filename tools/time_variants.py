@@ -34,8 +34,8 @@ var_out = torch.empty((N * G, F, T), device="cuda")
 clean = sp.stft(x, plan, mag_kind=sp.MAG_LOG10_EPS, t_out=T, want_spec=False)["mag"]
 out_bytes = N * G * F * T * 4
 t_full = timeit(lambda: sp.stft(xr, plan, gap_samples=gaps, mag_kind=sp.MAG_LOG10_EPS, t_out=T, want_spec=False, out=full_out))
-t_var = timeit(lambda: sp.stft_gap_variants(x, plan, gaps, G, t_out=T, clean_mag=clean, out=var_out))
-t_var_all = timeit(lambda: sp.stft_gap_variants(x, plan, gaps, G, t_out=T, out=var_out))
+t_var = timeit(lambda: sp.stft_gap_variants(x, plan, gaps, G, t_out=T, clean_mag=clean, out=var_out, gap_len_max=g))
+t_var_all = timeit(lambda: sp.stft_gap_variants(x, plan, gaps, G, t_out=T, out=var_out, gap_len_max=g))
 assert torch.equal(full_out["mag"], var_out)
 print(f"N={N} files x G={G} gaps, 5 s clips, P1, log10 magnitudes [{N * G}, {F}, {T}] = {out_bytes / 1e9:.3f} GB written")
 print(f"G full gapped transforms (pre-repeated waves)      {t_full:8.3f} ms   {out_bytes / t_full / 1e6:8.1f} GB/s of output")

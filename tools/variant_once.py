@@ -16,6 +16,6 @@ plan = sp.get_plan(512, 192, 384)
 clean = sp.stft(x, plan, mag_kind=sp.MAG_LOG10_EPS, t_out=T, want_spec=False)["mag"]
 out = torch.empty((N * G, 257, T), device="cuda")
 for _ in range(reps):
-    sp.stft_gap_variants(x, plan, gaps, G, t_out=T, clean_mag=clean, out=out)
+    sp.stft_gap_variants(x, plan, gaps, G, t_out=T, clean_mag=clean, out=out, gap_len_max=g)
 torch.cuda.synchronize()
 print("ok")
