@@ -91,6 +91,7 @@ struct FwdParams {
   unsigned* tile_counter;   // device counter of the dynamic schedule, zero at launch
   int vec_ok;               // 16-byte bulk copies of the waveform are legal (alignment)
   int zero_groups;          // win_zero_groups(win_length): the first / last 32 * zero_groups window taps are zero
+  int var_prefetch;         // gap-variant mode: request the lines of a tile's row segments from L2 ahead of its stores
   const int* var_meta;      // gap-variant mode: [B, 4] = {gap start, gap end, var_frame_base, wave row} per variant, written by
                             // variant_meta_kernel (no divisions or dependent index loads inside the tile loops)
 };
