@@ -10,6 +10,10 @@
 //                        optional per-clip peak for the fused normalisation.
 //   istft512_tma_kernel  the same with stage A's rows staged by 4-D TMA tensor boxes (switch AIP_INV_TMA=1).
 //   gl_update*_kernel    the Griffin-Lim phase update between the two transforms.
+//   gap variants         (aip_stft_gap_variants_f32: G gapped spectrograms per file from ONE clean transform)
+//                        variant_meta_kernel -> variant_fill_tma_kernel (clean block staged in shared memory at the four
+//                        16-byte phases, one bulk copy shared -> global per chunk and variant) -> stft512_fwd_kernel
+//                        <mode | FWD_VARIANT> (re-transform of the one or two tiles a gap touches).
 //   stft_generic_* / istft_generic_*   any power-of-two n_fft in [32, 4096] (or odd hop): one frame
 //                        per CTA, shared-memory radix-2.  Correct, not tuned: the reference's
 //                        models only ever use n_fft = 512 (config.py:28, GAN/config.yaml:12).
