@@ -1057,7 +1057,7 @@ static bool inv_make_map(CUtensorMap* map, const float2* spec, int B, int T, int
 }
 
 static bool inv_tma_ok(const InvParams& P) {
-  if (!P.spec || (P.T & 1) || (reinterpret_cast<uintptr_t>(P.spec) & 15)) return false;
+  if (!P.spec || P.gl_mag || (P.T & 1) || (reinterpret_cast<uintptr_t>(P.spec) & 15)) return false;
   // Off unless AIP_INV_TMA=1: measured 0.568 ms against 0.535 ms for the direct-load kernel (1024 x 10 s, hop 192) -- the
   // staging slots leave room for ONE exchange buffer only, and stage A is not the slower role (profiles/README.md).
   const char* e = getenv("AIP_INV_TMA");
@@ -1260,6 +1260,7 @@ static int run_inv(const aip_stft_desc* desc, InvParams P, long long length, voi
       AIP_INV_CASE(inv_mag_mode(1, true))
       AIP_INV_CASE(inv_mag_mode(2, false))
       AIP_INV_CASE(INV_BLEND)
+      AIP_INV_CASE(INV_GL)
       default: kern = P.ola_fast == 1 ? istft512_kernel<inv_mag_mode(2, true), 1>
                                       : (P.ola_fast == 2 ? istft512_kernel<inv_mag_mode(2, true), 2> : istft512_kernel<inv_mag_mode(2, true), 0>);
                break;
@@ -1432,6 +1433,11 @@ int aip_griffinlim_f32(const aip_stft_desc* desc, const float* mag, float* angle
   const long long n2 = n / 2;
   long long g = (n2 + 255) / 256;
   if (g > (long long)di.sms * 32) g = (long long)di.sms * 32;
+  // With the two ping-pong buffers the phase update needs no kernel and no `angles` array of its own: the inverse kernel of
+  // the NEXT iteration (or the final one) reads rebuilt[it], rebuilt[it - 1] and |S| and projects while it loads (INV_GL,
+  // InvLoadGL) -- 3 array passes fewer per iteration.  The forward kernel of iteration `it` overwrites rebuilt[it - 2], which
+  // the inverse kernel before it on the stream was the last to read.  Needs the fast n_fft = 512 path.
+  const bool fused = pingpong && fwd_fast_ok(desc, di) && inv_fast_ok(desc) && !getenv("AIP_GL_UNFUSED");
   for (int it = 0; it < n_iter; ++it) {
     int rc = run_inv(desc, I, 0, workspace, workspace_bytes, st);
     if (rc != AIP_OK) return rc;
@@ -1442,7 +1448,10 @@ int aip_griffinlim_f32(const aip_stft_desc* desc, const float* mag, float* angle
     P.spec = rebuilt;
     rc = run_fwd(desc, P, T, st);
     if (rc != AIP_OK) return rc;
-    if (pingpong) {
+    if (fused) {
+      I.spec = rebuilt; I.gl_mag = mag;
+      I.gl_prev = it > 0 ? rb[(it + 1) & 1] : rebuilt; I.gl_alpha = it > 0 ? alpha : 0.0f;      // librosa: tprev is None at first
+    } else if (pingpong) {
       const float2* prev = rb[(it + 1) & 1];
       if (n2 > 0)
         gl_update_pp_kernel<<<(unsigned)g, 256, 0, st>>>(reinterpret_cast<const float4*>(rebuilt), reinterpret_cast<const float4*>(prev),

@@ -467,6 +467,11 @@ struct InvParams {
   int wss_ref;              // inv_wss[wss_ref + r] = periodic value for frame offset r; < 0: no interior
   int ola_fast;             // compile-time specialised overlap-add of interior tiles: 0 none, 1 = hop 192 with the 2 x 64 zero
                             // taps of a win <= 384 window (2 terms), 2 = hop 128, full window (4 terms); centre padding only
+  // Griffin-Lim (INV_GL): `spec` is the spectrum the forward kernel rebuilt in the previous iteration and the phase update
+  // of librosa.griffinlim runs inside the load: a = spec - gl_alpha * gl_prev; a *= gl_mag / (|a| + tiny)
+  const float2* gl_prev;    // [B,257,T] rebuilt spectrum of the iteration before (first iteration: = spec, with gl_alpha 0)
+  const float* gl_mag;      // [B,257,T] target magnitudes; non-null selects INV_GL
+  float gl_alpha;           // momentum / (1 + momentum)
 
 };
 
@@ -530,6 +535,28 @@ struct InvLoadSpec {        // complex input straight from HBM
   }
 };
 
+// Griffin-Lim: the phase update fused into the load (same arithmetic as gl_update_pp_kernel, which it replaces: the
+// projected spectrum `angles` is never written to or read from HBM)
+struct InvLoadGL {
+  const float2* reb;        // column pointers: array + b*F*T + t
+  const float2* prev;
+  const float* mag;
+  int T;
+  float alpha;              // 0 in the first iteration (prev = reb then: branch-free)
+  int olo, ohi, s16;
+  AIP_HM void rows(int k_lo, int k_hi) { olo = k_lo * T; ohi = k_hi * T; s16 = 16 * T; }
+  AIP_HM void lo(int j, float& xr, float& xi) const { get(olo + j * s16, xr, xi); }
+  AIP_HM void hi(int j, float& xr, float& xi) const { get(ohi - j * s16, xr, xi); }
+  AIP_HM void get(int o, float& xr, float& xi) const {
+    const float2 r = ldg_stream(reb + o);
+    const float2 t = ldg_stream(prev + o);
+    const float m = mag[o];
+    const float ax = r.x - alpha * t.x, ay = r.y - alpha * t.y;
+    const float sc = fast_div(m, fast_sqrt(ax * ax + ay * ay) + kFltMin);      // MUFU.SQRT + MUFU.RCP: ~2 ulp each
+    xr = ax * sc; xi = ay * sc;
+  }
+};
+
 // run-time flavoured element fetch (generic n_fft kernels only)
 AIP_HD void inv_load_runtime(const InvParams& P, long long idx, bool db, float& xr, float& xi) {
   if (P.spec) { const float2 v = P.spec[idx]; xr = v.x; xi = v.y; return; }
@@ -550,10 +577,11 @@ AIP_HD void inv_load_runtime(const InvParams& P, long long idx, bool db, float& 
 // an LDS per element; see profiles/README.md.)
 constexpr int INV_SPEC = 0;
 constexpr int INV_BLEND = 7;
+constexpr int INV_GL = 8;       // complex input + the Griffin-Lim phase update (InvLoadGL)
 AIP_HDX constexpr int inv_mag_mode(int dom, bool phase) { return 1 + 2 * dom + (phase ? 1 : 0); }
 
 AIP_HDX int inv_mode_of(const InvParams& P) {
-  if (P.spec) return INV_SPEC;
+  if (P.spec) return P.gl_mag ? INV_GL : INV_SPEC;
   if (P.blend_in) return INV_BLEND;
   const int dom = (P.mag_domain == DOM_LINEAR) ? 0 : (P.mag_domain == DOM_EXPM1 ? 2 : 1);
   return inv_mag_mode(dom, P.phase != nullptr);
@@ -573,6 +601,9 @@ AIP_HD void inv_phase0(const InvParams& P, int tid, const TileCursor& c, float2*
   const long long col = (long long)c.b * kBins * P.T + t;
   if (kMode == INV_SPEC) {
     InvLoadSpec load{P.spec + col, P.T, nullptr, nullptr, 0u};
+    inv_stageA(exch, w, lane, warp, live, load, before_store);
+  } else if (kMode == INV_GL) {
+    InvLoadGL load{P.spec + col, P.gl_prev + col, P.gl_mag + col, P.T, P.gl_alpha, 0, 0, 0};
     inv_stageA(exch, w, lane, warp, live, load, before_store);
   } else if (kMode == INV_BLEND) {
     InvLoadMag<1, true, true> load{P.mag + col, P.phase + col, P.blend_in + col, P.blend_mask + col, P.T,
