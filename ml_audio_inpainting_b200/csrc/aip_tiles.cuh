@@ -538,9 +538,10 @@ struct InvLoadSpec {        // complex input straight from HBM
 // Griffin-Lim: the phase update fused into the load (same arithmetic as gl_update_pp_kernel, which it replaces: the
 // projected spectrum `angles` is never written to or read from HBM)
 struct InvLoadGL {
-  const float2* reb;        // column pointers: array + b*F*T + t
+  const float2* reb;        // ARRAY bases (uniform: they stay in the constant bank); the thread keeps one column index
   const float2* prev;
   const float* mag;
+  long long col;            // b*F*T + t
   int T;
   float alpha;              // 0 in the first iteration (prev = reb then: branch-free)
   int olo, ohi, s16;
@@ -548,9 +549,10 @@ struct InvLoadGL {
   AIP_HM void lo(int j, float& xr, float& xi) const { get(olo + j * s16, xr, xi); }
   AIP_HM void hi(int j, float& xr, float& xi) const { get(ohi - j * s16, xr, xi); }
   AIP_HM void get(int o, float& xr, float& xi) const {
-    const float2 r = ldg_stream(reb + o);
-    const float2 t = ldg_stream(prev + o);
-    const float m = mag[o];
+    const long long i = col + o;
+    const float2 r = ldg_stream(reb + i);
+    const float2 t = ldg_stream(prev + i);
+    const float m = mag[i];
     const float ax = r.x - alpha * t.x, ay = r.y - alpha * t.y;
     const float sc = fast_div(m, fast_sqrt(ax * ax + ay * ay) + kFltMin);      // MUFU.SQRT + MUFU.RCP: ~2 ulp each
     xr = ax * sc; xi = ay * sc;
@@ -603,7 +605,7 @@ AIP_HD void inv_phase0(const InvParams& P, int tid, const TileCursor& c, float2*
     InvLoadSpec load{P.spec + col, P.T, nullptr, nullptr, 0u};
     inv_stageA(exch, w, lane, warp, live, load, before_store);
   } else if (kMode == INV_GL) {
-    InvLoadGL load{P.spec + col, P.gl_prev + col, P.gl_mag + col, P.T, P.gl_alpha, 0, 0, 0};
+    InvLoadGL load{P.spec, P.gl_prev, P.gl_mag, col, P.T, P.gl_alpha, 0, 0, 0};
     inv_stageA(exch, w, lane, warp, live, load, before_store);
   } else if (kMode == INV_BLEND) {
     InvLoadMag<1, true, true> load{P.mag + col, P.phase + col, P.blend_in + col, P.blend_mask + col, P.T,
