@@ -12,8 +12,9 @@ installed in this image, so this module carries a small self-contained codec:
   * RIFF/WAVE PCM-16 / PCM-24 / PCM-32 / float32 read, PCM-16 write.
 
 Integer PCM becomes float32 by dividing by 2**(bits-1), which is what libsndfile hands
-librosa for ``dtype=float32``.  Floats are written as ``rint(x * 32767)`` clipped to
-int16, libsndfile's default float -> PCM_16 conversion.
+librosa for ``dtype=float32``.  Floats are written to FLAC as ``rint(x * 32768)`` clipped to int16
+(what the reference's shipped FLAC outputs show) and to WAV as ``rint(x * 32767)`` (libsndfile's
+default float -> PCM_16 conversion).
 If the optional ``soundfile`` package is importable it is NOT used: results must not
 depend on what happens to be installed.
 """
@@ -489,9 +490,9 @@ def read_wav(data: bytes) -> Tuple[np.ndarray, int]:
     raise ValueError("WAV: no data chunk")
 
 
-def _to_int16(audio: np.ndarray) -> np.ndarray:
+def _to_int16(audio: np.ndarray, scale: float = 32767.0) -> np.ndarray:
     a = np.asarray(audio, dtype=np.float64)
-    return np.clip(np.rint(a * 32767.0), -32768, 32767).astype(np.int16)
+    return np.clip(np.rint(a * scale), -32768, 32767).astype(np.int16)
 
 
 def write_wav(audio: np.ndarray, sample_rate: int) -> bytes:
@@ -521,7 +522,10 @@ def read_audio(path, max_samples: Optional[int] = None) -> Tuple[np.ndarray, int
 def write_audio(path, audio: np.ndarray, sample_rate: int, file_format: str = "flac") -> None:
     fmt = file_format.lower()
     if fmt == "flac":
-        blob = encode_flac(_to_int16(audio), sample_rate)
+        # FLAC: x * 32768 with clipping.  Pinned by the reference's own outputs: after save_audio's peak normalisation five of
+        # the nine test_samples_reconstructed/*_cnnlstm_inpainted.flac hold a -32768 sample (|x| = 1 at a negative peak) and the
+        # other four peak at +32767 (the clipped +32768) -- tests/test_reference_outputs.py.
+        blob = encode_flac(_to_int16(audio, 32768.0), sample_rate)
     elif fmt == "wav":
         blob = write_wav(audio, sample_rate)
     else:

@@ -13,6 +13,8 @@ on the reference's call sites:
   librosa.db_to_amplitude <- utils.py:314
   librosa.util.normalize  <- utils.py:84
   librosa.time_to_frames  <- models/CNNBLSTM/dataset.py:116-117, models/model_eval.py:148-149
+  librosa.feature.melspectrogram <- utils.py:268-277
+  librosa.filters.mel     <- utils.py:367-373
 
 dtype flow is kept as librosa has it: the forward window product is float64 (float64
 window x float32 frames) so the forward FFT runs in double and is rounded to
@@ -30,7 +32,7 @@ __all__ = [
     "get_window", "pad_center", "fft_window", "tiny", "stft", "istft",
     "window_sumsquare", "griffinlim", "time_to_samples", "samples_to_frames",
     "time_to_frames", "db_to_power", "db_to_amplitude", "normalize",
-    "phasor", "n_frames_for",
+    "phasor", "n_frames_for", "hz_to_mel", "mel_to_hz", "mel_frequencies", "mel", "melspectrogram",
 ]
 
 
@@ -312,3 +314,83 @@ def normalize(S, norm=np.inf, axis=0):
     out = np.empty_like(S)
     out[:] = S / length
     return out
+
+
+# --- mel (librosa.filters.mel / librosa.feature.melspectrogram; reference utils.py:268-277, :367-373) ---------------
+
+def hz_to_mel(frequencies, htk=False):
+    """librosa.hz_to_mel: Slaney's auditory-toolbox scale (linear below 1 kHz, log above) unless ``htk``."""
+    f = np.asanyarray(frequencies)
+    if htk:
+        return 2595.0 * np.log10(1.0 + f / 700.0)
+    f_min, f_sp = 0.0, 200.0 / 3
+    mels = (f - f_min) / f_sp
+    min_log_hz = 1000.0
+    min_log_mel = (min_log_hz - f_min) / f_sp
+    logstep = np.log(6.4) / 27.0
+    if f.ndim:
+        log_t = f >= min_log_hz
+        mels[log_t] = min_log_mel + np.log(f[log_t] / min_log_hz) / logstep
+    elif f >= min_log_hz:
+        mels = min_log_mel + np.log(f / min_log_hz) / logstep
+    return mels
+
+
+def mel_to_hz(mels, htk=False):
+    """librosa.mel_to_hz."""
+    m = np.asanyarray(mels)
+    if htk:
+        return 700.0 * (10.0 ** (m / 2595.0) - 1.0)
+    f_min, f_sp = 0.0, 200.0 / 3
+    freqs = f_min + f_sp * m
+    min_log_hz = 1000.0
+    min_log_mel = (min_log_hz - f_min) / f_sp
+    logstep = np.log(6.4) / 27.0
+    if m.ndim:
+        log_t = m >= min_log_mel
+        freqs[log_t] = min_log_hz * np.exp(logstep * (m[log_t] - min_log_mel))
+    elif m >= min_log_mel:
+        freqs = min_log_hz * np.exp(logstep * (m - min_log_mel))
+    return freqs
+
+
+def mel_frequencies(n_mels=128, fmin=0.0, fmax=11025.0, htk=False):
+    """librosa.mel_frequencies: n_mels points uniformly spaced on the mel axis."""
+    return mel_to_hz(np.linspace(hz_to_mel(fmin, htk=htk), hz_to_mel(fmax, htk=htk), n_mels), htk=htk)
+
+
+def mel(sr, n_fft, n_mels=128, fmin=0.0, fmax=None, htk=False, norm="slaney", dtype=np.float32):
+    """librosa.filters.mel: triangular filters [n_mels, 1 + n_fft//2], area-normalised (``norm='slaney'``).
+
+    The weight matrix is ``dtype`` (float32) from the start, as in librosa: every row is rounded to float32 when it is
+    stored and the Slaney normalisation multiplies the rounded rows."""
+    if fmax is None:
+        fmax = float(sr) / 2
+    n_mels = int(n_mels)
+    weights = np.zeros((n_mels, int(1 + n_fft // 2)), dtype=dtype)
+    fftfreqs = np.fft.rfftfreq(n=n_fft, d=1.0 / sr)
+    mel_f = mel_frequencies(n_mels + 2, fmin=fmin, fmax=fmax, htk=htk)
+    fdiff = np.diff(mel_f)
+    ramps = np.subtract.outer(mel_f, fftfreqs)
+    for i in range(n_mels):
+        lower = -ramps[i] / fdiff[i]
+        upper = ramps[i + 2] / fdiff[i + 1]
+        weights[i] = np.maximum(0, np.minimum(lower, upper))
+    if norm == "slaney":
+        enorm = 2.0 / (mel_f[2:n_mels + 2] - mel_f[:n_mels])
+        weights *= enorm[:, np.newaxis]
+    elif norm is not None:
+        raise ValueError("oracle restates norm='slaney' / None only")
+    return weights
+
+
+def melspectrogram(y=None, sr=22050, S=None, n_fft=2048, hop_length=512, win_length=None, window="hann", center=True,
+                   pad_mode="constant", power=2.0, **kwargs):
+    """librosa.feature.melspectrogram: mel basis contracted with |stft(y)| ** power (utils.py:268-277)."""
+    if S is None:
+        S = np.abs(stft(y, n_fft=n_fft, hop_length=hop_length, win_length=win_length, window=window, center=center,
+                        pad_mode=pad_mode)) ** power
+    else:
+        n_fft = 2 * (S.shape[-2] - 1)
+    mel_basis = mel(sr=sr, n_fft=n_fft, **kwargs)
+    return np.einsum("...ft,mf->...mt", S, mel_basis, optimize=True)
