@@ -10,10 +10,14 @@ One step = ONE launch of ``stft512_fwd_kernel`` per rank.  The JSON line also ca
 leg (configs[2]: iSTFT overlap-add, batch 1024) and the round trip under ``"legs"``.
 
   value     whole-job audio-s/s, inputs resident in HBM, CUDA events, max over ranks
-  e2e       same metric through ``frontend.logmag_gap_host`` (pinned HOST buffers in, HOST buffers
-            out; H2D + kernel + D2H inside the timed region, chunked over 3 streams)
+  e2e       same metric through ``frontend.HostPipeline`` (pinned HOST buffers in, HOST buffers
+            out; H2D + kernel + D2H inside the timed region, 64-clip chunks on 4 streams), and the same chunked copies
+            WITHOUT the kernel beside it (``copy_ceiling``: what the host / PCIe side allows on this box at this N)
   roofline  algorithmic bytes (4 L + 4 F T per clip) / kernel time vs MEASURED_PEAKS.json
-  cpu_baseline  the numpy/scipy oracle port of the same step on the host cores (bounded sample)
+  cpu_baseline  the numpy/scipy oracle port of the same step on the host cores (bounded sample; clips generated BEFORE the
+            clock starts), with the one-thread figure and torch.stft on the CPU (a stronger CPU implementation) beside it
+  istft / roundtrip / cnnblstm_e2e   top-level copies of the legs the metric's name also covers (configs[2], the STFT -> mask ->
+            iSTFT round trip, and configs[4]: front-end -> the reference's CNN-BLSTM architecture -> back-end)
 
 ``--impl reference`` times only that CPU port (the reference's own librosa path cannot be
 installed here: librosa/soundfile are absent from the image and the wheelhouse).
@@ -43,17 +47,28 @@ _RESULT_OUT = sys.stdout
 
 
 # ----------------------------------------------------------------------------------------------- CPU
-def _cpu_worker(args):
-    """Oracle port of one step on `n` clips: gap zeroing -> librosa.stft -> log10(|S| + 1e-9)."""
-    seed, n, L = args
-    from oracle import librosa_port as lr          # bench.py's cpu_baseline / reference arm only
+_CPU_DISTINCT = 32      # distinct synthetic clips per worker (20 MB); the timed loop cycles over them
+
+
+def _cpu_inputs(seed, L):
+    """The worker's synthetic clips and gap starts -- generated BEFORE the clock starts, like the GPU arm's."""
     rng = np.random.default_rng(seed)
     g = int(GAP_S * SR)
-    t0 = time.perf_counter()
+    clips = [np.clip(0.1 * rng.standard_normal(L), -1, 1).astype(np.float32) for _ in range(_CPU_DISTINCT)]
+    starts = [int(rng.integers(0, L - g)) for _ in range(_CPU_DISTINCT)]
+    return clips, starts, g
+
+
+def _cpu_worker(args):
+    """Oracle port of one step on `n` clips: gap zeroing -> librosa.stft -> log10(|S| + 1e-9).  Timed: that work only."""
+    seed, n, L = args
+    from oracle import librosa_port as lr          # bench.py's cpu_baseline / reference arm only
+    clips, starts, g = _cpu_inputs(seed, L)
     acc = 0.0
-    for _ in range(n):
-        x = np.clip(0.1 * rng.standard_normal(L), -1, 1).astype(np.float32)
-        s = int(rng.integers(0, L - g))
+    t0 = time.perf_counter()
+    for i in range(n):
+        x = clips[i % _CPU_DISTINCT].copy()        # the step's own gapped copy (utils.add_random_gap builds a new array too)
+        s = starts[i % _CPU_DISTINCT]
         x[s:s + g] = 0.0
         S = lr.stft(x, n_fft=N_FFT, hop_length=HOP, win_length=WIN)
         m = np.log10(np.abs(S) + EPS).astype(np.float32)
@@ -61,15 +76,34 @@ def _cpu_worker(args):
     return time.perf_counter() - t0, acc
 
 
-def cpu_pass(pool, workers: int, clips_per_worker: int, L: int, seed: int = 0):
-    """Returns (audio-s/s, wall seconds) of the CPU port over workers*clips_per_worker clips."""
+def _torch_cpu_worker(args):
+    """The same step with torch.stft on the CPU (not the reference's implementation: a stronger CPU baseline)."""
+    seed, n, L, threads = args
+    import torch
+    torch.set_num_threads(threads)
+    clips, starts, g = _cpu_inputs(seed, L)
+    from oracle import librosa_port as lr
+    w = torch.from_numpy(lr.fft_window("hann", WIN, N_FFT).astype(np.float32))
+    xs = [torch.from_numpy(c) for c in clips]
+    acc = 0.0
     t0 = time.perf_counter()
-    jobs = [(seed * 1000 + w, clips_per_worker, L) for w in range(workers)]
-    if pool is None:
-        [_cpu_worker(j) for j in jobs]
-    else:
-        pool.map(_cpu_worker, jobs)
-    dt = time.perf_counter() - t0
+    for i in range(n):
+        x = xs[i % _CPU_DISTINCT].clone()
+        s = starts[i % _CPU_DISTINCT]
+        x[s:s + g] = 0.0
+        S = torch.stft(x, N_FFT, HOP, N_FFT, window=w, center=True, pad_mode="constant", return_complex=True)
+        m = torch.log10(S.abs() + EPS)
+        acc += float(m[0, 0])
+    return time.perf_counter() - t0, acc
+
+
+def cpu_pass(pool, workers: int, clips_per_worker: int, L: int, seed: int = 0, fn=None, extra=()):
+    """Returns (audio-s/s, seconds) of the CPU step over workers*clips_per_worker clips.  The workers run concurrently and each
+    times its own loop (input generation excluded); the pass takes as long as the slowest of them."""
+    fn = fn or _cpu_worker
+    jobs = [(seed * 1000 + w, clips_per_worker, L, *extra) for w in range(workers)]
+    res = [fn(j) for j in jobs] if pool is None else pool.map(fn, jobs)
+    dt = max(r[0] for r in res)
     return workers * clips_per_worker * (L / SR) / dt, dt
 
 
@@ -172,14 +206,14 @@ def reference_arm(args, rank: int):
         pool.close()
     ms = 1e3 * float(np.mean(t))
     value = workers * per * CLIP_S / (ms * 1e-3)
-    sample = f"{workers * per} clips x {CLIP_S:g} s per step ({workers} processes x {per} clips), oracle port (numpy + scipy.fft)"
+    sample = (f"each step = a bounded sample of the configured workload: {workers * per} of its {args.clips} clips x {CLIP_S:g} s "
+              f"({workers} processes x {per} clips, inputs generated before the clock starts), oracle port (numpy + scipy.fft pocketfft = "
+              "what librosa runs); librosa itself is not installable here")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_fft": N_FFT, "win_length": WIN, "hop_length": HOP,
-                   "sample_rate": SR, "clip_seconds": CLIP_S, "gap_seconds": GAP_S,
-                   "note": "librosa is not installable here; the CPU arm is the oracle restatement of the same path"},
+        "config": make_config(args.clips, max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -189,6 +223,36 @@ def reference_arm(args, rank: int):
 
 WORKLOAD = ("configs[1]: batched STFT log-magnitude + gap masking, 4096 synthetic 16 kHz 10 s clips per GPU "
             "(n_fft 512 / win 384 / hop 192, gap 0.2 s, log10(|S|+1e-9))")
+
+
+def make_config(clips_per_gpu: int, world: int) -> dict:
+    """One config for both arms (ours and --impl reference): the workload both are measured on."""
+    L = int(CLIP_S * SR)
+    return {"workload": WORKLOAD, "clips_per_gpu": clips_per_gpu, "n_fft": N_FFT, "win_length": WIN, "hop_length": HOP,
+            "sample_rate": SR, "clip_seconds": CLIP_S, "gap_seconds": GAP_S, "frames": 1 + L // HOP,
+            "outputs": "log10(|S|+1e-9) f32 [B,257,T]", "sharding": f"by clip, {world} rank(s), no collective",
+            "l2": "inputs (2.6 GB) and outputs (3.5 GB) per step exceed the 126 MB L2; no flush needed"}
+
+
+def pin_to_gpu_cpus(index: int):
+    """Bind this rank to the CPUs NVML reports as local to its GPU (pinned buffers are then first-touched from there)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1 and 64 * i + b < n}
+        numa = None
+        try:
+            numa = int(pynvml.nvmlDeviceGetNumaNodeId(h))
+        except Exception:
+            pass
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"cpus": len(cpus), "first": min(cpus) if cpus else None, "last": max(cpus) if cpus else None, "numa_node": numa}
+    except Exception as e:          # affinity is an optimisation, never a requirement
+        return {"error": str(e)[:80]}
 
 
 def main():
@@ -202,6 +266,7 @@ def main():
     ap.add_argument("--ref-clips", type=int, default=1024, help="clips per step of the CPU arm")
     ap.add_argument("--cpu-clips", type=int, default=2048, help="clips of the cpu_baseline sample (rank 0, N=1)")
     ap.add_argument("--gl-clips", type=int, default=1024, help="clips per GPU of the Griffin-Lim leg (configs[2], 32 iterations)")
+    ap.add_argument("--model-clips", type=int, default=32, help="clips per GPU of the configs[4] leg (batch 256 on 8 GPUs = 32 per GPU)")
     ap.add_argument("--no-legs", action="store_true", help="headline step only (profiling runs)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -231,11 +296,20 @@ def main():
         per = max(1, args.cpu_clips // workers)
         cpu_pass(pool, workers, 1, L, seed=7)                      # warm the workers
         v, dt = cpu_pass(pool, workers, per, L, seed=1)
+        v1, dt1 = cpu_pass(None, 1, 96, L, seed=2)                  # one process, one thread
+        tv1, tdt1 = cpu_pass(None, 1, 256, L, seed=3, fn=_torch_cpu_worker, extra=(1,))
+        tvn, tdtn = cpu_pass(pool, workers, per, L, seed=4, fn=_torch_cpu_worker, extra=(1,))
         if pool is not None:
             pool.close()
         cpu_baseline = {"value": v, "unit": "audio-s/s", "cores": workers, "kind": "port",
-                        "sample": f"{workers * per} clips x {CLIP_S:g} s of the same step ({dt:.1f} s wall), "
-                                  "oracle port (numpy + scipy.fft pocketfft, one process per core)"}
+                        "sample": f"{workers * per} clips x {CLIP_S:g} s of the same step ({dt:.1f} s, inputs generated before the clock "
+                                  "starts), oracle port (numpy + scipy.fft pocketfft = what librosa runs), one process per core",
+                        "single_thread": {"value": v1, "unit": "audio-s/s", "cores": 1, "sample": f"96 clips ({dt1:.1f} s)"},
+                        "torch_stft": {"note": "torch.stft + abs + log10 on the CPU: NOT the reference's implementation, a stronger CPU "
+                                               "baseline (SURVEY 8d); fp32",
+                                       "single_thread": {"value": tv1, "unit": "audio-s/s", "cores": 1, "sample": f"256 clips ({tdt1:.1f} s)"},
+                                       "all_cores": {"value": tvn, "unit": "audio-s/s", "cores": workers,
+                                                     "sample": f"{workers * per} clips, one single-threaded process per core ({tdtn:.1f} s)"}}}
 
     import torch
     import torch.distributed as dist
@@ -243,6 +317,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    affinity = pin_to_gpu_cpus(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -324,6 +399,12 @@ def main():
     e2e = None
     if not args.no_e2e:
         e2e = e2e_leg(args, frontend, plan, wave, starts, g, B, L, F, T, world, dev, barrier)
+        e2e["cpu_affinity"] = affinity
+    # ---- configs[4]: waveform (pinned host) -> front-end -> CNN-BLSTM -> back-end -> waveform (pinned host)
+    if not args.no_legs and args.model_clips > 0:
+        del wave, out
+        torch.cuda.empty_cache()
+        legs["cnnblstm_e2e"] = cnnblstm_leg(args, frontend, sp, world, dev, barrier)
 
     if rank == 0:
         emit_line(args, world, value, ms, B, T, roofline, cpu_baseline, e2e, clocks, legs)
@@ -463,9 +544,91 @@ def e2e_leg(args, frontend, plan, wave, starts, g, B, L, F, T, world, dev, barri
         t = torch.tensor([dt], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-    return {"value": world * B * CLIP_S / dt, "unit": "audio-s/s", "h2d_bytes_per_step": int(B * L * 4 + B * 8),
-            "d2h_bytes_per_step": int(B * F * T * 4), "ms_per_step": dt * 1e3, "steps": n_e2e,
-            "api": "ml_audio_inpainting_b200.frontend.HostPipeline.logmag_gap (pinned host in/out, 64-clip chunks on 4 streams)"}
+    # the platform's ceiling for this step at this N: the SAME chunked H2D + D2H traffic on the same streams with no kernel
+    # between the copies, all ranks at once (PCIe link per GPU + the host's memory / root complexes shared by the ranks)
+    def copy_step():
+        pipe.logmag_gap(h_wave, gaps_np, h_out, eps=EPS, copies_only=True)
+
+    copy_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        copy_step()
+    barrier()
+    dtc = (time.perf_counter() - t0) / n_e2e
+    if world > 1:
+        t = torch.tensor([dtc], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dtc = float(t.item())
+    h2d, d2h = int(B * L * 4 + B * 8), int(B * F * T * 4)
+    return {"value": world * B * CLIP_S / dt, "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "steps": n_e2e,
+            "api": "ml_audio_inpainting_b200.frontend.HostPipeline.logmag_gap (pinned host in/out, 64-clip chunks on 4 streams)",
+            "copy_ceiling": {"value": world * B * CLIP_S / dtc, "unit": "audio-s/s", "ms_per_step": dtc * 1e3,
+                             "h2d_GBps_per_gpu": h2d / dtc / 1e9, "d2h_GBps_per_gpu": d2h / dtc / 1e9,
+                             "aggregate_GBps": world * (h2d + d2h) / dtc / 1e9,
+                             "what": "the same chunked H2D + D2H copies on the same streams with no kernel, all ranks concurrently"},
+            "frac_of_copy_ceiling": dtc / dt}
+
+
+def cnnblstm_leg(args, frontend, sp, world, dev, barrier):
+    """BASELINE configs[4]: end-to-end CNN-BLSTM inference (models/model_eval.py:48-194 for a batch), 256 clips x 5 s over 8 GPUs =
+    32 per GPU: waveform in pinned host memory -> H2D -> eval_cnnlstm_batch (STFT, phase, spectrum-domain gap, log10) -> the
+    reference's StackedBLSTMCNN architecture (cnn_blstm.yaml, random init, eval; stock cuDNN, out of scope) -> blend + 10** +
+    phase reuse + iSTFT in one kernel -> D2H.  Only 2 x 320 KB per clip cross PCIe."""
+    import torch
+    import torch.distributed as dist
+    from tools.cnnblstm_model import StandInBLSTMCNN
+    Bm, L5 = args.model_clips, 80000
+    torch.manual_seed(0)
+    model = StandInBLSTMCNN().to(dev).eval()
+    gen = torch.Generator().manual_seed(4321)
+    h_wave = (0.1 * torch.randn((Bm, L5), generator=gen)).clamp_(-1, 1).pin_memory()
+    h_out = torch.empty((Bm, 79872), dtype=torch.float32).pin_memory()
+    d_wave = torch.empty((Bm, L5), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # 256 MB > L2: written between timed iterations
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+
+    def step(record=False):
+        if record: ev[0].record()
+        d_wave.copy_(h_wave, non_blocking=True)
+        if record: ev[1].record()
+        fe = frontend.eval_cnnlstm_batch(d_wave)
+        if record: ev[2].record()
+        with torch.no_grad():
+            raw = model(fe["log_impaired_magnitude"].unsqueeze(1))
+        if record: ev[3].record()
+        y = frontend.cnnblstm_backend_batch(raw, fe["log_impaired_magnitude"], fe["mask"], fe["original_phase"])
+        h_out.copy_(y, non_blocking=True)
+        if record: ev[4].record()
+
+    for _ in range(3):
+        step()
+    barrier()
+    n = max(3, min(args.steps, 10))
+    tot, parts = [], []
+    for _ in range(n):
+        flush.fill_(1)
+        barrier()
+        t0 = time.perf_counter()
+        step(record=True)
+        torch.cuda.synchronize()
+        tot.append(time.perf_counter() - t0)
+        parts.append([ev[i].elapsed_time(ev[i + 1]) for i in range(4)])
+    dt = float(np.mean(tot))
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    p = np.mean(np.array(parts), 0)
+    return {"workload": f"configs[4]: end-to-end CNN-BLSTM inference, {Bm} clips x 5 s per GPU ({world * Bm} over {world} GPU(s); batch 256 on "
+                        "8 GPUs = 32 per GPU), pinned host waveform in -> pinned host waveform out",
+            "value": world * Bm * 5.0 / dt, "unit": "audio-s/s", "ms_per_step": dt * 1e3, "steps": n,
+            "ms_h2d": float(p[0]), "ms_front_end": float(p[1]), "ms_model": float(p[2]), "ms_back_end_and_d2h": float(p[3]),
+            "front_plus_back_share": float((p[1] + p[3]) / max(p.sum(), 1e-9)),
+            "model": "tools/cnnblstm_model.py: the reference's StackedBLSTMCNN architecture (state_dict compatible), random init, fp32 eval",
+            "h2d_bytes_per_step": Bm * L5 * 4, "d2h_bytes_per_step": Bm * 79872 * 4,
+            "l2": "a 256 MB buffer is written between timed iterations"}
 
 
 def emit_line(args, world, value, ms, B, T, roofline, cpu_baseline, e2e, clocks, legs):
@@ -473,12 +636,14 @@ def emit_line(args, world, value, ms, B, T, roofline, cpu_baseline, e2e, clocks,
         "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "clips_per_gpu": B, "n_fft": N_FFT, "win_length": WIN, "hop_length": HOP,
-                   "sample_rate": SR, "clip_seconds": CLIP_S, "gap_seconds": GAP_S, "frames": T,
-                   "outputs": "log10(|S|+1e-9) f32 [B,257,T]", "sharding": f"by clip, {world} rank(s), no collective",
-                   "l2": "inputs (2.6 GB) and outputs (3.5 GB) per step exceed the 126 MB L2; no flush needed"},
+        "config": make_config(B, world),
+        "metric_note": "the timed step (value, roofline, e2e, cpu_baseline) is the forward half the metric names -- STFT -> "
+                       "log-magnitude + gap mask, BASELINE configs[1]; the inverse half (configs[2]), the STFT -> mask -> iSTFT round "
+                       "trip and configs[4] are measured in the same run and copied to the top-level keys istft / roundtrip / cnnblstm_e2e",
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": args.steps,
-        "clocks": clocks, "legs": legs,
+        "clocks": clocks,
+        "istft": legs.get("istft"), "roundtrip": legs.get("roundtrip"), "cnnblstm_e2e": legs.get("cnnblstm_e2e"),
+        "legs": {k: v for k, v in legs.items() if k not in ("istft", "roundtrip", "cnnblstm_e2e")},
     }
     print(json.dumps(line), file=_RESULT_OUT, flush=True)
 

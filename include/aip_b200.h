@@ -12,7 +12,11 @@
  *   aip_istft_f32           librosa.istft as called by utils.spectrogram_to_audio  utils.py:316-327
  *                           (complex input, or magnitude * exp(j*phase), dB / 10** / expm1 prologue)
  *   aip_istft_blend_f32     mask blend + 10** + phase reuse + istft               models/CNNBLSTM/model.py:108, models/model_eval.py:160-189
+ *   aip_istft_handoff_f32   the same for either model family (+ peak normalisation) models/GAN/train.py:470-482, models/model_eval.py:118-140
  *   aip_griffinlim_f32      librosa.griffinlim (momentum 0.99)                     utils.py:328-332
+ *   aip_griffinlim_c64_f32  librosa.griffinlim handed a COMPLEX "magnitude"        utils.py:328-332 via tests/utils_test.py:624-645
+ *   aip_mel_project_f32     librosa.feature.melspectrogram's filter-bank contraction  utils.py:268-277
+ *   aip_mel_inverse_f32     pinv(mel basis) @ mel (+ sqrt for power spectrograms)    utils.py:375-383
  *   aip_db_heuristic_f32    "max < 0 and mean < 0 => dB" test                      utils.py:313-314
  *   aip_gap_zero_f32        zero a sample range per clip                           utils.py:180-183, add_gaps.py:28-32, pre_process_dataset.py:38
  *   aip_gap_mask_f32        dense sample-domain 1/0 mask                           utils.py:141-142
@@ -27,11 +31,14 @@
  *   - spectrogram layout is the reference's: [B, F = n_fft/2 + 1, T] with T contiguous
  *     (complex as interleaved float pairs); waveforms are [B, L] rows with an explicit pitch;
  *   - return value: 0 = ok, < 0 = argument / support error (AIP_ERR_*), > 0 = cudaError_t;
- *   - re-entrant and thread-safe: the only mutable global state is a ring of 64 four-byte tile counters in device
- *     memory (the forward kernel's dynamic tile schedule); every launch takes the next one and zeroes it on its own
- *     stream, so launches are independent unless more than 64 of them are in flight at once;
- *   - there is NO CPU fallback: on a device that is not compute capability 10.x every entry point
- *     returns AIP_ERR_DEVICE.
+ *   - re-entrant and thread-safe.  The only mutable global state is the forward kernel's tile counter (dynamic tile
+ *     schedule, 4 bytes of device memory): every (device, stream) pair owns one for good, it is zeroed on that stream right
+ *     before each launch, and the zeroing + launch are enqueued under a lock -- launches on one stream are ordered by the
+ *     stream, launches on different streams or devices never share a counter, whatever number of them is in flight
+ *     (4096 distinct streams per device; one more returns cudaErrorLaunchOutOfResources);
+ *   - AIP_* environment variables (experiment switches, csrc/aip_host.h) are read once, when the library is loaded;
+ *   - there is NO CPU fallback: on a device that is not compute capability 10.0 (the library holds sm_100a code only)
+ *     every entry point returns AIP_ERR_DEVICE.
  */
 #ifndef AIP_B200_H_
 #define AIP_B200_H_
@@ -111,6 +118,20 @@ int aip_istft_blend_f32(const aip_stft_desc* desc, const float* model_out, const
                         int64_t B, int64_t T, int64_t length, const float* inv_wss,
                         float* wave_out, int64_t out_pitch,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* The model hand-off in general form: magnitudes blended with a mask in either family's convention, any magnitude domain,
+ * phase reuse, istft and -- when `peaks` is non-null -- the peak normalisation of save_audio (utils.py:84) on top.
+ *   mask_keeps_input = 0   m = model_out * mask + blend_in * (1 - mask)      mask is 1 INSIDE the gap
+ *                          (StackedBLSTMCNN.reconstruct_spectrogram, models/CNNBLSTM/model.py:108)
+ *   mask_keeps_input = 1   m = model_out * (1 - mask) + blend_in * mask      mask is 1 OUTSIDE the gap
+ *                          (combined_log_mag, models/GAN/train.py:473)
+ *   mag_domain: AIP_DOM_LINEAR (GAN/train.py:476 hands the log1p-domain blend to spectrogram_to_audio as it is),
+ *               AIP_DOM_POW10 (models/model_eval.py:163), AIP_DOM_DB, AIP_DOM_EXPM1 (undoing the GAN's log1p).
+ *   peaks: device [B] float or null; see aip_istft_normalized_f32.                                                      */
+int aip_istft_handoff_f32(const aip_stft_desc* desc, const float* model_out, const float* blend_in,
+                          const float* blend_mask, int32_t mask_keeps_input, const float* phase, int32_t mag_domain,
+                          int64_t B, int64_t T, int64_t length, const float* inv_wss,
+                          float* wave_out, int64_t out_pitch, float* peaks,
+                          void* workspace, size_t workspace_bytes, void* stream);
 /* 0 when the (n_fft, hop, center) combination runs the fused n_fft = 512 kernel. */
 size_t aip_istft_workspace_bytes(const aip_stft_desc* desc, int64_t B, int64_t T);
 
@@ -129,6 +150,26 @@ int aip_griffinlim_f32(const aip_stft_desc* desc, const float* mag, float* angle
                        int64_t B, int64_t T, int32_t n_iter, float momentum, const float* inv_wss,
                        float* wave_out, int64_t out_pitch,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* librosa.griffinlim when the caller hands it a COMPLEX matrix as "magnitude" (tests/utils_test.py:624-645 pass
+ * extract_spectrogram's complex output straight in): librosa multiplies the unit phasors by S as it is -- a complex product.
+ *   spec    [B,F,T,2] the complex "magnitude" S;  angles / tprev / workspace as for aip_griffinlim_f32, and the workspace MUST
+ *   hold the extra B*F*T*8 bytes (the rebuilt spectra ping-pong; the update runs as its own kernel).                     */
+int aip_griffinlim_c64_f32(const aip_stft_desc* desc, const float* spec, float* angles, float* tprev,
+                           int64_t B, int64_t T, int32_t n_iter, float momentum, const float* inv_wss,
+                           float* wave_out, int64_t out_pitch,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* mel_out[b, m, t] = sum_f basis[m, f] * spec_pow[b, f, t]: the contraction librosa.feature.melspectrogram applies to
+ * |stft| ** power (utils.py:268-277; spec_pow is aip_stft_fwd_f32's AIP_MAG_POW / AIP_MAG_ABS output).
+ *   basis  [n_mels, F] row major (librosa.filters.mel: triangular, so each row is non-zero on one short bin range);
+ *   bands  [n_mels, 2] int32: per row a range [f0, f1) that contains every non-zero entry of that row (host-computed).    */
+int aip_mel_project_f32(const float* basis, const int32_t* bands, const float* spec_pow, int64_t B, int64_t F, int64_t T,
+                        int64_t n_mels, float* mel_out, void* stream);
+/* out[b, f, t] = sum_m inv_basis[f, m] * mel[b, m, t], then sqrt() when take_sqrt != 0 (utils.py:375-383: pinv of the mel
+ * basis applied to a mel spectrogram; negative projections become NaN under the square root exactly as np.sqrt does). */
+int aip_mel_inverse_f32(const float* inv_basis, const float* mel, int64_t B, int64_t F, int64_t T, int64_t n_mels,
+                        int32_t take_sqrt, float* out, void* stream);
 
 /* flags[b] = (max(x_b) < 0 && mean(x_b) < 0), x_b = x[b*n .. (b+1)*n). */
 int aip_db_heuristic_f32(const float* x, int64_t B, int64_t n, int32_t* flags, void* stream);
@@ -172,10 +213,13 @@ int aip_stft_gap_variants_f32(const aip_stft_desc* desc, const float* wave, int6
 int aip_peak_normalize_f32(const float* in, int64_t in_pitch, float* out, int64_t out_pitch,
                            int64_t B, int64_t L, float* peaks, void* stream);
 
+/* Re-read the AIP_* experiment switches from the environment (they are otherwise read once, at load).  For A/B timing
+ * scripts and the tests of alternative kernels; not thread-safe against concurrent launches.                         */
+void aip_debug_reload_env(void);
 const char* aip_status_string(int status);
 /* "aip_b200 <version> sm_100a" */
 const char* aip_version(void);
-/* 1 when the current device can run the kernels (compute capability 10.x), else 0. */
+/* 1 when the current device can run the kernels (compute capability 10.0), else 0. */
 int aip_device_supported(void);
 
 #ifdef __cplusplus

@@ -211,7 +211,7 @@ int emul_istft512(const float* spec, const float* mag, const float* phase, int m
     for (int tid = 0; tid < kThreads; ++tid) {
       switch (inv_mode_of(P)) {
 #define AIP_CASE(M) case (M): inv_phase0<(M)>(P, tid, c, exch.data(), pw[tid], rel); break;
-        AIP_CASE(INV_SPEC) AIP_CASE(1) AIP_CASE(2) AIP_CASE(3) AIP_CASE(4) AIP_CASE(5) AIP_CASE(6) AIP_CASE(INV_BLEND)
+        AIP_CASE(INV_SPEC) AIP_CASE(1) AIP_CASE(2) AIP_CASE(3) AIP_CASE(4) AIP_CASE(5) AIP_CASE(6) AIP_CASE(INV_BLEND) AIP_CASE(INV_BLEND_LIN) AIP_CASE(INV_BLEND_EXPM1)
 #undef AIP_CASE
       }
     }

@@ -580,11 +580,13 @@ AIP_HD void inv_load_runtime(const InvParams& P, long long idx, bool db, float& 
 constexpr int INV_SPEC = 0;
 constexpr int INV_BLEND = 7;
 constexpr int INV_GL = 8;       // complex input + the Griffin-Lim phase update (InvLoadGL)
+constexpr int INV_BLEND_LIN = 9;     // the hand-off with the blended magnitude used as it is (models/GAN/train.py:473-482) ...
+constexpr int INV_BLEND_EXPM1 = 10;  // ... or through expm1 (the inverse of the GAN front-end's log1p)
 AIP_HDX constexpr int inv_mag_mode(int dom, bool phase) { return 1 + 2 * dom + (phase ? 1 : 0); }
 
 AIP_HDX int inv_mode_of(const InvParams& P) {
   if (P.spec) return P.gl_mag ? INV_GL : INV_SPEC;
-  if (P.blend_in) return INV_BLEND;
+  if (P.blend_in) return P.mag_domain == DOM_LINEAR ? INV_BLEND_LIN : (P.mag_domain == DOM_EXPM1 ? INV_BLEND_EXPM1 : INV_BLEND);
   const int dom = (P.mag_domain == DOM_LINEAR) ? 0 : (P.mag_domain == DOM_EXPM1 ? 2 : 1);
   return inv_mag_mode(dom, P.phase != nullptr);
 }
@@ -607,9 +609,10 @@ AIP_HD void inv_phase0(const InvParams& P, int tid, const TileCursor& c, float2*
   } else if (kMode == INV_GL) {
     InvLoadGL load{P.spec, P.gl_prev, P.gl_mag, col, P.T, P.gl_alpha, 0, 0, 0};
     inv_stageA(exch, w, lane, warp, live, load, before_store);
-  } else if (kMode == INV_BLEND) {
-    InvLoadMag<1, true, true> load{P.mag + col, P.phase + col, P.blend_in + col, P.blend_mask + col, P.T,
-                                   P.mag_domain == DOM_DB ? kLog2of10 * 0.05f : kLog2of10, false, 0, 0, 0};
+  } else if (kMode == INV_BLEND || kMode == INV_BLEND_LIN || kMode == INV_BLEND_EXPM1) {
+    constexpr int kDom = kMode == INV_BLEND ? 1 : (kMode == INV_BLEND_LIN ? 0 : 2);
+    InvLoadMag<kDom, true, true> load{P.mag + col, P.phase + col, P.blend_in + col, P.blend_mask + col, P.T,
+                                      P.mag_domain == DOM_DB ? kLog2of10 * 0.05f : kLog2of10, false, 0, 0, 0};
     inv_stageA(exch, w, lane, warp, live, load, before_store);
   } else {
     constexpr int kDom = (kMode - 1) >> 1;

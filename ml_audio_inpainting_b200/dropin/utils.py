@@ -162,106 +162,78 @@ def extract_spectrogram(audio_data: np.ndarray, n_fft: int = 2048, hop_length: i
     return S if audio_data.dtype == np.float32 else S.astype(np.complex128)
 
 
-def _mel_basis(sample_rate, n_fft, n_mels, fmin, fmax):
-    """librosa.filters.mel (Slaney scale, norm='slaney') -- host-side table, float32 [n_mels, 1 + n_fft/2]."""
-    if fmax is None:
-        fmax = float(sample_rate) / 2
-
-    def hz_to_mel(f):
-        f = np.asanyarray(f, dtype=np.float64)
-        mel = f / (200.0 / 3)
-        min_log_hz, logstep = 1000.0, np.log(6.4) / 27.0
-        min_log_mel = min_log_hz / (200.0 / 3)
-        return np.where(f >= min_log_hz, min_log_mel + np.log(np.maximum(f, 1e-300) / min_log_hz) / logstep, mel)
-
-    def mel_to_hz(m):
-        m = np.asanyarray(m, dtype=np.float64)
-        f = (200.0 / 3) * m
-        min_log_hz, logstep = 1000.0, np.log(6.4) / 27.0
-        min_log_mel = min_log_hz / (200.0 / 3)
-        return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f)
-
-    n_bins = 1 + n_fft // 2
-    fftfreqs = np.fft.rfftfreq(n=n_fft, d=1.0 / sample_rate)
-    mel_f = mel_to_hz(np.linspace(hz_to_mel(fmin), hz_to_mel(fmax), n_mels + 2))
-    fdiff = np.diff(mel_f)
-    ramps = np.subtract.outer(mel_f, fftfreqs)
-    weights = np.zeros((n_mels, n_bins), dtype=np.float64)
-    for i in range(n_mels):
-        lower = -ramps[i] / fdiff[i]
-        upper = ramps[i + 2] / fdiff[i + 1]
-        weights[i] = np.maximum(0, np.minimum(lower, upper))
-    enorm = 2.0 / (mel_f[2:n_mels + 2] - mel_f[:n_mels])
-    weights *= enorm[:, np.newaxis]
-    return weights.astype(np.float32)
-
-
 def extract_mel_spectrogram(audio_data: np.ndarray, sample_rate: int = DEFAULT_SAMPLE_RATE, n_fft: int = 2048,
                             hop_length: int = 512, n_mels: int = 128, fmin: float = 0.0,
                             fmax: Optional[float] = None, power: float = 2.0) -> np.ndarray:
-    """reference utils.py:236-277 (librosa.feature.melspectrogram): |STFT| ** power on the device, then the
-    mel projection as one library GEMM (no model script calls this)."""
+    """reference utils.py:236-277 (librosa.feature.melspectrogram with its defaults: hann window of n_fft taps, centred,
+    Slaney mel basis): |STFT| ** power in the forward kernel's epilogue, then the filter-bank contraction
+    (``aip_mel_project_f32``)."""
     if power < 0:
         raise ValueError("Power must be non-negative")
+    audio_data = np.asarray(audio_data)
     torch = _torch()
     sp = _spectral()
     plan = sp.get_plan(n_fft, hop_length, n_fft, "hann", True)
     x = torch.from_numpy(np.ascontiguousarray(audio_data, dtype=np.float32)).to(plan.device)
     mag = sp.stft(x, plan, mag_kind=sp.MAG_POW, power=float(power), want_spec=False)["mag"]
-    basis = torch.from_numpy(_mel_basis(sample_rate, n_fft, n_mels, fmin, fmax)).to(plan.device)
-    return (basis @ mag).cpu().numpy()
+    mel = sp.mel_project(mag, sample_rate, n_fft, n_mels, fmin, fmax).cpu().numpy()
+    return mel if audio_data.dtype == np.float32 else mel.astype(np.float64)
 
 
 def spectrogram_to_audio(spectrogram: np.ndarray, phase: Optional[np.ndarray] = None, phase_info: bool = False,
                          n_fft: int = 512, n_iter: int = 64, window: str = "hann", hop_length: int = 512,
                          win_length: Optional[int] = None, center: bool = True) -> np.ndarray:
     """reference utils.py:279-333: dB heuristic, then complex iSTFT / magnitude * exp(j phase) iSTFT /
-    Griffin-Lim (n_iter, momentum 0.99, random initial phases drawn on the device)."""
+    Griffin-Lim (n_iter, momentum 0.99, random initial phases drawn on the device).  The result has the dtype librosa
+    would return (float64 for float64 / complex128 input or a float64 phase, else float32); the arithmetic is fp32."""
     torch = _torch()
     sp = _spectral()
     spectrogram = np.asarray(spectrogram)
     plan = sp.get_plan(n_fft, hop_length, win_length, window, center)
     dev = plan.device
     is_complex = np.iscomplexobj(spectrogram)
+    wide = spectrogram.dtype in (np.float64, np.complex128) or \
+        (not phase_info and phase is not None and np.asarray(phase).dtype == np.float64)
+    out_dtype = np.float64 if wide else np.float32
     if is_complex:
         # np.max / np.mean of a complex array compare real parts first; the dB test is meant for real input
         if np.max(spectrogram) < 0 and np.mean(spectrogram) < 0:        # utils.py:313-314
             spectrogram = np.power(10.0, 0.05 * spectrogram)
         S = torch.from_numpy(np.ascontiguousarray(spectrogram, dtype=np.complex64)).to(dev)
         if phase_info:                                                  # utils.py:316-318
-            return sp.istft(plan, spec=S).cpu().numpy()
+            return sp.istft(plan, spec=S).cpu().numpy().astype(out_dtype, copy=False)
         if phase is not None:                                           # utils.py:321-327
             S = S * torch.from_numpy(np.exp(1j * np.asarray(phase)).astype(np.complex64)).to(dev)
-            return sp.istft(plan, spec=S).cpu().numpy()
-        raise NotImplementedError("Griffin-Lim on a complex 'magnitude' is not implemented on the GPU path")
+            return sp.istft(plan, spec=S).cpu().numpy().astype(out_dtype, copy=False)
+        # utils.py:328-332 on a complex "magnitude" (tests/utils_test.py:624-645): librosa multiplies the phasors by it as it is
+        return sp.griffinlim(plan, S, n_iter=n_iter).cpu().numpy().astype(out_dtype, copy=False)
     mag = torch.from_numpy(np.ascontiguousarray(spectrogram, dtype=np.float32)).to(dev)
     flags = sp.db_heuristic(mag.reshape(1, -1))                         # utils.py:313-314, on the device
     if phase_info:
         # librosa.istft of a real matrix: zero imaginary part
-        return sp.istft(plan, mag=mag, phase=None, db_auto=True).cpu().numpy()
+        return sp.istft(plan, mag=mag, phase=None, db_auto=True).cpu().numpy().astype(out_dtype, copy=False)
     if phase is not None:
         ph = torch.from_numpy(np.ascontiguousarray(phase, dtype=np.float32)).to(dev)
-        return sp.istft(plan, mag=mag, phase=ph, db_auto=True).cpu().numpy()
+        return sp.istft(plan, mag=mag, phase=ph, db_auto=True).cpu().numpy().astype(out_dtype, copy=False)
     if int(flags.item()):
         mag = torch.pow(10.0, 0.05 * mag)
-    return sp.griffinlim(plan, mag, n_iter=n_iter).cpu().numpy()       # utils.py:328-332
+    return sp.griffinlim(plan, mag, n_iter=n_iter).cpu().numpy().astype(out_dtype, copy=False)       # utils.py:328-332
 
 
 def mel_spectrogram_to_audio(mel_spectrogram: np.ndarray, sample_rate: int = DEFAULT_SAMPLE_RATE,
                              n_fft: int = 2048, hop_length: int = 512, n_iter: int = 32, n_mels: int = 128,
                              fmin: float = 0.0, fmax: Optional[float] = None, power: float = 2.0) -> np.ndarray:
-    """reference utils.py:335-393: pinv(mel basis) projection (host, tiny), sqrt for power spectrograms,
-    Griffin-Lim on the device."""
+    """reference utils.py:335-393: pinv(mel basis) @ mel and the square root for power spectrograms on the device
+    (``aip_mel_inverse_f32``), then Griffin-Lim (hann window of n_fft taps, centred, random initial phases).  As in the
+    reference, a negative projection becomes NaN under ``sqrt`` and spreads through Griffin-Lim."""
     torch = _torch()
     sp = _spectral()
-    inv = np.linalg.pinv(_mel_basis(sample_rate, n_fft, n_mels, fmin, fmax))
-    linear_spec = np.dot(inv, np.asarray(mel_spectrogram, dtype=np.float32))
-    if power == 2.0:
-        linear_spec = np.sqrt(linear_spec)
-    linear_spec = np.nan_to_num(linear_spec, nan=0.0)
+    mel_spectrogram = np.asarray(mel_spectrogram)
     plan = sp.get_plan(n_fft, hop_length, n_fft, "hann", True)
-    mag = torch.from_numpy(np.ascontiguousarray(linear_spec, dtype=np.float32)).to(plan.device)
-    return sp.griffinlim(plan, mag, n_iter=n_iter).cpu().numpy()
+    mel = torch.from_numpy(np.ascontiguousarray(mel_spectrogram, dtype=np.float32)).to(plan.device)
+    mag = sp.mel_inverse(mel, sample_rate, n_fft, n_mels, fmin, fmax, take_sqrt=(power == 2.0))
+    out = sp.griffinlim(plan, mag, n_iter=n_iter).cpu().numpy()
+    return out if mel_spectrogram.dtype != np.float64 else out.astype(np.float64)
 
 
 def visualize_spectrogram(*args, **kwargs):

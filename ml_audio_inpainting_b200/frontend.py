@@ -8,7 +8,7 @@ into the transform kernels and run for a whole batch of clips per launch.
   eval_cnnlstm_batch  models/model_eval.py:146-154       (spectrum-domain gap)
   eval_gan_batch      models/model_eval.py:61-111
   backend_batch       models/model_eval.py:131-140, :180-189 -> utils.spectrogram_to_audio(phase=...)
-  HostPipeline        host-buffer entry (pinned in / pinned out), H2D | kernel | D2H overlapped on 3 streams
+  HostPipeline        host-buffer entry (pinned in / pinned out), H2D | kernel | D2H overlapped on 4 streams
 
 All random draws come from the GLOBAL ``np.random`` stream in the reference's order (one draw per
 item; a vectorised ``randint(size=B)`` yields the same numbers as B scalar draws), and every index
@@ -199,8 +199,9 @@ def cnnblstm_backend_batch(model_out: torch.Tensor, log_spectrogram_gap: torch.T
 class HostPipeline:
     """Host-buffer entry point of the front-end: pinned host waveforms in, pinned host spectrograms out.
 
-    The batch is cut into chunks; chunk i's H2D copy, kernel and D2H copy run on stream i % 3 with
-    per-stream device buffers, so copies of neighbouring chunks overlap the kernel (PCIe is the bound)."""
+    The batch is cut into chunks; chunk i's H2D copy, kernel and D2H copy run on stream i % n_streams (4 by default) with
+    per-stream device buffers, so copies of neighbouring chunks overlap the kernel (PCIe is the bound).  Every stream owns
+    its own forward tile counter (aip_b200.h), so any number of chunks may be in flight."""
 
     def __init__(self, plan: sp.StftPlan, batch: int, n_samples: int, chunk: int = 64, n_streams: int = 4,
                  t_out: Optional[int] = None):
@@ -217,8 +218,9 @@ class HostPipeline:
         self.h_gaps = torch.empty((self.B, 2), dtype=torch.int32, pin_memory=True)
 
     def logmag_gap(self, h_wave: torch.Tensor, gap_samples: np.ndarray, h_out: torch.Tensor, eps: float = 1e-9,
-                   mag_kind: int = sp.MAG_LOG10_EPS) -> torch.Tensor:
-        """h_out[b] = log10(|stft(h_wave[b] with samples [g0,g1) zeroed)| + eps); returns h_out after a sync."""
+                   mag_kind: int = sp.MAG_LOG10_EPS, copies_only: bool = False) -> torch.Tensor:
+        """h_out[b] = log10(|stft(h_wave[b] with samples [g0,g1) zeroed)| + eps); returns h_out after a sync.
+        ``copies_only`` skips the kernel and moves the same bytes: the host / PCIe ceiling of this call (bench.py)."""
         if h_wave.is_cuda or h_out.is_cuda:
             raise ValueError("HostPipeline takes HOST tensors (pinned for speed)")
         if tuple(h_wave.shape) != (self.B, self.L) or tuple(h_out.shape) != (self.B, self.plan.n_bins, self.t_out):
@@ -234,8 +236,9 @@ class HostPipeline:
             with torch.cuda.stream(self.streams[k]):
                 self.d_wave[k][:n].copy_(h_wave[lo:hi], non_blocking=True)
                 self.d_gaps[k][:n].copy_(self.h_gaps[lo:hi], non_blocking=True)
-                sp.stft(self.d_wave[k][:n], self.plan, gap_samples=self.d_gaps[k][:n], mag_kind=mag_kind, eps=eps,
-                        t_out=self.t_out, want_spec=False, out={"mag": self.d_mag[k][:n]})
+                if not copies_only:
+                    sp.stft(self.d_wave[k][:n], self.plan, gap_samples=self.d_gaps[k][:n], mag_kind=mag_kind, eps=eps,
+                            t_out=self.t_out, want_spec=False, out={"mag": self.d_mag[k][:n]})
                 h_out[lo:hi].copy_(self.d_mag[k][:n], non_blocking=True)
         for s in self.streams:
             cur.wait_stream(s)

@@ -41,7 +41,7 @@ def preprocess_batch(wave: torch.Tensor, gap_len: float = 0.1, sample_rate: int 
     sam = np.stack([starts, starts + g], 1)
     sam_d = torch.as_tensor(sam.astype(np.int32), device=wave.device)
     lib = _cabi.load()
-    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    st = C.c_void_p(torch.cuda.current_stream(wave.device).cuda_stream)      # the stream of the tensors' device
     out = torch.empty_like(wave)
     with torch.cuda.device(wave.device):
         _cabi.check(lib.aip_gap_zero_f32(wave.data_ptr(), wave.stride(0), out.data_ptr(), out.stride(0), N, L,
@@ -65,10 +65,17 @@ def preprocess_batch(wave: torch.Tensor, gap_len: float = 0.1, sample_rate: int 
     return res
 
 
+DECODABLE = (".flac", ".wav")        # containers the built-in reader handles (audio_io); the reference lists ".mp3" too
+
+
 def preprocess_tree(src_root, dst_root, gap_len: float = 0.1, sample_rate: int = 16000, max_len: float = 5,
                     supported_formats=(".flac", ".wav"), batch: int = 256, device=None, progress: bool = True):
-    """The reference's loop with the device doing the arithmetic: files are visited in os.walk order, one
-    np.random draw per file in that order, results written under ``dst_root`` mirroring the tree."""
+    """The reference's loop (pre_process_dataset.py:19-43) with the device doing the arithmetic: files are visited in
+    os.walk order, one np.random draw per file in that order, results written under ``dst_root`` mirroring the tree.
+
+    Like ``utils.save_audio`` (utils.py:54-89, ``file_format='flac'``) every output holds FLAC data whatever its suffix.
+    A file whose suffix is in ``supported_formats`` but which the built-in reader cannot decode (".mp3": the reference
+    decodes it through librosa / audioread) is skipped with a warning and consumes no random draw."""
     src_root, dst_root = Path(src_root), Path(dst_root)
     device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
     jobs = []
@@ -79,6 +86,9 @@ def preprocess_tree(src_root, dst_root, gap_len: float = 0.1, sample_rate: int =
         if len(subdirs) == 0:
             for f in files:
                 if Path(f).suffix in supported_formats:
+                    if Path(f).suffix.lower() not in DECODABLE:
+                        print(f"Warning: {Path(root) / f}: no built-in decoder for this container, skipped")
+                        continue
                     jobs.append((Path(root) / f, dest / f))
     L = int(sample_rate * max_len)
     g = gaps.gap_len_samples(gap_len, sample_rate)
@@ -104,5 +114,5 @@ def preprocess_tree(src_root, dst_root, gap_len: float = 0.1, sample_rate: int =
         res = preprocess_batch(torch.from_numpy(host).to(device), gap_len, sample_rate, starts=starts_all[b0:b1])
         out = res["audio_gap_normalized"].cpu().numpy()
         for (_, dst), y in zip(jobs[b0:b1], out):
-            audio_io.write_audio(dst, y, sample_rate, Path(dst).suffix.lstrip(".") or "flac")
+            audio_io.write_audio(dst, y, sample_rate, "flac")           # utils.save_audio's default format, utils.py:59
     return len(jobs)

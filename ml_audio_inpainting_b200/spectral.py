@@ -13,7 +13,9 @@ Layout: waveforms ``[B, L]`` float32, spectrograms ``[B, F, T]`` (T contiguous, 
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Dict, Optional, Tuple
 
@@ -26,6 +28,7 @@ from ._cabi import (DOM_DB, DOM_EXPM1, DOM_LINEAR, DOM_POW10, MAG_ABS, MAG_LOG10
                     MAG_NONE, MAG_POW, StftDesc, check)
 
 __all__ = ["StftPlan", "get_plan", "stft", "stft_gap_variants", "istft", "istft_blend", "griffinlim", "db_heuristic", "fft_window",
+           "mel_basis", "mel_project", "mel_inverse", "experiment_env",
            "MAG_NONE", "MAG_ABS", "MAG_LOG10_EPS", "MAG_LOG1P_POW", "MAG_POW",
            "DOM_LINEAR", "DOM_POW10", "DOM_DB", "DOM_EXPM1"]
 
@@ -44,6 +47,29 @@ def fft_window(window, win_length: int, n_fft: int) -> np.ndarray:
         raise ValueError(f"Target size ({n_fft}) must be at least input size ({win_length})")
     lpad = (n_fft - win_length) // 2
     return np.pad(w, (lpad, n_fft - win_length - lpad))
+
+
+@contextlib.contextmanager
+def experiment_env(**env):
+    """A/B experiments and tests of alternative kernels: set ``AIP_*`` switches (``None`` unsets one), make the library
+    re-read them (it reads its environment once, at load: ``aip_debug_reload_env``), restore both on exit."""
+    lib = _cabi.load()
+    saved = {k: os.environ.get(k) for k in env}
+    try:
+        for k, v in env.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = str(v)
+        lib.aip_debug_reload_env()
+        yield
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        lib.aip_debug_reload_env()
 
 
 def _require_cuda(t: torch.Tensor, name: str) -> None:
@@ -85,7 +111,7 @@ class StftPlan:
     device: torch.device
     window_dev: torch.Tensor = field(repr=False, default=None)
     desc: StftDesc = field(repr=False, default=None)
-    _inv_wss: Dict[Tuple[int, int], torch.Tensor] = field(repr=False, default_factory=dict)
+    _inv_wss: Dict[Tuple[int, int], Tuple[torch.Tensor, "torch.cuda.Event"]] = field(repr=False, default_factory=dict)
 
     @property
     def n_bins(self) -> int:
@@ -103,15 +129,23 @@ class StftPlan:
 
     def inv_wss(self, n_frames: int, length: Optional[int] = None) -> torch.Tensor:
         key = (int(n_frames), int(length or 0))
-        t = self._inv_wss.get(key)
-        if t is None:
+        hit = self._inv_wss.get(key)
+        cur = torch.cuda.current_stream(self.device)
+        if hit is None:
             out_len = self.istft_length(n_frames, length)
             t = torch.empty(out_len, dtype=torch.float32, device=self.device)
-            check(_cabi.load().aip_inv_window_sumsquare_f32(C.byref(self.desc), key[0], key[1], _ptr(t),
-                                                            out_len, _stream()), "aip_inv_window_sumsquare_f32")
+            with torch.cuda.device(self.device):
+                check(_cabi.load().aip_inv_window_sumsquare_f32(C.byref(self.desc), key[0], key[1], _ptr(t),
+                                                                out_len, C.c_void_p(cur.cuda_stream)),
+                      "aip_inv_window_sumsquare_f32")
+                ready = torch.cuda.Event()
+                ready.record(cur)
             if len(self._inv_wss) > 64:
                 self._inv_wss.clear()
-            self._inv_wss[key] = t
+            self._inv_wss[key] = (t, ready)
+            return t
+        t, ready = hit
+        cur.wait_event(ready)      # the table was filled on whichever stream asked first: order later readers after that fill
         return t
 
 
@@ -339,9 +373,17 @@ def istft(plan: StftPlan, spec: Optional[torch.Tensor] = None, mag: Optional[tor
 
 
 def istft_blend(plan: StftPlan, model_out: torch.Tensor, blend_in: torch.Tensor, blend_mask: torch.Tensor,
-                phase: torch.Tensor, mag_domain: int = DOM_POW10, length: Optional[int] = None) -> torch.Tensor:
-    """istft(10 ** (model_out * mask + blend_in * (1 - mask)) * exp(j * phase)): the CNN-BLSTM hand-off
-    (reference models/CNNBLSTM/model.py:108 + models/model_eval.py:163, :179-189) in one kernel."""
+                phase: torch.Tensor, mag_domain: int = DOM_POW10, length: Optional[int] = None,
+                mask_keeps_input: bool = False, normalize: bool = False,
+                peaks_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The model hand-off in one kernel (``aip_istft_handoff_f32``): blend, un-log, phase reuse, istft.
+
+    ``mask_keeps_input=False``: ``m = model_out * mask + blend_in * (1 - mask)`` -- the CNN-BLSTM convention, mask 1 inside
+    the gap (reference models/CNNBLSTM/model.py:108; ``mag_domain=DOM_POW10`` adds models/model_eval.py:163).
+    ``mask_keeps_input=True``: ``m = model_out * (1 - mask) + blend_in * mask`` -- the GAN convention, mask 1 outside the gap
+    (``combined_log_mag``, models/GAN/train.py:473; the reference then hands the log1p-domain blend to
+    ``spectrogram_to_audio`` as it is: ``mag_domain=DOM_LINEAR``; ``DOM_EXPM1`` undoes the log1p instead).
+    ``normalize`` adds ``save_audio``'s peak normalisation (utils.py:84)."""
     ts = []
     for name, t in (("model_out", model_out), ("blend_in", blend_in), ("blend_mask", blend_mask), ("phase", phase)):
         _require_cuda(t, name)
@@ -359,10 +401,15 @@ def istft_blend(plan: StftPlan, model_out: torch.Tensor, blend_in: torch.Tensor,
     inv = plan.inv_wss(T, length)
     ws_bytes = int(lib.aip_istft_workspace_bytes(C.byref(plan.desc), B, T))
     ws = torch.empty(max(ws_bytes, 4) // 4, dtype=torch.float32, device=dev) if ws_bytes else None
+    peaks = None
+    if normalize:
+        peaks = peaks_out if peaks_out is not None else torch.empty(B, dtype=torch.float32, device=dev)
+        if tuple(peaks.shape) != (B,) or peaks.dtype != torch.float32 or not peaks.is_contiguous():
+            raise ValueError("peaks_out must be a contiguous float32 [B] tensor")
     with torch.cuda.device(dev):
-        check(lib.aip_istft_blend_f32(C.byref(plan.desc), _ptr(ts[0]), _ptr(ts[1]), _ptr(ts[2]), _ptr(ts[3]),
-                                      int(mag_domain), B, T, int(length or 0), _ptr(inv), _ptr(out), out.stride(0),
-                                      _ptr(ws), ws_bytes, _stream()), "aip_istft_blend_f32")
+        check(lib.aip_istft_handoff_f32(C.byref(plan.desc), _ptr(ts[0]), _ptr(ts[1]), _ptr(ts[2]), int(bool(mask_keeps_input)),
+                                        _ptr(ts[3]), int(mag_domain), B, T, int(length or 0), _ptr(inv), _ptr(out),
+                                        out.stride(0), _ptr(peaks), _ptr(ws), ws_bytes, _stream()), "aip_istft_handoff_f32")
     return out[0] if squeeze else out
 
 
@@ -377,9 +424,8 @@ def griffinlim(plan: StftPlan, mag: torch.Tensor, n_iter: int = 32, momentum: fl
     squeeze = mag.ndim == 2
     if squeeze:
         mag = mag.unsqueeze(0)
-    if torch.is_complex(mag):
-        raise NotImplementedError("griffinlim on a complex 'magnitude' is not implemented on the GPU path")
-    mag = mag.to(torch.float32).contiguous()
+    is_cplx = torch.is_complex(mag)      # librosa multiplies by whatever it is handed (tests/utils_test.py:624-645)
+    mag = mag.to(torch.complex64 if is_cplx else torch.float32).contiguous()
     B, F, T = mag.shape
     dev = mag.device
     if init_angles is not None:
@@ -400,8 +446,100 @@ def griffinlim(plan: StftPlan, mag: torch.Tensor, n_iter: int = 32, momentum: fl
     ws_bytes = ((int(lib.aip_istft_workspace_bytes(C.byref(plan.desc), B, T)) + 15) // 16) * 16 + B * F * T * 8
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        check(lib.aip_griffinlim_f32(C.byref(plan.desc), _ptr(mag), _ptr(ang.view(torch.float32)),
-                                     _ptr(tprev.view(torch.float32)), B, T, int(n_iter), float(momentum),
-                                     _ptr(inv), _ptr(out), out.stride(0), _ptr(ws), ws_bytes, _stream()),
-              "aip_griffinlim_f32")
+        if is_cplx:
+            check(lib.aip_griffinlim_c64_f32(C.byref(plan.desc), _ptr(torch.view_as_real(mag)), _ptr(ang.view(torch.float32)),
+                                             _ptr(tprev.view(torch.float32)), B, T, int(n_iter), float(momentum),
+                                             _ptr(inv), _ptr(out), out.stride(0), _ptr(ws), ws_bytes, _stream()),
+                  "aip_griffinlim_c64_f32")
+        else:
+            check(lib.aip_griffinlim_f32(C.byref(plan.desc), _ptr(mag), _ptr(ang.view(torch.float32)),
+                                         _ptr(tprev.view(torch.float32)), B, T, int(n_iter), float(momentum),
+                                         _ptr(inv), _ptr(out), out.stride(0), _ptr(ws), ws_bytes, _stream()),
+                  "aip_griffinlim_f32")
+    return out[0] if squeeze else out
+
+
+# --- mel (librosa.filters.mel / feature.melspectrogram; reference utils.py:236-277, :335-393) -----------------------
+
+_mel_cache: Dict[tuple, tuple] = {}
+
+
+def mel_basis(sr: float, n_fft: int, n_mels: int = 128, fmin: float = 0.0, fmax: Optional[float] = None) -> np.ndarray:
+    """librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax) with its defaults (Slaney scale, norm='slaney', float32):
+    a host-side parameter table like the window [n_mels, 1 + n_fft // 2]."""
+    if fmax is None:
+        fmax = float(sr) / 2
+
+    def hz_to_mel(f):
+        f = np.asanyarray(f, dtype=np.float64)
+        lin = f / (200.0 / 3)
+        return np.where(f >= 1000.0, 15.0 + np.log(np.maximum(f, 1e-300) / 1000.0) / (np.log(6.4) / 27.0), lin)
+
+    def mel_to_hz(m):
+        m = np.asanyarray(m, dtype=np.float64)
+        return np.where(m >= 15.0, 1000.0 * np.exp((np.log(6.4) / 27.0) * (m - 15.0)), (200.0 / 3) * m)
+
+    n_bins = 1 + n_fft // 2
+    fftfreqs = np.fft.rfftfreq(n=n_fft, d=1.0 / sr)
+    mel_f = mel_to_hz(np.linspace(hz_to_mel(fmin), hz_to_mel(fmax), int(n_mels) + 2))
+    fdiff = np.diff(mel_f)
+    ramps = np.subtract.outer(mel_f, fftfreqs)
+    weights = np.zeros((int(n_mels), n_bins), dtype=np.float32)          # float32 from the start, as librosa builds it
+    for i in range(int(n_mels)):
+        weights[i] = np.maximum(0, np.minimum(-ramps[i] / fdiff[i], ramps[i + 2] / fdiff[i + 1]))
+    weights *= (2.0 / (mel_f[2:int(n_mels) + 2] - mel_f[:int(n_mels)]))[:, np.newaxis]
+    return weights
+
+
+def _mel_tables(sr, n_fft, n_mels, fmin, fmax, device):
+    key = (float(sr), int(n_fft), int(n_mels), float(fmin), None if fmax is None else float(fmax), device.index)
+    hit = _mel_cache.get(key)
+    if hit is None:
+        w = mel_basis(sr, n_fft, n_mels, fmin, fmax)
+        nz = w != 0
+        f0 = np.where(nz.any(1), nz.argmax(1), 0)
+        f1 = np.where(nz.any(1), w.shape[1] - nz[:, ::-1].argmax(1), 0)
+        bands = np.stack([f0, f1], 1).astype(np.int32)
+        inv = np.linalg.pinv(w).astype(np.float32)                       # utils.py:375 (host: a parameter table)
+        hit = (torch.from_numpy(w).to(device), torch.from_numpy(bands).to(device), torch.from_numpy(np.ascontiguousarray(inv)).to(device))
+        if len(_mel_cache) > 16:
+            _mel_cache.clear()
+        _mel_cache[key] = hit
+    return hit
+
+
+def mel_project(spec_pow: torch.Tensor, sr: float, n_fft: int, n_mels: int = 128, fmin: float = 0.0,
+                fmax: Optional[float] = None) -> torch.Tensor:
+    """mel[b, m, t] = sum_f basis[m, f] * spec_pow[b, f, t] (``aip_mel_project_f32``): the contraction of
+    librosa.feature.melspectrogram (utils.py:268-277) on ``|stft| ** power`` [B, F, T] -> [B, n_mels, T]."""
+    _require_cuda(spec_pow, "spec_pow")
+    squeeze = spec_pow.ndim == 2
+    s = (spec_pow.unsqueeze(0) if squeeze else spec_pow).to(torch.float32).contiguous()
+    B, F, T = s.shape
+    if F != 1 + n_fft // 2:
+        raise ValueError(f"expected {1 + n_fft // 2} frequency bins for n_fft={n_fft}, got {F}")
+    basis, bands, _ = _mel_tables(sr, n_fft, n_mels, fmin, fmax, s.device)
+    out = torch.empty((B, int(n_mels), T), dtype=torch.float32, device=s.device)
+    with torch.cuda.device(s.device):
+        check(_cabi.load().aip_mel_project_f32(_ptr(basis), _ptr(bands), _ptr(s), B, F, T, int(n_mels), _ptr(out), _stream()),
+              "aip_mel_project_f32")
+    return out[0] if squeeze else out
+
+
+def mel_inverse(mel: torch.Tensor, sr: float, n_fft: int, n_mels: int = 128, fmin: float = 0.0,
+                fmax: Optional[float] = None, take_sqrt: bool = False) -> torch.Tensor:
+    """pinv(mel basis) @ mel (+ sqrt for power spectrograms): utils.py:375-383 on the device (``aip_mel_inverse_f32``).
+    Negative projections become NaN under the square root, exactly as ``np.sqrt`` makes them in the reference."""
+    _require_cuda(mel, "mel")
+    squeeze = mel.ndim == 2
+    m = (mel.unsqueeze(0) if squeeze else mel).to(torch.float32).contiguous()
+    B, M, T = m.shape
+    if M != int(n_mels):
+        raise ValueError(f"shapes ({1 + n_fft // 2},{int(n_mels)}) and ({M},{T}) not aligned")
+    F = 1 + n_fft // 2
+    _, _, inv = _mel_tables(sr, n_fft, n_mels, fmin, fmax, m.device)
+    out = torch.empty((B, F, T), dtype=torch.float32, device=m.device)
+    with torch.cuda.device(m.device):
+        check(_cabi.load().aip_mel_inverse_f32(_ptr(inv), _ptr(m), B, F, T, int(n_mels), int(bool(take_sqrt)), _ptr(out),
+                                               _stream()), "aip_mel_inverse_f32")
     return out[0] if squeeze else out

@@ -89,7 +89,7 @@ def test_istft_fused_peak_normalisation(sp, par, L):
 
 
 @pytest.mark.parametrize("L,hop,win", [(80000, 192, 384), (52000, 128, 512), (7000, 192, 384), (31000, 64, 256)])
-def test_istft_tma_staged_variant(sp, monkeypatch, L, hop, win):
+def test_istft_tma_staged_variant(sp, L, hop, win):
     """AIP_INV_TMA=1 stages stage A's rows with 4-D TMA tensor boxes (even T only; otherwise the direct-load kernel
     runs): same waveform as the default kernel, bit for bit, and within tolerance of the oracle."""
     x = _noise(3, L, seed=L + hop)
@@ -98,9 +98,8 @@ def test_istft_tma_staged_variant(sp, monkeypatch, L, hop, win):
     if S.shape[2] % 2:                       # make T even so that the TMA path is actually taken
         S = S[:, :, :-1].contiguous()
     base = sp.istft(plan, spec=S).cpu().numpy()
-    monkeypatch.setenv("AIP_INV_TMA", "1")
-    tma = sp.istft(plan, spec=S).cpu().numpy()
-    monkeypatch.delenv("AIP_INV_TMA")
+    with sp.experiment_env(AIP_INV_TMA="1"):
+        tma = sp.istft(plan, spec=S).cpu().numpy()
     assert np.array_equal(tma, base)
     ref = lr.istft(S[0].cpu().numpy(), hop_length=hop, win_length=win, n_fft=512)
     assert relerr(tma[0], ref) < TOL
@@ -442,11 +441,14 @@ def test_no_out_of_bounds_writes(sp, L, hop, win):
                          ids=["P1-dataset", "P1-unaligned", "P2", "P1-long-gap-crop", "P1-short-clip", "P1-4-frames-40-gaps",
                               "P1-3-frames"])
 @pytest.mark.parametrize("fill", ["tma", "scalar"])
-def test_gap_variants_bit_identical_to_full_transforms(sp, par, L, g, G, t_out, fill, monkeypatch):
+def test_gap_variants_bit_identical_to_full_transforms(sp, par, L, g, G, t_out, fill):
     """copy + re-transform of the touched frames == G full transforms of the gapped clips, bit for bit; gaps at the clip
     start / end / every phase against the 32-frame tile grid; then the oracle on a few variants."""
-    if fill == "scalar":
-        monkeypatch.setenv("AIP_VAR_FILL", "scalar")      # the store-instruction copy pass (used for very long rows)
+    with sp.experiment_env(AIP_VAR_FILL="scalar" if fill == "scalar" else None):   # "scalar": the store-instruction copy pass
+        _gap_variants_case(sp, par, L, g, G, t_out)
+
+
+def _gap_variants_case(sp, par, L, g, G, t_out):
     N = 3
     x = _noise(N, L, seed=L + G)
     rng = np.random.default_rng(G)

@@ -58,6 +58,25 @@ def test_fixture_is_what_the_reference_source_produces(fx):
         assert np.array_equal(again[k], fx[k]), k
 
 
+@pytest.mark.skipif(not refshim.reference_available(), reason="the reference checkout only exists in the build container")
+def test_configs4_model_is_the_references_architecture():
+    """tools/cnnblstm_model.py (the model between front- and back-end in bench.py's cnnblstm_e2e leg) takes the state_dict of the
+    reference's own StackedBLSTMCNN(cnn_blstm.yaml) unchanged and computes the same reconstruct_spectrogram, bit for bit."""
+    import torch
+    from tools.cnnblstm_model import StandInBLSTMCNN
+    with refshim.reference_modules() as ref:
+        torch.manual_seed(0)
+        theirs = ref.cnnblstm_model.StackedBLSTMCNN(str(refshim.REFERENCE / "models" / "CNNBLSTM" / "cnn_blstm.yaml")).eval()
+        ours = StandInBLSTMCNN().eval()
+        ours.load_state_dict(theirs.state_dict(), strict=True)
+        x = torch.randn(2, 257, 48)
+        mask = torch.zeros(2, 257, 48)
+        mask[:, :, 10:17] = 1
+        with torch.no_grad():
+            assert torch.equal(theirs.reconstruct_spectrogram(x, mask), ours.reconstruct_spectrogram(x, mask))
+            assert torch.equal(theirs(x.unsqueeze(1)), ours(x.unsqueeze(1)))
+
+
 def test_oracle_caller_restatement_equals_the_reference_source(fx, golden_clips):
     """oracle/callers_port.py + utils_port.py against what the reference's own source produced (bit for bit: both sit on
     the same librosa restatement, so any difference would be a mistake in the restated caller logic)."""

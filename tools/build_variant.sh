@@ -3,8 +3,14 @@
 #   tools/build_variant.sh <name> [-DAIP_...]...
 set -e
 cd "$(dirname "$0")/.."
-mkdir -p build/ab
+mkdir -p build/ab/obj_$1
 name=$1; shift
-nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -shared -Xcompiler -fPIC "$@" \
-     -o build/ab/$name.so ml_audio_inpainting_b200/csrc/aip_kernels.cu
+objs=()
+for u in ml_audio_inpainting_b200/csrc/aip_*.cu; do
+  o=build/ab/obj_$name/$(basename ${u%.cu}).o
+  nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -Xcompiler -fPIC "$@" -c -o $o $u &
+  objs+=($o)
+done
+wait
+nvcc -shared -o build/ab/$name.so "${objs[@]}"
 echo built build/ab/$name.so "$@"

@@ -13,8 +13,7 @@ gen = torch.Generator(device="cuda").manual_seed(99)
 ang = torch.polar(torch.ones_like(mag), 6.2831853 * torch.rand(mag.shape, device="cuda", generator=gen))
 res = {}
 for name, env in (("fused", None), ("unfused", "1")):
-    if env: os.environ["AIP_GL_UNFUSED"] = env
-    else: os.environ.pop("AIP_GL_UNFUSED", None)
+    sp.experiment_env(AIP_GL_UNFUSED=env).__enter__()
     y = sp.griffinlim(plan, mag, n_iter=32, init_angles=ang)
     torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
