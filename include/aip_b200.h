@@ -167,9 +167,11 @@ int aip_griffinlim_c64_f32(const aip_stft_desc* desc, const float* spec, float* 
 int aip_mel_project_f32(const float* basis, const int32_t* bands, const float* spec_pow, int64_t B, int64_t F, int64_t T,
                         int64_t n_mels, float* mel_out, void* stream);
 /* out[b, f, t] = sum_m inv_basis[f, m] * mel[b, m, t], then sqrt() when take_sqrt != 0 (utils.py:375-383: pinv of the mel
- * basis applied to a mel spectrogram; negative projections become NaN under the square root exactly as np.sqrt does). */
+ * basis applied to a mel spectrogram).  Negative projections become NaN under the square root exactly as np.sqrt makes
+ * them, EXCEPT those below the noise floor of an fp32 power spectrogram (|v| <= 1e-9 x the clip's largest projection), which
+ * are rounding residue of a non-negative exact value and are taken as 0.  peaks: [B] float scratch (needed for take_sqrt). */
 int aip_mel_inverse_f32(const float* inv_basis, const float* mel, int64_t B, int64_t F, int64_t T, int64_t n_mels,
-                        int32_t take_sqrt, float* out, void* stream);
+                        int32_t take_sqrt, float* out, float* peaks, void* stream);
 
 /* flags[b] = (max(x_b) < 0 && mean(x_b) < 0), x_b = x[b*n .. (b+1)*n). */
 int aip_db_heuristic_f32(const float* x, int64_t B, int64_t n, int32_t* flags, void* stream);

@@ -44,7 +44,7 @@ SIGNATURES = {
     "aip_griffinlim_f32": (C.c_int, [_D, _P, _P, _P, _I64, _I64, _I32, _F, _P, _P, _I64, _P, _SZ, _P]),
     "aip_griffinlim_c64_f32": (C.c_int, [_D, _P, _P, _P, _I64, _I64, _I32, _F, _P, _P, _I64, _P, _SZ, _P]),
     "aip_mel_project_f32": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _I64, _P, _P]),
-    "aip_mel_inverse_f32": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _I32, _P, _P]),
+    "aip_mel_inverse_f32": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _I32, _P, _P, _P]),
     "aip_db_heuristic_f32": (C.c_int, [_P, _I64, _I64, _P, _P]),
     "aip_gap_zero_f32": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, _P, _P]),
     "aip_gap_mask_f32": (C.c_int, [_P, _I64, _I64, _I64, _P, _P]),

@@ -77,7 +77,23 @@ __global__ void __launch_bounds__(256) mel_inverse_kernel(const float* __restric
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const long long f = fbase + ty + 8 * j;
-    if (f < F) out[(b * F + f) * T + t] = take_sqrt ? sqrtf(acc[j]) : acc[j];      // sqrt(negative) = NaN, like np.sqrt
+    if (f < F) out[(b * F + f) * T + t] = acc[j];
+  }
+}
+
+// np.sqrt of the projection (utils.py:381-383), in place.  A clearly negative projection becomes NaN exactly as in the reference.
+// A negative value BELOW THE NOISE FLOOR of an fp32 power spectrogram -- |v| <= kNegGuard x the clip's largest projected power;
+// an fp32 FFT leaves ~1e-7 of the peak amplitude in every bin, i.e. ~1e-14 of the peak power, and the pseudo-inverse amplifies
+// it by up to a few hundred -- is rounding residue of a projection whose exact value is >= 0 (librosa's float64-internal STFT
+// has a smooth leakage floor there and the reference gets a small positive number): it is taken as zero instead of
+// poisoning the whole waveform with NaN.  Documented deviation.
+constexpr float kNegGuard = 1e-9f;
+__global__ void sqrt_guard_kernel(float* x, long long n_per_clip, long long B, const float* peaks) {
+  const long long total = B * n_per_clip;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const float floor_v = -kNegGuard * peaks[i / n_per_clip];
+    x[i] = (v < 0.0f && v >= floor_v) ? 0.0f : sqrtf(v);
   }
 }
 
@@ -100,17 +116,25 @@ int aip_mel_project_f32(const float* basis, const int32_t* bands, const float* s
 }
 
 int aip_mel_inverse_f32(const float* inv_basis, const float* mel, int64_t B, int64_t F, int64_t T, int64_t n_mels,
-                        int32_t take_sqrt, float* out, void* stream) {
+                        int32_t take_sqrt, float* out, float* peaks, void* stream) {
   const DevInfo di = dev_info();
   if (!di.ok) return AIP_ERR_DEVICE;
-  if (!inv_basis || !mel || !out || B < 0 || F < 1 || T < 0 || n_mels < 1) return AIP_ERR_ARG;
+  if (!inv_basis || !mel || !out || B < 0 || F < 1 || T < 0 || n_mels < 1 || (take_sqrt && !peaks)) return AIP_ERR_ARG;
   if (B > 65535 || n_mels > 1024 || (F + kInvBins - 1) / kInvBins > 65535) return AIP_ERR_UNSUPPORTED;
   if (B == 0 || T == 0) return AIP_OK;
   const size_t smem = (size_t)kInvBins * (size_t)(n_mels + 1) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(mel_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const dim3 grid((unsigned)((T + 31) / 32), (unsigned)((F + kInvBins - 1) / kInvBins), (unsigned)B);
-  mel_inverse_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(inv_basis, mel, F, T, (int)n_mels, take_sqrt, out);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  mel_inverse_kernel<<<grid, 256, smem, st>>>(inv_basis, mel, F, T, (int)n_mels, 0, out);
+  e = cudaGetLastError();
+  if (e != cudaSuccess || !take_sqrt) return (int)e;
+  e = cudaMemsetAsync(peaks, 0, (size_t)B * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  e = launch_peak(out, F * T, B, F * T, peaks, st);
+  if (e != cudaSuccess) return (int)e;
+  sqrt_guard_kernel<<<ew_grid(B * F * T, di.sms), 256, 0, st>>>(out, F * T, B, peaks);
   return (int)cudaGetLastError();
 }
 

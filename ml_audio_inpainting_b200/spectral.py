@@ -529,7 +529,8 @@ def mel_project(spec_pow: torch.Tensor, sr: float, n_fft: int, n_mels: int = 128
 def mel_inverse(mel: torch.Tensor, sr: float, n_fft: int, n_mels: int = 128, fmin: float = 0.0,
                 fmax: Optional[float] = None, take_sqrt: bool = False) -> torch.Tensor:
     """pinv(mel basis) @ mel (+ sqrt for power spectrograms): utils.py:375-383 on the device (``aip_mel_inverse_f32``).
-    Negative projections become NaN under the square root, exactly as ``np.sqrt`` makes them in the reference."""
+    Negative projections become NaN under the square root as ``np.sqrt`` makes them in the reference -- except those below
+    the noise floor of an fp32 power spectrogram (<= 1e-9 of the clip's largest projection), which are taken as 0."""
     _require_cuda(mel, "mel")
     squeeze = mel.ndim == 2
     m = (mel.unsqueeze(0) if squeeze else mel).to(torch.float32).contiguous()
@@ -539,7 +540,8 @@ def mel_inverse(mel: torch.Tensor, sr: float, n_fft: int, n_mels: int = 128, fmi
     F = 1 + n_fft // 2
     _, _, inv = _mel_tables(sr, n_fft, n_mels, fmin, fmax, m.device)
     out = torch.empty((B, F, T), dtype=torch.float32, device=m.device)
+    peaks = torch.empty(B, dtype=torch.float32, device=m.device) if take_sqrt else None
     with torch.cuda.device(m.device):
         check(_cabi.load().aip_mel_inverse_f32(_ptr(inv), _ptr(m), B, F, T, int(n_mels), int(bool(take_sqrt)), _ptr(out),
-                                               _stream()), "aip_mel_inverse_f32")
+                                               _ptr(peaks), _stream()), "aip_mel_inverse_f32")
     return out[0] if squeeze else out
