@@ -486,6 +486,7 @@ AIP_HD void inv_stageA(float2* exch, const PairTw& w, int f, int p, bool live, L
         inv_pair(xr, xi, yr, yi, w.wr2[k1].y, w.wi2[k1].y, r[k1].y, i[k1].y, r[15 - k1].y, i[15 - k1].y);
       }
     }
+    load.done();        // every bin of this job is in registers (a staged loader refills its buffer from here)
     fft16x2(i, r);      // inverse transform: swapped roles
   } else {
 #pragma unroll

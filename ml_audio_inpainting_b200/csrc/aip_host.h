@@ -61,7 +61,7 @@ struct Tunables {
   int fwd_tile_bufs;      // AIP_FWD_TILE_BUFS   1..3: cap on the ring of staged-waveform buffers (0 = no cap)
   int fwd_no_shape;       // AIP_FWD_NO_SHAPE    1: never pick the shape-specialised (T_out 417 / 834) forward builds
   int fwd_chunk;          // AIP_FWD_CHUNK       tiles per draw of the dynamic schedule (0 = built-in choice)
-  int inv_tma;            // AIP_INV_TMA         1: stage the inverse kernel's rows with TMA tensor boxes
+  int inv_tma;            // AIP_INV_TMA         0: never stage the inverse kernel's rows with TMA tensor boxes (default: where legal)
   int ola_fast_mask;      // AIP_OLA_FAST        bit mask of the specialised overlap-adds that may be used (-1 = all)
   int inv_bufs;           // AIP_INV_BUFS        exchange buffers in the inverse ring (0 = built-in choice)
   int gl_unfused;         // AIP_GL_UNFUSED      1: Griffin-Lim with the separate phase-update kernel

@@ -86,30 +86,21 @@ __global__ void __launch_bounds__(kFwdThreads, 1) istft512_kernel(const InvParam
 
 // ---- complex input staged by TMA tensor tiles ---------------------------------------------------------
 // The direct-load kernel above keeps at most a few spectrum loads per thread in flight (the 64 data registers of the
-// packed codelet leave no room for more), which bounds it by HBM latency.  Here every stage-A warp owns a private,
-// double-buffered staging area that TMA fills one tile ahead: the spectrogram is described to the TMA unit as the
+// packed codelet leave no room for more), which bounds it by HBM latency.  Here every stage-A warp owns a private
+// staging slot that TMA fills one tile ahead: the spectrogram is described to the TMA unit as the
 // 4-D tensor (2t, p, j, b) with bin k = 16 j + p, so the 16 rows p + 16 j a pair-job reads are ONE box of
 // 68 floats x 1 x 16 x 1, the 16 partner rows 256 - p - 16 j a second one, and frames outside [0, n_frames) arrive
 // as zeros.  Needs an even T (row pitch 8 T bytes must be a multiple of 16) and a 16-byte aligned base.
 // The TMA unit needs the innermost start coordinate 16-byte aligned (an odd first frame raises an illegal-instruction
 // fault, tools/microbench/tma3d_probe.cu), so a box starts at the even frame below t0 and is 34 frames wide.
+// ONE slot per warp (8 x 9 KB): the warp moves its 32 / 33 bins into registers, asks for the NEXT tile's boxes right away
+// (InvLoadStaged::done) and only then runs its codelets and waits for an exchange buffer -- a whole stage-A phase hides the
+// copy -- which leaves room for the ring of TWO exchange buffers the direct-load kernel has (round 1 staged two slots per
+// warp, 142 KB, next to a single exchange buffer and lost to the direct loads: 0.568 against 0.527 ms).
 constexpr int kStageFr = kFR + 2;                       // frames per staged row
 constexpr int kStageB = 592;                            // float2 offset of region B (128-byte aligned: 4736 B)
 constexpr int kStageSlot = 1136;                        // float2 per slot (9088 B): A = rows 0..16 (17 x 34), B = 16 rows
-constexpr int kStageBytesWarp = 2 * kStageSlot * 8;     // two slots
-
-struct InvLoadStaged {      // stage-A loader out of the warp's staging slot (lane = frame)
-  const float2* slot;       // + lane + (t0 & 1)
-  const float2* plo;
-  const float2* phi;
-  __device__ __forceinline__ void rows(int k_lo, int k_hi) {
-    if (k_hi == 256) { plo = slot; phi = slot + 16 * kStageFr; }                               // job 0: rows j and 16 - j of region A
-    else if (k_lo == 8) { plo = slot + kStageB; phi = slot + kStageB + 15 * kStageFr; }       // job 8: region B
-    else { plo = slot; phi = slot + kStageB + 15 * kStageFr; }                                 // p > 0: A = p + 16 j, B = (16-p) + 16 j'
-  }
-  __device__ __forceinline__ void lo(int j, float& xr, float& xi) const { const float2 v = plo[j * kStageFr]; xr = v.x; xi = v.y; }
-  __device__ __forceinline__ void hi(int j, float& xr, float& xi) const { const float2 v = phi[-j * kStageFr]; xr = v.x; xi = v.y; }
-};
+constexpr int kStageBytesWarp = kStageSlot * 8;         // one slot
 
 // one elected lane: the two (p > 0) or three (p = 0) boxes of a tile into a staging slot
 __device__ __forceinline__ void inv_issue_stage(const InvParams& P, const CUtensorMap* map16, const CUtensorMap* map1,
@@ -127,25 +118,32 @@ __device__ __forceinline__ void inv_issue_stage(const InvParams& P, const CUtens
   }
 }
 
-struct StagedBefore {       // runs once the slot has been read into registers: refill it, then wait for the exchange buffer
+struct InvLoadStaged {      // stage-A loader out of the warp's staging slot (lane = frame)
+  const float2* slot;       // + lane + (t0 & 1)
+  const float2* plo;
+  const float2* phi;
+  // refill: the next tile's boxes into the same slot as soon as this tile's bins are in registers
   const InvParams& P;
   const CUtensorMap* map16;
   const CUtensorMap* map1;
-  const TileCursor& next2;
+  const TileCursor& next;
   int p;
-  float2* slot;
+  float2* slot_base;
   uint64_t* full;
   bool refill;
-  uint64_t* exch_bar;
-  uint32_t exch_parity;
-  bool exch_wait;
-  __device__ __forceinline__ void operator()() const {
+  __device__ __forceinline__ void rows(int k_lo, int k_hi) {
+    if (k_hi == 256) { plo = slot; phi = slot + 16 * kStageFr; }                               // job 0: rows j and 16 - j of region A
+    else if (k_lo == 8) { plo = slot + kStageB; phi = slot + kStageB + 15 * kStageFr; }       // job 8: region B
+    else { plo = slot; phi = slot + kStageB + 15 * kStageFr; }                                 // p > 0: A = p + 16 j, B = (16-p) + 16 j'
+  }
+  __device__ __forceinline__ void lo(int j, float& xr, float& xi) const { const float2 v = plo[j * kStageFr]; xr = v.x; xi = v.y; }
+  __device__ __forceinline__ void hi(int j, float& xr, float& xi) const { const float2 v = phi[-j * kStageFr]; xr = v.x; xi = v.y; }
+  __device__ __forceinline__ void done() const {
     __syncwarp();
     if (refill && (threadIdx.x & 31) == 0) {
       fence_proxy_async();
-      inv_issue_stage(P, map16, map1, next2, p, slot, full);
+      inv_issue_stage(P, map16, map1, next, p, slot_base, full);
     }
-    if (exch_wait) mbar_wait(exch_bar, exch_parity);
   }
 };
 
@@ -153,7 +151,7 @@ template <int kFast>
 __global__ void __launch_bounds__(kFwdThreads, 1) istft512_tma_kernel(const InvParams P, const __grid_constant__ CUtensorMap map16,
                                                                        const __grid_constant__ CUtensorMap map1) {
   extern __shared__ __align__(128) float smem[];
-  __shared__ __align__(8) uint64_t bars[2 * kInvBufs + 16];
+  __shared__ __align__(8) uint64_t bars[2 * kInvBufs + 8];
   __shared__ __align__(8) float wtab_s[kMaxWtab];
   __shared__ __align__(16) float win_s[kWinTable];
   __shared__ __align__(8) float2 tw_s[kTwTable];
@@ -164,16 +162,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) istft512_tma_kernel(const InvP
     for (int r = threadIdx.x; r < P.hop; r += blockDim.x) wtab_s[r] = P.inv_wss[P.wss_ref + r];
   uint64_t* exch_full = bars;
   uint64_t* exch_empty = bars + kInvBufs;
-  uint64_t* stage_full = bars + 2 * kInvBufs;      // [warp][slot], count 1 (+ tx bytes)
-  float2* stage0 = reinterpret_cast<float2*>(smem);                         // 8 warps x 2 slots
-  float2* exch0 = stage0 + 8 * 2 * kStageSlot;
+  uint64_t* stage_full = bars + 2 * kInvBufs;      // [warp], count 1 (+ tx bytes)
+  float2* stage0 = reinterpret_cast<float2*>(smem);                         // 8 warps x 1 slot
+  float2* exch0 = stage0 + 8 * kStageSlot;
   const int tid = threadIdx.x;
   if (tid == 0) {
     for (int i = 0; i < kInvBufs; ++i) {
       mbar_init(exch_full + i, kThreads / 32);
       mbar_init(exch_empty + i, kThreads / 32);
     }
-    for (int i = 0; i < 16; ++i) mbar_init(stage_full + i, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(stage_full + i, 1);
   }
   __syncthreads();
   const int first = blockIdx.x * P.tiles_per_cta;
@@ -185,26 +183,22 @@ __global__ void __launch_bounds__(kFwdThreads, 1) istft512_tma_kernel(const InvP
     const int warp = tid >> 5, lane = tid & 31;
     PairTw w;
     pair_tw_init(w, warp);
-    float2* my_stage = stage0 + warp * 2 * kStageSlot;
-    uint64_t* my_full = stage_full + 2 * warp;
-    TileCursor c2 = c;                                  // cursor of the tile two ahead (the next refill)
-    if (lane == 0) inv_issue_stage(P, &map16, &map1, c2, warp, my_stage, my_full);
-    tile_advance(c2, P.tiles_per_clip);
-    if (lane == 0 && n > 1) inv_issue_stage(P, &map16, &map1, c2, warp, my_stage + kStageSlot, my_full + 1);
-    tile_advance(c2, P.tiles_per_clip);
+    float2* my_stage = stage0 + warp * kStageSlot;
+    uint64_t* my_full = stage_full + warp;
+    TileCursor c1 = c;                                  // cursor of the next tile (the refill)
+    if (lane == 0) inv_issue_stage(P, &map16, &map1, c1, warp, my_stage, my_full);
+    tile_advance(c1, P.tiles_per_clip);
     int es = 0, use = 0;
 #pragma unroll 1
     for (int i = 0; i < n; ++i) {
-      const int s = i & 1;
-      float2* slot = my_stage + s * kStageSlot;
-      mbar_wait(my_full + s, (uint32_t)((i >> 1) & 1));
-      InvLoadStaged load{slot + lane + ((c.tt * P.g.FO - P.g.HL) & 1), nullptr, nullptr};
-      StagedBefore sb{P, &map16, &map1, c2, warp, slot, my_full + s, i + 2 < n,
-                      exch_empty + es, (uint32_t)((use - 1) & 1), use >= 1};
-      inv_stageA(exch0 + es * kExch, w, lane, warp, true, load, sb);
+      mbar_wait(my_full, (uint32_t)(i & 1));
+      InvLoadStaged load{my_stage + lane + ((c.tt * P.g.FO - P.g.HL) & 1), nullptr, nullptr,
+                         P, &map16, &map1, c1, warp, my_stage, my_full, i + 1 < n};
+      WaitBefore wb{exch_empty + es, (uint32_t)((use - 1) & 1), use >= 1};
+      inv_stageA(exch0 + es * kExch, w, lane, warp, true, load, wb);
       mbar_arrive_warp(exch_full + es);
       tile_advance(c, P.tiles_per_clip);
-      tile_advance(c2, P.tiles_per_clip);
+      tile_advance(c1, P.tiles_per_clip);
       if (++es == P.n_bufs) { es = 0; ++use; }
     }
   } else {
@@ -428,8 +422,8 @@ static bool inv_make_map(CUtensorMap* map, const float2* spec, int B, int T, int
 
 static bool inv_tma_ok(const InvParams& P) {
   if (!P.spec || P.gl_mag || (P.T & 1) || (reinterpret_cast<uintptr_t>(P.spec) & 15)) return false;
-  // Off unless AIP_INV_TMA=1: measured 0.568 ms against 0.535 ms for the direct-load kernel (1024 x 10 s, hop 192) -- the
-  // staging slots leave room for ONE exchange buffer only, and stage A is not the slower role (profiles/README.md).
+  // On by default (AIP_INV_TMA=0 runs the direct-load kernel): 0.479 ms against 0.524 ms (1024 x 10 s, hop 192), 0.681 against
+  // 0.730 ms at hop 128 -- one staging slot per warp next to the ring of two exchange buffers (profiles/README.md).
   return tunables().inv_tma != 0;
 }
 
@@ -489,8 +483,9 @@ static int run_inv(const aip_stft_desc* desc, InvParams P, long long length, voi
     if (inv_tma_ok(P)) {
       CUtensorMap map16, map1;
       if (inv_make_map(&map16, P.spec, P.B, P.T, P.n_frames, 16) && inv_make_map(&map1, P.spec, P.B, P.T, P.n_frames, 1)) {
-        P.n_bufs = 1;      // 8 x 2 staging slots (142 KB) + one exchange buffer (66 KB)
-        const size_t smem_tma = (size_t)8 * kStageBytesWarp + (size_t)kExch * sizeof(float2);
+        // 8 staging slots (71 KB) + the ring of exchange buffers (2 x 66 KB)
+        if (P.n_bufs > 2) P.n_bufs = 2;
+        const size_t smem_tma = (size_t)8 * kStageBytesWarp + (size_t)P.n_bufs * kExch * sizeof(float2);
         auto tk = P.ola_fast == 1 ? istft512_tma_kernel<1> : (P.ola_fast == 2 ? istft512_tma_kernel<2> : istft512_tma_kernel<0>);
         e = cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
         if (e != cudaSuccess) return (int)e;

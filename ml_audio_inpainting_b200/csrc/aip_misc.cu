@@ -131,7 +131,7 @@ static Tunables read_tunables() {
   t.fwd_tile_bufs = env_int("AIP_FWD_TILE_BUFS", 0);
   t.fwd_no_shape = getenv("AIP_FWD_NO_SHAPE") ? 1 : 0;
   t.fwd_chunk = env_int("AIP_FWD_CHUNK", 0);
-  t.inv_tma = env_int("AIP_INV_TMA", 0);
+  t.inv_tma = env_int("AIP_INV_TMA", 1);
   t.ola_fast_mask = env_int("AIP_OLA_FAST", -1);
   t.inv_bufs = env_int("AIP_INV_BUFS", 0);
   t.gl_unfused = getenv("AIP_GL_UNFUSED") ? 1 : 0;

@@ -491,6 +491,7 @@ struct InvLoadMag {
   bool db;                  // kDom == 0: this clip is in dB
   int olo, ohi, s16;
   AIP_HM void rows(int k_lo, int k_hi) { olo = k_lo * T; ohi = k_hi * T; s16 = 16 * T; }
+  AIP_HM void done() const {}
   AIP_HM void lo(int j, float& xr, float& xi) const { get(olo + j * s16, xr, xi); }
   AIP_HM void hi(int j, float& xr, float& xi) const { get(ohi - j * s16, xr, xi); }
   AIP_HM void get(int o, float& xr, float& xi) const {
@@ -519,6 +520,7 @@ struct InvLoadSpec {        // complex input straight from HBM
   const char* plo;
   const char* phi;
   unsigned s16b;            // bytes between rows k and k + 16 (T < 2^22)
+  AIP_HM void done() const {}
   AIP_HM void rows(int k_lo, int k_hi) {
     plo = reinterpret_cast<const char*>(col + k_lo * T);
     phi = reinterpret_cast<const char*>(col + k_hi * T);
@@ -546,6 +548,7 @@ struct InvLoadGL {
   float alpha;              // 0 in the first iteration (prev = reb then: branch-free)
   int olo, ohi, s16;
   AIP_HM void rows(int k_lo, int k_hi) { olo = k_lo * T; ohi = k_hi * T; s16 = 16 * T; }
+  AIP_HM void done() const {}
   AIP_HM void lo(int j, float& xr, float& xi) const { get(olo + j * s16, xr, xi); }
   AIP_HM void hi(int j, float& xr, float& xi) const { get(ohi - j * s16, xr, xi); }
   AIP_HM void get(int o, float& xr, float& xi) const {

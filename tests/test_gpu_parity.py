@@ -90,16 +90,16 @@ def test_istft_fused_peak_normalisation(sp, par, L):
 
 @pytest.mark.parametrize("L,hop,win", [(80000, 192, 384), (52000, 128, 512), (7000, 192, 384), (31000, 64, 256)])
 def test_istft_tma_staged_variant(sp, L, hop, win):
-    """AIP_INV_TMA=1 stages stage A's rows with 4-D TMA tensor boxes (even T only; otherwise the direct-load kernel
-    runs): same waveform as the default kernel, bit for bit, and within tolerance of the oracle."""
+    """Complex input with an even T is staged by 4-D TMA tensor boxes (the default); AIP_INV_TMA=0 forces the direct-load
+    kernel: same waveform bit for bit, and within tolerance of the oracle."""
     x = _noise(3, L, seed=L + hop)
     plan = sp.get_plan(512, hop, win, "hann", True, "cuda:0")
     S = sp.stft(torch.from_numpy(x).cuda(), plan)["spec"]
     if S.shape[2] % 2:                       # make T even so that the TMA path is actually taken
         S = S[:, :, :-1].contiguous()
-    base = sp.istft(plan, spec=S).cpu().numpy()
-    with sp.experiment_env(AIP_INV_TMA="1"):
-        tma = sp.istft(plan, spec=S).cpu().numpy()
+    tma = sp.istft(plan, spec=S).cpu().numpy()
+    with sp.experiment_env(AIP_INV_TMA="0"):
+        base = sp.istft(plan, spec=S).cpu().numpy()
     assert np.array_equal(tma, base)
     ref = lr.istft(S[0].cpu().numpy(), hop_length=hop, win_length=win, n_fft=512)
     assert relerr(tma[0], ref) < TOL

@@ -152,8 +152,108 @@ __global__ void __launch_bounds__(256, 1) probe(const float* __restrict__ Y, flo
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tbase) : "memory");
 }
 
+// Plan 2: Ahi and Alo in separate operand tiles (K = 32 each); per M-block 4 MMAs Ahi x [Bhi | Blo] (N = 64) + 4 MMAs Alo x Bhi
+// (N = 32): every A tile is read ONCE (the MMA is bound by its shared-memory operand reads: A = 4 KB per instruction).  The
+// read-back adds columns 32..63 (Ahi Blo) to columns 0..31.
+__global__ void __launch_bounds__(256, 1) probe2(const float* __restrict__ Y, float* __restrict__ out, int tiles, int reps, int lbo,
+                                                  long long* cycles) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int sbo = 8 * lbo, blk = 16 * sbo;
+  unsigned char* Ahi = sm;
+  unsigned char* Alo = sm + 4 * blk;
+  float* Bc = reinterpret_cast<float*>(sm + 8 * blk);      // 64 rows (Bhi rows 0..31, Blo rows 32..63) x K 32
+  constexpr int lboB = 128, sboB = 8 * 128;
+  for (int idx = tid; idx < 64 * 32; idx += blockDim.x) {
+    const int n = idx >> 5, k = idx & 31, q = k >> 2, s = k & 3, n1 = 2 * q + (s >> 1), cin = s & 1;
+    const int nn = n & 31, k1 = nn >> 1, c = nn & 1;
+    float sn, cs;
+    sincospif(-(float)((n1 * k1) & 15) / 8.0f, &sn, &cs);
+    const float coef = (c == 0) ? (cin == 0 ? cs : -sn) : (cin == 0 ? sn : cs);
+    const float hi = __uint_as_float(__float_as_uint(coef) & 0xffffe000u), lo = coef - hi;
+    Bc[(n & 7) * 4 + (n >> 3) * (sboB / 4) + q * (lboB / 4) + s] = n < 32 ? hi : lo;
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tbase = tmem_base;
+  const uint32_t idesc64 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+  uint32_t phase = 0;
+  long long t_mma = 0, t_ld = 0;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const float* y = Y + (long long)tile * 32 * 16 * 16 * 2;
+    for (int idx = tid; idx < 32 * 16 * 16; idx += blockDim.x) {
+      const int n1 = idx & 15, f = (idx >> 4) & 31, qi = idx >> 9;
+      const int w = qi >> 2, b = qi & 3, k2 = kQ[w][b];
+      const float2 v = *reinterpret_cast<const float2*>(y + ((f * 16 + k2) * 16 + n1) * 2);
+      const float hr = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u), hi_ = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+      const int row = w * 32 + f;
+      const int off = b * blk + (row & 7) * 16 + (row >> 3) * sbo + (n1 >> 1) * lbo + (n1 & 1) * 8;
+      *reinterpret_cast<float2*>(Ahi + off) = make_float2(hr, hi_);
+      *reinterpret_cast<float2*>(Alo + off) = make_float2(v.x - hr, v.y - hi_);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    long long c0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t b0 = make_desc(smem_u32(Bc), lboB, sboB);
+        for (int b = 0; b < 4; ++b) {
+          const uint32_t d = tbase + 64 * b;
+          const uint64_t ah = make_desc(smem_u32(Ahi + b * blk), lbo, sbo), al = make_desc(smem_u32(Alo + b * blk), lbo, sbo);
+          for (int j = 0; j < 4; ++j)
+            mma_tf32(d, ah + (uint64_t)((2 * j * lbo) >> 4), b0 + (uint64_t)((2 * j * lboB) >> 4), idesc64, j ? 1u : 0u);
+          for (int j = 0; j < 4; ++j)
+            mma_tf32(d, al + (uint64_t)((2 * j * lbo) >> 4), b0 + (uint64_t)((2 * j * lboB) >> 4), idesc32, 1u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+      }
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    long long c1 = clock64();
+    const int w = warp & 3, h = warp >> 2;
+    uint32_t va[32], vb[32], xa[32], xb[32];
+    for (int r = 0; r < reps; ++r) {
+      TMEM_LD32(tbase + ((uint32_t)(32 * w) << 16) + 64 * (2 * h), va);
+      TMEM_LD32(tbase + ((uint32_t)(32 * w) << 16) + 64 * (2 * h) + 32, xa);
+      TMEM_LD32(tbase + ((uint32_t)(32 * w) << 16) + 64 * (2 * h + 1), vb);
+      TMEM_LD32(tbase + ((uint32_t)(32 * w) << 16) + 64 * (2 * h + 1) + 32, xb);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    }
+    long long c2 = clock64();
+    t_mma += c1 - c0; t_ld += c2 - c1;
+    float* o = out + ((long long)tile * 32 + lane) * 16 * 16 * 2;
+    const int ka = kQ[w][2 * h], kb = kQ[w][2 * h + 1];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      o[ka * 32 + j] = __uint_as_float(va[j]) + __uint_as_float(xa[j]);
+      o[kb * 32 + j] = __uint_as_float(vb[j]) + __uint_as_float(xb[j]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+  }
+  if (tid == 0 && cycles) { cycles[2 * blockIdx.x] = t_mma; cycles[2 * blockIdx.x + 1] = t_ld; }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tbase) : "memory");
+}
+
 int main(int argc, char** argv) {
   const int lbo = argc > 1 ? atoi(argv[1]) : 144;
+  const int plan = argc > 3 ? atoi(argv[3]) : 1;
   const int tiles = 148 * 2, reps = argc > 2 ? atoi(argv[2]) : 1;
   const size_t n = (size_t)tiles * 32 * 16 * 16 * 2;
   std::vector<float> hy(n);
@@ -164,10 +264,12 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&dy, n * 4)); CK(cudaMalloc(&dout, n * 4)); CK(cudaMalloc(&dcyc, 148 * 2 * 8));
   CK(cudaMemcpy(dy, hy.data(), n * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(dout, 0, n * 4));
-  const int smem = 4 * 16 * 16 * lbo + 2 * 32 * 64 * 4;
+  const int smem = plan == 1 ? 4 * 16 * 16 * lbo + 2 * 32 * 64 * 4 : 8 * 16 * 8 * lbo + 64 * 32 * 4;
   CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  printf("lbo %d B, smem %d B, reps %d\n", lbo, smem, reps);
-  probe<<<148, 256, smem>>>(dy, dout, tiles, reps, lbo, dcyc);
+  CK(cudaFuncSetAttribute(probe2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  printf("plan %d, lbo %d B, smem %d B, reps %d\n", plan, lbo, smem, reps);
+  if (plan == 1) probe<<<148, 256, smem>>>(dy, dout, tiles, reps, lbo, dcyc);
+  else probe2<<<148, 256, smem>>>(dy, dout, tiles, reps, lbo, dcyc);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   std::vector<float> ho(n);
