@@ -220,6 +220,149 @@ __global__ void __launch_bounds__(kFwdThreads, 1) istft512_tma_kernel(const InvP
   }
 }
 
+// ---- Griffin-Lim inverse (INV_GL) with the two complex arrays staged by TMA -----------------------------------------
+// The fused phase update reads THREE arrays per bin (rebuilt[it], rebuilt[it - 1], |S|); with direct loads stage A is bound by
+// load latency (ncu, round 1: long_scoreboard 7.8 stall cycles per issued instruction, 36 B of spills).  Here the two complex
+// arrays arrive through the same per-warp staging slot as above (one slot holds both: 2 x 9 KB per warp), |S| is read with
+// one coalesced 4-byte load per bin, and a single exchange buffer fits beside the staging (145 + 66 KB).
+struct InvLoadStagedGL {
+  const float2* reb;        // staging slot of rebuilt[it] + lane + (t0 & 1); rebuilt[it - 1] sits kStageSlot float2 further
+  const float2* plo;
+  const float2* phi;
+  const float* mag;         // |S| column: array + b F T + t
+  int T;
+  float alpha;
+  int mlo, mhi;             // element offsets of the two row cursors in |S|
+  const InvParams& P;
+  const CUtensorMap* maps;  // [4]: rebuilt 16-row / 1-row boxes, previous 16-row / 1-row boxes
+  const TileCursor& next;
+  int p;
+  float2* slot_base;
+  uint64_t* full;
+  bool refill;
+  __device__ __forceinline__ void rows(int k_lo, int k_hi) {
+    if (k_hi == 256) { plo = reb; phi = reb + 16 * kStageFr; }
+    else if (k_lo == 8) { plo = reb + kStageB; phi = reb + kStageB + 15 * kStageFr; }
+    else { plo = reb; phi = reb + kStageB + 15 * kStageFr; }
+    mlo = k_lo * T; mhi = k_hi * T;
+  }
+  __device__ __forceinline__ void project(const float2* q, float m, float& xr, float& xi) const {
+    const float2 r = q[0], t = q[kStageSlot];
+    const float ax = r.x - alpha * t.x, ay = r.y - alpha * t.y;
+    const float sc = fast_div(1.0f, fast_sqrt(ax * ax + ay * ay) + kFltMin);
+    xr = (ax * sc) * m; xi = (ay * sc) * m;
+  }
+  __device__ __forceinline__ void lo(int j, float& xr, float& xi) const { project(plo + j * kStageFr, __ldcg(mag + mlo + j * 16 * T), xr, xi); }
+  __device__ __forceinline__ void hi(int j, float& xr, float& xi) const { project(phi - j * kStageFr, __ldcg(mag + mhi - j * 16 * T), xr, xi); }
+  __device__ __forceinline__ void done() const;
+};
+
+__device__ __forceinline__ void inv_issue_stage_gl(const InvParams& P, const CUtensorMap* maps, const TileCursor& c, int p,
+                                                   float2* slot, uint64_t* bar) {
+  const int t0e = (c.tt * P.g.FO - P.g.HL) & ~1;
+  mbar_expect_tx(bar, 2u * (p != 0 ? 32u : 33u) * kStageFr * 8u);
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    float2* s = slot + a * kStageSlot;
+    const CUtensorMap* m16 = maps + 2 * a;
+    const CUtensorMap* m1 = maps + 2 * a + 1;
+    if (p != 0) {
+      tma_load_4d(s, m16, 2 * t0e, p, 0, c.b, bar);
+      tma_load_4d(s + kStageB, m16, 2 * t0e, 16 - p, 0, c.b, bar);
+    } else {
+      tma_load_4d(s, m16, 2 * t0e, 0, 0, c.b, bar);
+      tma_load_4d(s + 16 * kStageFr, m1, 2 * t0e, 0, 16, c.b, bar);
+      tma_load_4d(s + kStageB, m16, 2 * t0e, 8, 0, c.b, bar);
+    }
+  }
+}
+
+__device__ __forceinline__ void InvLoadStagedGL::done() const {
+  __syncwarp();
+  if (refill && (threadIdx.x & 31) == 0) {
+    fence_proxy_async();
+    inv_issue_stage_gl(P, maps, next, p, slot_base, full);
+  }
+}
+
+struct GlMaps { CUtensorMap m[4]; };
+
+template <int kFast>
+__global__ void __launch_bounds__(kFwdThreads, 1) istft512_gl_tma_kernel(const InvParams P, const __grid_constant__ GlMaps maps) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bars[2 * kInvBufs + 8];
+  __shared__ __align__(8) float wtab_s[kMaxWtab];
+  __shared__ __align__(16) float win_s[kWinTable];
+  __shared__ __align__(8) float2 tw_s[kTwTable];
+  window_table_fill(win_s, P.window, 1.0f / 512.0f, threadIdx.x, blockDim.x);
+  twiddle_table_fill(tw_s, threadIdx.x, blockDim.x);
+  const float* wtab = (P.wss_ref >= 0 && P.hop <= kMaxWtab) ? wtab_s : nullptr;
+  if (wtab)
+    for (int r = threadIdx.x; r < P.hop; r += blockDim.x) wtab_s[r] = P.inv_wss[P.wss_ref + r];
+  uint64_t* exch_full = bars;
+  uint64_t* exch_empty = bars + kInvBufs;
+  uint64_t* stage_full = bars + 2 * kInvBufs;
+  float2* stage0 = reinterpret_cast<float2*>(smem);                         // 8 warps x (rebuilt slot, previous slot)
+  float2* exch0 = stage0 + 8 * 2 * kStageSlot;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int i = 0; i < kInvBufs; ++i) {
+      mbar_init(exch_full + i, kThreads / 32);
+      mbar_init(exch_empty + i, kThreads / 32);
+    }
+    for (int i = 0; i < 8; ++i) mbar_init(stage_full + i, 1);
+  }
+  __syncthreads();
+  const int first = blockIdx.x * P.tiles_per_cta;
+  int n = P.n_tiles - first;
+  if (n > P.tiles_per_cta) n = P.tiles_per_cta;
+  if (n <= 0) return;
+  TileCursor c = tile_cursor(first, P.tiles_per_clip);
+  if (tid < kThreads) {
+    const int warp = tid >> 5, lane = tid & 31;
+    PairTw w;
+    pair_tw_init(w, warp);
+    float2* my_stage = stage0 + warp * 2 * kStageSlot;
+    uint64_t* my_full = stage_full + warp;
+    TileCursor c1 = c;
+    if (lane == 0) inv_issue_stage_gl(P, maps.m, c1, warp, my_stage, my_full);
+    tile_advance(c1, P.tiles_per_clip);
+    int es = 0, use = 0;
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+      const int t0 = c.tt * P.g.FO - P.g.HL, t = t0 + lane;
+      const bool live = (t >= 0 && t < P.n_frames);
+      // lanes outside the clip read no |S| (their staged bins are TMA's zero fill): clamp the column, the result is dropped
+      const int tc = live ? t : (t < 0 ? 0 : P.n_frames - 1);
+      mbar_wait(my_full, (uint32_t)(i & 1));
+      InvLoadStagedGL load{my_stage + lane + (t0 & 1), nullptr, nullptr, P.gl_mag + (long long)c.b * kBins * P.T + tc, P.T,
+                           P.gl_alpha, 0, 0, P, maps.m, c1, warp, my_stage, my_full, i + 1 < n};
+      WaitBefore wb{exch_empty + es, (uint32_t)((use - 1) & 1), use >= 1};
+      inv_stageA(exch0 + es * kExch, w, lane, warp, true, load, wb);
+      mbar_arrive_warp(exch_full + es);
+      tile_advance(c, P.tiles_per_clip);
+      tile_advance(c1, P.tiles_per_clip);
+      if (++es == P.n_bufs) { es = 0; ++use; }
+    }
+  } else {
+    const int btid = tid - kThreads;
+    LaneConst lc;
+    lane_const_init(lc, tw_s, btid & 15);
+    int es = 0, use = 0;
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+      float2* exch = exch0 + es * kExch;
+      mbar_wait(exch_full + es, (uint32_t)(use & 1));
+      inv_phase1<kFast>(P, btid, c, exch, win_s, lc);
+      named_bar_sync(1, kThreads);
+      inv_phase2<kFast>(P, btid, c, exch, wtab);
+      mbar_arrive_warp(exch_empty + es);
+      tile_advance(c, P.tiles_per_clip);
+      if (++es == P.n_bufs) { es = 0; ++use; }
+    }
+  }
+}
+
 struct GenericInvParams {
   InvParams P;
   int N, logN, F;
@@ -312,9 +455,9 @@ __global__ void __launch_bounds__(256) gl_update_kernel(float4* __restrict__ spe
       ax -= alpha * tp.x; ay -= alpha * tp.y; bx -= alpha * tp.z; by -= alpha * tp.w;
     }
     tprev[i] = rb;
-    const float sa = m.x / (sqrtf(ax * ax + ay * ay) + kFltMin);
-    const float sb = m.y / (sqrtf(bx * bx + by * by) + kFltMin);
-    spec[i] = make_float4(ax * sa, ay * sa, bx * sb, by * sb);
+    const float sa = 1.0f / (sqrtf(ax * ax + ay * ay) + kFltMin);      // librosa's order: normalise, then scale by |S|
+    const float sb = 1.0f / (sqrtf(bx * bx + by * by) + kFltMin);
+    spec[i] = make_float4((ax * sa) * m.x, (ay * sa) * m.x, (bx * sb) * m.y, (by * sb) * m.y);
   }
 }
 
@@ -332,9 +475,9 @@ __global__ void __launch_bounds__(256) gl_update_pp_kernel(const float4* __restr
       const float4 tp = __ldcs(tprev + i);
       ax -= alpha * tp.x; ay -= alpha * tp.y; bx -= alpha * tp.z; by -= alpha * tp.w;
     }
-    const float sa = m.x / (sqrtf(ax * ax + ay * ay) + kFltMin);
-    const float sb = m.y / (sqrtf(bx * bx + by * by) + kFltMin);
-    angles[i] = make_float4(ax * sa, ay * sa, bx * sb, by * sb);
+    const float sa = 1.0f / (sqrtf(ax * ax + ay * ay) + kFltMin);
+    const float sb = 1.0f / (sqrtf(bx * bx + by * by) + kFltMin);
+    angles[i] = make_float4((ax * sa) * m.x, (ay * sa) * m.x, (bx * sb) * m.y, (by * sb) * m.y);
   }
 }
 
@@ -343,8 +486,8 @@ __global__ void gl_update_pp_tail_kernel(const float2* rebuilt, const float2* tp
   const float2 rb = rebuilt[i];
   float ax = rb.x, ay = rb.y;
   if (has_prev) { const float2 tp = tprev[i]; ax -= alpha * tp.x; ay -= alpha * tp.y; }
-  const float s = mag[i] / (sqrtf(ax * ax + ay * ay) + kFltMin);
-  angles[i] = make_float2(ax * s, ay * s);
+  const float s = 1.0f / (sqrtf(ax * ax + ay * ay) + kFltMin);
+  angles[i] = make_float2((ax * s) * mag[i], (ay * s) * mag[i]);
 }
 
 __global__ void gl_update_tail_kernel(float2* spec, float2* tprev, const float* mag, long long i, float alpha, int has_prev) {
@@ -352,8 +495,8 @@ __global__ void gl_update_tail_kernel(float2* spec, float2* tprev, const float* 
   float ax = rb.x, ay = rb.y;
   if (has_prev) { const float2 tp = tprev[i]; ax -= alpha * tp.x; ay -= alpha * tp.y; }
   tprev[i] = rb;
-  const float s = mag[i] / (sqrtf(ax * ax + ay * ay) + kFltMin);
-  spec[i] = make_float2(ax * s, ay * s);
+  const float s = 1.0f / (sqrtf(ax * ax + ay * ay) + kFltMin);
+  spec[i] = make_float2((ax * s) * mag[i], (ay * s) * mag[i]);
 }
 
 __global__ void scale_angles_kernel(float2* angles, const float* mag, long long n) {
@@ -427,6 +570,12 @@ static bool inv_tma_ok(const InvParams& P) {
   return tunables().inv_tma != 0;
 }
 
+static bool inv_gl_tma_ok(const InvParams& P) {
+  if (!P.spec || !P.gl_mag || !P.gl_prev || (P.T & 1)) return false;
+  if ((reinterpret_cast<uintptr_t>(P.spec) & 15) || (reinterpret_cast<uintptr_t>(P.gl_prev) & 15)) return false;
+  return tunables().inv_tma != 0;
+}
+
 static void inv_fill_ola(InvParams& P) {
   P.hop_magic = (unsigned)((0x100000000ULL + (unsigned)P.hop - 1) / (unsigned)P.hop);
   P.col_magic = (unsigned)((0x100000000ULL + (unsigned)(P.hop / 2) - 1) / (unsigned)(P.hop / 2));
@@ -480,6 +629,19 @@ static int run_inv(const aip_stft_desc* desc, InvParams P, long long length, voi
     if (grid > P.n_tiles) grid = P.n_tiles;
     P.tiles_per_cta = (P.n_tiles + grid - 1) / grid;
     grid = (P.n_tiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
+    if (inv_gl_tma_ok(P)) {
+      GlMaps gm;
+      if (inv_make_map(&gm.m[0], P.spec, P.B, P.T, P.n_frames, 16) && inv_make_map(&gm.m[1], P.spec, P.B, P.T, P.n_frames, 1) &&
+          inv_make_map(&gm.m[2], P.gl_prev, P.B, P.T, P.n_frames, 16) && inv_make_map(&gm.m[3], P.gl_prev, P.B, P.T, P.n_frames, 1)) {
+        P.n_bufs = 1;      // 8 x 2 staging slots (142 KB) + one exchange buffer (66 KB)
+        const size_t smem_gl = (size_t)8 * 2 * kStageBytesWarp + (size_t)kExch * sizeof(float2);
+        auto gk = P.ola_fast == 1 ? istft512_gl_tma_kernel<1> : (P.ola_fast == 2 ? istft512_gl_tma_kernel<2> : istft512_gl_tma_kernel<0>);
+        e = cudaFuncSetAttribute(gk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gl);
+        if (e != cudaSuccess) return (int)e;
+        gk<<<(unsigned)grid, kFwdThreads, smem_gl, st>>>(P, gm);
+        return (int)cudaGetLastError();
+      }
+    }
     if (inv_tma_ok(P)) {
       CUtensorMap map16, map1;
       if (inv_make_map(&map16, P.spec, P.B, P.T, P.n_frames, 16) && inv_make_map(&map1, P.spec, P.B, P.T, P.n_frames, 1)) {

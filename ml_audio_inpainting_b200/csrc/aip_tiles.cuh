@@ -557,8 +557,10 @@ struct InvLoadGL {
     const float2 t = ldg_stream(prev + i);
     const float m = mag[i];
     const float ax = r.x - alpha * t.x, ay = r.y - alpha * t.y;
-    const float sc = fast_div(m, fast_sqrt(ax * ax + ay * ay) + kFltMin);      // MUFU.SQRT + MUFU.RCP: ~2 ulp each
-    xr = ax * sc; xi = ay * sc;
+    // librosa's order: angles /= |angles| + tiny, THEN angles *= S.  (a * (S / (|a| + tiny)) is NaN for a = 0 as soon as
+    // S / tiny overflows, i.e. S > 4: an exactly silent bin of the rebuilt spectrum under a non-zero target.)
+    const float sc = fast_div(1.0f, fast_sqrt(ax * ax + ay * ay) + kFltMin);      // MUFU.SQRT + MUFU.RCP: ~2 ulp each
+    xr = (ax * sc) * m; xi = (ay * sc) * m;
   }
 };
 

@@ -18,7 +18,8 @@ def timeit(fn, n=20, w=5):
 
 L, g, T = 80000, 3200, 417
 plan = sp.get_plan(512, 192, 384)
-sp.experiment_env(AIP_VAR_NO_FILL="1").__enter__()
+_keep = sp.experiment_env(AIP_VAR_NO_FILL="1")      # keep a reference: the switch lasts as long as the context object
+_keep.__enter__()
 for name, N, G, mode in (("256 files x 25, random starts", 256, 25, "random"), ("256 files x 25, sorted starts", 256, 25, "sorted"),
                          ("256 files x 25, all at 2.0 s", 256, 25, "fixed"), ("6400 files x 1, random", 6400, 1, "random"),
                          ("6400 files x 1, fixed", 6400, 1, "fixed")):
