@@ -269,6 +269,7 @@ def main():
     ap.add_argument("--model-clips", type=int, default=32, help="clips per GPU of the configs[4] leg (batch 256 on 8 GPUs = 32 per GPU)")
     ap.add_argument("--no-legs", action="store_true", help="headline step only (profiling runs)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-clock-probe", action="store_true", help="skip the 1.5 s untimed continuation (ncu launch lists)")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
 
@@ -368,7 +369,7 @@ def main():
     # the timed region lasts only K x 1.8 ms, shorter than nvidia-smi's sampling period: keep the SAME step
     # running (untimed) for ~1.5 s so that the clock / throttle record is taken under this kernel's load
     t_probe = time.perf_counter()
-    while time.perf_counter() - t_probe < 1.5:
+    while time.perf_counter() - t_probe < (0.0 if args.no_clock_probe else 1.5):
         for _ in range(50):
             step()
         torch.cuda.synchronize()

@@ -470,14 +470,16 @@ def mel_basis(sr: float, n_fft: int, n_mels: int = 128, fmin: float = 0.0, fmax:
     if fmax is None:
         fmax = float(sr) / 2
 
+    f_sp, min_log_hz, logstep = 200.0 / 3, 1000.0, np.log(6.4) / 27.0
+    min_log_mel = min_log_hz / f_sp          # librosa's expression: 14.999999999999998, not 15.0
+
     def hz_to_mel(f):
         f = np.asanyarray(f, dtype=np.float64)
-        lin = f / (200.0 / 3)
-        return np.where(f >= 1000.0, 15.0 + np.log(np.maximum(f, 1e-300) / 1000.0) / (np.log(6.4) / 27.0), lin)
+        return np.where(f >= min_log_hz, min_log_mel + np.log(np.maximum(f, 1e-300) / min_log_hz) / logstep, f / f_sp)
 
     def mel_to_hz(m):
         m = np.asanyarray(m, dtype=np.float64)
-        return np.where(m >= 15.0, 1000.0 * np.exp((np.log(6.4) / 27.0) * (m - 15.0)), (200.0 / 3) * m)
+        return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
 
     n_bins = 1 + n_fft // 2
     fftfreqs = np.fft.rfftfreq(n=n_fft, d=1.0 / sr)

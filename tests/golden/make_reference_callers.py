@@ -61,13 +61,15 @@ def mask_range(mask2d, inside):
     return f0, f1
 
 
-def generate():
+def generate(utils_impl: str = "reference"):
+    """``utils_impl='dropin'`` runs the SAME reference caller source on the B200 drop-in utils (needs a GPU and the reference
+    checkout: tools/run_reference_callers_on_dropin.py)."""
     import torch
     import yaml
     from ml_audio_inpainting_b200 import audio_io
 
     out = {}
-    with refshim.reference_modules("reference") as ref:
+    with refshim.reference_modules(utils_impl) as ref:
         REF = refshim.REFERENCE
         names = sorted(p.stem for p in (REF / "test_samples").glob("*.flac"))
         out["names"] = np.array(names)
@@ -139,7 +141,7 @@ def generate():
         for i in range(PRE_FILES):
             src = REF / "test_samples" / (names[i] + ".flac")
             audio_new, gap_int = ref.utils.add_random_gap(src, 0.1)
-            assert audio_new.dtype == np.float64 and audio_new.shape == (80000,)
+            assert audio_new.dtype == np.float64 and audio_new.shape == (80000,)     # the float64 quirk of utils.py:180-183
             dst = ref.tmp / f"{names[i]}_pre.flac"
             ref.utils.save_audio(audio_new, dst)
             pcm, info = audio_io.decode_flac(dst.read_bytes(), verify_md5=True)

@@ -199,3 +199,23 @@ def test_caller_epilogues_shapes():
     assert np.all(it["gap_mask"][:, f0:f1] == 1) and it["gap_mask"].sum() == 257 * (f1 - f0)
     g = cp.gan_item(x)
     assert g["original_magnitude"].shape == (257, 626) and g["mask"].min() == 0 and g["mask"].max() == 1
+
+
+@pytest.mark.parametrize("sr,n_fft,n_mels,fmin,fmax", [(16000, 2048, 128, 0.0, None), (16000, 512, 128, 0.0, None),
+                                                       (16000, 512, 64, 50.0, 7000.0), (22050, 1024, 80, 0.0, None)])
+def test_mel_matches_torchaudio(sr, n_fft, n_mels, fmin, fmax):
+    """librosa.filters.mel restated (Slaney scale, norm='slaney') against torchaudio's independent implementation, and
+    librosa.feature.melspectrogram as the contraction of that basis with |stft| ** power (utils.py:268-277)."""
+    torchaudio = pytest.importorskip("torchaudio")
+    m = lr.mel(sr=sr, n_fft=n_fft, n_mels=n_mels, fmin=fmin, fmax=fmax)
+    t = torchaudio.functional.melscale_fbanks(n_fft // 2 + 1, fmin, fmax if fmax else sr / 2, n_mels, sr, norm="slaney",
+                                              mel_scale="slaney").T.numpy()
+    assert m.dtype == np.float32 and m.shape == t.shape == (n_mels, n_fft // 2 + 1)
+    assert np.abs(m - t).max() / np.abs(m).max() < 2e-5
+    x = sine(0.5)
+    S = np.abs(lr.stft(x, n_fft=n_fft, hop_length=n_fft // 4)) ** 2.0
+    M = lr.melspectrogram(y=x, sr=sr, n_fft=n_fft, hop_length=n_fft // 4, n_mels=n_mels, fmin=fmin, fmax=fmax, power=2.0)
+    assert M.shape == (n_mels, S.shape[1]) and np.allclose(M, m @ S, rtol=1e-5, atol=1e-9 * S.max())
+    # the product builds the same table (two separately written forms of the same published algorithm)
+    from ml_audio_inpainting_b200.spectral import mel_basis
+    assert np.array_equal(mel_basis(sr, n_fft, n_mels, fmin, fmax), m)
