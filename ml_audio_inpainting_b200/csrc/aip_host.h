@@ -63,6 +63,7 @@ struct Tunables {
   int fwd_chunk;          // AIP_FWD_CHUNK       tiles per draw of the dynamic schedule (0 = built-in choice)
   int inv_tma;            // AIP_INV_TMA         0: never stage the inverse kernel's rows with TMA tensor boxes (default: where legal)
   int ola_fast_mask;      // AIP_OLA_FAST        bit mask of the specialised overlap-adds that may be used (-1 = all)
+  int inv_l2_prefetch;    // AIP_INV_L2_PREFETCH 0: stage A of the inverse kernels does not request the next tile's rows from L2
   int inv_bufs;           // AIP_INV_BUFS        exchange buffers in the inverse ring (0 = built-in choice)
   int gl_unfused;         // AIP_GL_UNFUSED      1: Griffin-Lim with the separate phase-update kernel
   int var_no_prefetch;    // AIP_VAR_NO_PREFETCH 1: gap-variant tiles do not request their rows from L2 ahead of the stores

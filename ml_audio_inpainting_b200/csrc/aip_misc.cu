@@ -134,6 +134,7 @@ static Tunables read_tunables() {
   t.inv_tma = env_int("AIP_INV_TMA", 1);
   t.ola_fast_mask = env_int("AIP_OLA_FAST", -1);
   t.inv_bufs = env_int("AIP_INV_BUFS", 0);
+  t.inv_l2_prefetch = env_int("AIP_INV_L2_PREFETCH", 1);
   t.gl_unfused = getenv("AIP_GL_UNFUSED") ? 1 : 0;
   t.var_no_prefetch = getenv("AIP_VAR_NO_PREFETCH") ? 1 : 0;
   const char* f = getenv("AIP_VAR_FILL");

@@ -459,6 +459,7 @@ struct InvParams {
   int n_tiles;
   int tiles_per_cta;
   int n_bufs;               // exchange buffers in the ring (1..kInvBufs)
+  int l2_prefetch;          // stage A requests the next tile's row segments from L2 while it works on this one
   InvGeom g;
   unsigned hop_magic;       // ceil(2^32 / hop)
   unsigned col_magic;       // ceil(2^32 / (hop / 2))

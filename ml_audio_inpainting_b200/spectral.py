@@ -493,15 +493,22 @@ def mel_basis(sr: float, n_fft: int, n_mels: int = 128, fmin: float = 0.0, fmax:
     return weights
 
 
+def mel_bands(basis: np.ndarray) -> np.ndarray:
+    """Per row of a filter bank the bin range [f0, f1) that holds all of its non-zero entries (int32 [n_mels, 2];
+    an all-zero row gets the empty range (0, 0)): what ``aip_mel_project_f32`` loops over instead of all F bins."""
+    nz = np.asarray(basis) != 0
+    any_ = nz.any(1)
+    f0 = np.where(any_, nz.argmax(1), 0)
+    f1 = np.where(any_, basis.shape[1] - nz[:, ::-1].argmax(1), 0)
+    return np.stack([f0, f1], 1).astype(np.int32)
+
+
 def _mel_tables(sr, n_fft, n_mels, fmin, fmax, device):
     key = (float(sr), int(n_fft), int(n_mels), float(fmin), None if fmax is None else float(fmax), device.index)
     hit = _mel_cache.get(key)
     if hit is None:
         w = mel_basis(sr, n_fft, n_mels, fmin, fmax)
-        nz = w != 0
-        f0 = np.where(nz.any(1), nz.argmax(1), 0)
-        f1 = np.where(nz.any(1), w.shape[1] - nz[:, ::-1].argmax(1), 0)
-        bands = np.stack([f0, f1], 1).astype(np.int32)
+        bands = mel_bands(w)
         inv = np.linalg.pinv(w).astype(np.float32)                       # utils.py:375 (host: a parameter table)
         hit = (torch.from_numpy(w).to(device), torch.from_numpy(bands).to(device), torch.from_numpy(np.ascontiguousarray(inv)).to(device))
         if len(_mel_cache) > 16:

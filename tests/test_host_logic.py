@@ -111,12 +111,46 @@ def test_product_never_imports_the_oracle():
     for src in [q for q in (PKG / "csrc").glob("*") if q.is_file()]:
         assert "oracle" not in src.read_text(errors="ignore").replace("the oracle", ""), src
     assert "TEST INFRASTRUCTURE ONLY" in (ROOT / "oracle" / "librosa_port.py").read_text()
-    assert "parity unpinned" in (ROOT / "oracle" / "__init__.py").read_text()
+    hdr = (ROOT / "oracle" / "__init__.py").read_text()
+    assert "TEST INFRASTRUCTURE ONLY" in hdr and "PINNED TO VALUES THE REFERENCE ITSELF PRODUCED" in hdr and "unpinned" in hdr
 
 
 def test_bench_and_entry_only_use_oracle_as_checker():
     bench = (ROOT / "bench.py").read_text()
-    assert bench.count("from oracle") == 1 and "_cpu_worker" in bench      # the cpu_baseline / reference arm only
+    # the cpu_baseline / reference arm only: the two CPU workers (the port, and the torch.stft baseline's window table)
+    assert bench.count("from oracle") == 2 and "_cpu_worker" in bench and "_torch_cpu_worker" in bench
+    for m in re.finditer(r"from oracle", bench):
+        head = bench[:m.start()]
+        assert head.rfind("def _cpu_worker") > head.rfind("def main") or head.rfind("def _torch_cpu_worker") > head.rfind("def main")
     entry = (ROOT / "__graft_entry__.py").read_text()
     assert entry.count("from oracle") == 1 and "def smoke" in entry and "def build" in entry
     assert re.search(r"/root/reference", bench) is None and re.search(r"/root/reference", entry) is None
+
+
+def test_mel_bands_cover_every_nonzero_weight():
+    """aip_mel_project_f32 sums each mel row over a host-computed bin range only: the range must hold every non-zero weight."""
+    from ml_audio_inpainting_b200.spectral import mel_bands, mel_basis
+    for args in ((16000, 2048, 128), (16000, 512, 128), (22050, 1024, 40)):
+        w = mel_basis(*args)
+        b = mel_bands(w)
+        assert b.dtype == np.int32 and b.shape == (args[2], 2)
+        for m in range(args[2]):
+            inside = np.zeros(w.shape[1], bool)
+            inside[b[m, 0]:b[m, 1]] = True
+            assert np.all(w[m][~inside] == 0)
+        # a bin belongs to at most two neighbouring triangles: the banded contraction reads the spectrogram about twice
+        assert int(((w != 0).sum(0)).max()) <= 2 and int((b[:, 1] - b[:, 0]).sum()) <= 2 * w.shape[1] + args[2]
+    z = np.zeros((3, 9), np.float32)
+    z[1, 4] = 1
+    assert mel_bands(z).tolist() == [[0, 0], [4, 5], [0, 0]]
+
+
+def test_experiment_env_sets_reloads_and_restores(monkeypatch):
+    """AIP_* switches are read once when the library loads; experiment_env sets them, makes the library re-read, and restores."""
+    import os
+    from ml_audio_inpainting_b200 import spectral
+    monkeypatch.setenv("AIP_FWD_CHUNK", "7")
+    monkeypatch.delenv("AIP_INV_TMA", raising=False)
+    with spectral.experiment_env(AIP_FWD_CHUNK=None, AIP_INV_TMA="0"):
+        assert "AIP_FWD_CHUNK" not in os.environ and os.environ["AIP_INV_TMA"] == "0"
+    assert os.environ["AIP_FWD_CHUNK"] == "7" and "AIP_INV_TMA" not in os.environ
