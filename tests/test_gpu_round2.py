@@ -141,10 +141,14 @@ def _spec_corr(a, b):
 
 
 # Measured on a B200 (this test prints the values): the fp32 CUDA iteration against the oracle (complex64 state, float64 FFTs)
-# from IDENTICAL initial phasors.  Griffin-Lim is a fixed-point iteration without contraction: rounding differences grow with
-# the iteration count, so the waveform bound is stated per count, and what stays tight is the thing the algorithm optimises --
-# the magnitude spectrogram of the result (spectral convergence) -- which is asserted against the oracle's own value.
-GL_WAVE_BOUND = {0: 1e-4, 1: 1e-4, 2: 2e-4, 8: 5e-3, 32: 2.5e-1, 64: 5e-1}
+# from IDENTICAL initial phasors, relative max-abs error of the waveform on two 1-s noise clips:
+#     n_iter   0        1        2        8        32                 64
+#     error    2.4e-7   7.5e-7   2.0e-6   1.3e-5   4.6e-5 / 7.2e-4    1.7e-4 / 8.4e-4
+# Griffin-Lim is a fixed-point iteration without contraction: rounding differences grow with the iteration count, so beyond 8
+# iterations the 1e-4 bound of the single transforms no longer holds for the waveform (stated bound: 3e-3 = 3.5 x the measured
+# worst case); what stays tight is the thing the algorithm optimises -- the magnitude spectrogram of the result (spectral
+# convergence) -- asserted against the oracle's own value (measured: equal to 5 digits at every count).
+GL_WAVE_BOUND = {0: 1e-4, 1: 1e-4, 2: 1e-4, 8: 1e-4, 32: 3e-3, 64: 3e-3}
 
 
 def test_griffinlim_value_parity_at_the_references_iteration_counts(sp):
