@@ -375,7 +375,7 @@ def istft(plan: StftPlan, spec: Optional[torch.Tensor] = None, mag: Optional[tor
 def istft_blend(plan: StftPlan, model_out: torch.Tensor, blend_in: torch.Tensor, blend_mask: torch.Tensor,
                 phase: torch.Tensor, mag_domain: int = DOM_POW10, length: Optional[int] = None,
                 mask_keeps_input: bool = False, normalize: bool = False,
-                peaks_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                peaks_out: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """The model hand-off in one kernel (``aip_istft_handoff_f32``): blend, un-log, phase reuse, istft.
 
     ``mask_keeps_input=False``: ``m = model_out * mask + blend_in * (1 - mask)`` -- the CNN-BLSTM convention, mask 1 inside
@@ -397,7 +397,7 @@ def istft_blend(plan: StftPlan, model_out: torch.Tensor, blend_in: torch.Tensor,
         raise ValueError(f"expected {plan.n_bins} frequency bins for n_fft={plan.n_fft}, got {F}")
     dev = ts[0].device
     lib = _cabi.load()
-    out = torch.empty((B, plan.istft_length(T, length)), dtype=torch.float32, device=dev)
+    out = _out_buf(out, (B, plan.istft_length(T, length)), dev)
     inv = plan.inv_wss(T, length)
     ws_bytes = int(lib.aip_istft_workspace_bytes(C.byref(plan.desc), B, T))
     ws = torch.empty(max(ws_bytes, 4) // 4, dtype=torch.float32, device=dev) if ws_bytes else None
@@ -517,8 +517,16 @@ def _mel_tables(sr, n_fft, n_mels, fmin, fmax, device):
     return hit
 
 
+def _out_buf(out: Optional[torch.Tensor], shape, device) -> torch.Tensor:
+    if out is None:
+        return torch.empty(shape, dtype=torch.float32, device=device)
+    if tuple(out.shape) != tuple(shape) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != device:
+        raise ValueError("out has the wrong shape/dtype/layout/device")
+    return out
+
+
 def mel_project(spec_pow: torch.Tensor, sr: float, n_fft: int, n_mels: int = 128, fmin: float = 0.0,
-                fmax: Optional[float] = None) -> torch.Tensor:
+                fmax: Optional[float] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """mel[b, m, t] = sum_f basis[m, f] * spec_pow[b, f, t] (``aip_mel_project_f32``): the contraction of
     librosa.feature.melspectrogram (utils.py:268-277) on ``|stft| ** power`` [B, F, T] -> [B, n_mels, T]."""
     _require_cuda(spec_pow, "spec_pow")
@@ -528,7 +536,7 @@ def mel_project(spec_pow: torch.Tensor, sr: float, n_fft: int, n_mels: int = 128
     if F != 1 + n_fft // 2:
         raise ValueError(f"expected {1 + n_fft // 2} frequency bins for n_fft={n_fft}, got {F}")
     basis, bands, _ = _mel_tables(sr, n_fft, n_mels, fmin, fmax, s.device)
-    out = torch.empty((B, int(n_mels), T), dtype=torch.float32, device=s.device)
+    out = _out_buf(out, (B, int(n_mels), T), s.device)
     with torch.cuda.device(s.device):
         check(_cabi.load().aip_mel_project_f32(_ptr(basis), _ptr(bands), _ptr(s), B, F, T, int(n_mels), _ptr(out), _stream()),
               "aip_mel_project_f32")
@@ -536,7 +544,7 @@ def mel_project(spec_pow: torch.Tensor, sr: float, n_fft: int, n_mels: int = 128
 
 
 def mel_inverse(mel: torch.Tensor, sr: float, n_fft: int, n_mels: int = 128, fmin: float = 0.0,
-                fmax: Optional[float] = None, take_sqrt: bool = False) -> torch.Tensor:
+                fmax: Optional[float] = None, take_sqrt: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """pinv(mel basis) @ mel (+ sqrt for power spectrograms): utils.py:375-383 on the device (``aip_mel_inverse_f32``).
     Negative projections become NaN under the square root as ``np.sqrt`` makes them in the reference -- except those below
     the noise floor of an fp32 power spectrogram (<= 1e-9 of the clip's largest projection), which are taken as 0."""
@@ -548,7 +556,7 @@ def mel_inverse(mel: torch.Tensor, sr: float, n_fft: int, n_mels: int = 128, fmi
         raise ValueError(f"shapes ({1 + n_fft // 2},{int(n_mels)}) and ({M},{T}) not aligned")
     F = 1 + n_fft // 2
     _, _, inv = _mel_tables(sr, n_fft, n_mels, fmin, fmax, m.device)
-    out = torch.empty((B, F, T), dtype=torch.float32, device=m.device)
+    out = _out_buf(out, (B, F, T), m.device)
     peaks = torch.empty(B, dtype=torch.float32, device=m.device) if take_sqrt else None
     with torch.cuda.device(m.device):
         check(_cabi.load().aip_mel_inverse_f32(_ptr(inv), _ptr(m), B, F, T, int(n_mels), int(bool(take_sqrt)), _ptr(out),

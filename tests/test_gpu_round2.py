@@ -344,3 +344,53 @@ def test_mel_front_and_back_end(sp, utils, n_fft, hop, n_mels, power):
     # the whole back-end (tests/utils_test.py:420-443): a finite, non-silent waveform of librosa's length
     y = utils.mel_spectrogram_to_audio(ref, sample_rate=SR, n_fft=n_fft, hop_length=hop, n_iter=4, n_mels=n_mels, power=1.0)
     assert y.ndim == 1 and len(y) == hop * (ref.shape[1] - 1) and np.isfinite(y).all() and not np.allclose(y, 0)
+
+
+# ------------------------------------------------------------------------------------------- guard regions (round-2 kernels)
+@pytest.mark.parametrize("L,hop,win", [(16000, 192, 384), (16001, 192, 384), (7777, 128, 512), (700, 192, 384)])
+def test_round2_kernels_write_inside_their_outputs(sp, L, hop, win):
+    """compute-sanitizer is closed on this GPU pool: the outputs of the kernels added in round 2 (TMA-staged inverse for even
+    and the direct one for odd T, the hand-off in both mask conventions, Griffin-Lim with staged / direct loads, mel projection
+    and inverse) sit between sentinel guard regions that must survive, and every output element must have been written."""
+    B, G, SENT = 3, 4096, -12345.0
+    x = torch.from_numpy(_noise(B, L, seed=L)).cuda()
+    plan = sp.get_plan(512, hop, win, "hann", True, "cuda:0")
+    T, F = plan.num_frames(L), 257
+
+    def guarded(shape):
+        n = int(np.prod(shape))
+        flat = torch.full((n + 2 * G,), SENT, dtype=torch.float32, device="cuda")
+        return flat, flat[G:G + n].view(shape)
+
+    def check(flat, view, what):
+        torch.cuda.synchronize()
+        ref = torch.full((G,), SENT, dtype=torch.float32, device="cuda")
+        assert torch.equal(flat[:G], ref) and torch.equal(flat[-G:], ref), what
+        assert not bool(view.eq(SENT).any()), what
+
+    r = sp.stft(x, plan, mag_kind=sp.MAG_ABS, want_spec=True, want_phase=True)
+    for Tn in (T, T - 1):                                   # one even, one odd frame count: staged and direct stage A
+        S, mag, ph = (r[k][:, :, :Tn].contiguous() for k in ("spec", "mag", "phase"))
+        n = plan.istft_length(Tn)
+        flat, y = guarded((B, n))
+        sp.istft(plan, spec=S, out=y)
+        check(flat, y, ("istft", Tn))
+        mask = torch.zeros_like(mag)
+        mask[:, :, 3:6] = 1
+        for keeps in (False, True):
+            for dom in (sp.DOM_LINEAR, sp.DOM_POW10, sp.DOM_EXPM1):
+                flat, y = guarded((B, n))
+                sp.istft_blend(plan, mag * 0.5, mag * 0.1, mask, ph, mag_domain=dom, mask_keeps_input=keeps, normalize=True, out=y)
+                check(flat, y, ("handoff", Tn, keeps, dom))
+        y = sp.griffinlim(plan, mag, n_iter=3)              # state arrays are internal; the waveform must be finite and complete
+        assert tuple(y.shape) == (B, n) and bool(torch.isfinite(y).all())
+    flat, mel = guarded((B, 40, T))
+    sp.mel_project(r["mag"], SR, 512, 40, out=mel)
+    check(flat, mel, "mel_project")
+    for sq in (False, True):
+        flat, back = guarded((B, F, T))
+        sp.mel_inverse(mel, SR, 512, 40, take_sqrt=sq, out=back)
+        torch.cuda.synchronize()
+        ref = torch.full((G,), SENT, dtype=torch.float32, device="cuda")
+        assert torch.equal(flat[:G], ref) and torch.equal(flat[-G:], ref)
+        assert not bool(back.eq(SENT).any())
