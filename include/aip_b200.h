@@ -126,11 +126,12 @@ int aip_istft_blend_f32(const aip_stft_desc* desc, const float* model_out, const
  *                          (combined_log_mag, models/GAN/train.py:473)
  *   mag_domain: AIP_DOM_LINEAR (GAN/train.py:476 hands the log1p-domain blend to spectrogram_to_audio as it is),
  *               AIP_DOM_POW10 (models/model_eval.py:163), AIP_DOM_DB, AIP_DOM_EXPM1 (undoing the GAN's log1p).
- *   peaks: device [B] float or null; see aip_istft_normalized_f32.                                                      */
+ *   peaks: device [B] float or null; pcm_out: device [B, pcm_pitch] int16 or null -- see aip_istft_normalized_f32
+ *   (peaks null + pcm_out: the un-normalised waveform is quantised as it is).                                           */
 int aip_istft_handoff_f32(const aip_stft_desc* desc, const float* model_out, const float* blend_in,
                           const float* blend_mask, int32_t mask_keeps_input, const float* phase, int32_t mag_domain,
                           int64_t B, int64_t T, int64_t length, const float* inv_wss,
-                          float* wave_out, int64_t out_pitch, float* peaks,
+                          float* wave_out, int64_t out_pitch, float* peaks, int16_t* pcm_out, int64_t pcm_pitch,
                           void* workspace, size_t workspace_bytes, void* stream);
 /* 0 when the (n_fft, hop, center) combination runs the fused n_fft = 512 kernel. */
 size_t aip_istft_workspace_bytes(const aip_stft_desc* desc, int64_t B, int64_t T);
@@ -188,12 +189,16 @@ int aip_frame_mask_f32(float* mask, int64_t B, int64_t F, int64_t T, const int32
  * spectrogram_to_audio's result before writing it (utils.save_audio, utils.py:84; models/CNNBLSTM/train.py:184-186,
  * models/model_eval.py:130,179).  The per-clip peak max|y| is taken inside the overlap-add of the inverse kernel (one
  * atomic per warp and tile), so the waveform is read back only once, by the in-place scaling pass.
- * peaks: device [B] float, out (the peak of each clip BEFORE scaling); clips whose peak is < FLT_MIN stay unscaled.   */
+ * peaks: device [B] float, out (the peak of each clip BEFORE scaling); clips whose peak is < FLT_MIN stay unscaled.
+ * pcm_out: null, or device [B, pcm_pitch] int16 -- then that one pass writes what save_audio puts into its 16-bit FLAC
+ * (utils.py:87, soundfile's float -> PCM_16: x * 32768, round half to even, clip to [-32768, 32767]; SURVEY 8f rank 1
+ * "optional int16 quantisation for the encoder") and wave_out keeps the UN-normalised waveform: the float scaling pass
+ * and half of the device -> host bytes are saved.                                                                    */
 int aip_istft_normalized_f32(const aip_stft_desc* desc,
                              const float* spec, const float* mag, const float* phase, int32_t mag_domain,
                              const int32_t* db_flags,
                              int64_t B, int64_t T, int64_t length, const float* inv_wss,
-                             float* wave_out, int64_t out_pitch, float* peaks,
+                             float* wave_out, int64_t out_pitch, float* peaks, int16_t* pcm_out, int64_t pcm_pitch,
                              void* workspace, size_t workspace_bytes, void* stream);
 /* Gap variants of one file: models/CNNBLSTM/dataset.py:93-111 loads a file gaps_per_audio times, zeroes a
  * different random range each time (utils.add_random_gap, utils.py:179-183) and runs a full STFT per gap; a gap only changes
@@ -212,6 +217,16 @@ int aip_stft_gap_variants_f32(const aip_stft_desc* desc, const float* wave, int6
                               float* mag_out /* [N*G, F, T_out] */, void* workspace, size_t workspace_bytes, void* stream);
 
 /* y_b / max|y_b| unless max|y_b| < FLT_MIN; peaks: [B] float scratch/out (the per-clip max|y|). */
+/* save_audio's tail (utils.py:83-87) for a waveform that is already on the device: librosa.util.normalize + soundfile's
+ * float -> PCM_16 conversion (see aip_istft_normalized_f32), one read of `in`, int16 out.
+ *   AIP_PCM_RAW          quantise as is (save_audio(normalize=False)); peaks unused
+ *   AIP_PCM_NORMALIZE    take each clip's peak here (one more read of `in`), write it to peaks[B], divide, quantise
+ *   AIP_PCM_PEAKS_GIVEN  peaks[B] already holds max|in| per clip                                                        */
+#define AIP_PCM_RAW 0
+#define AIP_PCM_NORMALIZE 1
+#define AIP_PCM_PEAKS_GIVEN 2
+int aip_wave_to_pcm16_f32(const float* in, int64_t in_pitch, int16_t* pcm, int64_t pcm_pitch, int64_t B, int64_t L,
+                          int32_t peaks_mode, float* peaks, void* stream);
 int aip_peak_normalize_f32(const float* in, int64_t in_pitch, float* out, int64_t out_pitch,
                            int64_t B, int64_t L, float* peaks, void* stream);
 

@@ -36,9 +36,9 @@ SIGNATURES = {
     "aip_stft_fwd_f32": (C.c_int, [_D, _P, _I64, _I64, _I64, _P, _P, _P, _I32, _I32, _F, _F, _I64,
                                    _P, _P, _P, _P, _P]),
     "aip_istft_f32": (C.c_int, [_D, _P, _P, _P, _I32, _P, _I64, _I64, _I64, _P, _P, _I64, _P, _SZ, _P]),
-    "aip_istft_normalized_f32": (C.c_int, [_D, _P, _P, _P, _I32, _P, _I64, _I64, _I64, _P, _P, _I64, _P, _P, _SZ, _P]),
+    "aip_istft_normalized_f32": (C.c_int, [_D, _P, _P, _P, _I32, _P, _I64, _I64, _I64, _P, _P, _I64, _P, _P, _I64, _P, _SZ, _P]),
     "aip_istft_blend_f32": (C.c_int, [_D, _P, _P, _P, _P, _I32, _I64, _I64, _I64, _P, _P, _I64, _P, _SZ, _P]),
-    "aip_istft_handoff_f32": (C.c_int, [_D, _P, _P, _P, _I32, _P, _I32, _I64, _I64, _I64, _P, _P, _I64, _P, _P, _SZ, _P]),
+    "aip_istft_handoff_f32": (C.c_int, [_D, _P, _P, _P, _I32, _P, _I32, _I64, _I64, _I64, _P, _P, _I64, _P, _P, _I64, _P, _SZ, _P]),
     "aip_istft_workspace_bytes": (_SZ, [_D, _I64, _I64]),
     "aip_inv_window_sumsquare_f32": (C.c_int, [_D, _I64, _I64, _P, _I64, _P]),
     "aip_griffinlim_f32": (C.c_int, [_D, _P, _P, _P, _I64, _I64, _I32, _F, _P, _P, _I64, _P, _SZ, _P]),
@@ -52,6 +52,7 @@ SIGNATURES = {
     "aip_stft_gap_variants_workspace_bytes": (_SZ, [_I64, _I64]),
     "aip_stft_gap_variants_f32": (C.c_int, [_D, _P, _I64, _I64, _I64, _I64, _P, _I32, _I32, _F, _I64, _P, _P, _P, _SZ, _P]),
     "aip_peak_normalize_f32": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, _P, _P]),
+    "aip_wave_to_pcm16_f32": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, _I32, _P, _P]),
     "aip_status_string": (C.c_char_p, [C.c_int]),
     "aip_debug_reload_env": (None, []),
     "aip_version": (C.c_char_p, []),

@@ -496,7 +496,8 @@ def _to_int16(audio: np.ndarray, scale: float = 32767.0) -> np.ndarray:
 
 
 def write_wav(audio: np.ndarray, sample_rate: int) -> bytes:
-    pcm = _to_int16(audio)
+    audio = np.asarray(audio)
+    pcm = audio if audio.dtype == np.int16 else _to_int16(audio)
     if pcm.ndim == 1:
         pcm = pcm[:, None]
     nch = pcm.shape[1]
@@ -520,7 +521,19 @@ def read_audio(path, max_samples: Optional[int] = None) -> Tuple[np.ndarray, int
 
 
 def write_audio(path, audio: np.ndarray, sample_rate: int, file_format: str = "flac") -> None:
+    """Float audio is quantised here; an int16 array is taken as the 16-bit samples themselves (quantised on the device:
+    ``spectral.wave_to_pcm16`` / ``istft(..., pcm16=True)``)."""
     fmt = file_format.lower()
+    audio = np.asarray(audio)
+    if audio.dtype == np.int16:
+        if fmt == "flac":
+            blob = encode_flac(audio, sample_rate)
+        elif fmt == "wav":
+            blob = write_wav(audio, sample_rate)
+        else:
+            raise ValueError(f"unsupported output format {file_format!r} (flac and wav are built in)")
+        Path(path).write_bytes(blob)
+        return
     if fmt == "flac":
         # FLAC: x * 32768 with clipping.  Pinned by the reference's own outputs: after save_audio's peak normalisation five of
         # the nine test_samples_reconstructed/*_cnnlstm_inpainted.flac hold a -32768 sample (|x| = 1 at a negative peak) and the

@@ -78,6 +78,8 @@ void tunables_reload();
 int run_fwd(const aip_stft_desc* desc, FwdParams P, long long T_out, cudaStream_t st);
 bool fwd_fast_ok(const aip_stft_desc* d, const DevInfo& di);
 cudaError_t launch_peak(const float* in, long long pitch, long long B, long long L, float* peaks, cudaStream_t st);
+cudaError_t launch_pcm16(const float* in, long long in_pitch, short* pcm, long long pcm_pitch, long long B, long long L,
+                         const float* peaks, int sms, cudaStream_t st);
 cudaError_t launch_peak_scale(const float* in, long long in_pitch, float* out, long long out_pitch, long long B, long long L,
                               const float* peaks, int sms, cudaStream_t st);
 

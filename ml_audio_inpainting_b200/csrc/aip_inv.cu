@@ -759,13 +759,36 @@ int aip_istft_blend_f32(const aip_stft_desc* desc, const float* model_out, const
                         size_t workspace_bytes, void* stream) {
   if (mag_domain != DOM_POW10 && mag_domain != DOM_DB) return AIP_ERR_UNSUPPORTED;
   return aip_istft_handoff_f32(desc, model_out, blend_in, blend_mask, 0, phase, mag_domain, B, T, length, inv_wss, wave_out,
-                               out_pitch, nullptr, workspace, workspace_bytes, stream);
+                               out_pitch, nullptr, nullptr, 0, workspace, workspace_bytes, stream);
+}
+
+// inverse with the per-clip peak taken in its overlap-add, then ONE pass over the waveform: the in-place scaling of
+// librosa.util.normalize, or -- pcm_out given -- the same division followed by the float -> PCM_16 conversion, written to pcm_out
+// (P.out then keeps the un-normalised waveform)
+static int normalized_tail(const aip_stft_desc* desc, InvParams& P, int64_t length, long long out_len, float* peaks,
+                           int16_t* pcm_out, int64_t pcm_pitch, void* workspace, size_t workspace_bytes, const DevInfo& di,
+                           cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(peaks, 0, (size_t)P.B * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  const bool fused = inv_fast_ok(desc);
+  P.peaks = fused ? peaks : nullptr;
+  const int rc = run_inv(desc, P, length, workspace, workspace_bytes, st);
+  if (rc != AIP_OK) return rc;
+  if (out_len <= 0) return AIP_OK;
+  if (!fused) {      // generic n_fft path: separate peak pass
+    if (P.B > 65535) return AIP_ERR_UNSUPPORTED;
+    e = launch_peak(P.out, P.out_pitch, P.B, out_len, peaks, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (pcm_out)
+    return (int)launch_pcm16(P.out, P.out_pitch, reinterpret_cast<short*>(pcm_out), pcm_pitch, P.B, out_len, peaks, di.sms, st);
+  return (int)launch_peak_scale(P.out, P.out_pitch, P.out, P.out_pitch, P.B, out_len, peaks, di.sms, st);
 }
 
 int aip_istft_handoff_f32(const aip_stft_desc* desc, const float* model_out, const float* blend_in, const float* blend_mask,
                           int32_t mask_keeps_input, const float* phase, int32_t mag_domain, int64_t B, int64_t T,
                           int64_t length, const float* inv_wss, float* wave_out, int64_t out_pitch, float* peaks,
-                          void* workspace, size_t workspace_bytes, void* stream) {
+                          int16_t* pcm_out, int64_t pcm_pitch, void* workspace, size_t workspace_bytes, void* stream) {
   if (B > 0x7fffffffLL || T > 0x7fffffffLL || B < 0) return AIP_ERR_ARG;
   if (!desc || !model_out || !blend_in || !blend_mask || !phase) return AIP_ERR_ARG;
   if (mag_domain < DOM_LINEAR || mag_domain > DOM_EXPM1) return AIP_ERR_ARG;
@@ -780,21 +803,14 @@ int aip_istft_handoff_f32(const aip_stft_desc* desc, const float* model_out, con
   P.blend_in = mask_keeps_input ? model_out : blend_in;
   P.blend_mask = blend_mask; P.phase = phase; P.mag_domain = mag_domain;
   P.B = (int)B; P.T = (int)T; P.inv_wss = inv_wss; P.out = wave_out; P.out_pitch = out_pitch;
-  if (!peaks) return run_inv(desc, P, length, workspace, workspace_bytes, st);
-  cudaError_t e = cudaMemsetAsync(peaks, 0, (size_t)B * sizeof(float), st);
-  if (e != cudaSuccess) return (int)e;
-  const bool fused = inv_fast_ok(desc);
-  P.peaks = fused ? peaks : nullptr;
-  const int rc = run_inv(desc, P, length, workspace, workspace_bytes, st);
-  if (rc != AIP_OK) return rc;
   const long long out_len = istft_length(T, desc->n_fft, desc->hop, desc->center, length);
-  if (out_len <= 0) return AIP_OK;
-  if (!fused) {
-    if (B > 65535) return AIP_ERR_UNSUPPORTED;
-    e = launch_peak(wave_out, out_pitch, B, out_len, peaks, st);
-    if (e != cudaSuccess) return (int)e;
+  if (pcm_out && pcm_pitch < out_len) return AIP_ERR_ARG;
+  if (!peaks) {
+    const int rc = run_inv(desc, P, length, workspace, workspace_bytes, st);
+    if (rc != AIP_OK || !pcm_out || out_len <= 0) return rc;
+    return (int)launch_pcm16(wave_out, out_pitch, reinterpret_cast<short*>(pcm_out), pcm_pitch, B, out_len, nullptr, di.sms, st);
   }
-  return (int)launch_peak_scale(wave_out, out_pitch, wave_out, out_pitch, B, out_len, peaks, di.sms, st);
+  return normalized_tail(desc, P, length, out_len, peaks, pcm_out, pcm_pitch, workspace, workspace_bytes, di, st);
 }
 
 size_t aip_istft_workspace_bytes(const aip_stft_desc* desc, int64_t B, int64_t T) {
@@ -815,30 +831,19 @@ int aip_istft_f32(const aip_stft_desc* desc, const float* spec, const float* mag
 
 int aip_istft_normalized_f32(const aip_stft_desc* desc, const float* spec, const float* mag, const float* phase,
                              int32_t mag_domain, const int32_t* db_flags, int64_t B, int64_t T, int64_t length,
-                             const float* inv_wss, float* wave_out, int64_t out_pitch, float* peaks, void* workspace,
-                             size_t workspace_bytes, void* stream) {
+                             const float* inv_wss, float* wave_out, int64_t out_pitch, float* peaks, int16_t* pcm_out,
+                             int64_t pcm_pitch, void* workspace, size_t workspace_bytes, void* stream) {
   if (B > 0x7fffffffLL || T > 0x7fffffffLL || B < 0 || !peaks || !desc) return AIP_ERR_ARG;
   if (B == 0) return AIP_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const DevInfo di = dev_info();
   if (!di.ok) return AIP_ERR_DEVICE;
-  cudaError_t e = cudaMemsetAsync(peaks, 0, (size_t)B * sizeof(float), st);
-  if (e != cudaSuccess) return (int)e;
-  const bool fused = inv_fast_ok(desc);
+  const long long out_len = istft_length(T, desc->n_fft, desc->hop, desc->center, length);
+  if (pcm_out && pcm_pitch < out_len) return AIP_ERR_ARG;
   InvParams P{};
   P.spec = reinterpret_cast<const float2*>(spec); P.mag = mag; P.phase = phase; P.mag_domain = mag_domain;
   P.db_flags = db_flags; P.B = (int)B; P.T = (int)T; P.inv_wss = inv_wss; P.out = wave_out; P.out_pitch = out_pitch;
-  P.peaks = fused ? peaks : nullptr;
-  const int rc = run_inv(desc, P, length, workspace, workspace_bytes, st);
-  if (rc != AIP_OK) return rc;
-  const long long out_len = istft_length(T, desc->n_fft, desc->hop, desc->center, length);
-  if (out_len <= 0) return AIP_OK;
-  if (!fused) {      // generic n_fft path: separate peak pass
-    if (B > 65535) return AIP_ERR_UNSUPPORTED;
-    e = launch_peak(wave_out, out_pitch, B, out_len, peaks, st);
-    if (e != cudaSuccess) return (int)e;
-  }
-  return (int)launch_peak_scale(wave_out, out_pitch, wave_out, out_pitch, B, out_len, peaks, di.sms, st);
+  return normalized_tail(desc, P, length, out_len, peaks, pcm_out, pcm_pitch, workspace, workspace_bytes, di, st);
 }
 
 int aip_inv_window_sumsquare_f32(const aip_stft_desc* desc, int64_t T, int64_t length, float* inv_wss,

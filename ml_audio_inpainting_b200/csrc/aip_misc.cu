@@ -108,6 +108,43 @@ __global__ void peak_scale_kernel(const float* in, long long in_pitch, float* ou
   }
 }
 
+// save_audio's tail for the 16-bit FLAC it writes (utils.py:83-87): x / peak (librosa.util.normalize; peaks == nullptr: as is), then
+// libsndfile's float -> PCM_16 conversion for FLAC: x * 32768, round half to even, clip to [-32768, 32767].  One thread = two samples.
+__global__ void pcm16_kernel(const float* in, long long in_pitch, short* pcm, long long pcm_pitch, long long B, long long L,
+                             const float* peaks) {
+  const long long half = (L + 1) >> 1, total = B * half;
+  const bool vec = ((in_pitch | pcm_pitch) & 1) == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0 &&
+                   (reinterpret_cast<uintptr_t>(pcm) & 3) == 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / half, s = 2 * (i % half);
+    const float pk = peaks ? peaks[b] : 0.0f;
+    const bool two = s + 1 < L;
+    float v0, v1 = 0.0f;
+    if (vec && two) {
+      const float2 v = *reinterpret_cast<const float2*>(in + b * in_pitch + s);
+      v0 = v.x; v1 = v.y;
+    } else {
+      v0 = in[b * in_pitch + s];
+      if (two) v1 = in[b * in_pitch + s + 1];
+    }
+    if (pk >= kFltMin) { v0 = __fdiv_rn(v0, pk); v1 = __fdiv_rn(v1, pk); }
+    const int q0 = min(32767, max(-32768, __float2int_rn(v0 * 32768.0f)));
+    const int q1 = min(32767, max(-32768, __float2int_rn(v1 * 32768.0f)));
+    if (vec && two) {
+      *reinterpret_cast<short2*>(pcm + b * pcm_pitch + s) = make_short2((short)q0, (short)q1);
+    } else {
+      pcm[b * pcm_pitch + s] = (short)q0;
+      if (two) pcm[b * pcm_pitch + s + 1] = (short)q1;
+    }
+  }
+}
+
+cudaError_t launch_pcm16(const float* in, long long in_pitch, short* pcm, long long pcm_pitch, long long B, long long L,
+                         const float* peaks, int sms, cudaStream_t st) {
+  pcm16_kernel<<<ew_grid(B * ((L + 1) >> 1), sms), 256, 0, st>>>(in, in_pitch, pcm, pcm_pitch, B, L, peaks);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_peak(const float* in, long long pitch, long long B, long long L, float* peaks, cudaStream_t st) {
   long long gx = (L + 256 * 8 - 1) / (256 * 8);
   if (gx < 1) gx = 1;
@@ -220,6 +257,27 @@ int aip_peak_normalize_f32(const float* in, int64_t in_pitch, float* out, int64_
   if (e != cudaSuccess) return (int)e;
   peak_scale_kernel<<<ew_grid(B * L, di.sms), 256, 0, st>>>(in, in_pitch, out, out_pitch, B, L, peaks);
   return (int)cudaGetLastError();
+}
+
+int aip_wave_to_pcm16_f32(const float* in, int64_t in_pitch, int16_t* pcm, int64_t pcm_pitch, int64_t B, int64_t L,
+                          int32_t peaks_mode, float* peaks, void* stream) {
+  const DevInfo di = dev_info();
+  if (!di.ok) return AIP_ERR_DEVICE;
+  if (!in || !pcm || B < 0 || L < 0 || in_pitch < L || pcm_pitch < L) return AIP_ERR_ARG;
+  if (peaks_mode < AIP_PCM_RAW || peaks_mode > AIP_PCM_PEAKS_GIVEN || (peaks_mode != AIP_PCM_RAW && !peaks)) return AIP_ERR_ARG;
+  if (B * L == 0) return AIP_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (peaks_mode == AIP_PCM_NORMALIZE) {
+    cudaError_t e = cudaMemsetAsync(peaks, 0, (size_t)B * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+    for (long long lo = 0; lo < B; lo += 65535) {          // grid.y limit
+      const long long n = B - lo < 65535 ? B - lo : 65535;
+      e = launch_peak(in + lo * in_pitch, in_pitch, n, L, peaks + lo, st);
+      if (e != cudaSuccess) return (int)e;
+    }
+  }
+  return (int)launch_pcm16(in, in_pitch, reinterpret_cast<short*>(pcm), pcm_pitch, B, L,
+                           peaks_mode == AIP_PCM_RAW ? nullptr : peaks, di.sms, st);
 }
 
 const char* aip_status_string(int status) {

@@ -188,12 +188,15 @@ def backend_batch(magnitude: torch.Tensor, phase: torch.Tensor, n_fft: int = 512
 
 
 def cnnblstm_backend_batch(model_out: torch.Tensor, log_spectrogram_gap: torch.Tensor, gap_mask: torch.Tensor,
-                           phase: torch.Tensor, n_fft: int = 512, hop_length: int = 192, win_length: int = 384) -> torch.Tensor:
+                           phase: torch.Tensor, n_fft: int = 512, hop_length: int = 192, win_length: int = 384,
+                           save_pcm16: bool = False) -> torch.Tensor:
     """Everything between the network's raw output and the waveform in ONE kernel: reconstruct_spectrogram's blend
     ``out * mask + in * (1 - mask)`` (models/CNNBLSTM/model.py:108), ``10 **`` (models/model_eval.py:163) and
-    ``utils.spectrogram_to_audio(mag, phase=phase)`` (:179-189)."""
+    ``utils.spectrogram_to_audio(mag, phase=phase)`` (:179-189).  ``save_pcm16`` goes on to what ``utils.save_audio`` puts
+    into the inpainted FLAC (models/model_eval.py:190-192 -> utils.py:83-87): peak-normalised, 16-bit, returned as int16."""
     plan = sp.get_plan(n_fft, hop_length, win_length, "hann", True, model_out.device)
-    return sp.istft_blend(plan, model_out, log_spectrogram_gap, gap_mask, phase, mag_domain=sp.DOM_POW10)
+    return sp.istft_blend(plan, model_out, log_spectrogram_gap, gap_mask, phase, mag_domain=sp.DOM_POW10,
+                          normalize=save_pcm16, pcm16=save_pcm16)
 
 
 class HostPipeline:

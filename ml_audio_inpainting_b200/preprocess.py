@@ -26,9 +26,11 @@ __all__ = ["preprocess_batch", "preprocess_tree"]
 
 def preprocess_batch(wave: torch.Tensor, gap_len: float = 0.1, sample_rate: int = 16000,
                      starts: Optional[np.ndarray] = None, normalize: bool = True, want_logmag: bool = False,
-                     n_fft: int = 512, hop_length: int = 192, win_length: int = 384) -> dict:
+                     n_fft: int = 512, hop_length: int = 192, win_length: int = 384, want_pcm16: bool = False) -> dict:
     """``wave`` [N, L] float32 on the device (this rank's shard).  One np.random draw per clip unless ``starts``
-    is given (the caller draws for the WHOLE corpus and passes its slice: see ``sharding``)."""
+    is given (the caller draws for the WHOLE corpus and passes its slice: see ``sharding``).  ``want_pcm16`` replaces the
+    normalised float waveform by ``pcm16`` [N, L] int16: the samples ``save_audio`` writes into its 16-bit FLAC (utils.py:83-87),
+    straight from the gapped waveform (half the device -> host bytes, no host-side quantisation)."""
     if not wave.is_cuda:
         raise RuntimeError("wave must be a CUDA tensor: there is no CPU path")
     N, L = wave.shape
@@ -48,7 +50,12 @@ def preprocess_batch(wave: torch.Tensor, gap_len: float = 0.1, sample_rate: int 
                                          sam_d.data_ptr(), st), "aip_gap_zero_f32")
         res = {"audio_gap": out, "gap_samples": sam,
                "gap_int_s": np.stack(gaps.seconds_interval(starts, g, sample_rate), 1)}
-        if normalize:
+        if want_pcm16:
+            peaks = torch.empty(N, dtype=torch.float32, device=wave.device) if normalize else None
+            res["pcm16"] = sp.wave_to_pcm16(out, normalize=normalize, peaks_out=peaks)
+            if normalize:
+                res["peaks"] = peaks
+        elif normalize:
             peaks = torch.empty(N, dtype=torch.float32, device=wave.device)
             norm = torch.empty_like(wave)
             for lo in range(0, N, 65535):
@@ -111,8 +118,9 @@ def preprocess_tree(src_root, dst_root, gap_len: float = 0.1, sample_rate: int =
             if sr != sample_rate:
                 raise IOError(f"{src}: sample rate {sr} != {sample_rate} (resampling is not part of the bulk path)")
             host[i, : min(L, len(x))] = x[:L]
-        res = preprocess_batch(torch.from_numpy(host).to(device), gap_len, sample_rate, starts=starts_all[b0:b1])
-        out = res["audio_gap_normalized"].cpu().numpy()
+        res = preprocess_batch(torch.from_numpy(host).to(device), gap_len, sample_rate, starts=starts_all[b0:b1],
+                               want_pcm16=True)
+        out = res["pcm16"].cpu().numpy()                               # the FLAC's 16-bit samples, quantised on the device
         for (_, dst), y in zip(jobs[b0:b1], out):
             audio_io.write_audio(dst, y, sample_rate, "flac")           # utils.save_audio's default format, utils.py:59
     return len(jobs)

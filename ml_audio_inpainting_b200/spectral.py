@@ -28,7 +28,7 @@ from ._cabi import (DOM_DB, DOM_EXPM1, DOM_LINEAR, DOM_POW10, MAG_ABS, MAG_LOG10
                     MAG_NONE, MAG_POW, StftDesc, check)
 
 __all__ = ["StftPlan", "get_plan", "stft", "stft_gap_variants", "istft", "istft_blend", "griffinlim", "db_heuristic", "fft_window",
-           "mel_basis", "mel_project", "mel_inverse", "experiment_env",
+           "wave_to_pcm16", "PCM_RAW", "PCM_NORMALIZE", "PCM_PEAKS_GIVEN", "mel_basis", "mel_project", "mel_inverse", "experiment_env",
            "MAG_NONE", "MAG_ABS", "MAG_LOG10_EPS", "MAG_LOG1P_POW", "MAG_POW",
            "DOM_LINEAR", "DOM_POW10", "DOM_DB", "DOM_EXPM1"]
 
@@ -314,13 +314,15 @@ def db_heuristic(x: torch.Tensor) -> torch.Tensor:
 def istft(plan: StftPlan, spec: Optional[torch.Tensor] = None, mag: Optional[torch.Tensor] = None,
           phase: Optional[torch.Tensor] = None, mag_domain: int = DOM_LINEAR, db_auto: bool = False,
           length: Optional[int] = None, out: Optional[torch.Tensor] = None, normalize: bool = False,
-          peaks_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+          peaks_out: Optional[torch.Tensor] = None, pcm16: bool = False) -> torch.Tensor:
     """Inverse transform: complex ``spec`` or ``mag`` (+ ``phase``) -> waveform [B, out_len] float32.
 
     ``db_auto`` applies the reference's per-clip dB test to ``mag`` on the device (no host sync).
     ``normalize`` additionally peak-normalises every clip like ``librosa.util.normalize`` in the reference's
     ``save_audio`` (utils.py:84), with the per-clip peak taken inside the inverse kernel's overlap-add
-    (``aip_istft_normalized_f32``); ``peaks_out`` [B] float32 receives the peaks before scaling."""
+    (``aip_istft_normalized_f32``); ``peaks_out`` [B] float32 receives the peaks before scaling.
+    ``pcm16`` returns int16 [B, out_len] instead: the 16-bit samples ``save_audio`` writes into its FLAC (utils.py:87), produced
+    by the pass that would have scaled the waveform (``out`` then keeps the un-normalised float waveform)."""
     src = spec if spec is not None else mag
     if src is None:
         raise ValueError("istft needs spec or mag")
@@ -352,6 +354,7 @@ def istft(plan: StftPlan, spec: Optional[torch.Tensor] = None, mag: Optional[tor
     flags = db_heuristic(mag) if (db_auto and mag is not None) else None
     ws_bytes = int(lib.aip_istft_workspace_bytes(C.byref(plan.desc), B, T))
     ws = torch.empty(max(ws_bytes, 4) // 4, dtype=torch.float32, device=dev) if ws_bytes else None
+    pcm = torch.empty((B, out_len), dtype=torch.int16, device=dev) if pcm16 else None
     with torch.cuda.device(dev):
         if normalize:
             if peaks_out is None:
@@ -362,20 +365,58 @@ def istft(plan: StftPlan, spec: Optional[torch.Tensor] = None, mag: Optional[tor
                                                _ptr(spec.view(torch.float32) if spec is not None else None),
                                                _ptr(mag), _ptr(phase), int(mag_domain), _ptr(flags), B, T,
                                                int(length or 0), _ptr(inv), _ptr(out), out.stride(0), _ptr(peaks_out),
-                                               _ptr(ws), ws_bytes, _stream()),
+                                               _ptr(pcm), out_len, _ptr(ws), ws_bytes, _stream()),
                   "aip_istft_normalized_f32")
         else:
             check(lib.aip_istft_f32(C.byref(plan.desc), _ptr(spec.view(torch.float32) if spec is not None else None),
                                     _ptr(mag), _ptr(phase), int(mag_domain), _ptr(flags), B, T, int(length or 0),
                                     _ptr(inv), _ptr(out), out.stride(0), _ptr(ws), ws_bytes, _stream()),
                   "aip_istft_f32")
-    return out[0] if squeeze else out
+            if pcm16 and out_len > 0:
+                check(lib.aip_wave_to_pcm16_f32(_ptr(out), out.stride(0), _ptr(pcm), out_len, B, out_len, PCM_RAW, None,
+                                                _stream()), "aip_wave_to_pcm16_f32")
+    res = pcm if pcm16 else out
+    return res[0] if squeeze else res
+
+
+PCM_RAW, PCM_NORMALIZE, PCM_PEAKS_GIVEN = 0, 1, 2
+
+
+def wave_to_pcm16(wave: torch.Tensor, normalize: bool = True, peaks: Optional[torch.Tensor] = None,
+                  peaks_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``save_audio``'s tail on the device (utils.py:83-87): ``librosa.util.normalize`` (``normalize``) and soundfile's
+    float -> PCM_16 conversion for FLAC (x * 32768, round half to even, clip) -> int16 of the same shape.  ``peaks`` [B]: the
+    clips' max|x| when already known (skips the peak pass); ``peaks_out`` receives the peaks taken here."""
+    _require_cuda(wave, "wave")
+    squeeze = wave.ndim == 1
+    w = (wave.unsqueeze(0) if squeeze else wave).to(torch.float32)
+    if w.ndim != 2:
+        raise ValueError("wave must be [L] or [B, L]")
+    if w.stride(1) != 1:
+        w = w.contiguous()
+    B, L = w.shape
+    pcm = torch.empty((B, L), dtype=torch.int16, device=w.device)
+    mode, pk = PCM_RAW, None
+    if peaks is not None:
+        if tuple(peaks.shape) != (B,) or peaks.dtype != torch.float32 or not peaks.is_contiguous() or peaks.device != w.device:
+            raise ValueError("peaks must be a contiguous float32 [B] tensor on the waveform's device")
+        mode, pk = PCM_PEAKS_GIVEN, peaks
+    elif normalize:
+        pk = peaks_out if peaks_out is not None else torch.empty(B, dtype=torch.float32, device=w.device)
+        if tuple(pk.shape) != (B,) or pk.dtype != torch.float32 or not pk.is_contiguous():
+            raise ValueError("peaks_out must be a contiguous float32 [B] tensor")
+        mode = PCM_NORMALIZE
+    with torch.cuda.device(w.device):
+        check(_cabi.load().aip_wave_to_pcm16_f32(_ptr(w), w.stride(0), _ptr(pcm), L, B, L, mode, _ptr(pk), _stream()),
+              "aip_wave_to_pcm16_f32")
+    return pcm[0] if squeeze else pcm
 
 
 def istft_blend(plan: StftPlan, model_out: torch.Tensor, blend_in: torch.Tensor, blend_mask: torch.Tensor,
                 phase: torch.Tensor, mag_domain: int = DOM_POW10, length: Optional[int] = None,
                 mask_keeps_input: bool = False, normalize: bool = False,
-                peaks_out: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                peaks_out: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                pcm16: bool = False) -> torch.Tensor:
     """The model hand-off in one kernel (``aip_istft_handoff_f32``): blend, un-log, phase reuse, istft.
 
     ``mask_keeps_input=False``: ``m = model_out * mask + blend_in * (1 - mask)`` -- the CNN-BLSTM convention, mask 1 inside
@@ -383,7 +424,8 @@ def istft_blend(plan: StftPlan, model_out: torch.Tensor, blend_in: torch.Tensor,
     ``mask_keeps_input=True``: ``m = model_out * (1 - mask) + blend_in * mask`` -- the GAN convention, mask 1 outside the gap
     (``combined_log_mag``, models/GAN/train.py:473; the reference then hands the log1p-domain blend to
     ``spectrogram_to_audio`` as it is: ``mag_domain=DOM_LINEAR``; ``DOM_EXPM1`` undoes the log1p instead).
-    ``normalize`` adds ``save_audio``'s peak normalisation (utils.py:84)."""
+    ``normalize`` adds ``save_audio``'s peak normalisation (utils.py:84); ``pcm16`` returns the int16 samples of its 16-bit
+    FLAC (utils.py:87) instead of the float waveform (see ``istft``)."""
     ts = []
     for name, t in (("model_out", model_out), ("blend_in", blend_in), ("blend_mask", blend_mask), ("phase", phase)):
         _require_cuda(t, name)
@@ -406,11 +448,14 @@ def istft_blend(plan: StftPlan, model_out: torch.Tensor, blend_in: torch.Tensor,
         peaks = peaks_out if peaks_out is not None else torch.empty(B, dtype=torch.float32, device=dev)
         if tuple(peaks.shape) != (B,) or peaks.dtype != torch.float32 or not peaks.is_contiguous():
             raise ValueError("peaks_out must be a contiguous float32 [B] tensor")
+    pcm = torch.empty((B, out.shape[1]), dtype=torch.int16, device=dev) if pcm16 else None
     with torch.cuda.device(dev):
         check(lib.aip_istft_handoff_f32(C.byref(plan.desc), _ptr(ts[0]), _ptr(ts[1]), _ptr(ts[2]), int(bool(mask_keeps_input)),
                                         _ptr(ts[3]), int(mag_domain), B, T, int(length or 0), _ptr(inv), _ptr(out),
-                                        out.stride(0), _ptr(peaks), _ptr(ws), ws_bytes, _stream()), "aip_istft_handoff_f32")
-    return out[0] if squeeze else out
+                                        out.stride(0), _ptr(peaks), _ptr(pcm), out.shape[1], _ptr(ws), ws_bytes, _stream()),
+              "aip_istft_handoff_f32")
+    res = pcm if pcm16 else out
+    return res[0] if squeeze else res
 
 
 def griffinlim(plan: StftPlan, mag: torch.Tensor, n_iter: int = 32, momentum: float = 0.99,

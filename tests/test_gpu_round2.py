@@ -394,3 +394,63 @@ def test_round2_kernels_write_inside_their_outputs(sp, L, hop, win):
         ref = torch.full((G,), SENT, dtype=torch.float32, device="cuda")
         assert torch.equal(flat[:G], ref) and torch.equal(flat[-G:], ref)
         assert not bool(back.eq(SENT).any())
+
+
+# ------------------------------------------------------------------------------------------- 16-bit tail of save_audio
+def test_wave_to_pcm16_is_save_audios_quantisation(sp):
+    """aip_wave_to_pcm16_f32 = librosa.util.normalize + soundfile's float -> PCM_16 for FLAC (utils.py:83-87), bit for bit against
+    the host codec's conversion of the oracle's normalised waveform -- odd lengths and pitches, a silent clip (peak < tiny: left
+    alone), samples at +-peak (+32768 clips to 32767, -32768 stays), un-normalised input beyond +-1 (clipped)."""
+    from ml_audio_inpainting_b200 import audio_io
+    rng = np.random.default_rng(5)
+    for B, L, pitch in ((7, 8001, 8001), (3, 4096, 4100), (5, 1, 1), (2, 159936, 159937)):
+        x = (0.3 * rng.standard_normal((B, pitch))).astype(np.float32)
+        x[0, :L] *= 7.0                                             # far beyond +-1 before normalisation
+        if B > 1:
+            x[1] = 0.0
+        if B > 2 and L > 8:
+            x[2, :L] = np.clip(x[2, :L], -0.5, 0.5)
+            x[2, 3], x[2, 7] = 0.75, -0.75                          # the peak on both signs
+        xd = torch.from_numpy(x).cuda()[:, :L]
+        peaks = torch.empty(B, device="cuda")
+        got = sp.wave_to_pcm16(xd, normalize=True, peaks_out=peaks).cpu().numpy()
+        want = np.stack([audio_io._to_int16(up.peak_normalize(x[b, :L]), 32768.0) for b in range(B)])
+        assert got.dtype == np.int16 and np.array_equal(got, want)
+        assert np.array_equal(peaks.cpu().numpy(), np.abs(x[:, :L]).max(1))
+        if B > 2 and L > 8:
+            assert got[2, 3] == 32767 and got[2, 7] == -32768
+        raw = sp.wave_to_pcm16(xd, normalize=False).cpu().numpy()
+        assert np.array_equal(raw, audio_io._to_int16(x[:, :L], 32768.0))
+        given = sp.wave_to_pcm16(xd, peaks=peaks).cpu().numpy()
+        assert np.array_equal(given, want)
+    one = sp.wave_to_pcm16(torch.from_numpy(x[0, :L]).cuda())
+    assert one.shape == (L,) and np.array_equal(one.cpu().numpy(), want[0])
+
+
+@pytest.mark.parametrize("n_fft,hop,win", [(512, 192, 384), (512, 128, 512), (1024, 256, 1024)])
+def test_inverse_straight_to_pcm16(sp, n_fft, hop, win):
+    """istft(..., normalize=True, pcm16=True) and the hand-off with pcm16: the scaling pass writes the 16-bit samples instead --
+    identical to quantising the normalised float result, on the fused n_fft = 512 path and on the generic one."""
+    from ml_audio_inpainting_b200 import audio_io
+    B, L = 5, 24000
+    x = _noise(B, L, seed=n_fft + hop)
+    plan = sp.get_plan(n_fft, hop, win, "hann", True, "cuda:0")
+    S = sp.stft(torch.from_numpy(x).cuda(), plan)["spec"]
+    y = sp.istft(plan, spec=S, normalize=True).cpu().numpy()
+    keep = torch.empty((B, plan.istft_length(S.shape[2])), device="cuda")
+    peaks = torch.empty(B, device="cuda")
+    q = sp.istft(plan, spec=S, normalize=True, pcm16=True, out=keep, peaks_out=peaks)
+    assert q.dtype == torch.int16 and np.array_equal(q.cpu().numpy(), audio_io._to_int16(y, 32768.0))
+    raw = sp.istft(plan, spec=S).cpu().numpy()
+    assert np.array_equal(keep.cpu().numpy(), raw)                 # `out` keeps the un-normalised waveform
+    assert np.array_equal(peaks.cpu().numpy(), np.abs(raw).max(1))
+    assert np.array_equal(sp.istft(plan, spec=S, pcm16=True).cpu().numpy(), audio_io._to_int16(raw, 32768.0))
+    if n_fft == 512:
+        mag, ph = S.abs().log10().clamp_min(-9.0), S.angle()
+        mo = torch.full_like(mag, -2.0)
+        mask = torch.zeros_like(mag)
+        mask[:, :, 40:50] = 1.0
+        for kw in (dict(normalize=True), dict(normalize=False)):
+            f = sp.istft_blend(plan, mo, mag, mask, ph, **kw).cpu().numpy()
+            qq = sp.istft_blend(plan, mo, mag, mask, ph, pcm16=True, **kw).cpu().numpy()
+            assert np.array_equal(qq, audio_io._to_int16(f, 32768.0)), kw

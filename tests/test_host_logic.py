@@ -154,3 +154,21 @@ def test_experiment_env_sets_reloads_and_restores(monkeypatch):
     with spectral.experiment_env(AIP_FWD_CHUNK=None, AIP_INV_TMA="0"):
         assert "AIP_FWD_CHUNK" not in os.environ and os.environ["AIP_INV_TMA"] == "0"
     assert os.environ["AIP_FWD_CHUNK"] == "7" and "AIP_INV_TMA" not in os.environ
+
+
+def test_write_audio_takes_device_quantised_int16(tmp_path):
+    """An int16 array is the file's samples as they are (quantised by aip_wave_to_pcm16_f32 on the device), for both containers;
+    a float array goes through the host conversion and gives the same file when it holds the same samples."""
+    from ml_audio_inpainting_b200 import audio_io
+    rng = np.random.default_rng(0)
+    x = np.clip(0.4 * rng.standard_normal(5000), -1, 1).astype(np.float32)
+    q = audio_io._to_int16(x, 32768.0)
+    audio_io.write_audio(tmp_path / "a.flac", q, 16000, "flac")
+    audio_io.write_audio(tmp_path / "b.flac", x, 16000, "flac")
+    assert (tmp_path / "a.flac").read_bytes() == (tmp_path / "b.flac").read_bytes()
+    back, sr = audio_io.read_audio(tmp_path / "a.flac")
+    assert sr == 16000 and np.array_equal(np.rint(back[:, 0] * 32768).astype(np.int16) if back.ndim == 2 else
+                                          np.rint(back * 32768).astype(np.int16), q)
+    audio_io.write_audio(tmp_path / "c.wav", q, 16000, "wav")
+    back, _ = audio_io.read_audio(tmp_path / "c.wav")
+    assert np.array_equal(np.rint(np.asarray(back).reshape(-1) * 32768).astype(np.int16), q)

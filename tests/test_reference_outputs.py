@@ -129,3 +129,13 @@ def test_cuda_path_reproduces_the_references_own_outputs(shipped, golden_clips):
             assert worst <= LSB_BOUND and q999 <= 0.51, (n, worst, q999, a)
         dmax, frac = pcm_mismatch(y_norm[b].cpu().numpy(), shipped[n])          # no free parameter
         assert dmax <= 1 and frac < 2e-3, (n, dmax, frac)
+    # ... and with the 16-bit quantisation done on the device too (save_audio's whole tail, utils.py:83-87): these are the very
+    # integers the shipped FLAC files hold
+    pcm_dev = frontend.cnnblstm_backend_batch(model_out, ev["log_impaired_magnitude"], ev["mask"], ev["original_phase"],
+                                              save_pcm16=True).cpu().numpy()
+    assert pcm_dev.dtype == np.int16
+    sel = np.ones(pcm_dev.shape[1], bool)
+    sel[GAP_LO:GAP_HI] = False
+    for b, n in enumerate(names):
+        d = np.abs(pcm_dev[b].astype(np.int64) - shipped[n].astype(np.int64))[sel]
+        assert d.max() <= 1 and (d > 0).mean() < 2e-3, (n, int(d.max()), float((d > 0).mean()))
