@@ -25,7 +25,7 @@ EMUL_LIB = LIB / "libaip_emul.so"
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "-Xptxas", "-v", "-Xcompiler", "-fPIC"]
-CUDA_UNITS = ["aip_fwd.cu", "aip_fwd_tc.cu", "aip_inv.cu", "aip_mel.cu", "aip_misc.cu"]
+CUDA_UNITS = ["aip_fwd.cu", "aip_pow2.cu", "aip_inv.cu", "aip_mel.cu", "aip_misc.cu"]
 CUDA_HEADERS = ["aip_core.cuh", "aip_tiles.cuh", "aip_device.cuh", "aip_host.h", "aip_twiddles.inc"]
 
 

@@ -533,6 +533,8 @@ int run_fwd(const aip_stft_desc* desc, FwdParams P, long long T_out, cudaStream_
     P.vec_ok = ((P.hop & 3) == 0) && ((P.pad & 3) == 0) && ((P.wave_pitch & 3) == 0) &&
                ((reinterpret_cast<uintptr_t>(P.wave) & 15) == 0);
     e = launch_fwd512(P, di, st);
+  } else if (pow2_ok(desc->n_fft)) {
+    e = launch_fwd_pow2(P, desc->n_fft, di, st);
   } else {
     e = launch_fwd_generic(P, desc->n_fft, di, st);
   }

@@ -69,14 +69,18 @@ struct Tunables {
   int var_no_prefetch;    // AIP_VAR_NO_PREFETCH 1: gap-variant tiles do not request their rows from L2 ahead of the stores
   int var_fill_scalar;    // AIP_VAR_FILL=scalar gap-variant copy pass with store instructions instead of bulk copies
   int var_no_fill;        // AIP_VAR_NO_FILL     1: skip the copy pass (timing the transform kernel alone)
-  int fwd_tc;             // AIP_FWD_TC          0: register FFT only; 1: tensor-core stage 2 where available (default: built-in choice)
+  int pow2;               // AIP_POW2            0: n_fft != 512 runs the one-frame-per-CTA radix-2 kernels instead of the tiled radix-16 ones
 };
 const Tunables& tunables();
 void tunables_reload();
 
-// ---- cross-unit entry points (defined in aip_fwd.cu / aip_misc.cu) ---------------------------------------------------
+// ---- cross-unit entry points (defined in aip_fwd.cu / aip_pow2.cu / aip_misc.cu) ---------------------------------------------------
 int run_fwd(const aip_stft_desc* desc, FwdParams P, long long T_out, cudaStream_t st);
 bool fwd_fast_ok(const aip_stft_desc* d, const DevInfo& di);
+bool pow2_ok(int n_fft);
+cudaError_t launch_fwd_pow2(FwdParams P, int n_fft, const DevInfo& di, cudaStream_t st);
+bool pow2_ola_ok(int n_fft, int hop);
+cudaError_t launch_inv_pow2(InvParams P, int n_fft, float* frames, const DevInfo& di, cudaStream_t st);
 cudaError_t launch_peak(const float* in, long long pitch, long long B, long long L, float* peaks, cudaStream_t st);
 cudaError_t launch_pcm16(const float* in, long long in_pitch, short* pcm, long long pcm_pitch, long long B, long long L,
                          const float* peaks, int sms, cudaStream_t st);

@@ -724,6 +724,8 @@ static int run_inv(const aip_stft_desc* desc, InvParams P, long long length, voi
     if (e != cudaSuccess) return (int)e;
     kern<<<(unsigned)grid, kFwdThreads, smem, st>>>(P);
     e = cudaGetLastError();
+  } else if (pow2_ola_ok(desc->n_fft, desc->hop)) {
+    e = launch_inv_pow2(P, desc->n_fft, nullptr, di, st);
   } else {
     const size_t need = aip_istft_workspace_bytes(desc, P.B, P.T);
     if (!workspace || workspace_bytes < need) return AIP_ERR_WORKSPACE;
@@ -733,13 +735,17 @@ static int run_inv(const aip_stft_desc* desc, InvParams P, long long length, voi
     if ((long long)P.B * P.n_frames > 0x7fffffffLL) return AIP_ERR_UNSUPPORTED;
     P.n_tiles = (int)((long long)P.B * P.n_frames);
     G.P = P;
-    const size_t smem = (size_t)desc->n_fft * sizeof(float2);
-    e = cudaFuncSetAttribute(istft_generic_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    long long grid = (long long)di.sms * 8;
-    if (grid > P.n_tiles) grid = P.n_tiles;
-    istft_generic_frames_kernel<<<(unsigned)grid, 256, smem, st>>>(G);
-    e = cudaGetLastError();
+    if (pow2_ok(desc->n_fft)) {
+      e = launch_inv_pow2(P, desc->n_fft, G.frames, di, st);
+    } else {
+      const size_t smem = (size_t)desc->n_fft * sizeof(float2);
+      e = cudaFuncSetAttribute(istft_generic_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      long long grid = (long long)di.sms * 8;
+      if (grid > P.n_tiles) grid = P.n_tiles;
+      istft_generic_frames_kernel<<<(unsigned)grid, 256, smem, st>>>(G);
+      e = cudaGetLastError();
+    }
     if (e != cudaSuccess) return (int)e;
     istft_generic_ola_kernel<<<ew_grid((long long)P.B * P.out_len, di.sms), 256, 0, st>>>(G);
     e = cudaGetLastError();
@@ -814,7 +820,7 @@ int aip_istft_handoff_f32(const aip_stft_desc* desc, const float* model_out, con
 }
 
 size_t aip_istft_workspace_bytes(const aip_stft_desc* desc, int64_t B, int64_t T) {
-  if (!desc || B <= 0 || T <= 0 || desc->n_fft <= 0 || inv_fast_ok(desc)) return 0;
+  if (!desc || B <= 0 || T <= 0 || desc->n_fft <= 0 || inv_fast_ok(desc) || pow2_ola_ok(desc->n_fft, desc->hop)) return 0;
   return (size_t)B * (size_t)T * (size_t)desc->n_fft * sizeof(float);
 }
 

@@ -177,7 +177,7 @@ static Tunables read_tunables() {
   const char* f = getenv("AIP_VAR_FILL");
   t.var_fill_scalar = (f && f[0] == 's') ? 1 : 0;
   t.var_no_fill = getenv("AIP_VAR_NO_FILL") ? 1 : 0;
-  t.fwd_tc = env_int("AIP_FWD_TC", -1);
+  t.pow2 = env_int("AIP_POW2", 1);
   return t;
 }
 static Tunables g_tunables = read_tunables();        // once, when the shared object is loaded

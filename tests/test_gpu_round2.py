@@ -454,3 +454,68 @@ def test_inverse_straight_to_pcm16(sp, n_fft, hop, win):
             f = sp.istft_blend(plan, mo, mag, mask, ph, **kw).cpu().numpy()
             qq = sp.istft_blend(plan, mo, mag, mask, ph, pcm16=True, **kw).cpu().numpy()
             assert np.array_equal(qq, audio_io._to_int16(f, 32768.0)), kw
+
+
+# ------------------------------------------------------------------------------------------- power-of-two n_fft other than 512
+@pytest.mark.parametrize("n_fft,hop,win,L,center", [
+    (2048, 512, 2048, 40000, True), (2048, 512, None, 9000, True), (1024, 256, 1024, 30001, True), (1024, 333, 800, 20000, True),
+    (256, 64, 256, 12000, True), (256, 64, 200, 12000, False), (128, 32, 128, 5000, True), (64, 16, 64, 3000, True),
+    (2048, 2048, 2048, 30000, True), (1024, 255, 1024, 8192, False), (512, 191, 384, 20000, True)])
+def test_tiled_radix16_path_for_other_nfft(sp, n_fft, hop, win, L, center):
+    """n_fft in {64 .. 2048} \\ {512 with an even hop} -- the reference's own defaults (utils.py:192-193: n_fft 2048, hop 512) -- run
+    the tiled radix-16 kernels (csrc/aip_pow2.cu).  Against the oracle: complex output, every epilogue, gaps across tile borders,
+    odd hops (scalar loads), no centring, frame counts that are no multiple of the tile; the inverse for complex and
+    magnitude + phase input with `length`; and against the one-frame-per-CTA kernels they replace (AIP_POW2=0)."""
+    B = 3
+    win = win or n_fft
+    x = _noise(B, L, seed=n_fft + hop)
+    xd = torch.from_numpy(x).cuda()
+    plan = sp.get_plan(n_fft, hop, win, "hann", center, "cuda:0")
+    T = plan.num_frames(L)
+    g = max(1, min(L // 4, 3 * n_fft))
+    gaps = np.array([[0, g], [L // 2 - g // 2, L // 2 - g // 2 + g], [L - g, L]])
+    out = sp.stft(xd, plan, gap_samples=gaps, want_spec=True, want_phase=True, mag_kind=sp.MAG_LOG10_EPS)
+    with sp.experiment_env(AIP_POW2="0"):
+        old = sp.stft(xd, plan, gap_samples=gaps, want_spec=True, want_phase=True, mag_kind=sp.MAG_LOG10_EPS)
+    S = out["spec"].cpu().numpy()
+    assert S.shape == (B, n_fft // 2 + 1, T)
+    for b in range(B):
+        xg = x[b].copy()
+        xg[gaps[b, 0]:gaps[b, 1]] = 0
+        ref = lr.stft(xg, n_fft=n_fft, hop_length=hop, win_length=win, center=center)
+        assert ref.shape == S[b].shape and relerr(S[b], ref) < TOL, (b, relerr(S[b], ref))
+        assert relerr(S[b], old["spec"][b].cpu().numpy()) < TOL
+        big = np.abs(ref) > 1e-3 * np.abs(ref).max()
+        assert np.abs(out["mag"][b].cpu().numpy() - np.log10(np.abs(ref) + 1e-9))[big].max() < 1e-3
+        assert np.abs(np.exp(1j * out["phase"][b].cpu().numpy()) - np.exp(1j * np.angle(ref)))[big].max() < 2e-3
+    # crop + masks + spectrum-domain gap through the general emitter
+    if T > 9:
+        frm = np.array([[0, 3], [T // 2, T // 2 + 4], [T - 5, T - 1]])
+        o2 = sp.stft(xd, plan, mag_kind=sp.MAG_LOG1P_POW, want_spec=False, want_mask=True, mask_frames=frm,
+                     mask_in_gap_is_one=True, zero_frames=frm, t_out=T - 1)
+        for b in range(B):
+            ref = np.abs(lr.stft(x[b], n_fft=n_fft, hop_length=hop, win_length=win, center=center))[:, :T - 1]
+            ref[:, frm[b, 0]:frm[b, 1]] = 0
+            m = np.zeros_like(ref)
+            m[:, frm[b, 0]:frm[b, 1]] = 1
+            assert np.array_equal(o2["mask"][b].cpu().numpy(), m)
+            assert np.abs(o2["mag"][b].cpu().numpy() - np.log1p(ref)).max() < 1e-4 * max(1.0, np.log1p(ref).max())
+    # inverse
+    if center:
+        Sc = sp.stft(xd, plan)["spec"]
+        y = sp.istft(plan, spec=Sc).cpu().numpy()
+        # (hop == n_fft: no overlap, the window sum-square reaches ~0 at the frame borders and the division amplifies rounding
+        #  there -- compare where it is well conditioned, as test_gpu_parity does for the reference's hop-512 default)
+        wss = lr.window_sumsquare("hann", T, hop_length=hop, win_length=win, n_fft=n_fft, dtype=np.float32)[n_fft // 2:]
+        for b in range(B):
+            ref = lr.istft(Sc[b].cpu().numpy(), hop_length=hop, win_length=win, n_fft=n_fft)
+            ok = wss[:len(ref)] > 1e-2
+            assert y[b].shape == ref.shape and relerr(y[b][ok], ref[ok]) < TOL, relerr(y[b][ok], ref[ok])
+        length = L - 7
+        y2 = sp.istft(plan, mag=Sc.abs(), phase=Sc.angle(), length=length).cpu().numpy()
+        with sp.experiment_env(AIP_POW2="0"):
+            y2_old = sp.istft(plan, mag=Sc.abs(), phase=Sc.angle(), length=length).cpu().numpy()
+        ref = lr.istft(Sc[1].cpu().numpy(), hop_length=hop, win_length=win, n_fft=n_fft, length=length)
+        ok = np.zeros(length, bool)
+        ok[:min(length, len(wss))] = wss[:length] > 1e-2
+        assert y2.shape == (B, length) and relerr(y2[1][ok], ref[ok]) < 5 * TOL and relerr(y2[:, ok], y2_old[:, ok]) < 5 * TOL
