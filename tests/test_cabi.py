@@ -54,10 +54,14 @@ def test_host_only_entry_points(lib):
     assert b"no fallback" in lib.aip_status_string(-3)
     d = _cabi.StftDesc(512, 192, 1, 0, None)
     assert lib.aip_istft_workspace_bytes(C.byref(d), 4, 100) == 0
-    d2 = _cabi.StftDesc(2048, 512, 1, 0, None)
-    assert lib.aip_istft_workspace_bytes(C.byref(d2), 4, 100) == 4 * 100 * 2048 * 4
-    d3 = _cabi.StftDesc(512, 191, 1, 0, None)
-    assert lib.aip_istft_workspace_bytes(C.byref(d3), 1, 10) == 10 * 512 * 4
+    d2 = _cabi.StftDesc(2048, 512, 1, 0, None)      # tiled radix-16 inverse, overlap-add fused: no workspace either
+    assert lib.aip_istft_workspace_bytes(C.byref(d2), 4, 100) == 0
+    d3 = _cabi.StftDesc(2048, 16, 1, 0, None)       # more than two tiles reach a sample: frames go through the workspace
+    assert lib.aip_istft_workspace_bytes(C.byref(d3), 4, 100) == 4 * 100 * 2048 * 4
+    d4 = _cabi.StftDesc(4096, 1024, 1, 0, None)     # outside the tiled kernels' range
+    assert lib.aip_istft_workspace_bytes(C.byref(d4), 4, 100) == 4 * 100 * 4096 * 4
+    d5 = _cabi.StftDesc(512, 191, 1, 0, None)       # n_fft 512 with an odd hop: off the fused kernel, on the tiled one
+    assert lib.aip_istft_workspace_bytes(C.byref(d5), 1, 10) == 0
 
 
 def test_sass_is_sm100a_with_tma(lib):
