@@ -37,6 +37,22 @@ struct Pow2Geom {
   int r3, logNs3;      // radix of the last pass (1: none) and log2 of its sub-transform length Ns = M / r3
 };
 
+__host__ __device__ constexpr int p2_ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+// The kernels are instantiated per n_fft with this as a compile-time constant: every stride, trip count and shift below folds.
+__host__ __device__ constexpr Pow2Geom pow2_geom(int n_fft) {
+  Pow2Geom g{};
+  g.N = n_fft; g.M = n_fft / 2;
+  g.logJ = p2_ilog2(g.M) - 4;
+  g.fps = kP2Points / g.M;
+  g.FT = kP2Warps * g.fps; g.logFT = p2_ilog2(g.FT);
+  // transposed access: a half-warp reads FT (or 16) frames x 16 / FT bins as 8-byte words -> PB == 16 / min(FT, 16) (mod 16)
+  g.PB = g.M + g.M / 16 + (g.FT == 8 ? 2 : 1);
+  g.two16 = g.M >= 256;
+  g.r3 = g.two16 ? g.M / 256 : g.M / 16;
+  g.logNs3 = g.r3 > 1 ? p2_ilog2(g.M / g.r3) : 0;
+  return g;
+}
+
 __device__ __forceinline__ int p2_pad(int a) { return a + (a >> 4); }
 
 // Shared-memory tables of a CTA (floats): tw [2 M] = W_N^e, e < M (split pass) | win [N] | tw2 [512] = W_256^(m k) at [16 m + k]
@@ -173,7 +189,7 @@ template <int R>
 __device__ __forceinline__ void p2_pass_last(const Pow2Geom& g, float2* sf, const float2* twl, int lane) {
   const int Ns = 1 << g.logNs3;
   const int stride = p2_pad(Ns);                  // Ns is a multiple of 16: p2_pad(j + r Ns) = p2_pad(j) + r p2_pad(Ns)
-#pragma unroll 1
+#pragma unroll
   for (int q = lane; q < kP2Points / R; q += 32) {
     const int f = q >> g.logNs3, j = q & (Ns - 1);
     float2* p = sf + f * g.PB + p2_pad(j);
@@ -208,7 +224,6 @@ __device__ __forceinline__ void p2_passes_rest(const Pow2Geom& g, const P2Slots&
 // ---- forward -----------------------------------------------------------------------------------------------------------------
 struct Pow2FwdParams {
   FwdParams P;
-  Pow2Geom g;
   int F;               // bins = M + 1
   int vec;             // float2 loads of the waveform are legal (even hop / pad / pitch, 8-byte aligned base)
 };
@@ -248,7 +263,7 @@ struct P2WaveChecked {
 // real-input split pass of one super-frame, in place: Z (M packed points) -> X[0..M]
 __device__ __forceinline__ void p2_split_fwd(const Pow2Geom& g, float2* sf, const float2* tw, int lane) {
   const int H = g.M >> 1, logH = g.logJ + 3;
-#pragma unroll 1
+#pragma unroll 4
   for (int q = lane; q < kP2Points / 2; q += 32) {
     const int f = q >> logH, k = q & (H - 1);
     float2* z = sf + f * g.PB;
@@ -268,9 +283,10 @@ __device__ __forceinline__ void p2_split_fwd(const Pow2Geom& g, float2* sf, cons
   }
 }
 
-__global__ void __launch_bounds__(kP2Threads) stft_pow2_fwd_kernel(const Pow2FwdParams G) {
+template <int kN>
+__global__ void __launch_bounds__(kP2Threads, 2) stft_pow2_fwd_kernel(const Pow2FwdParams G) {
   extern __shared__ __align__(16) float smem[];
-  const Pow2Geom& g = G.g;
+  constexpr Pow2Geom g = pow2_geom(kN);
   const FwdParams& P = G.P;
   const P2Smem sm = p2_smem(g, smem);
   const float2* tw = sm.tw;
@@ -318,16 +334,31 @@ __global__ void __launch_bounds__(kP2Threads) stft_pow2_fwd_kernel(const Pow2Fwd
           maskv = (in == (P.mask_in_gap_is_one != 0)) ? 1.0f : 0.0f;
         }
         const float2* z = bufs + f * g.PB;
-        const long long base = (long long)b * G.F * P.T_out + t;
+        const long long step = (long long)kstep * P.T_out;
+        long long idx = (long long)b * G.F * P.T_out + t + (long long)k0 * P.T_out;
+        if (P.spec && !P.phase && !P.mask && P.mag_kind == MAG_NONE && !P.zero_frames) {       // complex output only
+          float2* o = P.spec + idx;
+#pragma unroll 8
+          for (int k = k0; k <= g.M; k += kstep, o += step) *o = z[p2_pad(k)];
+        } else if (!P.spec && !P.phase && !P.mask && !P.zero_frames) {                          // one magnitude flavour only
+          float* o = P.mag + idx;
+          const int mk = P.mag_kind;
+          const float eps = P.eps, power = P.power;
 #pragma unroll 4
-        for (int k = k0; k <= g.M; k += kstep) {
-          float2 v = z[p2_pad(k)];
-          if (zero) v = make_float2(0.0f, 0.0f);
-          const long long idx = base + (long long)k * P.T_out;
-          if (P.spec) P.spec[idx] = v;
-          if (P.phase) P.phase[idx] = fast_atan2(v.y, v.x);
-          if (P.mask) P.mask[idx] = maskv;
-          if (P.mag_kind != MAG_NONE) P.mag[idx] = mag_value(P.mag_kind, v.x, v.y, P.eps, P.power);
+          for (int k = k0; k <= g.M; k += kstep, o += step) {
+            const float2 v = z[p2_pad(k)];
+            *o = mag_value(mk, v.x, v.y, eps, power);
+          }
+        } else {
+#pragma unroll 2
+          for (int k = k0; k <= g.M; k += kstep, idx += step) {
+            float2 v = z[p2_pad(k)];
+            if (zero) v = make_float2(0.0f, 0.0f);
+            if (P.spec) P.spec[idx] = v;
+            if (P.phase) P.phase[idx] = fast_atan2(v.y, v.x);
+            if (P.mask) P.mask[idx] = maskv;
+            if (P.mag_kind != MAG_NONE) P.mag[idx] = mag_value(P.mag_kind, v.x, v.y, P.eps, P.power);
+          }
         }
       }
     }
@@ -338,7 +369,6 @@ __global__ void __launch_bounds__(kP2Threads) stft_pow2_fwd_kernel(const Pow2Fwd
 // ---- inverse: frames to the workspace --------------------------------------------------------------------------------------------
 struct Pow2InvParams {
   InvParams P;
-  Pow2Geom g;
   int F;
   float* frames;       // workspace [B, T, N]
 };
@@ -354,7 +384,7 @@ struct P2SmemLoad {
 // inverse transform (swap(IDFT(Z)) * M = DFT(swap(Z))).  scipy.fft.irfft ignores imag(DC) and imag(Nyquist); so does this.
 __device__ __forceinline__ void p2_split_inv(const Pow2Geom& g, float2* sf, const float2* tw, int lane) {
   const int H = g.M >> 1, logH = g.logJ + 3;
-#pragma unroll 1
+#pragma unroll 4
   for (int q = lane; q < kP2Points / 2; q += 32) {
     const int f = q >> logH, k = q & (H - 1);
     float2* z = sf + f * g.PB;
@@ -382,10 +412,10 @@ __device__ __forceinline__ void p2_split_inv(const Pow2Geom& g, float2* sf, cons
 //               written once; the <= N - hop samples at either end that the neighbouring tile also reaches are combined with
 //               one atomic add each into the zeroed output -- two contributions per sample (the launcher guarantees
 //               N <= (FT + 1) hop), and 0 + a + b == 0 + b + a, so the result does not depend on the order the tiles finish in.
-template <bool kOla>
-__global__ void __launch_bounds__(kP2Threads) istft_pow2_kernel(const Pow2InvParams G) {
+template <int kN, bool kOla>
+__global__ void __launch_bounds__(kP2Threads, 2) istft_pow2_kernel(const Pow2InvParams G) {
   extern __shared__ __align__(16) float smem[];
-  const Pow2Geom& g = G.g;
+  constexpr Pow2Geom g = pow2_geom(kN);
   const InvParams& P = G.P;
   const P2Smem sm = p2_smem(g, smem);
   const float2* tw = sm.tw;
@@ -450,8 +480,9 @@ __global__ void __launch_bounds__(kP2Threads) istft_pow2_kernel(const Pow2InvPar
       for (int u = step * threadIdx.x; u < span; u += step * kP2Threads) {
         const int sidx = p0 + u - P.pad;
         if (sidx + step <= 0 || sidx >= P.out_len) continue;
-        const int q = u / P.hop;                                                  // last frame that starts at or before u
-        const int below = u >= g.N ? (u - g.N) / P.hop + 1 : 0;                   // first frame that still reaches u
+        // (divisions by the hop through its reciprocal, InvParams::hop_magic: exact for the tile-local operands, pow2_ola_ok)
+        const int q = magic_div(u, P.hop_magic);                                  // last frame that starts at or before u
+        const int below = u >= g.N ? magic_div(u - g.N, P.hop_magic) + 1 : 0;     // first frame that still reaches u
         const int f_hi = q < nv - 1 ? q : nv - 1;
         float a0 = 0.0f, a1 = 0.0f;
         int n = u - below * P.hop;
@@ -467,7 +498,7 @@ __global__ void __launch_bounds__(kP2Threads) istft_pow2_kernel(const Pow2InvPar
           }
         }
         // frames of the CLIP that reach this position: [T_lo, T_hi]; all of them in this tile -> the sample is complete
-        const int T_lo = u >= g.N ? t0 + below : t0 - (g.N - u - 1) / P.hop;      // may be negative: clip start
+        const int T_lo = u >= g.N ? t0 + below : t0 - magic_div(g.N - u - 1, P.hop_magic);      // may be negative: clip start
         const int T_hi = t0 + q;                                                   // may exceed n_frames - 1: clip end
         const bool whole = (T_lo >= t0 || T_lo <= 0 && t0 == 0) && (T_hi < t0 + g.FT || t0 + g.FT >= P.n_frames);
         float* o = orow + sidx;
@@ -488,39 +519,35 @@ __global__ void __launch_bounds__(kP2Threads) istft_pow2_kernel(const Pow2InvPar
 // ---- host side -------------------------------------------------------------------------------------------------------------------
 bool pow2_ok(int n_fft) { return tunables().pow2 != 0 && is_pow2(n_fft) && n_fft >= 64 && n_fft <= 2048; }
 
-static Pow2Geom pow2_geom(int n_fft) {
-  Pow2Geom g{};
-  g.N = n_fft; g.M = n_fft / 2;
-  g.logJ = ilog2(g.M) - 4;
-  g.fps = kP2Points / g.M;
-  g.FT = kP2Warps * g.fps; g.logFT = ilog2(g.FT);
-  // transposed access: a half-warp reads FT (or 16) frames x 16 / FT bins as 8-byte words -> PB == 16 / min(FT, 16) (mod 16)
-  g.PB = g.M + g.M / 16 + (g.FT == 8 ? 2 : 1);
-  g.two16 = g.M >= 256;
-  g.r3 = g.two16 ? g.M / 256 : g.M / 16;
-  g.logNs3 = g.r3 > 1 ? ilog2(g.M / g.r3) : 0;
-  return g;
-}
-
 static size_t pow2_smem(const Pow2Geom& g) {
   return ((size_t)2 * g.M + g.N + kP2TabFloats) * sizeof(float) + (size_t)g.FT * g.PB * sizeof(float2);
 }
 
+// one instantiation per n_fft
+#define AIP_P2_SIZES(X) X(64) X(128) X(256) X(512) X(1024) X(2048)
+
 cudaError_t launch_fwd_pow2(FwdParams P, int n_fft, const DevInfo& di, cudaStream_t st) {
   Pow2FwdParams G;
-  G.g = pow2_geom(n_fft);
-  G.F = G.g.M + 1;
-  P.tiles_per_clip = (P.T_out + G.g.FT - 1) / G.g.FT;
+  const Pow2Geom g = pow2_geom(n_fft);
+  G.F = g.M + 1;
+  P.tiles_per_clip = (P.T_out + g.FT - 1) / g.FT;
   if ((long long)P.B * P.tiles_per_clip > 0x7fffffffLL) return cudaErrorInvalidValue;
   P.n_tiles = (int)((long long)P.B * P.tiles_per_clip);
   G.vec = ((P.hop & 1) == 0) && ((P.pad & 1) == 0) && ((P.wave_pitch & 1) == 0) && ((reinterpret_cast<uintptr_t>(P.wave) & 7) == 0);
   G.P = P;
-  const size_t smem = pow2_smem(G.g);
-  cudaError_t e = cudaFuncSetAttribute(stft_pow2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  void (*kern)(Pow2FwdParams) = nullptr;
+  switch (n_fft) {
+#define X(n) case n: kern = stft_pow2_fwd_kernel<n>; break;
+    AIP_P2_SIZES(X)
+#undef X
+    default: return cudaErrorInvalidValue;
+  }
+  const size_t smem = pow2_smem(g);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   long long grid = (long long)di.sms * 2;
   if (grid > P.n_tiles) grid = P.n_tiles;
-  stft_pow2_fwd_kernel<<<(unsigned)grid, kP2Threads, smem, st>>>(G);
+  kern<<<(unsigned)grid, kP2Threads, smem, st>>>(G);
   return cudaGetLastError();
 }
 
@@ -528,22 +555,30 @@ cudaError_t launch_fwd_pow2(FwdParams P, int n_fft, const DevInfo& di, cudaStrea
 bool pow2_ola_ok(int n_fft, int hop) {
   if (!pow2_ok(n_fft) || hop <= 0) return false;
   const Pow2Geom g = pow2_geom(n_fft);
-  return (long long)n_fft <= (long long)(g.FT + 1) * hop;
+  // ... and the tile-local positions (< FT hop + N) stay in the range where the reciprocal division is exact (< 2^32 / hop)
+  return (long long)n_fft <= (long long)(g.FT + 1) * hop && ((long long)g.FT * hop + n_fft) * hop < (1LL << 32);
 }
 
 // frames == nullptr: overlap-add fused (pow2_ola_ok; P.out is zeroed here first); else the frames [B, T, N] (windowed, scaled)
 // of the first P.n_frames frames of every clip go to `frames`
 cudaError_t launch_inv_pow2(InvParams P, int n_fft, float* frames, const DevInfo& di, cudaStream_t st) {
   Pow2InvParams G;
-  G.g = pow2_geom(n_fft);
-  G.F = G.g.M + 1;
+  const Pow2Geom g = pow2_geom(n_fft);
+  G.F = g.M + 1;
   G.frames = frames;
-  P.tiles_per_clip = (P.n_frames + G.g.FT - 1) / G.g.FT;
+  P.tiles_per_clip = (P.n_frames + g.FT - 1) / g.FT;
   if ((long long)P.B * P.tiles_per_clip > 0x7fffffffLL) return cudaErrorInvalidValue;
   P.n_tiles = (int)((long long)P.B * P.tiles_per_clip);
+  P.hop_magic = (unsigned)((0x100000000ULL + (unsigned)P.hop - 1) / (unsigned)P.hop);
   G.P = P;
-  const size_t smem = pow2_smem(G.g);
-  auto kern = frames ? istft_pow2_kernel<false> : istft_pow2_kernel<true>;
+  void (*kern)(Pow2InvParams) = nullptr;
+  switch (n_fft) {
+#define X(n) case n: kern = frames ? istft_pow2_kernel<n, false> : istft_pow2_kernel<n, true>; break;
+    AIP_P2_SIZES(X)
+#undef X
+    default: return cudaErrorInvalidValue;
+  }
+  const size_t smem = pow2_smem(g);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (!frames) {

@@ -16,6 +16,8 @@ def timeit(fn, n=10):
 
 B, L = 512, 160000
 x = (0.1 * torch.randn(B, L, device="cuda")).clamp_(-1, 1)
+import os
+print("AIP_POW2 =", os.environ.get("AIP_POW2", "1 (tiled radix-16 kernels)"))
 for n_fft, hop, win in ((2048, 512, 2048), (1024, 256, 1024), (256, 64, 256), (512, 192, 384)):
     plan = sp.get_plan(n_fft, hop, win)
     T = plan.num_frames(L)
