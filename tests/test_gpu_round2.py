@@ -519,3 +519,45 @@ def test_tiled_radix16_path_for_other_nfft(sp, n_fft, hop, win, L, center):
         ok = np.zeros(length, bool)
         ok[:min(length, len(wss))] = wss[:length] > 1e-2
         assert y2.shape == (B, length) and relerr(y2[1][ok], ref[ok]) < 5 * TOL and relerr(y2[:, ok], y2_old[:, ok]) < 5 * TOL
+
+
+@pytest.mark.parametrize("n_fft,hop,L", [(2048, 512, 20000), (1024, 256, 9001), (256, 64, 3000), (64, 16, 777), (512, 191, 5000),
+                                         (2048, 16, 6000)])
+def test_tiled_radix16_kernels_write_inside_their_outputs(sp, n_fft, hop, L):
+    """Guard regions around every output of the tiled power-of-two kernels (forward: complex / magnitude / phase / mask with a
+    crop; inverse with the fused overlap-add, with `length`, and through the frame workspace for a very small hop); every
+    element written, the sentinels intact, and the PCM tail on top."""
+    B, G, SENT = 2, 4096, -12345.0
+    x = torch.from_numpy(_noise(B, L, seed=n_fft + L)).cuda()
+    plan = sp.get_plan(n_fft, hop, n_fft, "hann", True, "cuda:0")
+    T, F = plan.num_frames(L), n_fft // 2 + 1
+
+    def guarded(shape, dtype=torch.float32):
+        n = int(np.prod(shape)) * (2 if dtype == torch.complex64 else 1)
+        flat = torch.full((n + 2 * G,), SENT, dtype=torch.float32, device="cuda")
+        body = flat[G:G + n]
+        return flat, (torch.view_as_complex(body.view(*shape, 2)) if dtype == torch.complex64 else body.view(shape))
+
+    def check(flat, view, what):
+        torch.cuda.synchronize()
+        ref = torch.full((G,), SENT, dtype=torch.float32, device="cuda")
+        assert torch.equal(flat[:G], ref) and torch.equal(flat[-G:], ref), what
+        v = torch.view_as_real(view) if view.is_complex() else view
+        assert not bool(v.eq(SENT).any()), what
+
+    for Tn in (T, T - 1):
+        bufs = {k: guarded((B, F, Tn), torch.complex64 if k == "spec" else torch.float32) for k in ("spec", "mag", "phase", "mask")}
+        frm = np.array([[1, 3], [Tn - 2, Tn]])
+        sp.stft(x, plan, mag_kind=sp.MAG_LOG10_EPS, want_spec=True, want_phase=True, want_mask=True, mask_frames=frm,
+                t_out=Tn, out={k: v[1] for k, v in bufs.items()})
+        for k, (flat, view) in bufs.items():
+            check(flat, view, ("fwd", k, Tn))
+        S = bufs["spec"][1]
+        for length in (None, plan.istft_length(Tn) - 5, plan.istft_length(Tn) + 7):
+            n = plan.istft_length(Tn, length)
+            flat, y = guarded((B, n))
+            sp.istft(plan, spec=S, out=y, length=length)
+            check(flat, y, ("inv", Tn, length))
+            assert bool(torch.isfinite(y).all())
+        q = sp.istft(plan, spec=S, normalize=True, pcm16=True)
+        assert q.dtype == torch.int16 and int(q.to(torch.int32).abs().max()) >= 32767
