@@ -449,6 +449,22 @@ def extra_legs(args, sp, plan, wave, gap_dev, Bi, T, F, L, world, peak, timed):
                        "value": world * Bi * CLIP_S / (ms_2 * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_2,
                        "hbm_frac": b2 / (np.mean(per_2) * 1e-3) / 1e9 / peak}
     del out2, spec, sout
+    # the reference's function defaults (utils.extract_spectrogram: n_fft 2048 / hop 512, utils.py:192-193): the tiled radix-16
+    # kernels of csrc/aip_pow2.cu, complex spectrogram out and back in
+    Bd = min(512, Bi)
+    plan_d = sp.get_plan(2048, 512, 2048, "hann", True, dev)
+    Td, Fd = plan_d.num_frames(L), 1025
+    dout = {"spec": torch.empty((Bd, Fd, Td), dtype=torch.complex64, device=dev)}
+    ms_df, _ = timed(lambda: sp.stft(wave[:Bd], plan_d, out=dout), args.steps, args.warmup)
+    yd = torch.empty((Bd, plan_d.istft_length(Td)), dtype=torch.float32, device=dev)
+    ms_di, _ = timed(lambda: sp.istft(plan_d, spec=dout["spec"], out=yd), args.steps, args.warmup)
+    legs["default_params_2048"] = {
+        "workload": f"utils.extract_spectrogram / spectrogram_to_audio at the reference's default n_fft 2048 / hop 512, batch {Bd} per GPU",
+        "stft": {"value": world * Bd * CLIP_S / (ms_df * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_df,
+                 "hbm_frac": Bd * (4 * L + 8 * Fd * Td) / (ms_df * 1e-3) / 1e9 / peak},
+        "istft": {"value": world * Bd * CLIP_S / (ms_di * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_di,
+                  "hbm_frac": Bd * (8 * Fd * Td + 4 * yd.shape[1]) / (ms_di * 1e-3) / 1e9 / peak}}
+    del dout, yd
     # dataset-shaped collate (models/CNNBLSTM/dataset.py:74-121): 256 files x 25 gaps x 5 s, log-magnitudes of
     # all variants from ONE clean transform per file (aip_stft_gap_variants_f32) against 25 full gapped transforms
     Nf, G, L5 = min(256, Bi), 25, 80000
