@@ -570,3 +570,42 @@ def test_tiled_radix16_kernels_write_inside_their_outputs(sp, n_fft, hop, L):
             assert bool(torch.isfinite(y).all())
         q = sp.istft(plan, spec=S, normalize=True, pcm16=True)
         assert q.dtype == torch.int16 and int(q.to(torch.int32).abs().max()) >= 32767
+
+
+# ------------------------------------------------------------------------------------------- size limits
+def test_ten_minute_clip_and_seventy_thousand_clips(sp):
+    """Index ranges: one 10-minute clip (9.6 M samples, 50 001 frames: row offsets beyond 2^31 bytes in the complex output) and
+    70 000 short clips (more rows than a grid's y extent) through forward, inverse, normalisation and the PCM tail --
+    round-trip SNR >= 100 dB on the long clip, every short clip against the oracle's first / last rows."""
+    from ml_audio_inpainting_b200 import audio_io
+    L = 9_600_000
+    x = torch.from_numpy(_noise(1, L, seed=77)).cuda()
+    for n_fft, hop, win in ((512, 192, 384), (2048, 512, 2048)):
+        plan = sp.get_plan(n_fft, hop, win, "hann", True, "cuda:0")
+        S = sp.stft(x, plan)["spec"]
+        assert S.shape == (1, n_fft // 2 + 1, 1 + L // hop)
+        y = sp.istft(plan, spec=S, length=L)
+        err = (y - x).double()
+        snr = 10 * torch.log10(x.double().pow(2).sum() / err.pow(2).sum()).item()
+        assert snr >= 100.0, (n_fft, snr)
+        # the far end of the rows against the oracle: the last 44 hops as a clip of their own (L is a multiple of both hops, so
+        # its frames line up with the long clip's); all but its first n_fft / (2 hop) frames see the same samples
+        ref = lr.stft(x[0, L - 44 * hop:].cpu().numpy(), n_fft=n_fft, hop_length=hop, win_length=win)
+        assert ref.shape[1] == 45
+        got = S[0, :, -40:].cpu().numpy()
+        assert relerr(got, ref[:, -40:]) < TOL, relerr(got, ref[:, -40:])
+        del S, y
+    B, L2 = 70_000, 2048
+    xs = torch.from_numpy(_noise(B, L2, seed=3)).cuda()
+    plan = sp.get_plan(512, 192, 384, "hann", True, "cuda:0")
+    out = sp.stft(xs, plan, mag_kind=sp.MAG_LOG10_EPS, want_spec=True)
+    yb = sp.istft(plan, spec=out["spec"], normalize=True, length=L2)
+    q = sp.wave_to_pcm16(xs, normalize=True)
+    for b in (0, 65535, 65536, B - 1):
+        xb = xs[b].cpu().numpy()
+        ref = lr.stft(xb, n_fft=512, hop_length=192, win_length=384)
+        assert relerr(out["spec"][b].cpu().numpy(), ref) < TOL
+        assert np.abs(out["mag"][b].cpu().numpy() - np.log10(np.abs(ref) + 1e-9)).max() < 1e-3
+        ry = up.peak_normalize(lr.istft(ref, hop_length=192, win_length=384, n_fft=512, length=L2))
+        assert relerr(yb[b].cpu().numpy(), ry) < TOL
+        assert np.array_equal(q[b].cpu().numpy(), audio_io._to_int16(up.peak_normalize(xb), 32768.0))
