@@ -903,7 +903,8 @@ int aip_griffinlim_f32(const aip_stft_desc* desc, const float* mag, float* angle
   // the NEXT iteration (or the final one) reads rebuilt[it], rebuilt[it - 1] and |S| and projects while it loads (INV_GL,
   // InvLoadGL) -- 3 array passes fewer per iteration.  The forward kernel of iteration `it` overwrites rebuilt[it - 2], which
   // the inverse kernel before it on the stream was the last to read.  Needs the fast n_fft = 512 path.
-  const bool fused = pingpong && fwd_fast_ok(desc, di) && inv_fast_ok(desc) && !tunables().gl_unfused;
+  // ... or the tiled power-of-two kernels, whose transposed load does the same (istft_pow2_kernel).
+  const bool fused = pingpong && ((fwd_fast_ok(desc, di) && inv_fast_ok(desc)) || pow2_ok(desc->n_fft)) && !tunables().gl_unfused;
   for (int it = 0; it < n_iter; ++it) {
     int rc = run_inv(desc, I, 0, workspace, workspace_bytes, st);
     if (rc != AIP_OK) return rc;

@@ -436,6 +436,20 @@ __global__ void __launch_bounds__(kP2Threads, 2) istft_pow2_kernel(const Pow2Inv
       const long long base = (long long)b * G.F * P.T + t;
       if (t >= P.n_frames) {
         for (int k = k0; k <= g.M; k += kstep) z[p2_pad(k)] = make_float2(0.0f, 0.0f);
+      } else if (P.spec && P.gl_mag) {      // Griffin-Lim: the phase update of librosa.griffinlim inside the load (InvLoadGL's arithmetic)
+        const float2* __restrict__ reb = P.spec + base;
+        const float2* __restrict__ prv = P.gl_prev + base;
+        const float* __restrict__ mg = P.gl_mag + base;
+        const float alpha = P.gl_alpha;
+#pragma unroll 4
+        for (int k = k0; k <= g.M; k += kstep) {
+          const long long o = (long long)k * P.T;
+          const float2 r = __ldg(reb + o), t2 = __ldg(prv + o);
+          const float m = __ldg(mg + o);
+          const float ax = r.x - alpha * t2.x, ay = r.y - alpha * t2.y;
+          const float sc = fast_div(1.0f, fast_sqrt(ax * ax + ay * ay) + kFltMin);
+          z[p2_pad(k)] = make_float2((ax * sc) * m, (ay * sc) * m);
+        }
       } else if (P.spec) {             // complex input: nothing but loads, eight in flight per thread
         const float2* __restrict__ src = P.spec + base;
 #pragma unroll 8

@@ -609,3 +609,26 @@ def test_ten_minute_clip_and_seventy_thousand_clips(sp):
         ry = up.peak_normalize(lr.istft(ref, hop_length=192, win_length=384, n_fft=512, length=L2))
         assert relerr(yb[b].cpu().numpy(), ry) < TOL
         assert np.array_equal(q[b].cpu().numpy(), audio_io._to_int16(up.peak_normalize(xb), 32768.0))
+
+
+@pytest.mark.parametrize("n_fft,hop", [(2048, 512), (1024, 256), (256, 64)])
+def test_griffinlim_on_the_tiled_kernels(sp, n_fft, hop):
+    """Griffin-Lim at the reference's default transform size (utils.mel_spectrogram_to_audio: n_fft 2048 / hop 512, utils.py:335-341)
+    and the other tiled sizes: injected initial phasors, value parity with the oracle, and the phase update fused into the tiled
+    inverse's load against the separate update kernel (AIP_GL_UNFUSED=1)."""
+    B, L = 2, 24000
+    x = _noise(B, L, seed=n_fft)
+    m = np.stack([np.abs(lr.stft(x[b], n_fft=n_fft, hop_length=hop)) for b in range(B)]).astype(np.float32)
+    rng = np.random.default_rng(n_fft)
+    ang = np.exp(2j * np.pi * rng.random(m.shape)).astype(np.complex64)
+    plan = sp.get_plan(n_fft, hop, n_fft, "hann", True, "cuda:0")
+    mag = torch.from_numpy(m).cuda()
+    for n_iter, bound in ((0, 1e-4), (1, 1e-4), (2, 1e-4), (8, 1e-4), (32, 3e-3)):
+        y = sp.griffinlim(plan, mag, n_iter=n_iter, init_angles=torch.from_numpy(ang).cuda()).cpu().numpy()
+        with sp.experiment_env(AIP_GL_UNFUSED="1"):
+            y_unf = sp.griffinlim(plan, mag, n_iter=n_iter, init_angles=torch.from_numpy(ang).cuda()).cpu().numpy()
+        assert relerr(y, y_unf) < bound, (n_iter, relerr(y, y_unf))
+        if n_iter <= 8:
+            for b in range(B):
+                ref = lr.griffinlim(m[b], n_iter=n_iter, hop_length=hop, win_length=n_fft, n_fft=n_fft, init_angles=ang[b])
+                assert y[b].shape == ref.shape and relerr(y[b], ref) < bound, (n_iter, b, relerr(y[b], ref))
