@@ -9,10 +9,10 @@
 
 namespace aip {
 
-struct DevInfo { int ok; int sms; int max_smem; };
+struct DevInfo { int ok; int sms; int max_smem; int max_smem_sm; };
 
 static DevInfo dev_info() {
-  DevInfo d{0, 0, 0};
+  DevInfo d{0, 0, 0, 0};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return d;
   int major = 0, minor = -1;
@@ -20,6 +20,7 @@ static DevInfo dev_info() {
   cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
   cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&d.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaDeviceGetAttribute(&d.max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
   // the library holds sm_100a SASS only, and arch-specific ("a") code runs on exactly that compute capability: 10.0.
   // Any other 10.x part (sm_103, ...) would fail every launch with "no kernel image"; it gets AIP_ERR_DEVICE instead.
   d.ok = (major == 10 && minor == 0);
@@ -69,6 +70,7 @@ struct Tunables {
   int var_no_prefetch;    // AIP_VAR_NO_PREFETCH 1: gap-variant tiles do not request their rows from L2 ahead of the stores
   int var_fill_scalar;    // AIP_VAR_FILL=scalar gap-variant copy pass with store instructions instead of bulk copies
   int var_no_fill;        // AIP_VAR_NO_FILL     1: skip the copy pass (timing the transform kernel alone)
+  int pow2_span;          // AIP_POW2_SPAN       0: the tiled forward kernel loads every frame from global instead of staging the tile's span
   int pow2;               // AIP_POW2            0: n_fft != 512 runs the one-frame-per-CTA radix-2 kernels instead of the tiled radix-16 ones
 };
 const Tunables& tunables();

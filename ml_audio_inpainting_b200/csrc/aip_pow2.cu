@@ -226,6 +226,8 @@ struct Pow2FwdParams {
   FwdParams P;
   int F;               // bins = M + 1
   int vec;             // float2 loads of the waveform are legal (even hop / pad / pitch, 8-byte aligned base)
+  int span;            // > 0: floats of the tile's waveform span (FT - 1) hop + N, staged ONCE in shared memory by a bulk copy
+                       //      that runs while the previous tile is written out; 0: every warp loads its frames from global
 };
 
 // Waveform loaders of the first pass: the lane's two frames start at clip samples gA and gB.  P2WaveClean: both frames lie inside
@@ -260,6 +262,45 @@ struct P2WaveChecked {
   __device__ __forceinline__ float2 b(int idx) const { return get(gB, idx); }
 };
 
+// ... and from the staged span (already zero-padded and gap-zeroed by the bulk copy + fwd_fixup): pa / pb = the frames' first sample
+struct P2WaveStaged {
+  const float* pa;
+  const float* pb;
+  const float* win;
+  __device__ __forceinline__ float2 get(const float* p, int idx) const {
+    const float2 v = *reinterpret_cast<const float2*>(p + 2 * idx);
+    const float2 t = *reinterpret_cast<const float2*>(win + 2 * idx);
+    return make_float2(v.x * t.x, v.y * t.y);
+  }
+  __device__ __forceinline__ float2 a(int idx) const { return get(pa, idx); }
+  __device__ __forceinline__ float2 b(int idx) const { return get(pb, idx); }
+};
+
+// the span of tile (b, t0) as a bulk-copy plan (aip_tiles.cuh: the in-range, 16-byte part moves by ONE cp.async.bulk, the zero
+// padding, a ragged end and the gap are patched by fwd_fixup once it has landed)
+__device__ __forceinline__ FwdTilePlan p2_span_plan(const FwdParams& P, int b, int t0, int span, int gs, int ge) {
+  FwdTilePlan q;
+  q.len = span;
+  q.g0 = t0 * P.hop - P.pad;
+  q.src = P.wave + (long long)b * P.wave_pitch;
+  q.v_lo = q.g0 < 0 ? -q.g0 : 0;
+  const int hi = P.L - q.g0;
+  q.v_hi = hi < q.len ? (hi > 0 ? hi : 0) : q.len;
+  if (q.v_lo > q.v_hi) q.v_lo = q.v_hi;
+  q.n_bulk = (q.v_hi - q.v_lo) & ~3;
+  q.gs = gs; q.ge = ge;
+  return q;
+}
+__device__ __forceinline__ void p2_span_issue(const FwdTilePlan& q, float* span, uint64_t* bar) {
+  if (q.n_bulk > 0) {
+    const uint32_t bytes = (uint32_t)q.n_bulk * 4u;
+    mbar_expect_tx(bar, bytes);
+    tma_load_1d(span + q.v_lo, q.src + q.g0 + q.v_lo, bytes, bar);
+  } else {
+    mbar_arrive(bar);
+  }
+}
+
 // real-input split pass of one super-frame, in place: Z (M packed points) -> X[0..M]
 __device__ __forceinline__ void p2_split_fwd(const Pow2Geom& g, float2* sf, const float2* tw, int lane) {
   const int H = g.M >> 1, logH = g.logJ + 3;
@@ -292,11 +333,19 @@ __global__ void __launch_bounds__(kP2Threads, 2) stft_pow2_fwd_kernel(const Pow2
   const float2* tw = sm.tw;
   const float* win = sm.win;
   float2* bufs = sm.bufs;
+  __shared__ __align__(8) uint64_t span_bar;
+  float* span = reinterpret_cast<float*>(bufs + g.FT * g.PB);
   p2_fill_tables(g, P.window, sm, 1.0f);
+  if (threadIdx.x == 0) mbar_init(&span_bar, 1);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const P2Slots s = p2_slots(g, lane);
   float2* sf = bufs + warp * g.fps * g.PB;
+  uint32_t phase = 0;
+  if (G.span > 0 && threadIdx.x == 0 && (int)blockIdx.x < P.n_tiles) {
+    const int b = blockIdx.x / P.tiles_per_clip, t0 = (blockIdx.x - b * P.tiles_per_clip) * g.FT;
+    p2_span_issue(p2_span_plan(P, b, t0, G.span, 0, 0), span, &span_bar);
+  }
   for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
     const int b = tile / P.tiles_per_clip, t0 = (tile - b * P.tiles_per_clip) * g.FT;
     int gs = 0, ge = 0;
@@ -309,7 +358,17 @@ __global__ void __launch_bounds__(kP2Threads, 2) stft_pow2_fwd_kernel(const Pow2
       const int gA = tA * P.hop - P.pad, gB = tB * P.hop - P.pad;
       const bool clean = gA >= 0 && gA + g.N <= P.L && (ge <= gs || ge <= gA || gs >= gA + g.N) &&
                          gB >= 0 && gB + g.N <= P.L && (ge <= gs || ge <= gB || gs >= gB + g.N);
-      if (G.vec && __all_sync(0xffffffffu, clean)) {
+      if (G.span > 0) {
+        const FwdTilePlan q = p2_span_plan(P, b, t0, G.span, gs, ge);
+        mbar_wait(&span_bar, phase);
+        phase ^= 1;
+        if (fwd_needs_fixup(q)) {
+          fwd_fixup(q, threadIdx.x, span);
+          __syncthreads();
+        }
+        const P2WaveStaged load{span + (tA - t0) * P.hop, span + (tB - t0) * P.hop, win};
+        p2_pass_first(g, s, sf, load);
+      } else if (G.vec && __all_sync(0xffffffffu, clean)) {
         const P2WaveClean load{src, win, gA, gB};
         p2_pass_first(g, s, sf, load);
       } else {
@@ -319,7 +378,15 @@ __global__ void __launch_bounds__(kP2Threads, 2) stft_pow2_fwd_kernel(const Pow2
     }
     p2_passes_rest(g, s, sf, sm, lane);
     p2_split_fwd(g, sf, tw, lane);
+    if (G.span > 0) fence_proxy_async();             // this thread's reads of the span come before the next copy into it
     __syncthreads();
+    if (G.span > 0 && threadIdx.x == 0) {            // the next tile's span arrives while this one is written out
+      const int nt = tile + gridDim.x;
+      if (nt < P.n_tiles) {
+        const int nb = nt / P.tiles_per_clip, nt0 = (nt - nb * P.tiles_per_clip) * g.FT;
+        p2_span_issue(p2_span_plan(P, nb, nt0, G.span, 0, 0), span, &span_bar);
+      }
+    }
     // transposed store: thread = (frame f, bins k0 + i * 256 / FT); the epilogue switches are CTA-uniform
     {
       const int f = threadIdx.x & (g.FT - 1), k0 = threadIdx.x >> g.logFT, kstep = kP2Threads >> g.logFT;
@@ -548,6 +615,15 @@ cudaError_t launch_fwd_pow2(FwdParams P, int n_fft, const DevInfo& di, cudaStrea
   if ((long long)P.B * P.tiles_per_clip > 0x7fffffffLL) return cudaErrorInvalidValue;
   P.n_tiles = (int)((long long)P.B * P.tiles_per_clip);
   G.vec = ((P.hop & 1) == 0) && ((P.pad & 1) == 0) && ((P.wave_pitch & 1) == 0) && ((reinterpret_cast<uintptr_t>(P.wave) & 7) == 0);
+  // stage the tile's span when the bulk copy is legal (16-byte granules on both sides) and two CTAs per SM still fit
+  size_t smem = pow2_smem(g);
+  const long long span = (long long)(g.FT - 1) * P.hop + n_fft;
+  const bool vec16 = ((P.hop & 3) == 0) && ((P.pad & 3) == 0) && ((P.wave_pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.wave) & 15) == 0);
+  G.span = 0;
+  if (tunables().pow2_span && vec16 && 2 * (smem + (size_t)span * sizeof(float) + 1024) <= (size_t)di.max_smem_sm) {
+    G.span = (int)span;
+    smem += (size_t)span * sizeof(float);
+  }
   G.P = P;
   void (*kern)(Pow2FwdParams) = nullptr;
   switch (n_fft) {
@@ -556,7 +632,6 @@ cudaError_t launch_fwd_pow2(FwdParams P, int n_fft, const DevInfo& di, cudaStrea
 #undef X
     default: return cudaErrorInvalidValue;
   }
-  const size_t smem = pow2_smem(g);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   long long grid = (long long)di.sms * 2;
