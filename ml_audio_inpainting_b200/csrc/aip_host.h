@@ -70,6 +70,7 @@ struct Tunables {
   int var_no_prefetch;    // AIP_VAR_NO_PREFETCH 1: gap-variant tiles do not request their rows from L2 ahead of the stores
   int var_fill_scalar;    // AIP_VAR_FILL=scalar gap-variant copy pass with store instructions instead of bulk copies
   int var_no_fill;        // AIP_VAR_NO_FILL     1: skip the copy pass (timing the transform kernel alone)
+  int pow2_ola_fast;      // AIP_POW2_OLA_FAST   0: the tiled inverse always uses the general overlap-add gather
   int pow2_span;          // AIP_POW2_SPAN       0: the tiled forward kernel loads every frame from global instead of staging the tile's span
   int pow2;               // AIP_POW2            0: n_fft != 512 runs the one-frame-per-CTA radix-2 kernels instead of the tiled radix-16 ones
 };

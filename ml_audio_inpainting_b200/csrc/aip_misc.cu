@@ -179,6 +179,7 @@ static Tunables read_tunables() {
   t.var_no_fill = getenv("AIP_VAR_NO_FILL") ? 1 : 0;
   t.pow2 = env_int("AIP_POW2", 1);
   t.pow2_span = env_int("AIP_POW2_SPAN", 1);
+  t.pow2_ola_fast = env_int("AIP_POW2_OLA_FAST", 1);
   return t;
 }
 static Tunables g_tunables = read_tunables();        // once, when the shared object is loaded

@@ -438,6 +438,7 @@ struct Pow2InvParams {
   InvParams P;
   int F;
   float* frames;       // workspace [B, T, N]
+  int ola_k, log_hop;  // fused overlap-add, fast form: hop = N / ola_k is a power of two <= 512 (ola_k in 1..8); 0: general gather
 };
 
 struct P2SmemLoad {
@@ -493,6 +494,18 @@ __global__ void __launch_bounds__(kP2Threads, 2) istft_pow2_kernel(const Pow2Inv
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const P2Slots s = p2_slots(g, lane);
   float2* sf = bufs + warp * g.fps * g.PB;
+  float2 ola_w[8];
+  int ola_off[8], ola_q0 = 0;
+  if (kOla && G.ola_k > 0) {
+    const int r = (2 * threadIdx.x) & (P.hop - 1);
+    ola_q0 = (2 * threadIdx.x) >> G.log_hop;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = j < G.ola_k ? j * P.hop + r : 0;
+      ola_w[j] = *reinterpret_cast<const float2*>(win + n);
+      ola_off[j] = p2_pad(n >> 1);
+    }
+  }
   for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
     const int b = tile / P.tiles_per_clip, t0 = (tile - b * P.tiles_per_clip) * g.FT;
     const bool db = P.db_flags ? (P.db_flags[b] != 0) : false;
@@ -518,9 +531,17 @@ __global__ void __launch_bounds__(kP2Threads, 2) istft_pow2_kernel(const Pow2Inv
           z[p2_pad(k)] = make_float2((ax * sc) * m, (ay * sc) * m);
         }
       } else if (P.spec) {             // complex input: nothing but loads, eight in flight per thread
-        const float2* __restrict__ src = P.spec + base;
+        const float2* __restrict__ src = P.spec + base + (long long)k0 * P.T;
+        if (kstep >= 16) {             // kstep is a multiple of 16: the padded index advances by a constant, like the source row
+          const long long rs = (long long)kstep * P.T;
+          float2* zz = z + p2_pad(k0);
 #pragma unroll 8
-        for (int k = k0; k <= g.M; k += kstep) z[p2_pad(k)] = __ldg(src + (long long)k * P.T);
+          for (int i = 0; i < g.M / kstep; ++i, src += rs, zz += kstep + kstep / 16) *zz = __ldg(src);
+          if (k0 == 0) z[p2_pad(g.M)] = __ldg(P.spec + base + (long long)g.M * P.T);
+        } else {
+#pragma unroll 8
+          for (int k = k0; k <= g.M; k += kstep) z[p2_pad(k)] = __ldg(P.spec + base + (long long)k * P.T);
+        }
       } else {
 #pragma unroll 4
         for (int k = k0; k <= g.M; k += kstep) {
@@ -555,6 +576,39 @@ __global__ void __launch_bounds__(kP2Threads, 2) istft_pow2_kernel(const Pow2Inv
       const int span = (nv - 1) * P.hop + g.N;
       const int p0 = t0 * P.hop;                                                     // padded-signal position of the tile
       float* orow = P.out + (long long)b * P.out_pitch;
+      if (G.ola_k > 0) {
+        // hop = N / K, a power of two <= 512: a thread's pairs u = 2 tid + 512 it all sit at the same offset r inside their hop, so
+        // the K window taps and buffer offsets it needs are per-thread constants (ola_w / ola_off, set up before the tile loop) and
+        // the frames covering a pair are q - K + 1 .. q with q = u / hop = q0 + it (512 / hop): no division, no address arithmetic
+        const int dq = 512 >> G.log_hop;
+        for (int it = 0, u = 2 * threadIdx.x, q = ola_q0; u < span; ++it, u += 2 * kP2Threads, q += dq) {
+          const int sidx = p0 + u - P.pad;
+          if (sidx < 0 || sidx >= P.out_len) continue;
+          float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+          for (int j = 7; j >= 0; --j) {                                            // increasing frame order, like librosa.istft
+            if (j < G.ola_k) {
+              const int f = q - j;
+              if (f >= 0 && f < nv) {
+                const float2 v = bufs[f * g.PB + ola_off[j]];
+                a0 += v.y * ola_w[j].x;
+                a1 += v.x * ola_w[j].y;
+              }
+            }
+          }
+          const int T_lo = t0 + q - G.ola_k + 1, T_hi = t0 + q;
+          const bool whole = (T_lo >= t0 || T_lo <= 0 && t0 == 0) && (T_hi < t0 + g.FT || t0 + g.FT >= P.n_frames);
+          float* o = orow + sidx;
+          const float v0 = a0 * P.inv_wss[sidx];
+          if (whole) *o = v0; else atomicAdd(o, v0);
+          if (sidx + 1 < P.out_len) {
+            const float v1 = a1 * P.inv_wss[sidx + 1];
+            if (whole) o[1] = v1; else atomicAdd(o + 1, v1);
+          }
+        }
+        __syncthreads();
+        continue;
+      }
       // a thread takes the sample pair (u, u + 1), u even, when the hop is even (both samples then lie in the same frames
       // and in one float2 of each), else single samples.  Frames covering tile position u: f hop <= u < f hop + N.
       const int step = (P.hop & 1) ? 1 : 2;
@@ -659,6 +713,11 @@ cudaError_t launch_inv_pow2(InvParams P, int n_fft, float* frames, const DevInfo
   if ((long long)P.B * P.tiles_per_clip > 0x7fffffffLL) return cudaErrorInvalidValue;
   P.n_tiles = (int)((long long)P.B * P.tiles_per_clip);
   P.hop_magic = (unsigned)((0x100000000ULL + (unsigned)P.hop - 1) / (unsigned)P.hop);
+  G.ola_k = 0; G.log_hop = 0;
+  if (is_pow2(P.hop) && P.hop >= 2 && P.hop <= 512 && n_fft % P.hop == 0 && n_fft / P.hop <= 8 && tunables().pow2_ola_fast) {
+    G.ola_k = n_fft / P.hop;
+    G.log_hop = ilog2(P.hop);
+  }
   G.P = P;
   void (*kern)(Pow2InvParams) = nullptr;
   switch (n_fft) {

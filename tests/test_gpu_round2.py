@@ -504,6 +504,10 @@ def test_tiled_radix16_path_for_other_nfft(sp, n_fft, hop, win, L, center):
     if center:
         Sc = sp.stft(xd, plan)["spec"]
         y = sp.istft(plan, spec=Sc).cpu().numpy()
+        with sp.experiment_env(AIP_POW2_OLA_FAST="0"):      # the general gather and the power-of-two-hop one add in the same order
+            assert np.array_equal(sp.istft(plan, spec=Sc).cpu().numpy(), y)
+        with sp.experiment_env(AIP_POW2_SPAN="0"):          # per-warp global loads instead of the staged span: same samples
+            assert torch.equal(sp.stft(xd, plan)["spec"], Sc)
         # (hop == n_fft: no overlap, the window sum-square reaches ~0 at the frame borders and the division amplifies rounding
         #  there -- compare where it is well conditioned, as test_gpu_parity does for the reference's hop-512 default)
         wss = lr.window_sumsquare("hann", T, hop_length=hop, win_length=win, n_fft=n_fft, dtype=np.float32)[n_fft // 2:]
