@@ -23,6 +23,7 @@
 
 namespace aip {
 
+constexpr int kP2LoadUnroll = 8;      // complex rows a thread of the tiled inverse keeps in flight (16 / 32 measured: 2048 slower, 1024 3 % faster)
 constexpr int kP2Threads = 256;
 constexpr int kP2Warps = kP2Threads / 32;
 constexpr int kP2Points = 1024;                 // complex points per super-frame (32 lanes x 2 packed butterflies x 16)
@@ -535,7 +536,7 @@ __global__ void __launch_bounds__(kP2Threads, 2) istft_pow2_kernel(const Pow2Inv
         if (kstep >= 16) {             // kstep is a multiple of 16: the padded index advances by a constant, like the source row
           const long long rs = (long long)kstep * P.T;
           float2* zz = z + p2_pad(k0);
-#pragma unroll 8
+#pragma unroll kP2LoadUnroll
           for (int i = 0; i < g.M / kstep; ++i, src += rs, zz += kstep + kstep / 16) *zz = __ldg(src);
           if (k0 == 0) z[p2_pad(g.M)] = __ldg(P.spec + base + (long long)g.M * P.T);
         } else {

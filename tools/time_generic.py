@@ -3,7 +3,10 @@ import sys
 from pathlib import Path
 import torch
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
-from ml_audio_inpainting_b200 import spectral as sp
+from ml_audio_inpainting_b200 import _cabi, spectral as sp
+if "--lib" in sys.argv:          # A/B of a variant build (tools/build_variant.sh): experiment tooling only
+    _cabi.LIB_PATH = Path(sys.argv[sys.argv.index("--lib") + 1]).resolve()
+    print("library:", _cabi.LIB_PATH)
 
 def timeit(fn, n=10):
     for _ in range(3): fn()
