@@ -2,6 +2,7 @@
 
   lib/libaip_b200.so   nvcc, sm_100a SASS only -- the product (one object per csrc/aip_*.cu, compiled in parallel)
   lib/libaip_emul.so   g++, host replay of the kernels' phase functions -- test support only
+  lib/libaip_codec.so  gcc, the host-side FLAC codec of load_audio / save_audio (csrc/aip_flac.c) -- product, no CUDA
 
 A library is rebuilt when the SHA-256 of its sources + flags differs from the one recorded next to it
 (``lib/<name>.sha256``), never by file times: a pushed prebuilt .so whose sources changed is recompiled, and
@@ -22,6 +23,7 @@ LIB = PKG / "lib"
 OBJ = LIB / "obj"
 CUDA_LIB = LIB / "libaip_b200.so"
 EMUL_LIB = LIB / "libaip_emul.so"
+CODEC_LIB = LIB / "libaip_codec.so"
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "-Xptxas", "-v", "-Xcompiler", "-fPIC"]
@@ -103,6 +105,24 @@ def build_emul(force: bool = False) -> Path:
     return EMUL_LIB
 
 
+def build_codec(force: bool = False) -> Path:
+    """The host-side FLAC codec (plain C, no CUDA): gcc -> lib/libaip_codec.so."""
+    LIB.mkdir(exist_ok=True)
+    srcs = [CSRC / "aip_flac.c", PKG.parent / "include" / "aip_codec.h"]
+    flags = ["-O2", "-std=c11", "-shared", "-fPIC"]
+    digest = _digest(srcs, flags)
+    if force or _stale(CODEC_LIB, digest):
+        cc = shutil.which("gcc") or shutil.which("cc")
+        if not cc:
+            raise RuntimeError("no C compiler (gcc) to build lib/libaip_codec.so: the host codec has no pure-Python fallback")
+        res = subprocess.run([cc, *flags, "-o", str(CODEC_LIB), str(CSRC / "aip_flac.c")], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("gcc failed:\n" + res.stdout + res.stderr)
+        CODEC_LIB.with_suffix(".sha256").write_text(digest)
+    return CODEC_LIB
+
+
 if __name__ == "__main__":
     print(build_cuda(force=True, verbose=True))
     print(build_emul(force=True))
+    print(build_codec(force=True))

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 from typing import Optional
 
@@ -76,7 +77,8 @@ DECODABLE = (".flac", ".wav")        # containers the built-in reader handles (a
 
 
 def preprocess_tree(src_root, dst_root, gap_len: float = 0.1, sample_rate: int = 16000, max_len: float = 5,
-                    supported_formats=(".flac", ".wav"), batch: int = 256, device=None, progress: bool = True):
+                    supported_formats=(".flac", ".wav"), batch: int = 256, device=None, progress: bool = True,
+                    io_threads: Optional[int] = None):
     """The reference's loop (pre_process_dataset.py:19-43) with the device doing the arithmetic: files are visited in
     os.walk order, one np.random draw per file in that order, results written under ``dst_root`` mirroring the tree.
 
@@ -109,18 +111,27 @@ def preprocess_tree(src_root, dst_root, gap_len: float = 0.1, sample_rate: int =
             it = tqdm(it, desc="Pre-Processing Dataset")
         except ImportError:
             pass
-    for b0 in it:
-        b1 = min(hi, b0 + batch)
-        host = np.zeros((b1 - b0, L), dtype=np.float32)
-        for i, (src, _) in enumerate(jobs[b0:b1]):
-            pcm, sr = audio_io.read_audio(src, max_samples=L if True else None)
-            x = pcm.mean(axis=1, dtype=np.float32) if pcm.ndim == 2 else pcm
-            if sr != sample_rate:
-                raise IOError(f"{src}: sample rate {sr} != {sample_rate} (resampling is not part of the bulk path)")
-            host[i, : min(L, len(x))] = x[:L]
-        res = preprocess_batch(torch.from_numpy(host).to(device), gap_len, sample_rate, starts=starts_all[b0:b1],
-                               want_pcm16=True)
-        out = res["pcm16"].cpu().numpy()                               # the FLAC's 16-bit samples, quantised on the device
-        for (_, dst), y in zip(jobs[b0:b1], out):
-            audio_io.write_audio(dst, y, sample_rate, "flac")           # utils.save_audio's default format, utils.py:59
+    # decode and encode are host work in the native codec (csrc/aip_flac.c), which runs outside the GIL: one file per thread
+    pool = ThreadPoolExecutor(max_workers=io_threads or min(32, os.cpu_count() or 1))
+
+    def decode_into(args):
+        host, i, src = args
+        pcm, sr = audio_io.read_audio(src, max_samples=L)
+        x = pcm.mean(axis=1, dtype=np.float32) if pcm.ndim == 2 else pcm
+        if sr != sample_rate:
+            raise IOError(f"{src}: sample rate {sr} != {sample_rate} (resampling is not part of the bulk path)")
+        host[i, : min(L, len(x))] = x[:L]
+
+    try:
+        for b0 in it:
+            b1 = min(hi, b0 + batch)
+            host = np.zeros((b1 - b0, L), dtype=np.float32)
+            list(pool.map(decode_into, [(host, i, src) for i, (src, _) in enumerate(jobs[b0:b1])]))
+            res = preprocess_batch(torch.from_numpy(host).to(device), gap_len, sample_rate, starts=starts_all[b0:b1],
+                                   want_pcm16=True)
+            out = res["pcm16"].cpu().numpy()                           # the FLAC's 16-bit samples, quantised on the device
+            # utils.save_audio's default format (utils.py:59)
+            list(pool.map(lambda a: audio_io.write_audio(a[0][1], a[1], sample_rate, "flac"), zip(jobs[b0:b1], out)))
+    finally:
+        pool.shutdown()
     return len(jobs)

@@ -3,9 +3,11 @@
 This package restates, in numpy + scipy.fft on the CPU, the reference's hot path:
 ``utils.py`` (gap masks, STFT, iSTFT / phase reuse / Griffin-Lim), the per-item
 epilogues of ``models/CNNBLSTM/dataset.py`` / ``models/GAN/dataset.py`` /
-``models/model_eval.py`` and the third-party ``librosa`` routines those call.
+``models/model_eval.py`` and the third-party ``librosa`` routines those call
+(``librosa_port``, ``utils_port``, ``callers_port``), plus ``flac_port``: the pure-Python FLAC
+codec that checks the product's native host codec (``csrc/aip_flac.c``).
 
-Rules (enforced by tests/test_layout.py):
+Rules (enforced by tests/test_host_logic.py):
   * only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
     ``--impl reference`` legs may import anything from here, and only as the checker
     or as the CPU baseline -- never as the thing shipped or measured as "ours";
