@@ -8,7 +8,7 @@
  *           fixed or variable block size; stops after the frame that reaches `max_samples` (load_audio needs the first
  *           sample_rate * max_len samples only).  Frame CRCs are not checked (the STREAMINFO MD5 is, by the caller, on request).
  *   encode  16-bit, independent channels, FIXED predictor of the order with the smallest sum |residual|, one Rice partition --
- *           bit for bit the stream ml_audio_inpainting_b200/audio_io.py's reference encoder writes (tests/test_codec.py).
+ *           bit for bit the stream the pure-Python checker codec writes (tests/test_codec.py).
  */
 #include <stdint.h>
 #include <stdlib.h>
