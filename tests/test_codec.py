@@ -274,3 +274,33 @@ def test_parallel_decodes_agree(golden_clips):
         par = list(pool.map(lambda b: audio_io.decode_flac(b)[0], blobs * 4))
     for i, p in enumerate(par):
         assert np.array_equal(p, serial[i % len(blobs)])
+
+
+def test_corrupted_streams_never_crash_the_decoder(golden_clips):
+    """Memory safety of the native decoder: random byte corruption, truncation and header damage either decode to something or
+    raise ValueError -- never touch memory outside the buffers (a crash would take the interpreter down with it)."""
+    rng = np.random.default_rng(11)
+    x = np.rint(golden_clips[sorted(golden_clips)[0]][:12000] * 32768).astype(np.int16)
+    streams = [audio_io.encode_flac(x, 16000, blocksize=1152), audio_io.encode_flac(np.stack([x, x[::-1]], 1), 16000)]
+    lpc8 = [1412, -1203, 601, -322, 188, -97, 41, -12]
+    streams.append(make_stream(speechlike(4096, 1, 16, 5), 16, 16000,
+                               [(4096, "indep", [("lpc", lpc8, 12, 10, 3, [4, 5, ("esc", 14), 3, 6, 4, 5, 7])])]))
+    outcomes = {"ok": 0, "raised": 0}
+    for s in streams:
+        for trial in range(250):
+            b = bytearray(s)
+            kind = trial % 3
+            if kind == 0:
+                for _ in range(int(rng.integers(1, 6))):
+                    b[int(rng.integers(4, len(b)))] = int(rng.integers(0, 256))
+            elif kind == 1:
+                b = b[:int(rng.integers(8, len(b)))]
+            else:
+                lo = int(rng.integers(42, len(b) - 8))
+                b[lo:lo + 8] = bytes(rng.integers(0, 256, 8, dtype=np.uint8))
+            try:
+                audio_io.decode_flac(bytes(b))
+                outcomes["ok"] += 1
+            except ValueError:
+                outcomes["raised"] += 1
+    assert outcomes["raised"] > 100 and sum(outcomes.values()) == 750
