@@ -175,10 +175,18 @@ def write_wav(audio: np.ndarray, sample_rate: int) -> bytes:
 
 
 # ----------------------------------------------------------------------------- front doors
-def read_audio(path, max_samples: Optional[int] = None) -> Tuple[np.ndarray, int]:
-    """Decode ``path`` to (float32 [n, channels], native sample rate)."""
+def read_audio(path, max_samples: Optional[int] = None, only_at_rate: Optional[int] = None) -> Tuple[np.ndarray, int]:
+    """Decode ``path`` to (float32 [n, channels], native sample rate).  ``max_samples``: stop after the frame that reaches that
+    many samples; with ``only_at_rate`` the limit applies only to files of that sample rate (a file that still has to be
+    resampled is decoded whole: the resampler's tail depends on what follows)."""
     data = Path(path).read_bytes()
     if data[:4] == b"fLaC":
+        if max_samples is not None and only_at_rate is not None:
+            ci = _codec.FlacInfoC()
+            raw = np.frombuffer(data, dtype=np.uint8)
+            _codec.check(_codec.load().aip_flac_info_read(raw.ctypes.data, raw.size, C.byref(ci)), "aip_flac_info_read")
+            if ci.sample_rate != only_at_rate:
+                max_samples = None
         pcm, info = decode_flac(data, max_samples=max_samples)
         scale = float(1 << (info.bits_per_sample - 1))
         return (pcm.astype(np.float32) / np.float32(scale)), info.sample_rate

@@ -42,7 +42,8 @@ def load_audio(file_path: Union[str, Path], sample_rate: int = DEFAULT_SAMPLE_RA
     """reference utils.py:14-52.  Decode (built-in FLAC / WAV reader), mono, resample if the file rate
     differs, then truncate / right-pad to ``int(sample_rate * max_len)`` samples.  Any failure -> IOError."""
     try:
-        pcm, sr = audio_io.read_audio(file_path)
+        # (only the first sample_rate * max_len samples are used: the decoder stops there when no resampling is needed)
+        pcm, sr = audio_io.read_audio(file_path, max_samples=int(sample_rate * max_len), only_at_rate=sample_rate)
         audio_data = pcm.mean(axis=1, dtype=np.float32) if (mono and pcm.ndim == 2) else pcm.T.squeeze()
         if sr != sample_rate:
             import math
