@@ -24,24 +24,24 @@ typedef struct {
   int err;
 } bitr;
 
-static inline uint32_t br_bit(bitr* b) {
-  if (b->pos >= b->n * 8) { b->err = 1; return 0; }
-  const uint32_t v = (b->p[b->pos >> 3] >> (7 - (b->pos & 7))) & 1u;
-  b->pos++;
-  return v;
+static inline uint64_t be64(const uint8_t* p) {
+  uint64_t w;
+  memcpy(&w, p, 8);
+  return __builtin_bswap64(w);
 }
 
 /* n <= 32 bits, big endian */
 static inline uint32_t br_read(bitr* b, int n) {
   if (n == 0) return 0;
   if (b->pos + (size_t)n > b->n * 8) { b->err = 1; b->pos = b->n * 8; return 0; }
-  uint64_t acc = 0;
-  size_t byte = b->pos >> 3;
+  const size_t byte = b->pos >> 3;
   const int off = (int)(b->pos & 7);
-  const int need = (off + n + 7) >> 3;          /* <= 5 bytes */
+  b->pos += (size_t)n;
+  if (byte + 8 <= b->n) return (uint32_t)((be64(b->p + byte) << off) >> (64 - n));      /* off + n <= 39 */
+  uint64_t acc = 0;
+  const int need = (off + n + 7) >> 3;          /* <= 5 bytes, all inside the buffer */
   for (int i = 0; i < need; ++i) acc = (acc << 8) | b->p[byte + i];
   acc >>= (need * 8 - off - n);
-  b->pos += (size_t)n;
   return (uint32_t)(acc & (n == 32 ? 0xFFFFFFFFull : ((1ull << n) - 1)));
 }
 
@@ -57,8 +57,20 @@ static inline uint32_t br_unary(bitr* b) {
   uint32_t z = 0;
   const size_t end = b->n * 8;
   while (b->pos < end) {
+    const size_t byte = b->pos >> 3;
     const int off = (int)(b->pos & 7);
-    const uint8_t rest = (uint8_t)(b->p[b->pos >> 3] << off);      /* remaining bits of this byte, left aligned */
+    if (byte + 8 <= b->n) {
+      const uint64_t w = be64(b->p + byte) << off;                 /* 64 - off valid bits, left aligned */
+      if (w) {
+        const int lead = __builtin_clzll(w);
+        b->pos += (size_t)lead + 1;
+        return z + (uint32_t)lead;
+      }
+      z += (uint32_t)(64 - off);
+      b->pos += (size_t)(64 - off);
+      continue;
+    }
+    const uint8_t rest = (uint8_t)(b->p[byte] << off);             /* the last few bytes: one at a time */
     if (rest) {
       const int lead = __builtin_clz((uint32_t)rest) - 24;
       b->pos += (size_t)lead + 1;
@@ -291,23 +303,28 @@ int64_t aip_flac_decode(const uint8_t* data, size_t n, int64_t max_samples, int3
 /* ------------------------------------------------------------------------------------------------ encode */
 typedef struct {
   uint8_t* p;
-  size_t cap, pos;   /* pos in bits */
+  size_t cap, pos;   /* bytes written */
+  uint64_t acc;      /* pending bits, right aligned */
+  int nacc;          /* < 8 between calls */
   int err;
 } bitw;
 
 static inline void bw_put(bitw* w, uint64_t v, int n) {          /* n <= 32 */
   if (n == 0) return;
-  if (w->pos + (size_t)n > w->cap * 8) { w->err = 1; return; }
-  for (int i = n - 1; i >= 0; --i) {
-    if ((v >> i) & 1) w->p[w->pos >> 3] |= (uint8_t)(0x80u >> (w->pos & 7));
-    w->pos++;
+  w->acc = (w->acc << n) | (v & (n == 32 ? 0xFFFFFFFFull : ((1ull << n) - 1)));
+  w->nacc += n;
+  while (w->nacc >= 8) {
+    if (w->pos >= w->cap) { w->err = 1; w->nacc = 0; return; }
+    w->p[w->pos++] = (uint8_t)(w->acc >> (w->nacc - 8));
+    w->nacc -= 8;
   }
 }
 static inline void bw_zeros_then_one(bitw* w, uint64_t zeros) {
-  if (w->pos + zeros + 1 > w->cap * 8) { w->err = 1; return; }
-  w->pos += zeros;                                                /* the buffer is zero-filled */
-  w->p[w->pos >> 3] |= (uint8_t)(0x80u >> (w->pos & 7));
-  w->pos++;
+  while (zeros >= 32) { bw_put(w, 0, 32); zeros -= 32; }
+  bw_put(w, 1, (int)zeros + 1);
+}
+static inline void bw_flush(bitw* w) {                            /* zero-pad to a byte boundary */
+  if (w->nacc) bw_put(w, 0, 8 - w->nacc);
 }
 
 static uint8_t crc8_tab[256];
@@ -389,7 +406,6 @@ int64_t aip_flac_encode16(const int16_t* pcm, int64_t n, int32_t channels, int32
     return AIP_CODEC_ERR_ARG;
   if (!crc_ready) crc_init();
   if (cap < 42) return AIP_CODEC_ERR_CAPACITY;
-  memset(out, 0, cap);
   int sr_code = 0;
   switch (sample_rate) {
     case 8000: sr_code = 4; break;   case 16000: sr_code = 5; break;  case 22050: sr_code = 6; break;
@@ -436,10 +452,11 @@ int64_t aip_flac_encode16(const int16_t* pcm, int64_t n, int32_t channels, int32
     if (pos + (size_t)h > cap) { rc = AIP_CODEC_ERR_CAPACITY; break; }
     memcpy(out + pos, hdr, (size_t)h);
     pos += (size_t)h;
-    bitw w = {out + pos, cap - pos, 0, 0};
+    bitw w = {out + pos, cap - pos, 0, 0, 0, 0};
     for (int c = 0; c < channels; ++c) encode_subframe(&w, pcm + s * channels + c, bs, channels, x, r);
+    bw_flush(&w);
     if (w.err) { rc = AIP_CODEC_ERR_CAPACITY; break; }
-    pos += (w.pos + 7) >> 3;
+    pos += w.pos;
     if (pos + 2 > cap) { rc = AIP_CODEC_ERR_CAPACITY; break; }
     uint16_t c16 = 0;
     for (size_t i = f0; i < pos; ++i) c16 = (uint16_t)((c16 << 8) ^ crc16_tab[(c16 >> 8) ^ out[i]]);
