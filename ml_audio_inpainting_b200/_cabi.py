@@ -5,6 +5,7 @@ There is no fallback: if the shared object is missing or the device is not a B20
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libaip_b200.so"
@@ -60,12 +61,17 @@ SIGNATURES = {
 }
 
 _lib = None
+_lock = threading.Lock()
 
 
 def load() -> C.CDLL:
     """Load libaip_b200.so (built in-tree by ``_build.build_cuda``) and type its entry points."""
     global _lib
-    if _lib is None:
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
         if not LIB_PATH.exists():
             raise ImportError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -7,6 +7,7 @@ ctypes releases the GIL around every call, so files decode in parallel from a th
 from __future__ import annotations
 
 import ctypes as C
+import threading
 
 from . import _build
 
@@ -28,18 +29,22 @@ SIGNATURES = {
 }
 
 _lib = None
+_lock = threading.Lock()
 
 
 def load() -> C.CDLL:
+    """Build (if the source hash changed) and load the codec once; safe to call from the I/O thread pools."""
     global _lib
     if _lib is None:
-        path = _build.build_codec()
-        lib = C.CDLL(str(path))
-        for name, (res, args) in SIGNATURES.items():
-            fn = getattr(lib, name)
-            fn.restype = res
-            fn.argtypes = args
-        _lib = lib
+        with _lock:
+            if _lib is None:
+                path = _build.build_codec()
+                lib = C.CDLL(str(path))
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(lib, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = lib
     return _lib
 
 

@@ -329,8 +329,8 @@ static inline void bw_flush(bitw* w) {                            /* zero-pad to
 
 static uint8_t crc8_tab[256];
 static uint16_t crc16_tab[256];
-static int crc_ready = 0;
-static void crc_init(void) {
+/* filled when the library is loaded: no lazily-initialised state, the entry points are re-entrant */
+__attribute__((constructor)) static void crc_init(void) {
   for (int i = 0; i < 256; ++i) {
     uint8_t c = (uint8_t)i;
     for (int k = 0; k < 8; ++k) c = (c & 0x80) ? (uint8_t)((c << 1) ^ 0x07) : (uint8_t)(c << 1);
@@ -339,7 +339,6 @@ static void crc_init(void) {
     for (int k = 0; k < 8; ++k) d = (d & 0x8000) ? (uint16_t)((d << 1) ^ 0x8005) : (uint16_t)(d << 1);
     crc16_tab[i] = d;
   }
-  crc_ready = 1;
 }
 
 static void encode_subframe(bitw* w, const int16_t* pcm, int n, int stride, int64_t* x, int64_t* r) {
@@ -404,7 +403,6 @@ int64_t aip_flac_encode16(const int16_t* pcm, int64_t n, int32_t channels, int32
   if (!pcm || !out || !md5 || n < 0 || channels < 1 || channels > 8 || blocksize < 16 || blocksize > 65535 ||
       sample_rate <= 0 || sample_rate >= (1 << 20))
     return AIP_CODEC_ERR_ARG;
-  if (!crc_ready) crc_init();
   if (cap < 42) return AIP_CODEC_ERR_CAPACITY;
   int sr_code = 0;
   switch (sample_rate) {
