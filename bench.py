@@ -458,6 +458,20 @@ def extra_legs(args, sp, plan, wave, gap_dev, Bi, T, F, L, world, peak, timed):
     ms_df, _ = timed(lambda: sp.stft(wave[:Bd], plan_d, out=dout), args.steps, args.warmup)
     yd = torch.empty((Bd, plan_d.istft_length(Td)), dtype=torch.float32, device=dev)
     ms_di, _ = timed(lambda: sp.istft(plan_d, spec=dout["spec"], out=yd), args.steps, args.warmup)
+    if world > 1:
+        # the OPTIONAL final gather: every rank's output shard to every rank over NVLink / NVSwitch.  Not part of the
+        # hot path (no collective there) and not in any other number: 512 clips' log-magnitudes per rank (the shard of a
+        # 4096-clip job on 8 GPUs, 439 MB) through torch.distributed.all_gather_into_tensor (NCCL).
+        import torch.distributed as dist
+        Bg = min(512, Bi)
+        shard = sp.stft(wave[:Bg], plan, gap_samples=gap_dev[:Bg], mag_kind=sp.MAG_LOG10_EPS, eps=EPS, want_spec=False)["mag"]
+        full = torch.empty((world * Bg, F, T), dtype=torch.float32, device=dev)
+        ms_g, _ = timed(lambda: dist.all_gather_into_tensor(full, shard), max(3, args.steps // 4), 2)
+        nbytes = shard.numel() * 4
+        legs["gather_outputs"] = {"workload": f"optional all-gather of {Bg} clips' log-magnitudes per rank to every rank (NCCL)",
+                                  "ms_per_step": ms_g, "bytes_per_rank": nbytes,
+                                  "received_GBps_per_gpu": (world - 1) * nbytes / (ms_g * 1e-3) / 1e9}
+        del shard, full
     legs["default_params_2048"] = {
         "workload": f"utils.extract_spectrogram / spectrogram_to_audio at the reference's default n_fft 2048 / hop 512, batch {Bd} per GPU",
         "stft": {"value": world * Bd * CLIP_S / (ms_df * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_df,
