@@ -66,6 +66,8 @@ int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, 
         AIP_CASE(FWD_MAG_ABS) AIP_CASE(FWD_MAG_LOG10) AIP_CASE(FWD_SPEC) AIP_CASE(MAG_LOG10_EPS | FWD_MASK)
         AIP_CASE(MAG_LOG1P_POW) AIP_CASE(MAG_LOG1P_POW | FWD_PHASE | FWD_MASK) AIP_CASE(FWD_SPEC | FWD_PHASE | FWD_MASK)
         AIP_CASE(MAG_LOG10_EPS | FWD_ZERO) AIP_CASE(MAG_ABS | FWD_PHASE) AIP_CASE(MAG_LOG1P_POW | FWD_PHASE) AIP_CASE(FWD_SPEC | FWD_PHASE)
+        AIP_CASE(MAG_POW) AIP_CASE(FWD_SPEC | MAG_ABS) AIP_CASE(FWD_SPEC | MAG_LOG10_EPS) AIP_CASE(FWD_SPEC | MAG_LOG1P_POW)
+        AIP_CASE(MAG_LOG10_EPS | FWD_PHASE)
 #undef AIP_CASE
         default: fwd_phase2<FWD_FULL>(P, tid, c, exch.data(), pw[tid], rel); break;
       }

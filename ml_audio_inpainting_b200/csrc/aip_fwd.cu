@@ -477,6 +477,11 @@ static cudaError_t launch_fwd512(const FwdParams& P, const DevInfo& di, cudaStre
     case FWD_SPEC: return launch_fwd512_t<FWD_SPEC>(P, di, st);
     case MAG_LOG10_EPS | FWD_MASK: return launch_fwd512_t<MAG_LOG10_EPS | FWD_MASK>(P, di, st);
     case MAG_LOG1P_POW: return launch_fwd512_t<MAG_LOG1P_POW>(P, di, st);
+    case MAG_POW: return launch_fwd512_t<MAG_POW>(P, di, st);
+    case FWD_SPEC | MAG_ABS: return launch_fwd512_t<FWD_SPEC | MAG_ABS>(P, di, st);
+    case FWD_SPEC | MAG_LOG10_EPS: return launch_fwd512_t<FWD_SPEC | MAG_LOG10_EPS>(P, di, st);
+    case FWD_SPEC | MAG_LOG1P_POW: return launch_fwd512_t<FWD_SPEC | MAG_LOG1P_POW>(P, di, st);
+    case MAG_LOG10_EPS | FWD_PHASE: return launch_fwd512_t<MAG_LOG10_EPS | FWD_PHASE>(P, di, st);
     case MAG_LOG1P_POW | FWD_PHASE | FWD_MASK: return launch_fwd512_t<MAG_LOG1P_POW | FWD_PHASE | FWD_MASK>(P, di, st);
     case FWD_SPEC | FWD_PHASE | FWD_MASK: return launch_fwd512_t<FWD_SPEC | FWD_PHASE | FWD_MASK>(P, di, st);
     case MAG_LOG10_EPS | FWD_ZERO: return launch_fwd512_t<MAG_LOG10_EPS | FWD_ZERO>(P, di, st);

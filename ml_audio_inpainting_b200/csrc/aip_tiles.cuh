@@ -249,6 +249,7 @@ AIP_HDX int win_zero_groups(int win_length) {
 }
 
 AIP_HD float mag_value(int mk, float xr, float xi, float eps, float power) {
+  if (mk == MAG_POW && power == 2.0f) return xr * xr + xi * xi;      // the power spectrogram (librosa.feature.melspectrogram's default)
   const float m = fast_sqrt(xr * xr + xi * xi);
   if (mk == MAG_ABS) return m;
   if (mk == MAG_LOG10_EPS) return fast_log2(m + eps) * kLog10of2;
@@ -256,9 +257,10 @@ AIP_HD float mag_value(int mk, float xr, float xi, float eps, float power) {
   return (mk == MAG_LOG1P_POW) ? fast_log1p(mp) : mp;
 }
 
-// two bins at once on FP32x2 (power == 1); the MUFU ops stay scalar
+// two bins at once on FP32x2 (power == 1; MAG_POW: power == 2); the MUFU ops stay scalar
 AIP_HD float2 mag_value2(int mk, float2 xr, float2 xi, float eps) {
   const float2 pw = fma2(xi, xi, mul2(xr, xr));
+  if (mk == MAG_POW) return pw;
   const float2 m = make_float2(fast_sqrt(pw.x), fast_sqrt(pw.y));
   if (mk == MAG_ABS) return m;
   if (mk == MAG_LOG10_EPS) {
@@ -270,7 +272,7 @@ AIP_HD float2 mag_value2(int mk, float2 xr, float2 xi, float eps) {
 
 // Forward kernel variants: a bit mask of what the epilogue produces, a template parameter of the kernel so
 // that each variant is straight-line code (no per-bin branches, no calls).
-//   bits 0..2  magnitude kind (MagKind: 0 none, 1 |S|, 2 log10(|S|+eps), 3 log1p(|S|), 4 reserved -> fallback)
+//   bits 0..2  magnitude kind (MagKind: 0 none, 1 |S|, 2 log10(|S|+eps), 3 log1p(|S|), 4 |S|**2)
 //   FWD_SPEC   complex output          FWD_PHASE  angle(S)        FWD_MASK  dense frame mask
 //   FWD_ZERO   spectrum-domain gap (frames [f0,f1) zeroed before the epilogue, models/model_eval.py:154)
 //   FWD_FULL   run-time flags, out-of-line epilogue: every other combination (|S|**p with p != 1, ...)
@@ -306,7 +308,7 @@ struct FwdEmitT {
     if (kM & FWD_SPEC) spec[o] = make_float2(xr, xi);
     if (kM & FWD_PHASE) phase[o] = fast_atan2(xi, xr);
     if (kM & FWD_MASK) mask[o] = maskv;
-    if (kM & 7) mag[o] = mag_value(kM & 7, xr, xi, eps, 1.0f);
+    if (kM & 7) mag[o] = mag_value(kM & 7, xr, xi, eps, (kM & 7) == MAG_POW ? 2.0f : 1.0f);
   }
   template <int SX, int SY>
   AIP_HM void put2(int ox, int oy, float2 xr, float2 xi) const {
@@ -319,8 +321,8 @@ struct FwdEmitT {
     if (kM & FWD_MASK) { mask[ox] = maskv; mask[oy] = maskv; }
     if (kM & 7) {
 #if defined(AIP_MAG_SCALAR)
-      mag[ox] = mag_value(kM & 7, xr.x, xi.x, eps, 1.0f);
-      mag[oy] = mag_value(kM & 7, xr.y, xi.y, eps, 1.0f);
+      mag[ox] = mag_value(kM & 7, xr.x, xi.x, eps, (kM & 7) == MAG_POW ? 2.0f : 1.0f);
+      mag[oy] = mag_value(kM & 7, xr.y, xi.y, eps, (kM & 7) == MAG_POW ? 2.0f : 1.0f);
 #else
       const float2 m = mag_value2(kM & 7, xr, xi, eps);
 #if defined(AIP_ABLATE_STORES)     // timing experiment only: everything is computed, (almost) nothing is written
@@ -335,43 +337,75 @@ struct FwdEmitT {
   }
 };
 
-// Epilogue, general path: any mix of complex / magnitude / phase / mask outputs and the spectrum-domain gap.
+// Epilogue, general path: any mix of complex / magnitude / phase / mask outputs, the spectrum-domain gap and |S| ** p.
+// The emitter carries COPIES of the few FwdParams fields it needs: holding a reference to the kernel parameter block made it
+// addressable (a 272-byte local-memory copy per thread, read back on every store) and the out-of-line store routine it used to
+// call 65 times per job kept half the register file alive across each call -- together 8.3 ms where two specialised launches
+// producing the same outputs take 0.86 ms.  Now the stores are inline behind CTA-uniform tests and only the rare transcendental
+// tails (|S| ** p for p other than 1 and 2, via powf) stay out of line.
+#if defined(__CUDACC__)
+static __device__ __noinline__
+#else
+static inline
+#endif
+float mag_value_general(int mk, float xr, float xi, float eps, float power) { return mag_value(mk, xr, xi, eps, power); }
+// every magnitude flavour that needs no powf: |S|, log10(|S| + eps), log1p(|S|), |S| ** 1, |S| ** 2 (`square`)
+AIP_HD float mag_value_nopow(int mk, float xr, float xi, float eps, bool square) {
+  const float pw = xr * xr + xi * xi;
+  if (mk == MAG_POW && square) return pw;
+  const float m = fast_sqrt(pw);
+  if (mk == MAG_LOG10_EPS) return fast_log2(m + eps) * kLog10of2;
+  if (mk == MAG_LOG1P_POW) return fast_log1p(m);
+  return m;
+}
+
 struct FwdEmitFull {
   typedef long long off_t;
-  const FwdParams& P;
+  float2* spec;             // array bases or null
+  float* phase;
+  float* mask;
+  float* mag;
+  int mag_kind, T_out;
+  float eps, power;
   long long base;           // b*F*T_out + t
-  bool active, zero;
+  bool active, zero, slow_mag, square;
   float maskv;
   long long off_lo, off_hi; // element offsets of the two row cursors
   int s16;                  // 16 * T_out
   AIP_HM void rows(int k_lo, int k_hi) {
-    off_lo = base + (long long)k_lo * P.T_out;
-    off_hi = base + (long long)k_hi * P.T_out;
-    s16 = 16 * P.T_out;
+    off_lo = base + (long long)k_lo * T_out;
+    off_hi = base + (long long)k_hi * T_out;
+    s16 = 16 * T_out;
   }
   AIP_HM long long lo(int j) const { return off_lo + j * s16; }
   AIP_HM long long hi(int j) const { return off_hi - j * s16; }
-  AIP_HM long long bin(int k) const { return base + (long long)k * P.T_out; }
+  AIP_HM long long bin(int k) const { return base + (long long)k * T_out; }
   template <int SX, int SY>
   AIP_HM void put2(long long ox, long long oy, float2 xr, float2 xi) const {
     put1(ox, xr.x, SX < 0 ? -xi.x : xi.x);
     put1(oy, xr.y, SY < 0 ? -xi.y : xi.y);
   }
-#if defined(__CUDACC__)
-  __device__ __noinline__      // called 65 times per job: keep the kernel inside the instruction cache
-#endif
-  void put1(long long idx, float xr, float xi) const {
+  AIP_HM void put1(long long idx, float xr, float xi) const {
     if (!active) return;
     if (zero) { xr = 0.0f; xi = 0.0f; }
-    if (P.spec) P.spec[idx] = make_float2(xr, xi);
-    if (P.phase) P.phase[idx] = fast_atan2(xi, xr);
-    if (P.mask) P.mask[idx] = maskv;
-    if (P.mag_kind != MAG_NONE) P.mag[idx] = mag_value(P.mag_kind, xr, xi, P.eps, P.power);
+    if (spec) spec[idx] = make_float2(xr, xi);
+    if (phase) phase[idx] = fast_atan2(xi, xr);
+    if (mask) mask[idx] = maskv;
+    if (mag_kind != MAG_NONE)
+      mag[idx] = slow_mag ? mag_value_general(mag_kind, xr, xi, eps, power) : mag_value_nopow(mag_kind, xr, xi, eps, square);
   }
 };
 
 AIP_HD FwdEmitFull fwd_make_emit_full(const FwdParams& P, int b, int t, int n_bins, bool active) {
-  FwdEmitFull emit{P, (long long)b * n_bins * P.T_out + t, active, false, 0.0f, 0, 0, 0};
+  FwdEmitFull emit;
+  emit.spec = P.spec; emit.phase = P.phase; emit.mask = P.mask; emit.mag = P.mag;
+  emit.mag_kind = P.mag_kind; emit.T_out = P.T_out; emit.eps = P.eps; emit.power = P.power;
+  emit.base = (long long)b * n_bins * P.T_out + t;
+  emit.active = active; emit.zero = false; emit.maskv = 0.0f;
+  emit.off_lo = emit.off_hi = 0; emit.s16 = 0;
+  // powers the straight-line magnitude code does not cover (it knows 1, and 2 for MAG_POW)
+  emit.slow_mag = (P.mag_kind == MAG_POW && P.power != 2.0f && P.power != 1.0f) || (P.mag_kind == MAG_LOG1P_POW && P.power != 1.0f);
+  emit.square = P.power == 2.0f;
   if (P.zero_frames) emit.zero = (t >= P.zero_frames[2 * b] && t < P.zero_frames[2 * b + 1]);
   if (P.mask) {
     bool in = false;
@@ -388,12 +422,16 @@ AIP_HDX bool fwd_mode_is_fast(int m) {
   return m == FWD_MAG_ABS || m == FWD_MAG_LOG10 || m == FWD_SPEC || m == (MAG_LOG10_EPS | FWD_MASK) ||
          m == MAG_LOG1P_POW || m == (MAG_LOG1P_POW | FWD_PHASE | FWD_MASK) || m == (FWD_SPEC | FWD_PHASE | FWD_MASK) ||
          m == (MAG_LOG10_EPS | FWD_ZERO) || m == (MAG_ABS | FWD_PHASE) || m == (MAG_LOG1P_POW | FWD_PHASE) ||
-         m == (FWD_SPEC | FWD_PHASE);
+         m == (FWD_SPEC | FWD_PHASE) || m == MAG_POW ||
+         // "the spectrogram and its magnitude" in one launch (what a caller asks for first; __graft_entry__.smoke does)
+         m == (FWD_SPEC | MAG_ABS) || m == (FWD_SPEC | MAG_LOG10_EPS) || m == (FWD_SPEC | MAG_LOG1P_POW) ||
+         m == (MAG_LOG10_EPS | FWD_PHASE);
 }
 
 AIP_HDX int fwd_mode_of(const FwdParams& P) {
   int m = P.mag_kind;
-  if (P.mag_kind == MAG_POW || (P.mag_kind == MAG_LOG1P_POW && P.power != 1.0f)) return FWD_FULL;
+  // |S| ** p: the power spectrogram p == 2 (the mel front-end, utils.py:268-277) is a variant of its own, any other p runs FWD_FULL
+  if ((P.mag_kind == MAG_POW && P.power != 2.0f) || (P.mag_kind == MAG_LOG1P_POW && P.power != 1.0f)) return FWD_FULL;
   if (P.spec) m |= FWD_SPEC;
   if (P.phase) m |= FWD_PHASE;
   if (P.mask) m |= FWD_MASK;

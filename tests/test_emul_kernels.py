@@ -297,6 +297,21 @@ def test_epilogue_atan2_and_log1p_accuracy():
     assert (np.abs(l - ref_l) / np.maximum(ref_l, 1e-30)).max() < 1e-6
 
 
+@pytest.mark.parametrize("hop,wl", [(192, 384), (128, 512)])
+def test_forward_power_spectrogram_variant_and_general_powers(hop, wl):
+    """|S| ** p (the mel front-end's epilogue, utils.py:268-277): p = 2 is a straight-line variant (re^2 + im^2, no sqrt),
+    any other p the general emitter; both against the oracle, with a crop and a gap."""
+    x = noise(2, 9000, seed=hop)
+    gaps = np.array([[1000, 2600], [8000, 9000]])
+    for p in (2.0, 1.0, 0.5, 3.0):
+        got = emul.stft(x, hop, win(wl), win_length=wl, gap_samples=gaps, mag_kind=4, power=p, want_spec=False, t_out=40)["mag"]
+        for b in range(2):
+            xg = x[b].copy()
+            xg[gaps[b, 0]:gaps[b, 1]] = 0
+            ref = np.abs(lr.stft(xg, n_fft=512, hop_length=hop, win_length=wl))[:, :40] ** p
+            assert got[b].shape == ref.shape and relerr(got[b], ref) < (TOL if p <= 2 else 3 * TOL), (p, relerr(got[b], ref))
+
+
 # ---- gap variants (aip_stft_gap_variants_f32; SURVEY 8f rank 3, models/CNNBLSTM/dataset.py:93-111) ----------------------
 @pytest.mark.parametrize("hop,wl,L,g,t_out", [(192, 384, 16000, 3200, None), (192, 384, 6001, 700, None),
                                               (192, 384, 16000, 3200, 80), (128, 512, 9000, 1280, None),

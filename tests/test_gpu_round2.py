@@ -636,3 +636,52 @@ def test_griffinlim_on_the_tiled_kernels(sp, n_fft, hop):
             for b in range(B):
                 ref = lr.griffinlim(m[b], n_iter=n_iter, hop_length=hop, win_length=n_fft, n_fft=n_fft, init_angles=ang[b])
                 assert y[b].shape == ref.shape and relerr(y[b], ref) < bound, (n_iter, b, relerr(y[b], ref))
+
+
+# ------------------------------------------------------------------------------------------- output combinations
+def test_combined_outputs_equal_separate_launches(sp):
+    """Every combination of outputs of aip_stft_fwd_f32 against the same outputs from single-purpose launches: the combinations
+    with a straight-line variant of their own (spectrogram + |S| / log10 / log1p, log10 + phase, |S|**2) bit for bit, the rest
+    (general emitter: run-time switches, |S|**p) to rounding; and the general emitter must not be the 10 - 20 x cliff it was."""
+    B, L = 6, 20000
+    x = torch.from_numpy(_noise(B, L, seed=9)).cuda()
+    plan = sp.get_plan(512, 192, 384, "hann", True, "cuda:0")
+    T = plan.num_frames(L)
+    gaps = np.stack([np.arange(B) * 1000 + 500, np.arange(B) * 1000 + 3700], 1)
+    spec = sp.stft(x, plan, gap_samples=gaps)["spec"]
+    single = {k: sp.stft(x, plan, gap_samples=gaps, mag_kind=k, want_spec=False)["mag"]
+              for k in (sp.MAG_ABS, sp.MAG_LOG10_EPS, sp.MAG_LOG1P_POW)}
+    phase = sp.stft(x, plan, gap_samples=gaps, mag_kind=sp.MAG_ABS, want_spec=False, want_phase=True)["phase"]
+    for k in single:                                            # own variants
+        o = sp.stft(x, plan, gap_samples=gaps, mag_kind=k, want_spec=True)
+        assert torch.equal(o["spec"], spec) and torch.equal(o["mag"], single[k]), k
+    o = sp.stft(x, plan, gap_samples=gaps, mag_kind=sp.MAG_LOG10_EPS, want_spec=False, want_phase=True)
+    assert torch.equal(o["mag"], single[sp.MAG_LOG10_EPS]) and torch.equal(o["phase"], phase)
+    p2 = sp.stft(x, plan, gap_samples=gaps, mag_kind=sp.MAG_POW, power=2.0, want_spec=False)["mag"]
+    assert torch.allclose(p2, single[sp.MAG_ABS] ** 2, rtol=2e-6, atol=0)
+    # general emitter: everything at once, and a power the straight-line code does not know
+    frm = np.stack([np.full(B, 10), np.full(B, 20)], 1)
+    o = sp.stft(x, plan, gap_samples=gaps, mag_kind=sp.MAG_LOG10_EPS, want_spec=True, want_phase=True, want_mask=True,
+                mask_frames=frm, t_out=T - 3)
+    assert torch.equal(o["spec"], spec[:, :, :T - 3]) and torch.equal(o["phase"], phase[:, :, :T - 3])
+    assert torch.allclose(o["mag"], single[sp.MAG_LOG10_EPS][:, :, :T - 3], rtol=0, atol=2e-6)
+    assert float(o["mask"][:, :, 10:20].min()) == 1.0 and float(o["mask"].sum()) == B * 257 * 10
+    p3 = sp.stft(x, plan, gap_samples=gaps, mag_kind=sp.MAG_POW, power=3.0, want_spec=True)
+    assert torch.equal(p3["spec"], spec) and torch.allclose(p3["mag"], single[sp.MAG_ABS] ** 3, rtol=2e-5, atol=0)
+    # timing guard (generous): the general emitter within 4 x of the two specialised launches it stands for
+    xb = torch.from_numpy(_noise(512, 80000, seed=1)).cuda()
+
+    def ms(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 5
+    t_sep = ms(lambda: sp.stft(xb, plan)) + ms(lambda: sp.stft(xb, plan, mag_kind=sp.MAG_ABS, want_spec=False, want_phase=True))
+    t_all = ms(lambda: sp.stft(xb, plan, mag_kind=sp.MAG_ABS, want_spec=True, want_phase=True, want_mask=True))
+    assert t_all < 4 * t_sep, (t_all, t_sep)

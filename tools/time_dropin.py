@@ -42,6 +42,21 @@ rows = [
     ("extract_mel_spectrogram", lambda: utils.extract_mel_spectrogram(x, 16000, 512, 192, 128),
      lambda: lr.melspectrogram(y=x, sr=16000, n_fft=512, hop_length=192, n_mels=128)),
 ]
+Sd = utils.extract_spectrogram(x)                      # the functions' own defaults: n_fft 2048, hop 512
+rows += [
+    ("extract_spectrogram (defaults 2048/512)", lambda: utils.extract_spectrogram(x), lambda: up.extract_spectrogram(x)),
+    ("spectrogram_to_audio(complex, 2048/512)", lambda: utils.spectrogram_to_audio(Sd, phase_info=True, n_fft=2048, hop_length=512),
+     lambda: up.spectrogram_to_audio(Sd, phase_info=True, n_fft=2048, hop_length=512)),
+    ("extract_mel_spectrogram (defaults)", lambda: utils.extract_mel_spectrogram(x), lambda: lr.melspectrogram(y=x, sr=16000)),
+]
+import tempfile
+from ml_audio_inpainting_b200 import audio_io
+with tempfile.TemporaryDirectory() as td:
+    f = Path(td) / "clip.flac"
+    t10 = np.arange(160000)
+    audio_io.write_audio(f, (0.3 * np.sin(0.05 * t10) * np.sin(3e-4 * t10) + 0.01 * rng.standard_normal(160000)).astype(np.float32), 16000)
+    print(f"{'load_audio (10 s FLAC -> 5 s)':38s} drop-in {med(lambda: utils.load_audio(f)):8.3f} ms", flush=True)
+    print(f"{'save_audio (5 s, normalize, FLAC)':38s} drop-in {med(lambda: utils.save_audio(x, Path(td) / 'o.flac')):8.3f} ms", flush=True)
 for name, gpu, cpu in rows:
     n = 10 if "griffin" in name else 30
     print(f"{name:38s} drop-in {med(gpu, n):8.3f} ms   oracle (1 core) {med(cpu, max(3, n // 3), 1):8.3f} ms", flush=True)
