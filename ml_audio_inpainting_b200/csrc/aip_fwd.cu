@@ -495,7 +495,7 @@ static cudaError_t launch_fwd512(const FwdParams& P, const DevInfo& di, cudaStre
 static cudaError_t launch_fwd_generic(FwdParams P, int n_fft, const DevInfo& di, cudaStream_t st) {
   GenericFwdParams G;
   G.N = n_fft; G.logN = ilog2(n_fft); G.F = n_fft / 2 + 1;
-  if ((long long)P.B * P.T_out > 0x7fffffffLL) return cudaErrorInvalidValue;
+  if ((long long)P.B * P.T_out > 0x7fffffffLL || (long long)G.F * P.T_out > 0x7fffffffLL) return cudaErrorInvalidValue;
   P.n_tiles = (int)((long long)P.B * P.T_out);
   G.P = P;
   const size_t smem = (size_t)n_fft * sizeof(float2);

@@ -359,50 +359,75 @@ AIP_HD float mag_value_nopow(int mk, float xr, float xi, float eps, bool square)
   return m;
 }
 
+// ... and two bins at once on FP32x2
+AIP_HD float2 mag_value2_nopow(int mk, float2 xr, float2 xi, float eps, bool square) {
+  const float2 pw = fma2(xi, xi, mul2(xr, xr));
+  if (mk == MAG_POW && square) return pw;
+  const float2 m = make_float2(fast_sqrt(pw.x), fast_sqrt(pw.y));
+  if (mk == MAG_LOG10_EPS) {
+    const float2 l = add2(m, make_float2(eps, eps));
+    return mul2s(make_float2(fast_log2(l.x), fast_log2(l.y)), kLog10of2);
+  }
+  return (mk == MAG_LOG1P_POW) ? make_float2(fast_log1p(m.x), fast_log1p(m.y)) : m;
+}
+
+// FwdEmitT with its template switches as CTA-uniform run-time tests: same column pointers, int offsets and packed pairs
 struct FwdEmitFull {
-  typedef long long off_t;
-  float2* spec;             // array bases or null
+  typedef int off_t;
+  float* mag;               // column pointers (array + b*F*T_out + t), null = not produced
+  float2* spec;
   float* phase;
   float* mask;
-  float* mag;
-  int mag_kind, T_out;
-  float eps, power;
-  long long base;           // b*F*T_out + t
+  int T, mag_kind;          // T = T_out
+  float eps, power, maskv;
   bool active, zero, slow_mag, square;
-  float maskv;
-  long long off_lo, off_hi; // element offsets of the two row cursors
-  int s16;                  // 16 * T_out
-  AIP_HM void rows(int k_lo, int k_hi) {
-    off_lo = base + (long long)k_lo * T_out;
-    off_hi = base + (long long)k_hi * T_out;
-    s16 = 16 * T_out;
-  }
-  AIP_HM long long lo(int j) const { return off_lo + j * s16; }
-  AIP_HM long long hi(int j) const { return off_hi - j * s16; }
-  AIP_HM long long bin(int k) const { return base + (long long)k * T_out; }
-  template <int SX, int SY>
-  AIP_HM void put2(long long ox, long long oy, float2 xr, float2 xi) const {
-    put1(ox, xr.x, SX < 0 ? -xi.x : xi.x);
-    put1(oy, xr.y, SY < 0 ? -xi.y : xi.y);
-  }
-  AIP_HM void put1(long long idx, float xr, float xi) const {
+  int olo, ohi, s16;
+  AIP_HM void rows(int k_lo, int k_hi) { olo = k_lo * T; ohi = k_hi * T; s16 = 16 * T; }
+  AIP_HM int lo(int j) const { return olo + j * s16; }
+  AIP_HM int hi(int j) const { return ohi - j * s16; }
+  AIP_HM int bin(int k) const { return k * T; }
+  AIP_HM void put1(int o, float xr, float xi) const {
     if (!active) return;
     if (zero) { xr = 0.0f; xi = 0.0f; }
-    if (spec) spec[idx] = make_float2(xr, xi);
-    if (phase) phase[idx] = fast_atan2(xi, xr);
-    if (mask) mask[idx] = maskv;
-    if (mag_kind != MAG_NONE)
-      mag[idx] = slow_mag ? mag_value_general(mag_kind, xr, xi, eps, power) : mag_value_nopow(mag_kind, xr, xi, eps, square);
+    if (spec) spec[o] = make_float2(xr, xi);
+    if (phase) phase[o] = fast_atan2(xi, xr);
+    if (mask) mask[o] = maskv;
+    if (mag) mag[o] = slow_mag ? mag_value_general(mag_kind, xr, xi, eps, power) : mag_value_nopow(mag_kind, xr, xi, eps, square);
+  }
+  template <int SX, int SY>
+  AIP_HM void put2(int ox, int oy, float2 xr, float2 xi) const {
+    if (!active) return;
+    if (zero) { xr = make_float2(0.0f, 0.0f); xi = make_float2(0.0f, 0.0f); }
+    if (spec || phase) {
+      const float ix = SX < 0 ? -xi.x : xi.x, iy = SY < 0 ? -xi.y : xi.y;
+      if (spec) { spec[ox] = make_float2(xr.x, ix); spec[oy] = make_float2(xr.y, iy); }
+      if (phase) { phase[ox] = fast_atan2(ix, xr.x); phase[oy] = fast_atan2(iy, xr.y); }
+    }
+    if (mask) { mask[ox] = maskv; mask[oy] = maskv; }
+    if (mag) {
+      if (slow_mag) {
+        mag[ox] = mag_value_general(mag_kind, xr.x, xi.x, eps, power);
+        mag[oy] = mag_value_general(mag_kind, xr.y, xi.y, eps, power);
+      } else {
+        const float2 m = mag_value2_nopow(mag_kind, xr, xi, eps, square);
+        mag[ox] = m.x;
+        mag[oy] = m.y;
+      }
+    }
   }
 };
 
+// (b, t): the frame the emitter's column pointers address; the row offsets k * T_out must fit an int (the launchers check)
 AIP_HD FwdEmitFull fwd_make_emit_full(const FwdParams& P, int b, int t, int n_bins, bool active) {
   FwdEmitFull emit;
-  emit.spec = P.spec; emit.phase = P.phase; emit.mask = P.mask; emit.mag = P.mag;
-  emit.mag_kind = P.mag_kind; emit.T_out = P.T_out; emit.eps = P.eps; emit.power = P.power;
-  emit.base = (long long)b * n_bins * P.T_out + t;
+  const long long col = (long long)b * n_bins * P.T_out + t;
+  emit.mag = (P.mag_kind != MAG_NONE && P.mag) ? P.mag + col : nullptr;
+  emit.spec = P.spec ? P.spec + col : nullptr;
+  emit.phase = P.phase ? P.phase + col : nullptr;
+  emit.mask = P.mask ? P.mask + col : nullptr;
+  emit.T = P.T_out; emit.mag_kind = P.mag_kind; emit.eps = P.eps; emit.power = P.power;
   emit.active = active; emit.zero = false; emit.maskv = 0.0f;
-  emit.off_lo = emit.off_hi = 0; emit.s16 = 0;
+  emit.olo = emit.ohi = emit.s16 = 0;
   // powers the straight-line magnitude code does not cover (it knows 1, and 2 for MAG_POW)
   emit.slow_mag = (P.mag_kind == MAG_POW && P.power != 2.0f && P.power != 1.0f) || (P.mag_kind == MAG_LOG1P_POW && P.power != 1.0f);
   emit.square = P.power == 2.0f;
