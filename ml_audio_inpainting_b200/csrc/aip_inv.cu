@@ -442,20 +442,18 @@ __global__ void __launch_bounds__(256) istft_generic_frames_kernel(const Generic
 __global__ void __launch_bounds__(256) istft_generic_ola_kernel(const GenericInvParams G) {
   const InvParams& P = G.P;
   const int N = G.N;
-  const long long total = (long long)P.B * P.out_len;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / P.out_len);
-    const int s = (int)(i % P.out_len);
-    const long long p = (long long)s + P.pad;
-    long long f_lo = p - (N - 1) + P.hop - 1;
-    f_lo = f_lo > 0 ? f_lo / P.hop : 0;
-    long long f_hi = p / P.hop;
-    if (f_hi > P.n_frames - 1) f_hi = P.n_frames - 1;
-    float acc = 0.0f;
-    for (long long f = f_lo; f <= f_hi; ++f)
-      acc += G.frames[((long long)b * P.T + f) * N + (p - f * P.hop)];
-    P.out[(long long)b * P.out_pitch + s] = acc * P.inv_wss[s];
+  for (int b = blockIdx.y; b < P.B; b += gridDim.y) {                     // clip per blockIdx.y: no division per sample
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.out_len; s += gridDim.x * blockDim.x) {
+      const long long p = (long long)s + P.pad;
+      long long f_lo = p - (N - 1) + P.hop - 1;
+      f_lo = f_lo > 0 ? f_lo / P.hop : 0;
+      long long f_hi = p / P.hop;
+      if (f_hi > P.n_frames - 1) f_hi = P.n_frames - 1;
+      float acc = 0.0f;
+      for (long long f = f_lo; f <= f_hi; ++f)
+        acc += G.frames[((long long)b * P.T + f) * N + (p - f * P.hop)];
+      P.out[(long long)b * P.out_pitch + s] = acc * P.inv_wss[s];
+    }
   }
 }
 
@@ -747,7 +745,11 @@ static int run_inv(const aip_stft_desc* desc, InvParams P, long long length, voi
       e = cudaGetLastError();
     }
     if (e != cudaSuccess) return (int)e;
-    istft_generic_ola_kernel<<<ew_grid((long long)P.B * P.out_len, di.sms), 256, 0, st>>>(G);
+    {
+      long long gx = ((long long)P.out_len + 2047) / 2048;
+      if (gx > 1024) gx = 1024;
+      istft_generic_ola_kernel<<<dim3((unsigned)gx, (unsigned)(P.B < 65535 ? P.B : 65535)), 256, 0, st>>>(G);
+    }
     e = cudaGetLastError();
   }
   return (int)e;
