@@ -685,3 +685,29 @@ def test_combined_outputs_equal_separate_launches(sp):
     t_sep = ms(lambda: sp.stft(xb, plan)) + ms(lambda: sp.stft(xb, plan, mag_kind=sp.MAG_ABS, want_spec=False, want_phase=True))
     t_all = ms(lambda: sp.stft(xb, plan, mag_kind=sp.MAG_ABS, want_spec=True, want_phase=True, want_mask=True))
     assert t_all < 4 * t_sep, (t_all, t_sep)
+
+
+# ------------------------------------------------------------------------------------------- the functions' own defaults on real speech
+def test_default_parameters_on_the_reference_clips(utils, golden_clips):
+    """utils.extract_spectrogram / spectrogram_to_audio / extract_mel_spectrogram called the way their signatures default
+    (n_fft 2048, hop 512: the tiled radix-16 kernels) on the reference's nine test clips: value parity with the oracle at the
+    1e-4 bound of SURVEY 8c, the reference suite's float64 round trip (tests/utils_test.py:780-809) as an SNR floor of
+    100 dB, and the mel front-end against librosa's melspectrogram."""
+    for name in sorted(golden_clips):
+        x = golden_clips[name]
+        S = utils.extract_spectrogram(x)
+        ref = up.extract_spectrogram(x)
+        assert S.shape == ref.shape == (1025, 157) and S.dtype == np.complex64
+        assert relerr(S, ref) < TOL, (name, relerr(S, ref))
+        y = utils.spectrogram_to_audio(S, phase_info=True, n_fft=2048, hop_length=512)
+        ry = up.spectrogram_to_audio(ref, phase_info=True, n_fft=2048, hop_length=512)
+        assert y.shape == ry.shape == (512 * 156,) and relerr(y, ry) < TOL, (name, relerr(y, ry))
+        n = len(y)
+        snr = 10 * np.log10(np.sum(x[:n].astype(np.float64) ** 2) / np.sum((y - x[:n]).astype(np.float64) ** 2))
+        assert snr >= 100.0, (name, snr)
+        m = utils.extract_mel_spectrogram(x)
+        rm = lr.melspectrogram(y=x, sr=SR)
+        assert m.shape == rm.shape == (128, 157) and relerr(m, rm) < TOL, (name, relerr(m, rm))
+        # float64 in -> the reference's dtypes out (complex128 / float64), values from the same fp32 kernels
+        S64 = utils.extract_spectrogram(x.astype(np.float64))
+        assert S64.dtype == np.complex128 and relerr(S64, ref) < TOL
