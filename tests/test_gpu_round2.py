@@ -711,3 +711,69 @@ def test_default_parameters_on_the_reference_clips(utils, golden_clips):
         # float64 in -> the reference's dtypes out (complex128 / float64), values from the same fp32 kernels
         S64 = utils.extract_spectrogram(x.astype(np.float64))
         assert S64.dtype == np.complex128 and relerr(S64, ref) < TOL
+
+
+# ------------------------------------------------------------------------------------------- the C ABI's error behaviour
+def test_c_abi_rejects_bad_arguments_without_touching_memory(sp):
+    """include/aip_b200.h: 0 on success, negative for argument errors (ARG -1, UNSUPPORTED -2, WORKSPACE -4), nothing launched,
+    nothing written -- called raw through ctypes the way a foreign binding would."""
+    import ctypes as C
+    from ml_audio_inpainting_b200 import _cabi
+    lib = _cabi.load()
+    B, L = 2, 4000
+    x = torch.from_numpy(_noise(B, L, seed=1)).cuda()
+    plan = sp.get_plan(512, 192, 384, "hann", True, "cuda:0")
+    T = plan.num_frames(L)
+    SENT = -777.0
+    mag = torch.full((B, 257, T), SENT, device="cuda")
+    spec = torch.full((B, 257, T, 2), SENT, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    d = C.byref(plan.desc)
+    win = plan.desc.window
+
+    def fwd(desc=d, wave=x.data_ptr(), b=B, l=L, pitch=L, mk=_cabi.MAG_LOG10_EPS, t_out=T, spec_p=None, mag_p=mag.data_ptr()):
+        return lib.aip_stft_fwd_f32(desc, wave, b, l, pitch, None, None, None, 1, mk, 1e-9, 1.0, t_out, spec_p, mag_p, None, None, st)
+
+    assert fwd() == 0 and not bool(mag.eq(SENT).any())
+    mag.fill_(SENT)
+    assert fwd(wave=None) == -1 and fwd(desc=None) == -1
+    assert fwd(mag_p=None) == -1                                   # a magnitude kind without its output
+    assert fwd(mk=_cabi.MAG_NONE) == -1                            # ... and an output without a kind
+    assert fwd(mk=9) == -1 and fwd(t_out=T + 1) == -1 and fwd(pitch=L - 1) == -1 and fwd(b=-1) == -1
+    assert fwd(b=0) == 0 and fwd(t_out=0) == 0
+    assert fwd(l=100) == -1                                        # 100 samples hold one frame, T_out asks for more
+    bad = _cabi.StftDesc(500, 192, 1, 0, win)                     # not a power of two
+    assert fwd(desc=C.byref(bad)) == -2
+    assert fwd(desc=C.byref(_cabi.StftDesc(512, 0, 1, 0, win))) == -2
+    assert fwd(desc=C.byref(_cabi.StftDesc(512, 192, 1, 0, None))) == -1
+    torch.cuda.synchronize()
+    assert bool(mag.eq(SENT).all())                                # none of the rejected calls wrote anything
+    # inverse
+    S = sp.stft(x, plan)["spec"]
+    n = plan.istft_length(T)
+    inv = plan.inv_wss(T)
+    y = torch.full((B, n), SENT, device="cuda")
+
+    def inverse(desc=d, spec_p=S.data_ptr(), mag_p=None, b=B, t=T, length=0, wss=inv.data_ptr(), out=y.data_ptr(), pitch=n, ws=None, wsb=0,
+                dom=0):
+        return lib.aip_istft_f32(desc, spec_p, mag_p, None, dom, None, b, t, length, wss, out, pitch, ws, wsb, st)
+
+    assert inverse() == 0 and not bool(y.eq(SENT).any())
+    y.fill_(SENT)
+    assert inverse(spec_p=None) == -1 and inverse(out=None) == -1 and inverse(wss=None) == -1
+    assert inverse(pitch=n - 1) == -1 and inverse(t=0) == -1 and inverse(length=-5) == -1 and inverse(dom=7) == -1
+    assert inverse(desc=C.byref(bad)) == -2
+    big = sp.get_plan(4096, 1024, 4096, "hann", True, "cuda:0")    # off every tiled kernel: needs the frame workspace
+    assert lib.aip_istft_workspace_bytes(C.byref(big.desc), B, 8) == B * 8 * 4096 * 4
+    S4 = torch.zeros((B, 2049, 8, 2), device="cuda")
+    y4 = torch.empty((B, big.istft_length(8)), device="cuda")
+    assert lib.aip_istft_f32(C.byref(big.desc), S4.data_ptr(), None, None, 0, None, B, 8, 0, big.inv_wss(8).data_ptr(), y4.data_ptr(),
+                             y4.shape[1], None, 0, st) == -4
+    q = torch.empty((B, L), dtype=torch.int16, device="cuda")
+    assert lib.aip_wave_to_pcm16_f32(x.data_ptr(), L, q.data_ptr(), L, B, L, 5, None, st) == -1
+    assert lib.aip_wave_to_pcm16_f32(x.data_ptr(), L, q.data_ptr(), L, B, L, 1, None, st) == -1      # normalise without a peaks array
+    assert lib.aip_wave_to_pcm16_f32(x.data_ptr(), L, q.data_ptr(), L - 1, B, L, 0, None, st) == -1
+    torch.cuda.synchronize()
+    assert bool(y.eq(SENT).all())
+    for code, word in ((0, b"ok"), (-1, b"argument"), (-2, b"unsupported"), (-3, b"no fallback"), (-4, b"workspace")):
+        assert word in lib.aip_status_string(code)
