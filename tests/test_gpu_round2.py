@@ -777,3 +777,42 @@ def test_c_abi_rejects_bad_arguments_without_touching_memory(sp):
     assert bool(y.eq(SENT).all())
     for code, word in ((0, b"ok"), (-1, b"argument"), (-2, b"unsupported"), (-3, b"no fallback"), (-4, b"workspace")):
         assert word in lib.aip_status_string(code)
+
+
+def test_randomised_geometry_on_the_tiled_kernels(sp):
+    """Seeded random geometries through the tiled power-of-two kernels (and n_fft 512 off its fused path): n_fft, hop (odd and even,
+    tiny to larger than the window), win_length, clip length, centring, batch size, gaps -- forward against the oracle, inverse
+    against the oracle where the overlap-add is well conditioned."""
+    rng = np.random.default_rng(2026)
+    for trial in range(24):
+        n_fft = int(rng.choice([64, 128, 256, 512, 1024, 2048]))
+        hop = int(rng.choice([max(1, n_fft // 16), n_fft // 8, n_fft // 4, n_fft // 4 + 1, n_fft // 2, n_fft // 3, n_fft, n_fft // 4 - 1]))
+        if n_fft == 512 and hop % 2 == 0:
+            hop += 1                                           # keep it off the fused n_fft = 512 kernels
+        win = int(rng.choice([n_fft, n_fft, 3 * n_fft // 4, n_fft // 2 + 3]))
+        center = bool(rng.integers(0, 2))
+        B = int(rng.integers(1, 4))
+        L = int(rng.integers(n_fft + 1, 12 * n_fft + 977))
+        x = _noise(B, L, seed=trial)
+        xd = torch.from_numpy(x).cuda()
+        plan = sp.get_plan(n_fft, hop, win, "hann", center, "cuda:0")
+        T = plan.num_frames(L)
+        g0 = rng.integers(0, L - 1, size=B)
+        gaps = np.stack([g0, np.minimum(L, g0 + rng.integers(1, L // 2 + 2, size=B))], 1)
+        S = sp.stft(xd, plan, gap_samples=gaps)["spec"]
+        what = dict(trial=trial, n_fft=n_fft, hop=hop, win=win, center=center, B=B, L=L)
+        assert S.shape == (B, n_fft // 2 + 1, T), what
+        for b in range(B):
+            xg = x[b].copy()
+            xg[gaps[b, 0]:gaps[b, 1]] = 0
+            ref = lr.stft(xg, n_fft=n_fft, hop_length=hop, win_length=win, center=center)
+            assert relerr(S[b].cpu().numpy(), ref) < TOL, (what, b, relerr(S[b].cpu().numpy(), ref))
+        if hop <= win // 2:                                    # enough overlap for a conditioned inverse
+            Sc = sp.stft(xd, plan)["spec"]
+            y = sp.istft(plan, spec=Sc).cpu().numpy()
+            wss = lr.window_sumsquare("hann", T, hop_length=hop, win_length=win, n_fft=n_fft, dtype=np.float32)
+            wss = wss[n_fft // 2:] if center else wss
+            for b in range(B):
+                ref = lr.istft(Sc[b].cpu().numpy(), hop_length=hop, win_length=win, n_fft=n_fft, center=center)
+                ok = wss[:len(ref)] > 1e-2 * wss.max()
+                assert y[b].shape == ref.shape and relerr(y[b][ok], ref[ok]) < TOL, (what, b, relerr(y[b][ok], ref[ok]))
