@@ -475,6 +475,52 @@ __device__ __forceinline__ void p2_split_inv(const Pow2Geom& g, float2* sf, cons
   __syncwarp();
 }
 
+// Overlap-add gather for hop = N / kK, a power of two <= 512: a thread's pairs u = 2 tid + 512 it all sit at the same offset
+// r inside their hop, so the kK window taps and buffer offsets it needs are per-thread constants (w / off, set up before the tile
+// loop) and the frames covering a pair are q - kK + 1 .. q with q = u / hop = q0 + it (512 / hop): no division, no address arithmetic.
+template <int kK>
+__device__ __forceinline__ void p2_gather_pow2hop(const InvParams& P, const float2* bufs, const float* win, int PB, int FT, int log_hop,
+                                                  int t0, int nv, int span, float* orow) {
+  // (set up per tile, not once per kernel: 3 kK registers that would otherwise stay live across the transform passes and push
+  //  the next tile's prefetched rows into local memory)
+  float2 w[kK];
+  int off[kK];
+  {
+    const int r = (2 * threadIdx.x) & (P.hop - 1);
+#pragma unroll
+    for (int j = 0; j < kK; ++j) {
+      const int n = j * P.hop + r;
+      w[j] = *reinterpret_cast<const float2*>(win + n);
+      off[j] = p2_pad(n >> 1);
+    }
+  }
+  const int p0 = t0 * P.hop;
+  const int dq = 512 >> log_hop;
+  for (int u = 2 * threadIdx.x, q = (2 * threadIdx.x) >> log_hop; u < span; u += 2 * kP2Threads, q += dq) {
+    const int sidx = p0 + u - P.pad;
+    if (sidx < 0 || sidx >= P.out_len) continue;
+    float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+    for (int j = kK - 1; j >= 0; --j) {                                             // increasing frame order, like librosa.istft
+      const int f = q - j;
+      if (f >= 0 && f < nv) {
+        const float2 v = bufs[f * PB + off[j]];
+        a0 += v.y * w[j].x;
+        a1 += v.x * w[j].y;
+      }
+    }
+    const int T_lo = t0 + q - kK + 1, T_hi = t0 + q;
+    const bool whole = (T_lo >= t0 || T_lo <= 0 && t0 == 0) && (T_hi < t0 + FT || t0 + FT >= P.n_frames);
+    float* o = orow + sidx;
+    const float v0 = a0 * P.inv_wss[sidx];
+    if (whole) *o = v0; else atomicAdd(o, v0);
+    if (sidx + 1 < P.out_len) {
+      const float v1 = a1 * P.inv_wss[sidx + 1];
+      if (whole) o[1] = v1; else atomicAdd(o + 1, v1);
+    }
+  }
+}
+
 // kOla = false: the windowed frames go to the workspace (istft_generic_ola_kernel adds them up afterwards).
 // kOla = true:  the tile's frames are overlap-added straight from their shared-memory buffers (thread = output sample, a gather
 //               over the <= N / hop frames that cover it, in increasing frame order like librosa.istft), scaled by 1 / wss and
@@ -495,18 +541,6 @@ __global__ void __launch_bounds__(kP2Threads, 2) istft_pow2_kernel(const Pow2Inv
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const P2Slots s = p2_slots(g, lane);
   float2* sf = bufs + warp * g.fps * g.PB;
-  float2 ola_w[8];
-  int ola_off[8], ola_q0 = 0;
-  if (kOla && G.ola_k > 0) {
-    const int r = (2 * threadIdx.x) & (P.hop - 1);
-    ola_q0 = (2 * threadIdx.x) >> G.log_hop;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int n = j < G.ola_k ? j * P.hop + r : 0;
-      ola_w[j] = *reinterpret_cast<const float2*>(win + n);
-      ola_off[j] = p2_pad(n >> 1);
-    }
-  }
   for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
     const int b = tile / P.tiles_per_clip, t0 = (tile - b * P.tiles_per_clip) * g.FT;
     const bool db = P.db_flags ? (P.db_flags[b] != 0) : false;
@@ -578,34 +612,11 @@ __global__ void __launch_bounds__(kP2Threads, 2) istft_pow2_kernel(const Pow2Inv
       const int p0 = t0 * P.hop;                                                     // padded-signal position of the tile
       float* orow = P.out + (long long)b * P.out_pitch;
       if (G.ola_k > 0) {
-        // hop = N / K, a power of two <= 512: a thread's pairs u = 2 tid + 512 it all sit at the same offset r inside their hop, so
-        // the K window taps and buffer offsets it needs are per-thread constants (ola_w / ola_off, set up before the tile loop) and
-        // the frames covering a pair are q - K + 1 .. q with q = u / hop = q0 + it (512 / hop): no division, no address arithmetic
-        const int dq = 512 >> G.log_hop;
-        for (int it = 0, u = 2 * threadIdx.x, q = ola_q0; u < span; ++it, u += 2 * kP2Threads, q += dq) {
-          const int sidx = p0 + u - P.pad;
-          if (sidx < 0 || sidx >= P.out_len) continue;
-          float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll
-          for (int j = 7; j >= 0; --j) {                                            // increasing frame order, like librosa.istft
-            if (j < G.ola_k) {
-              const int f = q - j;
-              if (f >= 0 && f < nv) {
-                const float2 v = bufs[f * g.PB + ola_off[j]];
-                a0 += v.y * ola_w[j].x;
-                a1 += v.x * ola_w[j].y;
-              }
-            }
-          }
-          const int T_lo = t0 + q - G.ola_k + 1, T_hi = t0 + q;
-          const bool whole = (T_lo >= t0 || T_lo <= 0 && t0 == 0) && (T_hi < t0 + g.FT || t0 + g.FT >= P.n_frames);
-          float* o = orow + sidx;
-          const float v0 = a0 * P.inv_wss[sidx];
-          if (whole) *o = v0; else atomicAdd(o, v0);
-          if (sidx + 1 < P.out_len) {
-            const float v1 = a1 * P.inv_wss[sidx + 1];
-            if (whole) o[1] = v1; else atomicAdd(o + 1, v1);
-          }
+        switch (G.ola_k) {
+          case 1: p2_gather_pow2hop<1>(P, bufs, win, g.PB, g.FT, G.log_hop, t0, nv, span, orow); break;
+          case 2: p2_gather_pow2hop<2>(P, bufs, win, g.PB, g.FT, G.log_hop, t0, nv, span, orow); break;
+          case 4: p2_gather_pow2hop<4>(P, bufs, win, g.PB, g.FT, G.log_hop, t0, nv, span, orow); break;
+          default: p2_gather_pow2hop<8>(P, bufs, win, g.PB, g.FT, G.log_hop, t0, nv, span, orow); break;
         }
         __syncthreads();
         continue;
@@ -715,7 +726,7 @@ cudaError_t launch_inv_pow2(InvParams P, int n_fft, float* frames, const DevInfo
   P.n_tiles = (int)((long long)P.B * P.tiles_per_clip);
   P.hop_magic = (unsigned)((0x100000000ULL + (unsigned)P.hop - 1) / (unsigned)P.hop);
   G.ola_k = 0; G.log_hop = 0;
-  if (is_pow2(P.hop) && P.hop >= 2 && P.hop <= 512 && n_fft % P.hop == 0 && n_fft / P.hop <= 8 && tunables().pow2_ola_fast) {
+  if (is_pow2(P.hop) && P.hop >= 2 && P.hop <= 512 && n_fft / P.hop <= 8 && tunables().pow2_ola_fast) {      // K = 1, 2, 4 or 8
     G.ola_k = n_fft / P.hop;
     G.log_hop = ilog2(P.hop);
   }
