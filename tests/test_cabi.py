@@ -94,3 +94,45 @@ def test_no_cpu_fallback():
     x = np.zeros(8, np.float32)
     rc = lib.aip_gap_mask_f32(x.ctypes.data, 8, 1, 8, None, None)
     assert rc != 0
+
+
+def test_headers_are_plain_c_and_a_c_host_links_the_library(tmp_path):
+    """include/*.h compile as C99 and as C++11 on their own, and a host written in C -- no Python, no torch -- links the
+    shared library and calls its host-only entry points (the device entry points need a GPU: tests/test_gpu_round2.py calls
+    them raw through ctypes)."""
+    import shutil
+    import subprocess
+    from ml_audio_inpainting_b200 import _build
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    inc = ROOT / "include"
+    for h in ("aip_b200.h", "aip_codec.h"):
+        for cmd in ([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c"],
+                    [shutil.which("g++") or gcc, "-std=c++11", "-fsyntax-only", "-x", "c++"]):
+            res = subprocess.run(cmd + [str(inc / h)], capture_output=True, text=True)
+            assert res.returncode == 0, res.stderr
+    src = tmp_path / "host.c"
+    src.write_text('''
+#include <stdio.h>
+#include <string.h>
+#include "aip_b200.h"
+#include "aip_codec.h"
+int main(void) {
+  if (aip_num_frames(160000, 512, 192, 1) != 834) return 1;
+  if (aip_istft_length(834, 512, 192, 1, 0) != 159936) return 2;
+  if (strcmp(aip_status_string(AIP_OK), "ok") != 0) return 3;
+  if (!strstr(aip_version(), "sm_100a")) return 4;
+  if (aip_flac_info_read((const unsigned char*)"nope", 4, &(aip_flac_info){0}) >= 0) return 5;
+  printf("%s\\n", aip_version());
+  return 0;
+}
+''')
+    exe = tmp_path / "host"
+    libdir = _build.CUDA_LIB.parent
+    _build.build_codec()
+    res = subprocess.run([gcc, "-std=c99", "-I", str(inc), "-o", str(exe), str(src), f"-L{libdir}", "-laip_b200", "-laip_codec",
+                          f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0 and "sm_100a" in run.stdout, (run.returncode, run.stdout, run.stderr)
