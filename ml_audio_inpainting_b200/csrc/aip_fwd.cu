@@ -519,6 +519,7 @@ int run_fwd(const aip_stft_desc* desc, FwdParams P, long long T_out, cudaStream_
   if ((P.mag_kind != MAG_NONE) != (P.mag != nullptr)) return AIP_ERR_ARG;
   if (P.mag_kind < MAG_NONE || P.mag_kind > MAG_POW) return AIP_ERR_ARG;
   if (P.B == 0 || T_out == 0) return AIP_OK;
+  if (!P.spec && !P.mag && !P.phase && !P.mask) return AIP_OK;      // no output requested: nothing to launch
   P.hop = desc->hop;
   P.pad = desc->center ? desc->n_fft / 2 : 0;
   P.T = (int)T;

@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(kP2Threads, 2) stft_pow2_fwd_kernel(const Pow2
           float2* o = P.spec + idx;
 #pragma unroll 8
           for (int k = k0; k <= g.M; k += kstep, o += step) *o = z[p2_pad(k)];
-        } else if (!P.spec && !P.phase && !P.mask && !P.zero_frames) {                          // one magnitude flavour only
+        } else if (!P.spec && !P.phase && !P.mask && !P.zero_frames && P.mag_kind != MAG_NONE) {   // one magnitude flavour only
           float* o = P.mag + idx;
           const int mk = P.mag_kind;
           const float eps = P.eps, power = P.power;

@@ -741,6 +741,9 @@ def test_c_abi_rejects_bad_arguments_without_touching_memory(sp):
     assert fwd(mk=_cabi.MAG_NONE) == -1                            # ... and an output without a kind
     assert fwd(mk=9) == -1 and fwd(t_out=T + 1) == -1 and fwd(pitch=L - 1) == -1 and fwd(b=-1) == -1
     assert fwd(b=0) == 0 and fwd(t_out=0) == 0
+    assert fwd(mk=_cabi.MAG_NONE, mag_p=None) == 0                 # no output at all: accepted, nothing launched
+    big_desc = sp.get_plan(2048, 512, 2048, "hann", True, "cuda:0").desc
+    assert lib.aip_stft_fwd_f32(C.byref(big_desc), x.data_ptr(), B, L, L, None, None, None, 1, 0, 0.0, 1.0, 1, None, None, None, None, st) == 0
     assert fwd(l=100) == -1                                        # 100 samples hold one frame, T_out asks for more
     bad = _cabi.StftDesc(500, 192, 1, 0, win)                     # not a power of two
     assert fwd(desc=C.byref(bad)) == -2
