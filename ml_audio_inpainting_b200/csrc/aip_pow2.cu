@@ -476,13 +476,12 @@ __device__ __forceinline__ void p2_split_inv(const Pow2Geom& g, float2* sf, cons
 }
 
 // Overlap-add gather for hop = N / kK, a power of two <= 512: a thread's pairs u = 2 tid + 512 it all sit at the same offset
-// r inside their hop, so the kK window taps and buffer offsets it needs are per-thread constants (w / off, set up before the tile
-// loop) and the frames covering a pair are q - kK + 1 .. q with q = u / hop = q0 + it (512 / hop): no division, no address arithmetic.
+// r inside their hop, so the kK window taps and buffer offsets it needs are the same for all of them (w / off) and the frames
+// covering a pair are q - kK + 1 .. q with q = u / hop = q0 + it (512 / hop): no division, no address arithmetic in the loop.
 template <int kK>
 __device__ __forceinline__ void p2_gather_pow2hop(const InvParams& P, const float2* bufs, const float* win, int PB, int FT, int log_hop,
                                                   int t0, int nv, int span, float* orow) {
-  // (set up per tile, not once per kernel: 3 kK registers that would otherwise stay live across the transform passes and push
-  //  the next tile's prefetched rows into local memory)
+  // (set up per tile, not once per kernel: 3 kK registers that would otherwise stay live across the transform passes)
   float2 w[kK];
   int off[kK];
   {
