@@ -147,6 +147,9 @@ int aip_inv_window_sumsquare_f32(const aip_stft_desc* desc, int64_t T, int64_t l
  *   tprev   [B,F,T,2] scratch (16-byte aligned);  wave_out [B, out_len] doubles as the iteration buffer;
  *   workspace: aip_istft_workspace_bytes(...) rounded up to 16, optionally followed by B*F*T*8 more bytes -- with that
  *   extra array the rebuilt spectra of consecutive iterations ping-pong and no `tprev = rebuilt` copy is made.       */
+/* librosa.griffinlim(init="random") (utils.py:330-332 leaves librosa's default): n unit phasors exp(2 pi j u), u uniform in
+ * [0, 1), from a Philox4x32-10 counter stream keyed by `seed` -- the `angles` array aip_griffinlim_f32 starts from.       */
+int aip_random_phasors_f32(float* angles /* [n, 2] */, int64_t n, uint64_t seed, void* stream);
 int aip_griffinlim_f32(const aip_stft_desc* desc, const float* mag, float* angles, float* tprev,
                        int64_t B, int64_t T, int32_t n_iter, float momentum, const float* inv_wss,
                        float* wave_out, int64_t out_pitch,

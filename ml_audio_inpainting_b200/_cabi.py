@@ -42,6 +42,7 @@ SIGNATURES = {
     "aip_istft_handoff_f32": (C.c_int, [_D, _P, _P, _P, _I32, _P, _I32, _I64, _I64, _I64, _P, _P, _I64, _P, _P, _I64, _P, _SZ, _P]),
     "aip_istft_workspace_bytes": (_SZ, [_D, _I64, _I64]),
     "aip_inv_window_sumsquare_f32": (C.c_int, [_D, _I64, _I64, _P, _I64, _P]),
+    "aip_random_phasors_f32": (C.c_int, [_P, _I64, C.c_uint64, _P]),
     "aip_griffinlim_f32": (C.c_int, [_D, _P, _P, _P, _I64, _I64, _I32, _F, _P, _P, _I64, _P, _SZ, _P]),
     "aip_griffinlim_c64_f32": (C.c_int, [_D, _P, _P, _P, _I64, _I64, _I32, _F, _P, _P, _I64, _P, _SZ, _P]),
     "aip_mel_project_f32": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _I64, _P, _P]),

@@ -541,6 +541,37 @@ __global__ void gl_update_tail_kernel(float2* spec, float2* tprev, const float* 
   spec[i] = make_float2((ax * s) * mag[i], (ay * s) * mag[i]);
 }
 
+// librosa.griffinlim(init="random"): angles = exp(2 pi j U[0, 1)) (np.random.default_rng: any uniform stream will do; the reference
+// never seeds it).  Philox4x32-10 (Salmon et al., SC'11) counter RNG: thread i turns counter (i, 0, 0, 0) under key `seed` into four
+// 32-bit words = four phases; nothing is read, the only traffic is the 8 bytes per bin written.
+__device__ __forceinline__ void philox_round(unsigned (&c)[4], unsigned k0, unsigned k1) {
+  const unsigned hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const unsigned hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const unsigned n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+  c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+}
+__global__ void __launch_bounds__(256) random_phasors_kernel(float2* angles, long long n, unsigned long long seed) {
+  const long long quads = (n + 3) >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < quads; i += (long long)gridDim.x * blockDim.x) {
+    unsigned c[4] = {(unsigned)i, (unsigned)(i >> 32), 0u, 0u};
+    unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      philox_round(c, k0, k1);
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long e = 4 * i + j;
+      if (e < n) {
+        float sn, cs;
+        sincospif((float)(c[j] >> 8) * (2.0f / 16777216.0f), &sn, &cs);      // phase 2 pi u, u = 24 random bits / 2^24
+        angles[e] = make_float2(cs, sn);
+      }
+    }
+  }
+}
+
 __global__ void scale_angles_kernel(float2* angles, const float* mag, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -864,6 +895,16 @@ int aip_inv_window_sumsquare_f32(const aip_stft_desc* desc, int64_t T, int64_t l
   const int nf = (int)istft_used_frames(T, desc->n_fft, desc->hop, desc->center, length);
   inv_wss_kernel<<<ew_grid(out_len, di.sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       desc->window, desc->n_fft, desc->hop, desc->center ? desc->n_fft / 2 : 0, nf, inv_wss, (int)out_len);
+  return (int)cudaGetLastError();
+}
+
+int aip_random_phasors_f32(float* angles, int64_t n, uint64_t seed, void* stream) {
+  const DevInfo di = dev_info();
+  if (!di.ok) return AIP_ERR_DEVICE;
+  if (!angles || n < 0 || (reinterpret_cast<uintptr_t>(angles) & 7)) return AIP_ERR_ARG;
+  if (n == 0) return AIP_OK;
+  random_phasors_kernel<<<ew_grid((n + 3) / 4, di.sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<float2*>(angles), n,
+                                                                                                   seed);
   return (int)cudaGetLastError();
 }
 

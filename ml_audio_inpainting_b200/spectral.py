@@ -476,8 +476,14 @@ def griffinlim(plan: StftPlan, mag: torch.Tensor, n_iter: int = 32, momentum: fl
     if init_angles is not None:
         ang = init_angles.to(device=dev, dtype=torch.complex64).reshape(B, F, T).contiguous().clone()
     elif init == "random":
-        u = torch.rand((B, F, T), dtype=torch.float32, device=dev, generator=generator)
-        ang = torch.polar(torch.ones_like(u), 2 * np.pi * u)
+        # one 62-bit key per call from torch's generator (the given one, else the global CPU generator: torch.manual_seed makes the
+        # call reproducible), the phases themselves from the device's counter RNG -- no [B, F, T] temporaries, 8 bytes per bin written
+        gen_dev = generator.device if generator is not None else "cpu"
+        seed = int(torch.randint(0, 2 ** 62, (1,), generator=generator, device=gen_dev).item())
+        ang = torch.empty((B, F, T), dtype=torch.complex64, device=dev)
+        with torch.cuda.device(dev):
+            check(_cabi.load().aip_random_phasors_f32(_ptr(ang.view(torch.float32)), B * F * T, seed, _stream()),
+                  "aip_random_phasors_f32")
     elif init is None:
         ang = torch.ones((B, F, T), dtype=torch.complex64, device=dev)
     else:

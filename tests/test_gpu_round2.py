@@ -842,3 +842,40 @@ def test_cpp_host_drives_the_c_abi_without_python(tmp_path):
     assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
     assert "round-trip SNR" in run.stdout
     print(run.stdout.strip())
+
+
+# ------------------------------------------------------------------------------------------- Griffin-Lim's random initial phases
+def test_random_phasors_and_seeded_griffinlim(sp):
+    """aip_random_phasors_f32: unit phasors with uniform, uncorrelated phases (Philox4x32-10 keyed by the seed); a seed fixes
+    the stream, torch.manual_seed fixes griffinlim(init='random'), two calls in a row differ."""
+    import ctypes as C
+    from ml_audio_inpainting_b200 import _cabi
+    lib = _cabi.load()
+    n = 1_000_003                                               # not a multiple of four: the last quad is partial
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    a = torch.full((n + 8, 2), -5.0, device="cuda")
+    b = torch.empty((n, 2), device="cuda")
+    assert lib.aip_random_phasors_f32(a.data_ptr(), n, 1234, st) == 0
+    assert lib.aip_random_phasors_f32(b.data_ptr(), n, 1234, st) == 0
+    assert torch.equal(a[:n], b) and bool((a[n:] == -5.0).all())                  # same key, same stream; nothing past n
+    assert lib.aip_random_phasors_f32(b.data_ptr(), n, 1235, st) == 0
+    z, z2 = torch.view_as_complex(a[:n].contiguous()), torch.view_as_complex(b)
+    assert float((z.abs() - 1).abs().max()) < 1e-6
+    phi = torch.angle(z).double()
+    hist = torch.histc(phi.float(), bins=64, min=-np.pi, max=np.pi).double()
+    chi2 = float(((hist - n / 64) ** 2 / (n / 64)).sum())
+    assert chi2 < 130, chi2                                     # 63 degrees of freedom: P(chi2 > 130) ~ 1e-6
+    assert float(z.mean().abs()) < 5e-3 and float((z * z2.conj()).mean().abs()) < 5e-3     # no bias, keys independent
+    assert float((z[1:] * z[:-1].conj()).mean().abs()) < 5e-3 and float((z[4:] * z[:-4].conj()).mean().abs()) < 5e-3
+    plan = sp.get_plan(512, 192, 384, "hann", True, "cuda:0")
+    mag = sp.stft(torch.from_numpy(_noise(2, 8000, seed=4)).cuda(), plan, mag_kind=sp.MAG_ABS, want_spec=False)["mag"]
+    torch.manual_seed(7)
+    y1 = sp.griffinlim(plan, mag, n_iter=4)
+    y2 = sp.griffinlim(plan, mag, n_iter=4)
+    torch.manual_seed(7)
+    y3 = sp.griffinlim(plan, mag, n_iter=4)
+    assert torch.equal(y1, y3) and not torch.equal(y1, y2) and bool(torch.isfinite(y1).all())
+    g = torch.Generator(device="cuda").manual_seed(3)
+    y4 = sp.griffinlim(plan, mag, n_iter=4, generator=g)
+    y5 = sp.griffinlim(plan, mag, n_iter=4, generator=torch.Generator(device="cuda").manual_seed(3))
+    assert torch.equal(y4, y5)
