@@ -96,7 +96,7 @@ def test_no_cpu_fallback():
     assert rc != 0
 
 
-def test_headers_are_plain_c_and_a_c_host_links_the_library(tmp_path):
+def test_headers_are_plain_c_and_a_c_host_links_the_library(lib, tmp_path):
     """include/*.h compile as C99 and as C++11 on their own, and a host written in C -- no Python, no torch -- links the
     shared library and calls its host-only entry points (the device entry points need a GPU: tests/test_gpu_round2.py calls
     them raw through ctypes)."""
