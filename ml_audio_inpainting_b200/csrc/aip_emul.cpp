@@ -155,6 +155,10 @@ void emul_fast_math(int n, const float* y, const float* x, float* out_atan2, flo
   }
 }
 
+void emul_fast_expm1(int n, const float* x, float* out) {
+  for (int i = 0; i < n; ++i) out[i] = fast_expm1(x[i]);
+}
+
 int emul_istft512(const float* spec, const float* mag, const float* phase, int mag_domain,
                   const int* db_flags, int B, int T, int length, int hop, int center, int win_length,
                   const float* window, const float* inv_wss, float* out, long long out_pitch,

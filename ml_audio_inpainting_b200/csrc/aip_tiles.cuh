@@ -53,6 +53,16 @@ AIP_HD float fast_atan2(float y, float x) {
 }
 
 // log1p(m), m >= 0 (models/GAN/dataset.py:122,135): log(u) * m / (u - 1) with u = fl(1 + m) cancels the rounding of u
+// expm1 for the GAN back-end's un-log (the inverse of its front-end's log1p): ex2.approx - 1 away from zero (relative error of the
+// difference <= 5 x 2^-22 for |x| >= 0.25), a degree-6 Taylor polynomial near it (remainder x^6 / 5040 < 5e-8 relative).  Measured
+// against expm1 in float64 over [-20, 20]: <= 1.2e-6 relative (tests/test_emul_kernels.py); libdevice's expm1f cost the mag + phase
+// inverse 0.24 ms of 0.62.
+AIP_HD float fast_expm1(float x) {
+  if (fabsf(x) >= 0.25f) return fast_exp2(x * 1.44269504088896341f) - 1.0f;
+  const float p = fmaf(x, fmaf(x, fmaf(x, fmaf(x, 1.0f / 720.0f, 1.0f / 120.0f), 1.0f / 24.0f), 1.0f / 6.0f), 0.5f);
+  return fmaf(x * x, p, x);
+}
+
 AIP_HD float fast_log1p(float m) {
   const float u = 1.0f + m, d = u - 1.0f;
   const float r = fast_log2(u) * 0.693147180559945309f;
@@ -563,7 +573,7 @@ struct InvLoadMag {
     if (kBlend) { const float g = bmask[o]; m = m * g + bin[o] * (1.0f - g); }
     if (kDom == 0) m = db ? fast_exp2(m * (kLog2of10 * 0.05f)) : m;
     else if (kDom == 1) m = fast_exp2(m * scale);
-    else m = expm1f(m);
+    else m = fast_expm1(m);
     if (kPhase) {
       float s, c;
       fast_sincos(phase[o], s, c);
@@ -636,7 +646,7 @@ AIP_HD void inv_load_runtime(const InvParams& P, long long idx, bool db, float& 
   const int dom = db ? (int)DOM_DB : P.mag_domain;
   if (dom == DOM_POW10) m = fast_exp2(m * kLog2of10);
   else if (dom == DOM_DB) m = fast_exp2(m * (kLog2of10 * 0.05f));
-  else if (dom == DOM_EXPM1) m = expm1f(m);
+  else if (dom == DOM_EXPM1) m = fast_expm1(m);
   if (P.phase) { float sn, cs; fast_sincos(P.phase[idx], sn, cs); xr = m * cs; xi = m * sn; }
   else { xr = m; xi = 0.0f; }
 }

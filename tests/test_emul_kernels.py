@@ -297,6 +297,21 @@ def test_epilogue_atan2_and_log1p_accuracy():
     assert (np.abs(l - ref_l) / np.maximum(ref_l, 1e-30)).max() < 1e-6
 
 
+def test_fast_expm1_accuracy():
+    """fast_expm1 (the GAN back-end's un-log, AIP_DOM_EXPM1) against numpy.expm1 in float64: the two branches and their seam."""
+    import ctypes as C
+    rng = np.random.default_rng(8)
+    x = np.concatenate([rng.uniform(-20, 20, 100000), rng.uniform(-0.3, 0.3, 100000), 10.0 ** rng.uniform(-30, -1, 20000),
+                        [0.0, -0.0, 0.25, -0.25, 0.2499999, 1e-38]]).astype(np.float32)
+    out = np.empty_like(x)
+    FP = C.POINTER(C.c_float)
+    emul.lib().emul_fast_expm1(len(x), x.ctypes.data_as(FP), out.ctypes.data_as(FP))
+    ref = np.expm1(x.astype(np.float64))
+    nz = ref != 0
+    assert (np.abs(out[nz] - ref[nz]) / np.abs(ref[nz])).max() < 1.5e-6
+    assert np.array_equal(out[~nz], x[~nz])
+
+
 @pytest.mark.parametrize("hop,wl", [(192, 384), (128, 512)])
 def test_forward_power_spectrogram_variant_and_general_powers(hop, wl):
     """|S| ** p (the mel front-end's epilogue, utils.py:268-277): p = 2 is a straight-line variant (re^2 + im^2, no sqrt),

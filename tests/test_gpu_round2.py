@@ -879,3 +879,19 @@ def test_random_phasors_and_seeded_griffinlim(sp):
     y4 = sp.griffinlim(plan, mag, n_iter=4, generator=g)
     y5 = sp.griffinlim(plan, mag, n_iter=4, generator=torch.Generator(device="cuda").manual_seed(3))
     assert torch.equal(y4, y5)
+
+
+def test_expm1_back_end_on_the_device(sp):
+    """AIP_DOM_EXPM1 (undoing the GAN front-end's log1p) with the device's ex2.approx-based expm1 against numpy.expm1 in float64:
+    magnitudes spanning tiny to large, through both the fused n_fft = 512 inverse and the tiled one."""
+    rng = np.random.default_rng(12)
+    for n_fft, hop in ((512, 128), (1024, 256)):
+        plan = sp.get_plan(n_fft, hop, n_fft, "hann", True, "cuda:0")
+        F, T, B = n_fft // 2 + 1, 40, 2
+        logm = np.concatenate([rng.uniform(0, 6, (B, F, T // 2)), 10.0 ** rng.uniform(-6, -1, (B, F, T - T // 2))], 2).astype(np.float32)
+        ph = rng.uniform(-np.pi, np.pi, (B, F, T)).astype(np.float32)
+        y = sp.istft(plan, mag=torch.from_numpy(logm).cuda(), phase=torch.from_numpy(ph).cuda(), mag_domain=sp.DOM_EXPM1).cpu().numpy()
+        for b in range(B):
+            S = (np.expm1(logm[b].astype(np.float64)) * np.exp(1j * ph[b].astype(np.float64))).astype(np.complex64)
+            ref = lr.istft(S, hop_length=hop, win_length=n_fft, n_fft=n_fft)
+            assert relerr(y[b], ref) < TOL, (n_fft, relerr(y[b], ref))
