@@ -72,7 +72,9 @@ extern "C" {
 typedef struct aip_stft_desc {
   int32_t n_fft;        /* power of two, 32 .. 4096; 512 runs the register-FFT kernels */
   int32_t hop;          /* > 0 */
-  int32_t center;       /* 1: zero-pad n_fft/2 on both sides (librosa >= 0.10 pad_mode="constant") */
+  int32_t center;       /* 0: no padding; 1: zero-pad n_fft/2 on both sides (librosa >= 0.10 pad_mode="constant");
+                           2: the same amount mirrored about the first / last sample (pad_mode="reflect", librosa < 0.10's
+                           default; forward only -- the inverse trims n_fft/2 either way) */
   int32_t win_length;   /* 0 or n_fft: every tap may be non-zero.  Otherwise the caller GUARANTEES that `window` is a
                            win_length window centre-padded with zeros (librosa util.pad_center, what librosa.stft /
                            istft build from win_length): the kernels then skip the zero taps (config.py: 384 in 512) */

@@ -22,7 +22,7 @@ int emul_stft512_fwd(const float* wave, int B, int L, long long pitch, int hop, 
   FwdParams P;
   memset(&P, 0, sizeof(P));
   P.wave = wave; P.wave_pitch = pitch; P.B = B; P.L = L;
-  P.hop = hop; P.pad = center ? 256 : 0;
+  P.hop = hop; P.pad = center ? 256 : 0; P.reflect = center == 2;
   P.T = 1 + (L + 2 * P.pad - 512) / hop;
   if (T_out > P.T || (hop & 1)) return -1;
   P.T_out = T_out;
@@ -84,7 +84,7 @@ int emul_stft512_variants(const float* wave, int N, int L, long long pitch, int 
   FwdParams P;
   memset(&P, 0, sizeof(P));
   P.wave = wave; P.wave_pitch = pitch; P.B = N * G; P.L = L;
-  P.hop = hop; P.pad = center ? 256 : 0;
+  P.hop = hop; P.pad = center ? 256 : 0; P.reflect = center == 2;
   P.T = 1 + (L + 2 * P.pad - 512) / hop;
   if (T_out > P.T || (hop & 1)) return -1;
   P.T_out = T_out;

@@ -258,7 +258,8 @@ __global__ void __launch_bounds__(256) stft_generic_fwd_kernel(const GenericFwdP
     if (P.gap_samples) { gs = P.gap_samples[2 * b]; ge = P.gap_samples[2 * b + 1]; }
     const long long g0 = (long long)t * P.hop - P.pad;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
-      const long long g = g0 + n;
+      long long g = g0 + n;
+      if (P.reflect && (g < 0 || g >= P.L)) g = g < 0 ? -g : 2LL * (P.L - 1) - g;
       float v = (g >= 0 && g < P.L && !(g >= gs && g < ge)) ? src[g] : 0.0f;
       v *= P.window[n];
       buf[__brev((unsigned)n) >> (32 - G.logN)] = make_float2(v, 0.0f);
@@ -522,6 +523,8 @@ int run_fwd(const aip_stft_desc* desc, FwdParams P, long long T_out, cudaStream_
   if (!P.spec && !P.mag && !P.phase && !P.mask) return AIP_OK;      // no output requested: nothing to launch
   P.hop = desc->hop;
   P.pad = desc->center ? desc->n_fft / 2 : 0;
+  P.reflect = desc->center == 2;
+  if (P.reflect && P.L <= P.pad) return AIP_ERR_UNSUPPORTED;        // np.pad(mode="reflect") needs pad < L
   P.T = (int)T;
   P.T_out = (int)T_out;
   P.window = desc->window;
@@ -591,6 +594,8 @@ int aip_stft_gap_variants_f32(const aip_stft_desc* desc, const float* wave, int6
   P.wave = wave; P.wave_pitch = wave_pitch; P.B = (int)(N * G); P.L = (int)L;
   P.gap_samples = gap_samples; P.mag_kind = mag_kind; P.eps = eps; P.power = 1.0f; P.mag = mag_out;
   P.hop = desc->hop; P.pad = desc->center ? desc->n_fft / 2 : 0;
+  P.reflect = desc->center == 2;
+  if (P.reflect && L <= P.pad) return AIP_ERR_UNSUPPORTED;
   P.T = (int)T; P.T_out = (int)T_out; P.window = desc->window;
   P.var_div = (int)G;
   P.tiles_per_clip = var_tiles(gap_len_max, P.hop, P.T_out);

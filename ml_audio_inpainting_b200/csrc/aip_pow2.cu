@@ -249,8 +249,9 @@ struct P2WaveClean {
 struct P2WaveChecked {
   const float* __restrict__ src;
   const float* win;
-  int gA, gB, L, gs, ge;
+  int gA, gB, L, gs, ge, reflect;
   __device__ __forceinline__ float one(int g) const {
+    if (reflect && (g < 0 || g >= L)) g = g < 0 ? -g : 2 * (L - 1) - g;      // np.pad(mode="reflect") of the gapped clip
     const bool ok = g >= 0 && g < L && !(g >= gs && g < ge);
     const float v = __ldg(src + (ok ? g : 0));
     return ok ? v : 0.0f;
@@ -290,6 +291,7 @@ __device__ __forceinline__ FwdTilePlan p2_span_plan(const FwdParams& P, int b, i
   if (q.v_lo > q.v_hi) q.v_lo = q.v_hi;
   q.n_bulk = (q.v_hi - q.v_lo) & ~3;
   q.gs = gs; q.ge = ge;
+  q.L = P.L; q.reflect = P.reflect;
   return q;
 }
 __device__ __forceinline__ void p2_span_issue(const FwdTilePlan& q, float* span, uint64_t* bar) {
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(kP2Threads, 2) stft_pow2_fwd_kernel(const Pow2
         const P2WaveClean load{src, win, gA, gB};
         p2_pass_first(g, s, sf, load);
       } else {
-        const P2WaveChecked load{src, win, gA, gB, P.L, gs, ge};
+        const P2WaveChecked load{src, win, gA, gB, P.L, gs, ge, P.reflect};
         p2_pass_first(g, s, sf, load);
       }
     }

@@ -99,6 +99,7 @@ struct FwdParams {
                             // tiles starting at frame var_frame_base(P, gap start of b) are transformed
   int chunk;                // tiles per draw from the dynamic schedule
   unsigned* tile_counter;   // device counter of the dynamic schedule, zero at launch
+  int reflect;              // centre padding by reflection (librosa < 0.10's default pad_mode; aip_stft_desc.center == 2), else zeros
   int vec_ok;               // 16-byte bulk copies of the waveform are legal (alignment)
   int zero_groups;          // win_zero_groups(win_length): the first / last 32 * zero_groups window taps are zero
   int var_prefetch;         // gap-variant mode: request the lines of a tile's row segments from L2 ahead of its stores
@@ -119,6 +120,7 @@ struct FwdTilePlan {
   int v_lo, v_hi;       // tile elements that map to real samples: [v_lo, v_hi)
   int n_bulk;           // elements moved by the bulk copy (multiple of 4), starting at v_lo
   int gs, ge;           // gap range in clip samples
+  int L, reflect;       // clip length; padding outside [0, L) by reflection instead of zeros
 };
 
 // A CTA owns a contiguous run of tiles; (clip b, tile-in-clip tt) advance without divisions.
@@ -146,6 +148,7 @@ AIP_HD FwdTilePlan fwd_tile_plan(const FwdParams& P, const TileCursor& c) {
   if (q.v_lo > q.v_hi) q.v_lo = q.v_hi;
   q.n_bulk = P.vec_ok ? ((q.v_hi - q.v_lo) & ~3) : 0;
   q.gs = q.ge = 0;
+  q.L = P.L; q.reflect = P.reflect;
   if (P.gap_samples) { q.gs = P.gap_samples[2 * c.b]; q.ge = P.gap_samples[2 * c.b + 1]; }
   return q;
 }
@@ -163,6 +166,7 @@ AIP_HD FwdTilePlan fwd_tile_plan_gap(const FwdParams& P, const TileCursor& c, in
   if (q.v_lo > q.v_hi) q.v_lo = q.v_hi;
   q.n_bulk = P.vec_ok ? ((q.v_hi - q.v_lo) & ~3) : 0;
   q.gs = gs; q.ge = ge;
+  q.L = P.L; q.reflect = P.reflect;
   return q;
 }
 
@@ -199,6 +203,7 @@ AIP_HD FwdTilePlan fwd_tile_plan_var(const FwdParams& P, const TileCursor& c, in
   // the bulk copy needs a 16-byte aligned source: g0 + v_lo is a multiple of 4 when hop, pad are (vec_ok) and fb is any int
   q.n_bulk = P.vec_ok ? ((q.v_hi - q.v_lo) & ~3) : 0;
   q.gs = gs; q.ge = ge;
+  q.L = P.L; q.reflect = P.reflect;
   return q;
 }
 
@@ -210,14 +215,25 @@ AIP_HD bool fwd_needs_fixup(const FwdTilePlan& q) {
 // Every element is written by at most ONE thread here: the scalar copy applies the gap itself (a separate zeroing
 // pass by other threads would race with it -- seen on hardware with unaligned waveforms), the zeroing pass below only
 // touches what the bulk copy delivered.
+// element i of the tile lies outside the clip: zero (librosa >= 0.10, pad_mode="constant") or the GAPPED clip mirrored about its
+// first / last sample (np.pad(..., mode="reflect"), librosa < 0.10); positions past the mirror's reach belong to frames that do
+// not exist and read as zero
+AIP_HD float fwd_pad_value(const FwdTilePlan& q, int i) {
+  if (!q.reflect) return 0.0f;
+  int g = q.g0 + i;
+  g = g < 0 ? -g : 2 * (q.L - 1) - g;
+  if (g < 0 || g >= q.L || (g >= q.gs && g < q.ge)) return 0.0f;
+  return q.src[g];
+}
+
 AIP_HD void fwd_fixup(const FwdTilePlan& q, int tid, float* tile) {
   int a = q.gs - q.g0, e = q.ge - q.g0;        // gap range (utils.py:141-142, :180-183) in tile elements
   if (a < 0) a = 0;
   if (e > q.len) e = q.len;
-  for (int i = tid; i < q.v_lo; i += kThreads) tile[i] = 0.0f;
+  for (int i = tid; i < q.v_lo; i += kThreads) tile[i] = fwd_pad_value(q, i);
   const int bulk_end = q.v_lo + q.n_bulk;
   for (int i = bulk_end + tid; i < q.v_hi; i += kThreads) tile[i] = (i >= a && i < e) ? 0.0f : q.src[q.g0 + i];
-  for (int i = q.v_hi + tid; i < q.len; i += kThreads) tile[i] = 0.0f;
+  for (int i = q.v_hi + tid; i < q.len; i += kThreads) tile[i] = fwd_pad_value(q, i);
   if (a < q.v_lo) a = q.v_lo;
   if (e > bulk_end) e = bulk_end;
   for (int i = a + tid; i < e; i += kThreads) tile[i] = 0.0f;

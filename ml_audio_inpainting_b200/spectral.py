@@ -109,6 +109,7 @@ class StftPlan:
     window: object
     center: bool
     device: torch.device
+    pad_mode: str = "constant"
     window_dev: torch.Tensor = field(repr=False, default=None)
     desc: StftDesc = field(repr=False, default=None)
     _inv_wss: Dict[Tuple[int, int], Tuple[torch.Tensor, "torch.cuda.Event"]] = field(repr=False, default_factory=dict)
@@ -151,10 +152,20 @@ class StftPlan:
 
 _plans: Dict[tuple, StftPlan] = {}
 
+# librosa.stft's centre padding when a caller does not say: "constant" (librosa >= 0.10, the oracle's choice) or
+# "reflect" (librosa < 0.10) -- the reference never passes pad_mode and pins librosa>=0.8.1 only, so which one ITS results carry
+# depends on the installed librosa; set AIP_LIBROSA_PAD_MODE=reflect (or this variable) to reproduce an old installation.
+DEFAULT_PAD_MODE = os.environ.get("AIP_LIBROSA_PAD_MODE", "constant")
+
 
 def get_plan(n_fft: int, hop_length: Optional[int] = None, win_length: Optional[int] = None, window="hann",
-             center: bool = True, device=None) -> StftPlan:
-    """Cached plan.  Defaults follow librosa: win_length = n_fft, hop_length = win_length // 4."""
+             center: bool = True, device=None, pad_mode: Optional[str] = None) -> StftPlan:
+    """Cached plan.  Defaults follow librosa >= 0.10: win_length = n_fft, hop_length = win_length // 4, zero centre padding;
+    ``pad_mode="reflect"`` is librosa < 0.10's default (the reference pins ``librosa>=0.8.1`` only) and affects the forward
+    transform alone."""
+    pad_mode = DEFAULT_PAD_MODE if pad_mode is None else pad_mode
+    if pad_mode not in ("constant", "reflect"):
+        raise NotImplementedError(f"pad_mode={pad_mode!r}: 'constant' and 'reflect' are implemented")
     lib = _cabi.load()
     device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
     if device.type != "cuda":
@@ -169,7 +180,7 @@ def get_plan(n_fft: int, hop_length: Optional[int] = None, win_length: Optional[
     if n_fft < 32 or n_fft > 4096 or (n_fft & (n_fft - 1)):
         raise NotImplementedError(f"n_fft={n_fft}: the CUDA kernels cover powers of two in [32, 4096]")
     wkey = window if isinstance(window, (str, tuple, float, int)) else ("array", np.asarray(window).tobytes())
-    key = (n_fft, hop_length, win_length, wkey, bool(center), device.index)
+    key = (n_fft, hop_length, win_length, wkey, bool(center), device.index, pad_mode)
     plan = _plans.get(key)
     if plan is None:
         with torch.cuda.device(device):
@@ -178,8 +189,8 @@ def get_plan(n_fft: int, hop_length: Optional[int] = None, win_length: Optional[
                                    "the kernels are built for sm_100a only and there is no fallback")
         w = fft_window(window, win_length, n_fft).astype(np.float32)
         wd = torch.from_numpy(w).to(device)
-        desc = StftDesc(n_fft, hop_length, int(bool(center)), win_length, wd.data_ptr())
-        plan = StftPlan(n_fft, hop_length, win_length, window, bool(center), device, wd, desc)
+        desc = StftDesc(n_fft, hop_length, (2 if pad_mode == "reflect" else 1) if center else 0, win_length, wd.data_ptr())
+        plan = StftPlan(n_fft, hop_length, win_length, window, bool(center), device, pad_mode, wd, desc)
         _plans[key] = plan
     return plan
 

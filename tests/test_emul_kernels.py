@@ -297,6 +297,22 @@ def test_epilogue_atan2_and_log1p_accuracy():
     assert (np.abs(l - ref_l) / np.maximum(ref_l, 1e-30)).max() < 1e-6
 
 
+@pytest.mark.parametrize("hop,wl,L", [(192, 384, 6001), (128, 512, 3000), (192, 384, 300), (250, 500, 777)])
+def test_forward_reflect_padding(hop, wl, L):
+    """aip_stft_desc.center == 2: the centre padding mirrored about the first / last sample (np.pad mode="reflect", librosa < 0.10's
+    default pad_mode) instead of zeros -- of the GAPPED clip, as the reference zeroes the gap before it calls librosa."""
+    x = noise(3, L, seed=L)
+    gaps = np.array([[0, min(L, 120)], [L - min(L, 150), L], [L // 3, L // 2]])
+    out = emul.stft(x, hop, win(wl), center=2, win_length=wl, gap_samples=gaps, mag_kind=2, want_spec=True, vec_ok=(hop % 4 == 0))
+    for b in range(3):
+        xg = x[b].copy()
+        xg[gaps[b, 0]:gaps[b, 1]] = 0
+        ref = lr.stft(xg, n_fft=512, hop_length=hop, win_length=wl, pad_mode="reflect")
+        assert out["spec"][b].shape == ref.shape and relerr(out["spec"][b], ref) < TOL, (b, relerr(out["spec"][b], ref))
+        zero = lr.stft(xg, n_fft=512, hop_length=hop, win_length=wl)
+        assert relerr(zero, ref) > 1e-2                          # the two paddings really differ on this signal
+
+
 def test_fast_expm1_accuracy():
     """fast_expm1 (the GAN back-end's un-log, AIP_DOM_EXPM1) against numpy.expm1 in float64: the two branches and their seam."""
     import ctypes as C

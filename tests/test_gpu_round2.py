@@ -895,3 +895,51 @@ def test_expm1_back_end_on_the_device(sp):
             S = (np.expm1(logm[b].astype(np.float64)) * np.exp(1j * ph[b].astype(np.float64))).astype(np.complex64)
             ref = lr.istft(S, hop_length=hop, win_length=n_fft, n_fft=n_fft)
             assert relerr(y[b], ref) < TOL, (n_fft, relerr(y[b], ref))
+
+
+# ------------------------------------------------------------------------------------------- librosa < 0.10's centre padding
+@pytest.mark.parametrize("n_fft,hop,win", [(512, 192, 384), (512, 128, 512), (512, 191, 384), (2048, 512, 2048), (1024, 255, 1024),
+                                           (256, 64, 256), (4096, 1024, 4096)])
+def test_reflect_padding_mode(sp, n_fft, hop, win):
+    """get_plan(pad_mode="reflect") = librosa.stft's default before 0.10 (the reference pins librosa>=0.8.1 only): the fused
+    n_fft = 512 kernels (bulk copy + fix-up), the tiled kernels (staged span and per-warp checked loads) and the one-frame-per-CTA
+    kernel, gaps touching both clip ends, against the oracle's np.pad(mode="reflect") path; the inverse is unaffected and a
+    clip no longer than the padding is refused like np.pad refuses it."""
+    B, L = 3, 5 * n_fft + 333
+    x = _noise(B, L, seed=n_fft + hop)
+    xd = torch.from_numpy(x).cuda()
+    plan = sp.get_plan(n_fft, hop, win, "hann", True, "cuda:0", pad_mode="reflect")
+    gaps = np.array([[0, n_fft // 3], [L - n_fft // 4, L], [L // 2, L // 2 + 100]])
+    out = sp.stft(xd, plan, gap_samples=gaps, mag_kind=sp.MAG_LOG10_EPS, want_spec=True)
+    zero_plan = sp.get_plan(n_fft, hop, win, "hann", True, "cuda:0")
+    assert zero_plan is not plan and plan.pad_mode == "reflect"
+    for b in range(B):
+        xg = x[b].copy()
+        xg[gaps[b, 0]:gaps[b, 1]] = 0
+        ref = lr.stft(xg, n_fft=n_fft, hop_length=hop, win_length=win, pad_mode="reflect")
+        got = out["spec"][b].cpu().numpy()
+        assert got.shape == ref.shape and relerr(got, ref) < TOL, (b, relerr(got, ref))
+    S = sp.stft(xd, plan)["spec"]
+    assert relerr(sp.stft(xd, zero_plan)["spec"].cpu().numpy(), S.cpu().numpy()) > 1e-2      # the modes do differ
+    y = sp.istft(plan, spec=S, length=L).cpu().numpy()
+    for b in range(B):
+        ref = lr.istft(S[b].cpu().numpy(), hop_length=hop, win_length=win, n_fft=n_fft, length=L)
+        assert relerr(y[b], ref) < TOL
+    with pytest.raises(Exception):
+        sp.stft(xd[:, :n_fft // 2], plan)
+    with pytest.raises(NotImplementedError):
+        sp.get_plan(n_fft, hop, win, "hann", True, "cuda:0", pad_mode="edge")
+
+
+def test_dropin_follows_the_default_pad_mode(sp, utils, monkeypatch):
+    """spectral.DEFAULT_PAD_MODE = "reflect" makes every caller that does not choose (the drop-in utils.py, the front-ends) behave
+    like a librosa < 0.10 installation."""
+    x = _noise(1, 9000, seed=5)[0]
+    monkeypatch.setattr(sp, "DEFAULT_PAD_MODE", "reflect")
+    S = utils.extract_spectrogram(x, n_fft=512, hop_length=192, win_length=384)
+    assert relerr(S, lr.stft(x, n_fft=512, hop_length=192, win_length=384, pad_mode="reflect")) < TOL
+    S2 = utils.extract_spectrogram(x)
+    assert relerr(S2, lr.stft(x, n_fft=2048, hop_length=512, pad_mode="reflect")) < TOL
+    monkeypatch.setattr(sp, "DEFAULT_PAD_MODE", "constant")
+    S = utils.extract_spectrogram(x, n_fft=512, hop_length=192, win_length=384)
+    assert relerr(S, lr.stft(x, n_fft=512, hop_length=192, win_length=384)) < TOL

@@ -172,3 +172,16 @@ def test_write_audio_takes_device_quantised_int16(tmp_path):
     audio_io.write_audio(tmp_path / "c.wav", q, 16000, "wav")
     back, _ = audio_io.read_audio(tmp_path / "c.wav")
     assert np.array_equal(np.rint(np.asarray(back).reshape(-1) * 32768).astype(np.int16), q)
+
+
+def test_default_pad_mode_switch(monkeypatch):
+    """spectral.DEFAULT_PAD_MODE: "constant" unless AIP_LIBROSA_PAD_MODE says otherwise at import time."""
+    import importlib
+    import ml_audio_inpainting_b200.spectral as spmod
+    assert spmod.DEFAULT_PAD_MODE == "constant"
+    monkeypatch.setenv("AIP_LIBROSA_PAD_MODE", "reflect")
+    importlib.reload(spmod)
+    assert spmod.DEFAULT_PAD_MODE == "reflect"
+    monkeypatch.delenv("AIP_LIBROSA_PAD_MODE")
+    importlib.reload(spmod)
+    assert spmod.DEFAULT_PAD_MODE == "constant"
