@@ -115,11 +115,30 @@ static int read_residual(bitr* b, int blocksize, int order, int64_t* out) {
       const int raw = (int)br_read(b, 5);
       for (int i = 0; i < n; ++i) out[w + i] = raw ? br_signed(b, raw) : 0;
     } else {
+      /* one 8-byte window per residual: unary run + stop bit + k low bits fit its >= 57 valid bits almost always; the rare
+         long run (or the last 8 bytes of the stream) takes the general readers */
+      size_t pos = b->pos;
+      const size_t safe_bits = b->n >= 8 ? (b->n - 8) * 8 : 0;
       for (int i = 0; i < n; ++i) {
-        uint64_t u = br_unary(b);
+        uint64_t u;
+        if (pos <= safe_bits) {
+          const uint64_t win = be64(b->p + (pos >> 3)) << (pos & 7);
+          const int lead = win ? __builtin_clzll(win) : 64;
+          if (lead + 1 + (int)k <= 57) {
+            u = (uint64_t)lead;
+            if (k) u = (u << k) | ((win << (lead + 1)) >> (64 - k));
+            pos += (size_t)lead + 1 + k;
+            out[w + i] = (int64_t)(u >> 1) ^ -(int64_t)(u & 1);
+            continue;
+          }
+        }
+        b->pos = pos;
+        u = br_unary(b);
         if (k) u = (u << k) | br_read(b, (int)k);
+        pos = b->pos;
         out[w + i] = (int64_t)(u >> 1) ^ -(int64_t)(u & 1);
       }
+      b->pos = pos;
     }
     if (b->err) return AIP_CODEC_ERR_TRUNCATED;
     w += n;
@@ -170,11 +189,29 @@ static int read_subframe(bitr* b, int blocksize, int bps, int64_t* s, int64_t* r
     if (order == 0) {
       memcpy(s, res, (size_t)blocksize * sizeof(int64_t));
     } else {
-      for (int n = order; n < blocksize; ++n) {
-        int64_t acc = 0;
-        for (int i = 0; i < order; ++i) acc += c[i] * s[n - 1 - i];
-        s[n] = res[n - order] + (acc >> shift);          /* arithmetic shift: floor, as the format specifies */
+      /* s[n] = res[n - order] + (sum_i c[i] s[n - 1 - i] >> shift), arithmetic shift = floor as the format specifies.  The
+         orders encoders actually emit (libFLAC -5 .. -8: up to 12) get a fully unrolled inner loop: with the trip count a
+         run-time value the restore took most of the decode time */
+#define AIP_LPC_CASE(ORD)                                                        \
+  case ORD:                                                                      \
+    for (int n = ORD; n < blocksize; ++n) {                                      \
+      int64_t acc = 0;                                                           \
+      /* the term that depends on the sample just restored goes last: the others are off the critical path */ \
+      _Pragma("GCC unroll 16") for (int i = ORD - 1; i >= 0; --i) acc += c[i] * s[n - 1 - i]; \
+      s[n] = res[n - ORD] + (acc >> shift);                                      \
+    }                                                                            \
+    break;
+      switch (order) {
+        AIP_LPC_CASE(1) AIP_LPC_CASE(2) AIP_LPC_CASE(3) AIP_LPC_CASE(4) AIP_LPC_CASE(5) AIP_LPC_CASE(6) AIP_LPC_CASE(7)
+        AIP_LPC_CASE(8) AIP_LPC_CASE(9) AIP_LPC_CASE(10) AIP_LPC_CASE(11) AIP_LPC_CASE(12)
+        default:
+          for (int n = order; n < blocksize; ++n) {
+            int64_t acc = 0;
+            for (int i = 0; i < order; ++i) acc += c[i] * s[n - 1 - i];
+            s[n] = res[n - order] + (acc >> shift);
+          }
       }
+#undef AIP_LPC_CASE
     }
   } else {
     return AIP_CODEC_ERR_FORMAT;
