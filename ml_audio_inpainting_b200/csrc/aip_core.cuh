@@ -430,9 +430,14 @@ AIP_HD void fwd_pair2s(float2 zkr, float2 zki, float2 znr, float2 zni, float2 wr
   emit.template put2<-1, -1>(hi_x, hi_y, sub2(er, ti), add2(ei, tr));
 }
 
-template <class Emit>
-AIP_HD void fwd_stage2_compute(float2 (&r)[16], float2 (&i)[16], const PairTw& w, int p, Emit& emit) {
+struct NoHook { AIP_HM void operator()() const {} };
+
+// `hook` runs once: between the two DFTs and the split pass (kHookAt < 0) or after kHookAt + 1 of the 8 split-pass / epilogue
+// rounds (see fwd_phase2: the late release of the exchange buffer)
+template <class Emit, class Hook, int kHookAt = -1>
+AIP_HD void fwd_stage2_compute(float2 (&r)[16], float2 (&i)[16], const PairTw& w, int p, Emit& emit, Hook& hook) {
   fft16x2(r, i);     // .x = job a, .y = job b
+  if (kHookAt < 0) hook();
   if (p != 0) {
     emit.rows(p, 256 - p);
 #if defined(AIP_SPLIT_SCALAR)
@@ -442,9 +447,11 @@ AIP_HD void fwd_stage2_compute(float2 (&r)[16], float2 (&i)[16], const PairTw& w
                pair_tw_i(w, k1), emit.lo(k1), emit.hi(k1), emit);
 #else
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < 8; ++j) {
       fwd_pair2(r[perm16(j)], i[perm16(j)], r[perm16(15 - j)], i[perm16(15 - j)], w.wr2[j], w.wi2[j],
                 emit.lo(j), emit.lo(15 - j), emit.hi(j), emit.hi(15 - j), emit);
+      if (j == kHookAt) hook();
+    }
 #endif
   } else {
     // Job 0 (.x: bins 16 k1, pairs k1 <-> 16 - k1) and job 8 (.y: bins 8 + 16 k1, pairs k1 <-> 15 - k1).  Pair j + 1 of
@@ -460,7 +467,9 @@ AIP_HD void fwd_stage2_compute(float2 (&r)[16], float2 (&i)[16], const PairTw& w
       const float2 zki = make_float2(i[perm16(j + 1)].x, i[perm16(j)].y);
       fwd_pair2s(zkr, zki, r[perm16(15 - j)], i[perm16(15 - j)], w.wr2[j], w.wi2[j], emit.bin(16 * (j + 1)),
                  emit.bin(8 + 16 * j), emit.bin(256 - 16 * (j + 1)), emit.bin(248 - 16 * j), emit);
+      if (j == kHookAt) hook();
     }
+    if (kHookAt >= 7) hook();
     fwd_pair(r[perm16(7)].y, i[perm16(7)].y, r[perm16(8)].y, i[perm16(8)].y, w.wr2[7].y, w.wi2[7].y, emit.bin(120),
              emit.bin(136), emit);
   }

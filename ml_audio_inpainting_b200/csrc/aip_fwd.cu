@@ -129,9 +129,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
     lane_const_init(lc, tw_s, ptid & 15);
     TileFeed fn{0, 0, TileCursor{0, 0}};     // request cursor (thread ptid == 0 only): draws the chunks
     bool more = true;                        // the request cursor has not hit the end of the batch yet
+    int next_s = 0;                          // the next chunk, drawn ahead
+    bool have_next = false;
     auto request = [&](float* buf, uint64_t* bar) {      // ptid == 0: start the copy of the next tile, if there is one
       if (fn.left == 0) {
-        const int s = (int)atomicAdd(P.tile_counter, (unsigned)P.chunk);
+        const int s = have_next ? next_s : (int)atomicAdd(P.tile_counter, (unsigned)P.chunk);
+        have_next = false;
         sched_start[fn.k & (kSchedRing - 1)] = s;
         mbar_arrive(sched_bar + (fn.k & (kSchedRing - 1)));          // release: publishes the chunk to the CTA
         int cnt = P.n_tiles - s;
@@ -149,6 +152,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stft512_fwd_kernel(const FwdPa
       }
       tile_advance(fn.c, P.tiles_per_clip);
       --fn.left;
+      // The next draw (an atomic on L2, ~1 us under load) is issued now and read one request later: 0.464 -> 0.455 ms (hop 192),
+      // 0.709 -> 0.679 ms (hop 128) for 1024 clips with complex output, where the stage-1 warps are the slower role.  (Where
+      // stage 2 is the slower role it cost 1 % as long as stage 2 handed the exchange buffer back early -- see fwd_phase2 --
+      // and is neutral since.)
+      if (fn.left == 0) {
+        next_s = (int)atomicAdd(P.tile_counter, (unsigned)P.chunk);
+        have_next = true;
+      }
     };
     if (ptid == 0) {
       for (int k = 0; k < (ntb > 1 ? ntb - 1 : 1) && more; ++k) request(smem + k * P.tile_floats, tile_full + k);
@@ -449,9 +460,11 @@ static cudaError_t launch_fwd512_t(FwdParams P, const DevInfo& di, cudaStream_t 
   // Tiles per draw.  Besides balancing the SMs, the chunk size sets how close in memory the tiles are that the 148 CTAs
   // work on at the same time: measured 1.73 / 1.58 / 1.52 / 1.50 / 1.51 / 1.55 / 1.58 ms for 1 / 4 / 8 / 12 / 16 / 32 / 64
   // tiles per draw on the log-magnitude variant (4096 x 10 s; static equal runs: 1.60 ms), while the complex-output variant
-  // (8 bytes per bin) is fastest at 2 (0.468 ms against 0.529 ms static, 0.507 ms at 8).
+  // (8 bytes per bin) is fastest at 2 (0.468 ms against 0.529 ms static, 0.507 ms at 8).  Re-measured after the late release of
+  // the exchange buffer (fwd_phase2) and the draw-ahead: 1.446 / 1.424 / 1.415 / 1.411 / 1.413 / 1.416 / 1.429 / 1.480 ms for
+  // 4 / 6 / 7 / 8 / 9 / 10 / 12 / 16 tiles per draw (hop 128, 1024 clips: 0.587 ms at 7 - 8, 0.604 at 12).
   const int out_bytes = (P.mag ? 4 : 0) + (P.phase ? 4 : 0) + (P.mask ? 4 : 0) + (P.spec ? 8 : 0);
-  P.chunk = out_bytes <= 4 ? 12 : (P.spec ? 2 : 4);
+  P.chunk = out_bytes <= 4 ? 8 : (P.spec ? 2 : 4);
   if (kMode & FWD_VARIANT) P.chunk = 4;      // few tiles per CTA (one or two per variant): balance matters more than locality
   if (const int cv = tunables().fwd_chunk) { if (cv >= 1 && cv <= 4096) P.chunk = cv; }
   const int n_chunks = (P.n_tiles + P.chunk - 1) / P.chunk;

@@ -503,11 +503,23 @@ AIP_HD void fwd_phase2(const FwdParams& P, int tid, const TileCursor& c, const f
   const int fr = lane < n_valid ? lane : n_valid - 1;     // lanes past the end replay the last valid frame
   float2 zr[16], zi[16];
   fwd_stage2_load(exch, fr, p, zr, zi);
-  release();
+#ifndef AIP_FWD_LATE_RELEASE
+#define AIP_FWD_LATE_RELEASE 4
+#endif
+  // When is the exchange buffer handed back to the stage-1 warps?  As soon as it has been read, where stage 1 is the slower
+  // role (complex / phase outputs).  In the magnitude-only variants stage 2 is the slower role and stage 1 has time to spare;
+  // handed the buffer early, stage 1 of the tile after next starts at once and competes for the FP32 pipe with this tile's
+  // two DFTs, which are FP32-pipe bound -- every change that made stage 1 faster made these variants SLOWER.  There the
+  // buffer is handed back only after AIP_FWD_LATE_RELEASE - 1 of the 8 split-pass / epilogue rounds (MUFU, stores: the FP32
+  // pipe has room).  Headline launch, A/B on one box: release after the loads 1.465 ms, after the DFTs 1.448, after 2 / 3 / 4
+  // rounds 1.430 / 1.433 / 1.430, after 6 / 8 rounds 1.52 / 1.56 (stage 1 starts too late).
+  constexpr bool kLate = AIP_FWD_LATE_RELEASE && (kMode & (FWD_SPEC | FWD_PHASE)) == 0 && kMode != FWD_FULL;
+  if (!kLate) release();
+  NoHook no_hook;
   const long long col = (long long)c.b * kBins * T_out + t0 + fr;
   if (kMode == FWD_FULL) {
     FwdEmitFull emit = fwd_make_emit_full(P, c.b, t0 + fr, kBins, lane < n_valid);
-    fwd_stage2_compute(zr, zi, w, p, emit);
+    fwd_stage2_compute(zr, zi, w, p, emit, no_hook);
   } else {
     const int t = t0 + fr;
     FwdEmitT<kMode, kT> emit{(kMode & 7) ? P.mag + col : nullptr, (kMode & FWD_SPEC) ? P.spec + col : nullptr,
@@ -519,7 +531,8 @@ AIP_HD void fwd_phase2(const FwdParams& P, int tid, const TileCursor& c, const f
       emit.maskv = (in == (P.mask_in_gap_is_one != 0)) ? 1.0f : 0.0f;
     }
     if (kMode & FWD_ZERO) emit.zero = (t >= P.zero_frames[2 * c.b] && t < P.zero_frames[2 * c.b + 1]);
-    fwd_stage2_compute(zr, zi, w, p, emit);
+    if (kLate) fwd_stage2_compute<FwdEmitT<kMode, kT>, Release, AIP_FWD_LATE_RELEASE - 2>(zr, zi, w, p, emit, release);
+    else fwd_stage2_compute(zr, zi, w, p, emit, no_hook);
   }
 }
 
