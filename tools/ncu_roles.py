@@ -11,7 +11,7 @@ hdr = rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
 data, seen = [], set()
 for r in rows[2:]:
-    if len(r) < 10 or r[0] in seen:
+    if len(r) < 10 or r[0] in seen or not r[0].startswith("0x"):      # repeated headers: the report holds several launches
         continue
     seen.add(r[0])
     data.append(r)
@@ -35,5 +35,6 @@ for name, lo, hi in roles:
         op = t[1] if t[0].startswith("@") else t[0]
         ops[op.split(".")[0]] += f(r, "Instructions Executed")
     print(f"== {name}: {len(sel)} SASS lines, {inst:.4g} warp-instr, {smp:.0f} samples ({100 * smp / tot_samples:.1f}% of all)")
+    smp = smp or 1.0
     print("   stalls: " + ", ".join(f"{h[6:]}={100 * v / smp:.1f}%" for h, v in sorted(st.items(), key=lambda t: -t[1])[:9]))
     print("   opcodes: " + ", ".join(f"{o}={100 * n / inst:.1f}%" for o, n in ops.most_common(14)))
