@@ -507,13 +507,14 @@ AIP_HD void fwd_phase2(const FwdParams& P, int tid, const TileCursor& c, const f
 #define AIP_FWD_LATE_RELEASE 4
 #endif
   // When is the exchange buffer handed back to the stage-1 warps?  As soon as it has been read, where stage 1 is the slower
-  // role (complex / phase outputs).  In the magnitude-only variants stage 2 is the slower role and stage 1 has time to spare;
-  // handed the buffer early, stage 1 of the tile after next starts at once and competes for the FP32 pipe with this tile's
-  // two DFTs, which are FP32-pipe bound -- every change that made stage 1 faster made these variants SLOWER.  There the
+  // role (complex output alone).  In every variant that computes magnitudes or phases stage 2 is the slower role and stage 1 has
+  // time to spare; handed the buffer early, stage 1 of the tile after next starts at once and competes for the FP32 pipe with this
+  // tile's two DFTs, which are FP32-pipe bound -- every change that made stage 1 faster made these variants SLOWER.  There the
   // buffer is handed back only after AIP_FWD_LATE_RELEASE - 1 of the 8 split-pass / epilogue rounds (MUFU, stores: the FP32
   // pipe has room).  Headline launch, A/B on one box: release after the loads 1.465 ms, after the DFTs 1.448, after 2 / 3 / 4
-  // rounds 1.430 / 1.433 / 1.430, after 6 / 8 rounds 1.52 / 1.56 (stage 1 starts too late).
-  constexpr bool kLate = AIP_FWD_LATE_RELEASE && (kMode & (FWD_SPEC | FWD_PHASE)) == 0 && kMode != FWD_FULL;
+  // rounds 1.430 / 1.433 / 1.430, after 6 / 8 rounds 1.52 / 1.56 (stage 1 starts too late).  The GAN front-end (log1p + phase +
+  // mask, win 512 / hop 128, 1024 x 5 s): 1.513 -> 1.433 ms; the eval front-end (complex + phase, then log10 + spectrum gap): 0.890 -> 0.839.
+  constexpr bool kLate = AIP_FWD_LATE_RELEASE && (kMode & (7 | FWD_PHASE)) != 0 && kMode != FWD_FULL;
   if (!kLate) release();
   NoHook no_hook;
   const long long col = (long long)c.b * kBins * T_out + t0 + fr;
