@@ -544,7 +544,7 @@ int run_fwd(const aip_stft_desc* desc, FwdParams P, long long T_out, cudaStream_
   cudaError_t e;
   if (fwd_fast_ok(desc, di)) {
     P.tiles_per_clip = (int)((T_out + kFR - 1) / kFR);
-    // (the dynamic schedule's counter overshoots n_tiles by up to grid * chunk draws: keep clear of the int range)
+    // (the dynamic schedule's counter overshoots n_tiles by up to 2 * grid * chunk -- every CTA draws one chunk ahead: keep clear of the int range)
     if ((long long)P.B * P.tiles_per_clip > 0x3fffffffLL || T_out > (1 << 22)) return AIP_ERR_UNSUPPORTED;
     P.n_tiles = (int)((long long)P.B * P.tiles_per_clip);
     P.tile_floats = (fwd_tile_len(P.hop) + 31) & ~31;
