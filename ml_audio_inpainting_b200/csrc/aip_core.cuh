@@ -306,9 +306,12 @@ AIP_HD void window_table_fill(float* win_s, const float* window, float scale, in
 // ZP = number of leading AND trailing n2 groups (32 samples each) whose window taps are all zero -- librosa's
 // pad_center of a win_length < n_fft window (config.py: win 384 in n_fft 512 => 64 zero taps each side => ZP = 2):
 // those samples are neither loaded nor multiplied, and the first radix-4 pass runs its pruned form.
-template <int ZP>
+struct NoWait { AIP_HM void operator()() const {} };
+
+// `before_store` runs between the DFT and the twiddle / store loop: the exchange buffer is not touched before it
+template <int ZP, class Before>
 AIP_HD void fwd_stage1(const float* tile, float2* exch, const float* win_s, int hop, int fa, int fb, int n1,
-                       const LaneConst& c) {
+                       const LaneConst& c, Before& before_store) {
   float2 r[16], i[16];
   const float* sa = tile + fa * hop + 2 * n1;
   const float* sb = tile + fb * hop + 2 * n1;
@@ -327,6 +330,7 @@ AIP_HD void fwd_stage1(const float* tile, float2* exch, const float* win_s, int 
   }
   if (ZP == 2) fft16x2_in_z2(r, i);
   else fft16x2(r, i);
+  before_store();
   float2* da = exch + n1 * kXP + fa;
   float2* db = exch + n1 * kXP + fb;
 #pragma unroll

@@ -261,12 +261,18 @@ AIP_HD void fwd_gap_zero_own(const FwdTilePlan& q, int hop, int tid, float* tile
 
 // stage 1 of the FFT for one tile: 256 threads, lane = n1 (16 lanes per frame); a thread owns column n1 of
 // frames fa and fa + 16 and runs them as the two lanes of the packed FP32x2 codelet
+template <int ZP, class Before>
+AIP_HD void fwd_phase1(const FwdParams& P, int tid, const float* tile, float2* exch, const float* win_s,
+                       const LaneConst& lc, Before& before_store) {
+  const int warp = tid >> 5, lane = tid & 31;
+  const int fa = 2 * warp + (lane >> 4);
+  fwd_stage1<ZP>(tile, exch, win_s, P.hop, fa, fa + 16, lane & 15, lc, before_store);
+}
 template <int ZP>
 AIP_HD void fwd_phase1(const FwdParams& P, int tid, const float* tile, float2* exch, const float* win_s,
                        const LaneConst& lc) {
-  const int warp = tid >> 5, lane = tid & 31;
-  const int fa = 2 * warp + (lane >> 4);
-  fwd_stage1<ZP>(tile, exch, win_s, P.hop, fa, fa + 16, lane & 15, lc);
+  NoWait nw;
+  fwd_phase1<ZP>(P, tid, tile, exch, win_s, lc, nw);
 }
 
 // zero n2 groups (32 taps) at each end of the centre-padded window that the kernels exploit: 2 or 0
@@ -504,7 +510,7 @@ AIP_HD void fwd_phase2(const FwdParams& P, int tid, const TileCursor& c, const f
   float2 zr[16], zi[16];
   fwd_stage2_load(exch, fr, p, zr, zi);
 #ifndef AIP_FWD_LATE_RELEASE
-#define AIP_FWD_LATE_RELEASE 4
+#define AIP_FWD_LATE_RELEASE 5
 #endif
   // When is the exchange buffer handed back to the stage-1 warps?  As soon as it has been read, where stage 1 is the slower
   // role (complex output alone).  In every variant that computes magnitudes or phases stage 2 is the slower role and stage 1 has
@@ -512,7 +518,8 @@ AIP_HD void fwd_phase2(const FwdParams& P, int tid, const TileCursor& c, const f
   // tile's two DFTs, which are FP32-pipe bound -- every change that made stage 1 faster made these variants SLOWER.  There the
   // buffer is handed back only after AIP_FWD_LATE_RELEASE - 1 of the 8 split-pass / epilogue rounds (MUFU, stores: the FP32
   // pipe has room).  Headline launch, A/B on one box: release after the loads 1.465 ms, after the DFTs 1.448, after 2 / 3 / 4
-  // rounds 1.430 / 1.433 / 1.430, after 6 / 8 rounds 1.52 / 1.56 (stage 1 starts too late).  The GAN front-end (log1p + phase +
+  // rounds 1.430 / 1.433 / 1.430, after 6 / 8 rounds 1.52 / 1.56 (stage 1 starts too late).  Since stage 1 transforms its tile before
+  // it waits for the buffer (aip_fwd.cu) the release sits after 4 rounds: 1.410 -> 1.388 ms.  The GAN front-end (log1p + phase +
   // mask, win 512 / hop 128, 1024 x 5 s): 1.513 -> 1.433 ms; the eval front-end (complex + phase, then log10 + spectrum gap): 0.890 -> 0.839.
   constexpr bool kLate = AIP_FWD_LATE_RELEASE && (kMode & (7 | FWD_PHASE)) != 0 && kMode != FWD_FULL;
   if (!kLate) release();
